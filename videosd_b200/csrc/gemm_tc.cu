@@ -1,0 +1,476 @@
+// tcgen05/TMEM implicit-GEMM kernel for the UNet / TAESD convolutions (3x3 stride-1 pad-1, 1x1) and all
+// nn.Linear projections of the hot path.
+//
+// One CTA computes a 128 x block_n output tile. The 128 rows are a BW x BH x BN rectangle of NHWC pixels, so
+// every 3x3 tap is ONE 4-D TMA box load at a shifted (w, h) coordinate; TMA's out-of-bounds zero fill is the
+// convolution padding. Operands land in shared memory in the 128-byte swizzled K-major layout that
+// tcgen05.mma reads directly; accumulators live in TMEM and are read back with tcgen05.ld by 4 epilogue warps
+// that fuse bias, time-embedding broadcast, residual add and GEGLU before the bf16 (or fp32) store.
+//
+// warp 0: TMA producer | warp 1: TMEM alloc + MMA issue | warps 2..5: epilogue (TMEM lane quarter = warp % 4)
+#include "tc_common.cuh"
+#include "vsd_internal.h"
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace vsd {
+
+static constexpr int kBlockM = 128;
+static constexpr int kBlockK = 64;
+static constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB per stage
+static constexpr int kGemmThreads = 192;
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// Applies bias / per-image vector / residual to 32 consecutive accumulator columns and stores them.
+__device__ __forceinline__ void epilogue_store32(const GemmParams& p, float (&v)[32], int n_img, long grow, int col,
+                                                 int ncols) {
+    if (ncols <= 0) return;
+    const bool full = (ncols >= 32);
+    if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (full || j < ncols) v[j] += __ldg(p.bias + col + j);
+    }
+    if (p.rowvec) {
+        const float* rv = p.rowvec + (long)n_img * p.N + col;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (full || j < ncols) v[j] += __ldg(rv + j);
+    }
+    if (p.residual) {
+        const bf16* r = p.residual + grow * p.ldr + col;
+        if (full && ((p.ldr & 7) == 0) && ((col & 7) == 0)) {
+            const uint4* r4 = reinterpret_cast<const uint4*>(r);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint4 t = r4[q];
+                float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y), c = unpack_bf16x2(t.z), d = unpack_bf16x2(t.w);
+                v[q * 8 + 0] += a.x; v[q * 8 + 1] += a.y; v[q * 8 + 2] += b.x; v[q * 8 + 3] += b.y;
+                v[q * 8 + 4] += c.x; v[q * 8 + 5] += c.y; v[q * 8 + 6] += d.x; v[q * 8 + 7] += d.y;
+            }
+        } else {
+            for (int j = 0; j < 32; ++j)
+                if (j < ncols) v[j] += __bfloat162float(r[j]);
+        }
+    }
+    if (p.out_f32) {
+        float* o = reinterpret_cast<float*>(p.out) + grow * p.ldo + col;
+        if (full && ((p.ldo & 3) == 0) && ((col & 3) == 0)) {
+            float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o4[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+        } else {
+            for (int j = 0; j < 32; ++j)
+                if (j < ncols) o[j] = v[j];
+        }
+    } else {
+        bf16* o = reinterpret_cast<bf16*>(p.out) + grow * p.ldo + col;
+        if (full && ((p.ldo & 7) == 0) && ((col & 7) == 0)) {
+            uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                o4[q] = make_uint4(pack_bf16x2(v[q * 8], v[q * 8 + 1]), pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]),
+                                   pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
+        } else {
+            for (int j = 0; j < 32; ++j)
+                if (j < ncols) o[j] = __float2bfloat16(v[j]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                 const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stages = p.stages;
+    const uint32_t b_bytes = (uint32_t)p.block_n * 128u;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + (size_t)stages * kABytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + (size_t)stages * b_bytes);
+    uint64_t* empty_bar = full_bar + stages;
+    uint64_t* tmem_full_bar = empty_bar + stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int mt = blockIdx.x;
+    const int tw = mt % p.tiles_w;
+    const int th = (mt / p.tiles_w) % p.tiles_h;
+    const int tn = mt / (p.tiles_w * p.tiles_h);
+    const int w0 = tw * p.BW, h0 = th * p.BH, n0 = tn * p.BN;
+    const int col0 = blockIdx.y * p.block_n;
+    const int split = blockIdx.z;
+    const int kb_begin = split * p.kb_per_split;
+    const int kb_end = min(kb_begin + p.kb_per_split, p.kb_total);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapB);
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int kpt = p.cin >> 6;  // 64-channel blocks per tap
+            int it = 0;
+            for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+                const int s = it % stages;
+                const uint32_t ph = (uint32_t)(it / stages) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u, 1);
+                mbar_expect_tx(&full_bar[s], (uint32_t)kABytes + b_bytes);
+                const int tap = kb / kpt;
+                const int cb = kb - tap * kpt;
+                int dy = 0, dx = 0;
+                if (p.taps == 9) {
+                    dy = tap / 3 - 1;
+                    dx = tap - (tap / 3) * 3 - 1;
+                }
+                tma_load_4d(sA + (size_t)s * kABytes, &mapA, &full_bar[s], cb * 64, w0 + dx, h0 + dy, n0);
+                tma_load_2d(sB + (size_t)s * b_bytes, &mapB, &full_bar[s], kb * 64, col0);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        const uint32_t idesc = umma_idesc_bf16(kBlockM, (uint32_t)p.block_n);
+        int it = 0;
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+            const int s = it % stages;
+            const uint32_t ph = (uint32_t)(it / stages) & 1u;
+            mbar_wait(&full_bar[s], ph, 2);
+            tc_fence_after_sync();
+            if (lane == 0) {
+                const uint32_t a_addr = smem_u32(sA + (size_t)s * kABytes);
+                const uint32_t b_addr = smem_u32(sB + (size_t)s * b_bytes);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                    umma_bf16(tmem_base, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                              (it > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+            }
+            __syncwarp();
+        }
+        if (lane == 0) umma_commit(tmem_full_bar);
+        __syncwarp();
+    } else {
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int bw = r % p.BW;
+        const int bh = (r / p.BW) % p.BH;
+        const int bn = r / (p.BW * p.BH);
+        const int n_img = n0 + bn, hh = h0 + bh, ww = w0 + bw;
+        const bool row_ok = (n_img < p.NB) && (hh < p.H) && (ww < p.W);
+        const long grow = ((long)n_img * p.H + hh) * p.W + ww;
+        const long rows_total = (long)p.NB * p.H * p.W;
+        mbar_wait(tmem_full_bar, 0, 3);
+        tc_fence_after_sync();
+        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
+        if (p.splits > 1) {
+            float* dst = p.partial + ((long)split * rows_total + grow) * p.N;
+            for (int c = 0; c < p.block_n; c += 32) {
+                uint32_t u[32];
+                tmem_ld32(tbase + c, u);
+                tmem_ld_wait();
+                const int col = col0 + c;
+                const int ncols = min(32, p.N - col);
+                if (row_ok && ncols > 0) {
+                    if (ncols == 32 && ((p.N & 3) == 0)) {
+                        float4* d4 = reinterpret_cast<float4*>(dst + col);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            d4[j] = make_float4(__uint_as_float(u[4 * j]), __uint_as_float(u[4 * j + 1]),
+                                                __uint_as_float(u[4 * j + 2]), __uint_as_float(u[4 * j + 3]));
+                    } else {
+                        for (int j = 0; j < ncols; ++j) dst[col + j] = __uint_as_float(u[j]);
+                    }
+                }
+            }
+        } else if (p.act == ACT_GEGLU) {
+            // weight rows were interleaved at load time: tile = [half value rows | half gate rows]
+            const int half = p.block_n >> 1;
+            const int ocol0 = col0 >> 1;
+            for (int c = 0; c < half; c += 32) {
+                uint32_t u[32], g[32];
+                tmem_ld32(tbase + c, u);
+                tmem_ld32(tbase + half + c, g);
+                tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float uv = __uint_as_float(u[j]) + __ldg(p.bias + col0 + c + j);
+                    const float gv = __uint_as_float(g[j]) + __ldg(p.bias + col0 + half + c + j);
+                    v[j] = uv * gelu_erf(gv);
+                }
+                if (row_ok) {
+                    bf16* o = reinterpret_cast<bf16*>(p.out) + grow * p.ldo + ocol0 + c;
+                    uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq)
+                        o4[qq] = make_uint4(pack_bf16x2(v[qq * 8], v[qq * 8 + 1]), pack_bf16x2(v[qq * 8 + 2], v[qq * 8 + 3]),
+                                            pack_bf16x2(v[qq * 8 + 4], v[qq * 8 + 5]), pack_bf16x2(v[qq * 8 + 6], v[qq * 8 + 7]));
+                }
+            }
+        } else {
+            for (int c = 0; c < p.block_n; c += 32) {
+                uint32_t u[32];
+                tmem_ld32(tbase + c, u);
+                tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]);
+                const int col = col0 + c;
+                if (row_ok) epilogue_store32(p, v, n_img, grow, col, min(32, p.N - col));
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// Sums split-K partials and applies the same epilogue. One thread per (row, 32-column chunk).
+__global__ void splitk_reduce_kernel(const GemmParams p, long rows) {
+    const int chunks = (p.N + 31) / 32;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * chunks) return;
+    const long grow = idx / chunks;
+    const int col = (int)(idx - grow * chunks) * 32;
+    const int ncols = min(32, p.N - col);
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    for (int s = 0; s < p.splits; ++s) {
+        const float* src = p.partial + ((long)s * rows + grow) * p.N + col;
+        if (ncols == 32 && ((p.N & 3) == 0)) {
+            const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float4 t = s4[j];
+                v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+            }
+        } else {
+            for (int j = 0; j < ncols; ++j) v[j] += src[j];
+        }
+    }
+    const int n_img = (int)(grow / ((long)p.H * p.W));
+    epilogue_store32(p, v, n_img, grow, col, ncols);
+}
+
+// ------------------------------------------------------------------------------------------ host side
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+static std::once_flag g_encode_once;
+
+static void resolve_encode() {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+        g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+}
+
+static int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                  const cuuint32_t* box) {
+    std::call_once(g_encode_once, resolve_encode);
+    VSD_REQUIRE(g_encode != nullptr, "cuTensorMapEncodeTiled driver entry point not available (no CUDA driver?)");
+    VSD_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map base must be 16-byte aligned");
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides,
+                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r) + " rank=" +
+                  std::to_string(rank) + " dims=" + std::to_string(dims[0]) + "," + std::to_string(dims[1]) +
+                  " box=" + std::to_string(box[0]) + "," + std::to_string(box[1]));
+        return -3;
+    }
+    return 0;
+}
+
+int make_tmap_act(CUtensorMap* m, const void* base, int C, int W, int H, int N, int ld, int boxW, int boxH, int boxN) {
+    VSD_REQUIRE((ld % 8) == 0, "activation pixel stride must be a multiple of 8 elements");
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)boxW, (cuuint32_t)boxH, (cuuint32_t)boxN};
+    return encode(m, base, 4, dims, strides, box);
+}
+
+int make_tmap_2d(CUtensorMap* m, const void* base, int K, int rows, int ld, int box_rows) {
+    VSD_REQUIRE((ld % 8) == 0, "matrix row stride must be a multiple of 8 elements");
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    return encode(m, base, 2, dims, strides, box);
+}
+
+static int g_num_sms = 148;
+static int g_max_smem = 227 * 1024;
+
+int gemm_init() {
+    int dev = 0;
+    VSD_CHECK_CUDA(cudaGetDevice(&dev));
+    VSD_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    VSD_CHECK_CUDA(cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    return 0;
+}
+
+static int pow2_at_least(int v) {
+    int p = 32;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// Pick the pixel rectangle covered by one 128-row tile.
+static void pick_tile_rect(int NB, int H, int W, int* BW, int* BH, int* BN) {
+    int bw = 1;
+    while (bw * 2 <= W && bw * 2 <= 128) bw <<= 1;       // largest power of two <= min(W, 128)
+    // prefer an exact divisor of W if one exists that is at least half as wide (no wasted columns)
+    int best = bw;
+    for (int c = bw; c >= 1; c >>= 1) {
+        if (W % c == 0) {
+            if (c * 2 >= bw || c >= 32) best = c;
+            break;
+        }
+    }
+    bw = best;
+    int rem = 128 / bw;
+    int bh = 1;
+    while (bh * 2 <= rem && bh < H) bh <<= 1;            // smallest power of two >= min(H, rem)
+    if (bh > rem) bh = rem;
+    int bn = rem / bh;
+    *BW = bw; *BH = bh; *BN = bn;
+    (void)NB;
+}
+
+int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N, int ldw, void* out, int ldo,
+                  int out_f32, const float* bias, const float* rowvec, const bf16* residual, int ldr, int act,
+                  float* partial_ws, size_t partial_ws_bytes, int force_block_n, int force_splits) {
+    VSD_REQUIRE(taps == 1 || taps == 9, "taps must be 1 or 9");
+    VSD_REQUIRE(a.C % 64 == 0, "input channels must be a multiple of 64 for the tcgen05 path");
+    VSD_REQUIRE(a.ld >= a.C, "bad activation stride");
+    GemmParams& p = op->p;
+    p = GemmParams{};
+    p.taps = taps; p.cin = a.C; p.H = a.H; p.W = a.W; p.NB = a.NB;
+    pick_tile_rect(a.NB, a.H, a.W, &p.BW, &p.BH, &p.BN);
+    p.tiles_w = (a.W + p.BW - 1) / p.BW;
+    p.tiles_h = (a.H + p.BH - 1) / p.BH;
+    p.tiles_n = (a.NB + p.BN - 1) / p.BN;
+    p.N = N;
+    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    p.kb_total = taps * (a.C / 64);
+
+    // N tile: prefer a divisor of N that keeps the grid near a multiple of the SM count.
+    int bn = 0;
+    if (force_block_n > 0) {
+        bn = force_block_n;
+    } else if (act == ACT_GEGLU) {
+        bn = 128;
+    } else {
+        const int cands[6] = {256, 160, 128, 96, 64, 32};
+        double best_score = -1;
+        for (int i = 0; i < 6; ++i) {
+            const int c = cands[i];
+            if (c > ((N + 31) / 32) * 32 && c != 32) continue;
+            const int n_tiles = (N + c - 1) / c;
+            const double waste = (double)(n_tiles * c) / (double)N;      // padded columns
+            const long ctas = (long)m_tiles * n_tiles;
+            const double waves = (double)ctas / g_num_sms;
+            const double eff = waves / (double)((long)(waves + 0.999999));  // tail efficiency
+            // bigger tiles amortise A smem traffic; small tiles fill the machine
+            const double tile_eff = (c >= 128) ? 1.0 : (c >= 96 ? 0.9 : (c >= 64 ? 0.8 : 0.6));
+            const double score = eff * tile_eff / waste;
+            if (score > best_score) { best_score = score; bn = c; }
+        }
+    }
+    VSD_REQUIRE(bn % 32 == 0 && bn >= 32 && bn <= 256, "block_n must be a multiple of 32 in [32,256]");
+    if (act == ACT_GEGLU) VSD_REQUIRE(bn % 64 == 0 && N % bn == 0 && bias != nullptr, "GEGLU needs block_n | N and a bias");
+    p.block_n = bn;
+    p.tmem_cols = pow2_at_least(bn);
+    const int n_tiles = (N + bn - 1) / bn;
+
+    // split K when the tile grid cannot fill the machine and K is deep
+    int splits = 1;
+    if (force_splits > 0) {
+        splits = force_splits;
+    } else if (act == ACT_NONE && partial_ws != nullptr) {
+        const long ctas = (long)m_tiles * n_tiles;
+        if (ctas * 2 <= g_num_sms && p.kb_total >= 16) {
+            splits = (int)(g_num_sms / ctas);
+            const int max_by_k = p.kb_total / 8;
+            if (splits > max_by_k) splits = max_by_k;
+            if (splits > 16) splits = 16;
+            if (splits < 1) splits = 1;
+        }
+    }
+    p.kb_per_split = (p.kb_total + splits - 1) / splits;
+    splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+    p.splits = splits;
+    const long rows = (long)a.NB * a.H * a.W;
+    if (splits > 1) {
+        VSD_REQUIRE(partial_ws != nullptr && (size_t)splits * rows * N * 4 <= partial_ws_bytes,
+                    "split-K workspace too small");
+        VSD_REQUIRE(act == ACT_NONE, "split-K cannot be combined with GEGLU");
+    }
+    p.partial = partial_ws;
+
+    // Tiles up to 160 columns run two CTAs per SM (one CTA's epilogue overlaps the other's main loop);
+    // wider tiles take the whole SM with a deeper ring.
+    const int stage_bytes = kABytes + bn * 128;
+    const int smem_budget = (bn > 160) ? g_max_smem : (g_max_smem / 2 - 1024);
+    int stages = (smem_budget - 2048) / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages > p.kb_per_split) stages = p.kb_per_split;
+    if (stages < 1) stages = 1;
+    p.stages = stages;
+    op->smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + (2 * stages + 1) * 8 + 16;
+
+    p.out = out; p.ldo = ldo; p.out_f32 = out_f32;
+    p.bias = bias; p.rowvec = rowvec; p.residual = residual; p.ldr = ldr; p.act = act;
+
+    int rc = make_tmap_act(&op->mapA, a.ptr, a.C, a.W, a.H, a.NB, a.ld, p.BW, p.BH, p.BN);
+    if (rc) return rc;
+    rc = make_tmap_2d(&op->mapB, wt, p.kb_total * 64, N, ldw, bn);
+    if (rc) return rc;
+    op->grid = dim3(m_tiles, n_tiles, splits);
+    return 0;
+}
+
+int launch_gemm_op(const GemmOp& op, cudaStream_t st) {
+    conv_gemm_kernel<<<op.grid, kGemmThreads, op.smem_bytes, st>>>(op.mapA, op.mapB, op.p);
+    VSD_CHECK_CUDA(cudaGetLastError());
+    if (op.p.splits > 1) {
+        const long rows = (long)op.p.NB * op.p.H * op.p.W;
+        return launch_splitk_reduce(op.p, rows, st);
+    }
+    return 0;
+}
+
+int launch_splitk_reduce(const GemmParams& p, long rows, cudaStream_t st) {
+    const long work = rows * ((p.N + 31) / 32);
+    const int threads = 128;
+    splitk_reduce_kernel<<<(unsigned)((work + threads - 1) / threads), threads, 0, st>>>(p, rows);
+    VSD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+unsigned int read_trap_code_gemm() {
+    unsigned int v = 0, z = 0;
+    if (cudaMemcpyFromSymbol(&v, g_trap_code, sizeof(v)) != cudaSuccess) return 0xFFFFFFFFu;
+    if (v) cudaMemcpyToSymbol(g_trap_code, &z, sizeof(z));
+    return v;
+}
+
+}  // namespace vsd

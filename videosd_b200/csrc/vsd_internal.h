@@ -1,0 +1,126 @@
+// Internal host-side declarations shared by the translation units of libvideosd.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string>
+
+namespace vsd {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing: every host entry returns 0 or a negative code and records a message.
+void set_error(const std::string& msg);
+const char* get_error();
+#define VSD_CHECK_CUDA(expr)                                                                         \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess) {                                                                     \
+            ::vsd::set_error(std::string(#expr) + " -> " + cudaGetErrorString(_e) + " @" + __FILE__ + \
+                             ":" + std::to_string(__LINE__));                                        \
+            return -2;                                                                               \
+        }                                                                                            \
+    } while (0)
+#define VSD_REQUIRE(cond, msg)                                                             \
+    do {                                                                                   \
+        if (!(cond)) {                                                                     \
+            ::vsd::set_error(std::string("requirement failed: ") + #cond + " : " + (msg)); \
+            return -1;                                                                     \
+        }                                                                                  \
+    } while (0)
+
+// ---- tensor maps (driver entry point resolved at run time; the library does not link libcuda)
+int make_tmap_act(CUtensorMap* m, const void* base, int C, int W, int H, int N, int ld, int boxW, int boxH, int boxN);
+int make_tmap_2d(CUtensorMap* m, const void* base, int K, int rows, int ld, int box_rows);
+
+// ---- tcgen05 implicit-GEMM convolution / linear kernel -------------------------------------------
+// out[pixel, n] = epilogue( sum_{tap, c} A[pixel + tap offset, c] * Wt[n, tap*cin + c] )
+enum { ACT_NONE = 0, ACT_GEGLU = 1 };
+
+struct GemmParams {
+    // A operand traversal (NHWC activation, stride-1 taps; linear layers use H=NB=1, W=rows)
+    int taps, cin;        // 1 or 9 ; channels per tap (multiple of 64)
+    int H, W, NB;         // output == input spatial extent
+    int BW, BH, BN;       // tile rectangle, BW*BH*BN == 128
+    int tiles_w, tiles_h, tiles_n;
+    // B operand
+    int N;                // rows of the weight matrix (GEMM N)
+    int block_n;          // multiple of 32, <= 256
+    int tmem_cols;        // power of two >= block_n
+    int stages;
+    // K split
+    int kb_total, kb_per_split, splits;
+    // epilogue
+    void* out;            // bf16 or fp32 [rows, ldo]
+    int ldo, out_f32;
+    const float* bias;    // [N] or null
+    const float* rowvec;  // [NB, N] or null (per-image broadcast, e.g. time embedding projection)
+    const bf16* residual; // [rows, ldr] or null
+    int ldr;
+    int act;
+    float* partial;       // [splits, rows, N] fp32 when splits > 1
+};
+
+struct GemmOp {
+    CUtensorMap mapA, mapB;
+    GemmParams p;
+    dim3 grid;
+    int smem_bytes;
+};
+
+// Describe a conv3x3(stride 1, pad 1) / conv1x1 / linear as a GemmOp. `act_*` describe the NHWC input view.
+struct ActView {
+    const void* ptr;
+    int NB, H, W, C, ld;  // ld = elements between consecutive pixels (>= C)
+};
+int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N, int ldw, void* out, int ldo,
+                  int out_f32, const float* bias, const float* rowvec, const bf16* residual, int ldr, int act,
+                  float* partial_ws, size_t partial_ws_bytes, int force_block_n, int force_splits);
+int launch_gemm_op(const GemmOp& op, cudaStream_t st);
+int gemm_init();  // sets func attributes; call once per process after a device is selected
+
+// ---- tcgen05 attention ---------------------------------------------------------------------------
+struct AttnOp {
+    CUtensorMap mapQ, mapK, mapVt;
+    int heads, d, dk_pad, dv_pad;
+    int nq, nk;        // per image
+    int batch;
+    int q_rows_per_img, k_rows_per_img, vt_cols_per_img;
+    bf16* out; int ldo;
+    float scale_log2e;
+    int stages, tmem_cols, smem_bytes;
+    dim3 grid;
+};
+int build_attn_op(AttnOp* op, const bf16* q, int ldq, const bf16* k, int ldk, const bf16* vt, int ldvt, bf16* out,
+                  int ldo, int batch, int heads, int d, int nq, int nk, int q_rows_per_img, int k_rows_per_img,
+                  int vt_cols_per_img, int vt_rows);
+int launch_attn_op(const AttnOp& op, cudaStream_t st);
+int attn_init();
+
+// ---- bandwidth kernels ---------------------------------------------------------------------------
+int launch_groupnorm(const bf16* x, int ldx, bf16* y, int ldy, const float* gamma, const float* beta, int NB, int HW,
+                     int C, int groups, float eps, int silu, float* partial_ws, cudaStream_t st);
+int groupnorm_ws_floats(int NB, int HW, int C, int groups);
+int launch_layernorm(const bf16* x, int ldx, bf16* y, int ldy, const float* gamma, const float* beta, int rows, int C,
+                     float eps, cudaStream_t st);
+int launch_upsample_nearest(const bf16* x, int ldx, bf16* y, int ldy, int NB, int Hi, int Wi, int Ho, int Wo, int C,
+                            cudaStream_t st);
+int launch_im2col_s2(const bf16* x, int ldx, bf16* y, int NB, int Hi, int Wi, int C, int Ho, int Wo, cudaStream_t st);
+int launch_splitk_reduce(const GemmParams& p, long rows, cudaStream_t st);
+int launch_conv3x3_small_cin(const void* x, int x_kind, int NB, int H, int W, int Cin, const float* w, const float* bias,
+                             bf16* y, int ldy, int Cout, int relu, cudaStream_t st);
+int launch_add_noise(const float* x0, const float* noise, float* out, float a, float b, long n, cudaStream_t st);
+int launch_lcm_step(const float* eps, const float* x, const float* z, float* x_prev, float* denoised, float sqrt_a,
+                    float sqrt_1ma, float c_skip, float c_out, float sqrt_ap, float sqrt_1map, int has_noise, long n,
+                    cudaStream_t st);
+int launch_yuv420_to_rgb(const uint8_t* y, const uint8_t* u, const uint8_t* v, uint8_t* rgb, int NB, int H, int W,
+                         cudaStream_t st);
+int launch_pack_rgb_yuv420(const float* img, int ldi, uint8_t* rgb, uint8_t* y, uint8_t* u, uint8_t* v, int NB, int H,
+                           int W, int taesd_denorm, cudaStream_t st);
+int launch_relu_tanh_misc(int kind, const void* in, void* out, long n, cudaStream_t st);
+
+unsigned int read_trap_code_gemm();
+unsigned int read_trap_code_attn();
+
+}  // namespace vsd
