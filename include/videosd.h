@@ -46,6 +46,47 @@ int vsd_op_conv_gemm(const void* x, int nb, int h, int w, int c, int ldx, int ta
                      int ldo, int out_f32, const float* bias, const float* rowvec, const void* residual, int ldr,
                      int act, int block_n, int splits, void* stream);
 
+/* Fused flash-style attention on tcgen05 (replaces F.scaled_dot_product_attention in diffusers AttnProcessor2_0,
+ * reached from lcm_controlnet.py:568-577).
+ *   q, k : dev bf16 [batch*rows_per_img][heads*dk_pad], dk_pad = round_up(d, 64), per-head zero padding
+ *   vt   : dev bf16 [vt_rows = heads*d][batch*vt_cols_per_img]  (V transposed; keys along the row)
+ *   out  : dev bf16 [batch*nq][ldo], head h in columns [h*d, h*d+d)
+ * softmax scale is 1/sqrt(d); keys >= nk inside an image's slot are masked. */
+int vsd_op_attention(const void* q, int ldq, const void* k, int ldk, const void* vt, int ldvt, void* out, int ldo,
+                     int batch, int heads, int d, int nq, int nk, int q_rows_per_img, int k_rows_per_img,
+                     int vt_cols_per_img, int vt_rows, void* stream);
+
+/* GroupNorm (+ optional SiLU) over NHWC bf16; statistics in fp32 (torch.nn.GroupNorm in ResnetBlock2D /
+ * Transformer2DModel). x, y: dev bf16 [nb*hw][ld]. */
+int vsd_op_groupnorm(const void* x, int ldx, void* y, int ldy, const float* gamma, const float* beta, int nb, int hw,
+                     int c, int groups, float eps, int silu, void* stream);
+/* LayerNorm over the last dimension (BasicTransformerBlock.norm1/2/3). */
+int vsd_op_layernorm(const void* x, int ldx, void* y, int ldy, const float* gamma, const float* beta, int rows, int c,
+                     float eps, void* stream);
+/* F.interpolate(mode="nearest") on NHWC bf16 (Upsample2D / TAESD nn.Upsample). */
+int vsd_op_upsample_nearest(const void* x, int ldx, void* y, int ldy, int nb, int hi, int wi, int ho, int wo, int c,
+                            void* stream);
+/* 3x3 stride-2 pad-1 patch gather to [nb*ho*wo][9*c] (Downsample2D and the TAESD encoder strided convs). */
+int vsd_op_im2col_s2(const void* x, int ldx, void* y, int nb, int hi, int wi, int c, int ho, int wo, void* stream);
+/* 3x3 pad-1 convolution with <=4 input channels. x_kind 0: fp32 NHWC; 1: u8 RGB with the VaeImageProcessor
+ * normalisation and TAESD (x+1)/2 prologue; 2: fp32 NHWC with the TAESD decoder tanh(z/3)*3 prologue.
+ * wt: dev fp32 [cout][3][3][cin]. y: dev bf16. */
+int vsd_op_conv3x3_small_cin(const void* x, int x_kind, int nb, int h, int w, int cin, const float* wt,
+                             const float* bias, void* y, int ldy, int cout, int relu, void* stream);
+/* LCMScheduler_X.add_noise (lcm_controlnet.py:1046-1071) and .step (:948-1043) on fp32 latents. */
+int vsd_op_add_noise(const float* x0, const float* noise, float* out, float sqrt_alpha, float sqrt_one_minus_alpha,
+                     long n, void* stream);
+int vsd_op_lcm_step(const float* eps, const float* x, const float* z, float* x_prev, float* denoised, float sqrt_a,
+                    float sqrt_1ma, float c_skip, float c_out, float sqrt_ap, float sqrt_1map, int has_noise, long n,
+                    void* stream);
+/* YUV420P (BT.601 limited) -> RGB24, replacing frame.to_image() (server.py:108). Planar inputs, nb frames. */
+int vsd_op_yuv420_to_rgb(const uint8_t* y, const uint8_t* u, const uint8_t* v, uint8_t* rgb, int nb, int h, int w,
+                         void* stream);
+/* Decoder tail (x*2-1 if taesd_denorm) + VaeImageProcessor.postprocess (lcm_controlnet.py:609-611) + RGB24 ->
+ * YUV420P (VideoFrame.from_image + encoder reformat, server.py:117). Any of rgb / y,u,v may be NULL. */
+int vsd_op_pack_rgb_yuv420(const float* img, int ldi, uint8_t* rgb, uint8_t* y, uint8_t* u, uint8_t* v, int nb, int h,
+                           int w, int taesd_denorm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -173,6 +173,195 @@ def bench_gemm():
             print("EXC time", name, repr(e), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ attention
+def attn_case(name, batch, heads, d, nq, nk, k_slot=None, tol=1.5e-2):
+    def fn():
+        q = randn((batch, nq, heads, d), 21)
+        k = randn((batch, nk, heads, d), 22)
+        v = randn((batch, nk, heads, d), 23)
+        qb, kb, vb = q.bfloat16(), k.bfloat16(), v.bfloat16()
+        slot = nk if k_slot is None else k_slot
+        qp = ops.pad_heads(qb.reshape(batch * nq, heads * d), heads, d)
+        kfull = torch.zeros((batch, slot, heads * d), device=DEV, dtype=torch.bfloat16)
+        kfull[:, :nk] = kb.reshape(batch, nk, heads * d)
+        kp = ops.pad_heads(kfull.reshape(batch * slot, heads * d), heads, d)
+        vfull = torch.zeros((batch, slot, heads * d), device=DEV, dtype=torch.bfloat16)
+        vfull[:, :nk] = vb.reshape(batch, nk, heads * d)
+        vt = vfull.reshape(batch * slot, heads * d).t().contiguous()
+        o = ops.attention(qp, kp, vt, batch, heads, d, nq, nk, k_rows_per_img=slot, vt_cols_per_img=slot)
+        torch.cuda.synchronize()
+        ref = torch.nn.functional.scaled_dot_product_attention(
+            qb.float().transpose(1, 2), kb.float().transpose(1, 2), vb.float().transpose(1, 2))
+        ref = ref.transpose(1, 2).reshape(batch * nq, heads * d)
+        record(name, rel_err(o, ref), tol, {"b": batch, "h": heads, "d": d, "nq": nq, "nk": nk})
+
+    run(name, fn)
+
+
+def check_attn():
+    attn_case("attn_d64_128x128", 1, 1, 64, 128, 128)
+    attn_case("attn_d40_128x128_h8", 1, 8, 40, 128, 128)
+    attn_case("attn_d40_256x256", 1, 8, 40, 256, 256)
+    attn_case("attn_d40_4096", 1, 8, 40, 4096, 4096)
+    attn_case("attn_d80_1024", 1, 8, 80, 1024, 1024)
+    attn_case("attn_d160_256", 1, 8, 160, 256, 256)
+    attn_case("attn_d160_64", 1, 8, 160, 64, 64, k_slot=64)
+    attn_case("attn_d40_cross77", 1, 8, 40, 4096, 77, k_slot=128)
+    attn_case("attn_d80_cross77_b2", 2, 8, 80, 1024, 77, k_slot=128)
+    attn_case("attn_d160_cross77", 1, 8, 160, 64, 77, k_slot=128)
+    attn_case("attn_d40_b2_1024", 2, 8, 40, 1024, 1024)
+    attn_case("attn_d40_odd_b2_920", 2, 8, 40, 920, 920)
+    attn_case("attn_d40_9216", 1, 8, 40, 9216, 9216)
+
+    def timing():
+        for (b, h, d, n) in [(1, 8, 40, 4096), (1, 8, 80, 1024), (1, 8, 160, 256), (4, 8, 40, 9216)]:
+            q = randn((b * n, h * d), 1).bfloat16()
+            qp = ops.pad_heads(q, h, d)
+            vt = q.t().contiguous()
+            out = torch.empty((b * n, h * d), device=DEV, dtype=torch.bfloat16)
+            for _ in range(3):
+                ops.attention(qp, qp, vt, b, h, d, n, n, out=out)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                ops.attention(qp, qp, vt, b, h, d, n, n, out=out)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            fl = 4.0 * b * h * n * n * d
+            print(f"TIME attn b{b} h{h} d{d} n{n}: {ms*1e3:.1f} us {fl/ms/1e9:.1f} TFLOP/s", flush=True)
+
+    run("attn_timing", timing)
+
+
+# ------------------------------------------------------------------------------------------------ bandwidth kernels
+def check_norm():
+    for (nb, h, w, c, eps, silu) in [(1, 64, 64, 320, 1e-5, True), (1, 32, 32, 640, 1e-6, False), (2, 16, 16, 1280, 1e-5, True),
+                                     (1, 8, 8, 2560, 1e-5, True), (1, 16, 16, 1920, 1e-5, True), (1, 32, 32, 960, 1e-5, True),
+                                     (4, 96, 96, 320, 1e-5, True), (1, 23, 40, 640, 1e-5, True)]:
+        def fn(nb=nb, h=h, w=w, c=c, eps=eps, silu=silu):
+            x = (randn((nb, h, w, c), 31) * 2 + 0.5).bfloat16()
+            gam, bet = randn((c,), 32) * 0.2 + 1, randn((c,), 33) * 0.2
+            y = ops.groupnorm(x, gam, bet, 32, eps, silu)
+            ref = torch.nn.functional.group_norm(x.float().permute(0, 3, 1, 2), 32, gam, bet, eps)
+            if silu:
+                ref = torch.nn.functional.silu(ref)
+            record(f"groupnorm_{nb}x{h}x{w}x{c}", rel_err(y, ref.permute(0, 2, 3, 1)), 1e-2)
+        run("groupnorm", fn)
+    # strided input (a channel slice of a wider concat buffer)
+    def gn_strided():
+        buf = (randn((1, 32, 32, 1280), 34)).bfloat16()
+        x = buf[..., 640:]
+        gam, bet = randn((640,), 35) + 1, randn((640,), 36)
+        y = ops.groupnorm(x, gam, bet, 32, 1e-5, True)
+        ref = torch.nn.functional.silu(torch.nn.functional.group_norm(x.float().permute(0, 3, 1, 2), 32, gam, bet, 1e-5))
+        record("groupnorm_strided", rel_err(y, ref.permute(0, 2, 3, 1)), 1e-2)
+    run("groupnorm_strided", gn_strided)
+    for (rows, c) in [(4096, 320), (1024, 640), (256, 1280), (77, 320), (36864, 320)]:
+        def fn(rows=rows, c=c):
+            x = (randn((rows, c), 41) * 3 + 1).bfloat16()
+            gam, bet = randn((c,), 42) * 0.2 + 1, randn((c,), 43) * 0.2
+            y = ops.layernorm(x, gam, bet)
+            ref = torch.nn.functional.layer_norm(x.float(), (c,), gam, bet, 1e-5)
+            record(f"layernorm_{rows}x{c}", rel_err(y, ref), 1e-2)
+        run("layernorm", fn)
+
+
+def check_misc():
+    def ups():
+        x = randn((2, 16, 16, 640), 51).bfloat16()
+        y = ops.upsample_nearest(x, 32, 32)
+        ref = torch.nn.functional.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+        record("upsample_2x", (y.float() - ref.permute(0, 2, 3, 1)).abs().max().item(), 0.0)
+        x = randn((1, 12, 20, 320), 52).bfloat16()
+        y = ops.upsample_nearest(x, 23, 40)
+        ref = torch.nn.functional.interpolate(x.float().permute(0, 3, 1, 2), size=(23, 40), mode="nearest")
+        record("upsample_size", (y.float() - ref.permute(0, 2, 3, 1)).abs().max().item(), 0.0)
+    run("upsample", ups)
+
+    def s2():
+        for (nb, h, w, c, n) in [(1, 64, 64, 320, 320), (2, 45, 80, 64, 64), (1, 512, 512, 64, 64)]:
+            x = randn((nb, h, w, c), 53).bfloat16()
+            wt = randn((n, 9 * c), 54, scale=(9 * c) ** -0.5).bfloat16()
+            b = randn((n,), 55)
+            cols = ops.im2col_s2(x)
+            y = ops.conv_gemm(cols, wt, 1, bias=b)
+            ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt.float().view(n, 3, 3, c).permute(0, 3, 1, 2),
+                                             b, stride=2, padding=1).permute(0, 2, 3, 1)
+            record(f"conv3x3_s2_{nb}x{h}x{w}x{c}", rel_err(y, ref), 1e-2)
+    run("conv_s2", s2)
+
+    def small():
+        # UNet conv_in: fp32 latents, 4 -> 320
+        x = randn((2, 64, 64, 4), 56)
+        w = randn((320, 3, 3, 4), 57, scale=1 / 6.0)
+        b = randn((320,), 58)
+        y = ops.conv3x3_small_cin(x, 0, w, b)
+        ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), w.permute(0, 3, 1, 2), b, padding=1).permute(0, 2, 3, 1)
+        record("conv_in_4_320", rel_err(y, ref), 5e-3)
+        # TAESD encoder first conv from u8 RGB
+        u8 = torch.randint(0, 256, (1, 128, 96, 3), generator=g(59), dtype=torch.uint8).to(DEV)
+        w = randn((64, 3, 3, 3), 60, scale=0.2)
+        b = randn((64,), 61)
+        y = ops.conv3x3_small_cin(u8, 1, w, b)
+        xin = ((2.0 * (u8.float() / 255.0) - 1.0) + 1) / 2
+        ref = torch.nn.functional.conv2d(xin.permute(0, 3, 1, 2), w.permute(0, 3, 1, 2), b, padding=1).permute(0, 2, 3, 1)
+        record("taesd_enc_conv0_u8", rel_err(y, ref), 5e-3)
+        # TAESD decoder first conv with tanh prologue + ReLU
+        z = randn((1, 64, 64, 4), 62) * 3
+        w = randn((64, 3, 3, 4), 63, scale=0.2)
+        b = randn((64,), 64)
+        y = ops.conv3x3_small_cin(z, 2, w, b, relu=True)
+        zin = torch.tanh(z / 3) * 3
+        ref = torch.relu(torch.nn.functional.conv2d(zin.permute(0, 3, 1, 2), w.permute(0, 3, 1, 2), b, padding=1)).permute(0, 2, 3, 1)
+        record("taesd_dec_conv0_tanh", rel_err(y, ref), 5e-3)
+    run("small_cin", small)
+
+    def sched():
+        from oracle.scheduler import LCMSchedulerOracle
+        s = LCMSchedulerOracle()
+        s.set_timesteps(0.5, 4)
+        x0, nz = randn((1, 64, 64, 4), 70), randn((1, 64, 64, 4), 71)
+        sc = s.step_scalars(0)
+        out = ops.add_noise(x0, nz, float(sc["sqrt_alpha"]), float(sc["sqrt_beta"]))
+        ref = s.add_noise(x0.cpu(), nz.cpu(), s.timesteps[:1])
+        record("add_noise_bitexact", (out.cpu() - ref).abs().max().item(), 0.0)
+        for i in range(4):
+            eps, x, z = randn((2, 96, 96, 4), 72 + i), randn((2, 96, 96, 4), 80 + i), randn((2, 96, 96, 4), 90 + i)
+            sc = {k: float(v) for k, v in s.step_scalars(i).items()}
+            xp, den = ops.lcm_step(eps, x, z, sc)
+            rp, rd = s.step(eps.cpu(), i, x.cpu(), z.cpu())
+            record(f"lcm_step{i}_prev_bitexact", (xp.cpu() - rp).abs().max().item(), 0.0)
+            record(f"lcm_step{i}_den_bitexact", (den.cpu() - rd).abs().max().item(), 0.0)
+    run("scheduler", sched)
+
+    def colour():
+        import numpy as np
+        from oracle import imageproc
+        for (h, w) in [(512, 512), (360, 640), (768, 768), (2, 4)]:
+            gg = g(100 + h)
+            y = torch.randint(0, 256, (2, h, w), generator=gg, dtype=torch.uint8)
+            u = torch.randint(0, 256, (2, h // 2, w // 2), generator=gg, dtype=torch.uint8)
+            v = torch.randint(0, 256, (2, h // 2, w // 2), generator=gg, dtype=torch.uint8)
+            rgb = ops.yuv420_to_rgb(y.to(DEV), u.to(DEV), v.to(DEV)).cpu().numpy()
+            ref = np.stack([imageproc.yuv420_to_rgb(y[i].numpy(), u[i].numpy(), v[i].numpy()) for i in range(2)])
+            record(f"yuv420_to_rgb_{h}x{w}_bitexact", float(np.abs(rgb.astype(int) - ref.astype(int)).max()), 0.0)
+            img = torch.rand((2, h, w, 4), generator=gg) * 1.4 - 0.2   # decoder output before *2-1, incl. out-of-range
+            # exact .5 ties for round-half-even
+            img[0, 0, 0, :3] = torch.tensor([0.5 / 255, 1.5 / 255, 2.5 / 255])
+            r8, yy, uu, vv = ops.pack_rgb_yuv420(img.to(DEV), taesd_denorm=True)
+            ref_rgb = imageproc.postprocess((img[..., :3] * 2 - 1).permute(0, 3, 1, 2))
+            record(f"pack_rgb_{h}x{w}_bitexact", float(np.abs(r8.cpu().numpy().astype(int) - ref_rgb.astype(int)).max()), 0.0)
+            worst = 0
+            for i in range(2):
+                ry, ru, rv = imageproc.rgb_to_yuv420(ref_rgb[i])
+                worst = max(worst, np.abs(yy[i].cpu().numpy().astype(int) - ry).max(), np.abs(uu[i].cpu().numpy().astype(int) - ru).max(),
+                            np.abs(vv[i].cpu().numpy().astype(int) - rv).max())
+            record(f"rgb_to_yuv420_{h}x{w}_bitexact", float(worst), 0.0)
+    run("colour", colour)
+
+
 def main():
     which = sys.argv[1:] or ["gemm"]
     tag = "_".join(which)

@@ -1,0 +1,499 @@
+// HBM-bandwidth-bound kernels of the hot path: fused GroupNorm(+SiLU), LayerNorm, nearest upsample, stride-2
+// im2col, the 3/4-channel edge convolutions, the LCM scheduler step / add-noise, YUV420<->RGB and the uint8
+// pack. 128-bit vectorised accesses along the NHWC channel dimension, warp-shuffle / shared-memory reductions,
+// fp32 statistics.
+#include "vsd_internal.h"
+#include "tc_common.cuh"
+
+namespace vsd {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ void unpack8(const uint4& t, float (&f)[8]) {
+    float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y), c = unpack_bf16x2(t.z), d = unpack_bf16x2(t.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+// ------------------------------------------------------------------------------------------ GroupNorm
+// Pass 1: per (image, pixel-chunk) partial sum / sum-of-squares per group, deterministic (no global atomics).
+// blockDim.x = vpp * R (vpp = C/8 channel vectors per pixel): each thread owns one channel vector, so its
+// 8 group ids are loop-invariant.
+__global__ void gn_stats_kernel(const bf16* __restrict__ x, int ldx, int HW, int C, int groups, int px_per_chunk,
+                                float* __restrict__ partial /*[NB][chunks][groups][2]*/) {
+    extern __shared__ float sacc[];  // [groups][2]
+    const int vpp = C >> 3;
+    const int cpg = C / groups;
+    const int vi = threadIdx.x % vpp;
+    const int r0 = threadIdx.x / vpp;
+    const int R = blockDim.x / vpp;
+    const int n = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
+    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sacc[i] = 0.f;
+    __syncthreads();
+    const int p_begin = chunk * px_per_chunk;
+    const int p_end = min(HW, p_begin + px_per_chunk);
+    float s[8], ss[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] = 0.f; ss[j] = 0.f; }
+    if (r0 < R) {
+        const bf16* base = x + ((long)n * HW) * ldx + vi * 8;
+        for (int p = p_begin + r0; p < p_end; p += R) {
+            const uint4 t = *reinterpret_cast<const uint4*>(base + (long)p * ldx);
+            float f[8];
+            unpack8(t, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] += f[j] * f[j]; }
+        }
+        // fold the 8 channels into (at most two) groups, then one shared atomic per group touched
+        const int g0 = (vi * 8) / cpg;
+        float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;
+        int g1 = g0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int g = (vi * 8 + j) / cpg;
+            if (g == g0) { a0 += s[j]; b0 += ss[j]; }
+            else if (g == g0 + 1) { g1 = g; a1 += s[j]; b1 += ss[j]; }
+            else { atomicAdd(&sacc[g * 2], s[j]); atomicAdd(&sacc[g * 2 + 1], ss[j]); }  // cpg < 4 (not used by SD1.5)
+        }
+        atomicAdd(&sacc[g0 * 2], a0);
+        atomicAdd(&sacc[g0 * 2 + 1], b0);
+        if (g1 != g0) { atomicAdd(&sacc[g1 * 2], a1); atomicAdd(&sacc[g1 * 2 + 1], b1); }
+    }
+    __syncthreads();
+    float* dst = partial + ((long)n * chunks + chunk) * groups * 2;
+    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) dst[i] = sacc[i];
+}
+
+// Pass 2: reduce the partials, build per-channel scale/shift in smem, normalise (+SiLU), bf16 out.
+__global__ void gn_apply_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C,
+                                int groups, float eps, int silu, const float* __restrict__ partial, int chunks,
+                                int px_per_block) {
+    extern __shared__ float sm[];  // [groups*2] then [C] scale, [C] shift
+    float* gstat = sm;
+    float* scale = sm + groups * 2;
+    float* shift = scale + C;
+    const int n = blockIdx.y;
+    const int cpg = C / groups;
+    if (threadIdx.x < groups) {
+        const float* src = partial + (long)n * chunks * groups * 2 + threadIdx.x * 2;
+        float a = 0.f, b = 0.f;
+        for (int c = 0; c < chunks; ++c) { a += src[(long)c * groups * 2]; b += src[(long)c * groups * 2 + 1]; }
+        const float cnt = (float)HW * (float)cpg;
+        const float mean = a / cnt;
+        const float var = fmaxf(b / cnt - mean * mean, 0.f);
+        gstat[threadIdx.x * 2] = mean;
+        gstat[threadIdx.x * 2 + 1] = rsqrtf(var + eps);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        const float a = gstat[g * 2 + 1] * gamma[c];
+        scale[c] = a;
+        shift[c] = beta[c] - gstat[g * 2] * a;
+    }
+    __syncthreads();
+    const int vpp = C >> 3;
+    const int p_begin = blockIdx.x * px_per_block;
+    const int p_end = min(HW, p_begin + px_per_block);
+    const long total = (long)(p_end - p_begin) * vpp;
+    const bf16* xb = x + ((long)n * HW + p_begin) * ldx;
+    bf16* yb = y + ((long)n * HW + p_begin) * ldy;
+    for (long i = threadIdx.x; i < total; i += blockDim.x) {
+        const int p = (int)(i / vpp);
+        const int vi = (int)(i - (long)p * vpp);
+        const uint4 t = *reinterpret_cast<const uint4*>(xb + (long)p * ldx + vi * 8);
+        float f[8];
+        unpack8(t, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float v = f[j] * scale[vi * 8 + j] + shift[vi * 8 + j];
+            if (silu) v = v / (1.0f + __expf(-v));
+            f[j] = v;
+        }
+        *reinterpret_cast<uint4*>(yb + (long)p * ldy + vi * 8) = pack8(f);
+    }
+}
+
+static void gn_geometry(int NB, int HW, int* px_per_chunk, int* chunks) {
+    int target = 256 / (NB > 0 ? NB : 1);
+    if (target < 1) target = 1;
+    int ppc = (HW + target - 1) / target;
+    if (ppc < 8) ppc = 8;
+    *px_per_chunk = ppc;
+    *chunks = (HW + ppc - 1) / ppc;
+}
+
+int groupnorm_ws_floats(int NB, int HW, int C, int groups) {
+    int ppc, chunks;
+    gn_geometry(NB, HW, &ppc, &chunks);
+    (void)C;
+    return NB * chunks * groups * 2;
+}
+
+int launch_groupnorm(const bf16* x, int ldx, bf16* y, int ldy, const float* gamma, const float* beta, int NB, int HW,
+                     int C, int groups, float eps, int silu, float* partial_ws, cudaStream_t st) {
+    VSD_REQUIRE(C % 8 == 0 && C % groups == 0 && ldx % 8 == 0 && ldy % 8 == 0, "GroupNorm needs C%8==0 and 16-byte rows");
+    VSD_REQUIRE(C / 8 <= 1024, "GroupNorm channel count too large");
+    int ppc, chunks;
+    gn_geometry(NB, HW, &ppc, &chunks);
+    const int vpp = C / 8;
+    int R = 256 / vpp;
+    if (R < 1) R = 1;
+    gn_stats_kernel<<<dim3(chunks, NB), vpp * R, groups * 2 * sizeof(float), st>>>(x, ldx, HW, C, groups, ppc, partial_ws);
+    VSD_CHECK_CUDA(cudaGetLastError());
+    const size_t smem = (size_t)(groups * 2 + 2 * C) * sizeof(float);
+    gn_apply_kernel<<<dim3(chunks, NB), 256, smem, st>>>(x, ldx, y, ldy, gamma, beta, HW, C, groups, eps, silu,
+                                                          partial_ws, chunks, ppc);
+    VSD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ LayerNorm
+// One warp per row, row kept in registers (C <= 1280 -> <= 5 vectors per lane), two-pass mean / variance.
+template <int MAXV>
+__global__ void layernorm_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, int rows, int C,
+                                 float eps) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int vpp = C >> 3;
+    float f[MAXV][8];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+        const int vi = lane + k * 32;
+        if (vi < vpp) {
+            const uint4 t = *reinterpret_cast<const uint4*>(x + (long)row * ldx + vi * 8);
+            unpack8(t, f[k]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += f[k][j];
+        }
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+        const int vi = lane + k * 32;
+        if (vi < vpp) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float d = f[k][j] - mean; v += d * d; }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(v) / (float)C + eps);
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+        const int vi = lane + k * 32;
+        if (vi < vpp) {
+            float o[8];
+            const float4 g0 = *reinterpret_cast<const float4*>(gamma + vi * 8), g1 = *reinterpret_cast<const float4*>(gamma + vi * 8 + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(beta + vi * 8), b1 = *reinterpret_cast<const float4*>(beta + vi * 8 + 4);
+            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = (f[k][j] - mean) * rstd * gg[j] + bb[j];
+            *reinterpret_cast<uint4*>(y + (long)row * ldy + vi * 8) = pack8(o);
+        }
+    }
+}
+
+int launch_layernorm(const bf16* x, int ldx, bf16* y, int ldy, const float* gamma, const float* beta, int rows, int C,
+                     float eps, cudaStream_t st) {
+    VSD_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && C <= 2048, "LayerNorm needs C%8==0, C<=2048");
+    const int warps = 8;
+    dim3 grid((rows + warps - 1) / warps);
+    if (C <= 512) layernorm_kernel<2><<<grid, warps * 32, 0, st>>>(x, ldx, y, ldy, gamma, beta, rows, C, eps);
+    else if (C <= 1280) layernorm_kernel<5><<<grid, warps * 32, 0, st>>>(x, ldx, y, ldy, gamma, beta, rows, C, eps);
+    else layernorm_kernel<8><<<grid, warps * 32, 0, st>>>(x, ldx, y, ldy, gamma, beta, rows, C, eps);
+    VSD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ data movement
+// torch F.interpolate(mode="nearest"): src = min(floor(dst * in/out), in-1)
+__global__ void upsample_nearest_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy, int NB,
+                                        int Hi, int Wi, int Ho, int Wo, int C) {
+    const int vpp = C >> 3;
+    const long total = (long)NB * Ho * Wo * vpp;
+    const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int vi = (int)(i % vpp);
+        long p = i / vpp;
+        const int wo = (int)(p % Wo); p /= Wo;
+        const int ho = (int)(p % Ho);
+        const int n = (int)(p / Ho);
+        const int hi = min((int)floorf(ho * sh), Hi - 1);
+        const int wi = min((int)floorf(wo * sw), Wi - 1);
+        const uint4 t = *reinterpret_cast<const uint4*>(x + (((long)n * Hi + hi) * Wi + wi) * ldx + vi * 8);
+        *reinterpret_cast<uint4*>(y + (((long)n * Ho + ho) * Wo + wo) * ldy + vi * 8) = t;
+    }
+}
+
+int launch_upsample_nearest(const bf16* x, int ldx, bf16* y, int ldy, int NB, int Hi, int Wi, int Ho, int Wo, int C,
+                            cudaStream_t st) {
+    VSD_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "upsample needs C%8==0");
+    const long total = (long)NB * Ho * Wo * (C / 8);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    upsample_nearest_kernel<<<blocks, 256, 0, st>>>(x, ldx, y, ldy, NB, Hi, Wi, Ho, Wo, C);
+    VSD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// 3x3 stride-2 pad-1 patches -> rows of a [NB*Ho*Wo][9*C] matrix (tap-major), feeding the tcgen05 GEMM.
+__global__ void im2col_s2_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int NB, int Hi, int Wi,
+                                 int C, int Ho, int Wo) {
+    const int vpp = C >> 3;
+    const long total = (long)NB * Ho * Wo * 9 * vpp;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int vi = (int)(i % vpp);
+        long q = i / vpp;
+        const int tap = (int)(q % 9); q /= 9;
+        const int wo = (int)(q % Wo); q /= Wo;
+        const int ho = (int)(q % Ho);
+        const int n = (int)(q / Ho);
+        const int hi = 2 * ho + tap / 3 - 1, wi = 2 * wo + tap % 3 - 1;
+        uint4 t = make_uint4(0, 0, 0, 0);
+        if (hi >= 0 && hi < Hi && wi >= 0 && wi < Wi)
+            t = *reinterpret_cast<const uint4*>(x + (((long)n * Hi + hi) * Wi + wi) * ldx + vi * 8);
+        *reinterpret_cast<uint4*>(y + ((((long)n * Ho + ho) * Wo + wo) * 9 + tap) * C + vi * 8) = t;
+    }
+}
+
+int launch_im2col_s2(const bf16* x, int ldx, bf16* y, int NB, int Hi, int Wi, int C, int Ho, int Wo, cudaStream_t st) {
+    VSD_REQUIRE(C % 8 == 0 && ldx % 8 == 0, "im2col needs C%8==0");
+    const long total = (long)NB * Ho * Wo * 9 * (C / 8);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    im2col_s2_kernel<<<blocks, 256, 0, st>>>(x, ldx, y, NB, Hi, Wi, C, Ho, Wo);
+    VSD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ edge convolutions
+// 3x3 pad-1 stride-1 convolution with Cin <= 4 (UNet conv_in, TAESD encoder/decoder first layers) on CUDA cores.
+// x_kind 0: fp32 NHWC (Cin channels)          1: u8 RGB NHWC with the TAESD-encode prologue ((2*(u/255)-1)+1)/2
+//        2: fp32 NHWC with the TAESD-decode prologue tanh(z/3)*3
+// One thread = one pixel x 64 output channels (blockIdx.y selects the 64-channel slab); weights [Cout][3][3][Cin].
+__global__ void conv3x3_small_cin_kernel(const void* __restrict__ xin, int x_kind, int NB, int H, int W, int Cin,
+                                         const float* __restrict__ w, const float* __restrict__ bias,
+                                         bf16* __restrict__ y, int ldy, int Cout, int relu) {
+    __shared__ float sw[64 * 36];
+    __shared__ float sb[64];
+    const int co0 = blockIdx.y * 64;
+    const int K = 9 * Cin;
+    for (int i = threadIdx.x; i < 64 * K; i += blockDim.x) {
+        const int co = i / K;
+        sw[i] = (co0 + co < Cout) ? w[(long)(co0 + co) * K + (i - co * K)] : 0.f;
+    }
+    if (threadIdx.x < 64) sb[threadIdx.x] = (bias && co0 + threadIdx.x < Cout) ? bias[co0 + threadIdx.x] : 0.f;
+    __syncthreads();
+    const long pix = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= (long)NB * H * W) return;
+    const int wx = (int)(pix % W);
+    const int hy = (int)((pix / W) % H);
+    const int n = (int)(pix / ((long)W * H));
+    float patch[36];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const int hh = hy + t / 3 - 1, ww = wx + t % 3 - 1;
+        const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
+        const long src = ((long)n * H + hh) * W + ww;
+        for (int c = 0; c < 4; ++c) {
+            float v = 0.f;
+            if (ok && c < Cin) {
+                if (x_kind == 1) {
+                    const float u8 = (float)reinterpret_cast<const uint8_t*>(xin)[src * 3 + c];
+                    const float img = __fsub_rn(__fmul_rn(2.0f, __fdiv_rn(u8, 255.0f)), 1.0f);  // VaeImageProcessor
+                    v = __fmul_rn(__fadd_rn(img, 1.0f), 0.5f);                                   // TAESD encode
+                } else {
+                    v = reinterpret_cast<const float*>(xin)[src * Cin + c];
+                    if (x_kind == 2) v = tanhf(v / 3.0f) * 3.0f;
+                }
+            }
+            if (c < Cin) patch[t * Cin + c] = v;
+        }
+    }
+    bf16* out = y + pix * ldy + co0;
+    const int nco = min(64, Cout - co0);
+    for (int c8 = 0; c8 < nco; c8 += 8) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float a = sb[c8 + j];
+            const float* wr = sw + (c8 + j) * K;
+            for (int k = 0; k < K; ++k) a = fmaf(patch[k], wr[k], a);
+            acc[j] = relu ? fmaxf(a, 0.f) : a;
+        }
+        if (c8 + 8 <= nco) {
+            *reinterpret_cast<uint4*>(out + c8) = pack8(acc);
+        } else {
+            for (int j = 0; j < nco - c8; ++j) out[c8 + j] = __float2bfloat16(acc[j]);
+        }
+    }
+}
+
+int launch_conv3x3_small_cin(const void* x, int x_kind, int NB, int H, int W, int Cin, const float* w, const float* bias,
+                             bf16* y, int ldy, int Cout, int relu, cudaStream_t st) {
+    VSD_REQUIRE(Cin >= 1 && Cin <= 4 && ldy % 8 == 0 && Cout % 8 == 0, "small-Cin conv: Cin<=4, Cout%8==0");
+    VSD_REQUIRE(x_kind != 1 || Cin == 3, "u8 input implies 3 channels");
+    const long pixels = (long)NB * H * W;
+    dim3 grid((unsigned)((pixels + 127) / 128), (Cout + 63) / 64);
+    conv3x3_small_cin_kernel<<<grid, 128, 0, st>>>(x, x_kind, NB, H, W, Cin, w, bias, y, ldy, Cout, relu);
+    VSD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ LCM scheduler
+// lcm_controlnet.py:1046-1071: x_t = sqrt(abar)*x0 + sqrt(1-abar)*noise
+__global__ void add_noise_kernel(const float* __restrict__ x0, const float* __restrict__ noise, float* __restrict__ out,
+                                 float a, float b, long n) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        out[i] = __fadd_rn(__fmul_rn(a, x0[i]), __fmul_rn(b, noise[i]));
+}
+int launch_add_noise(const float* x0, const float* noise, float* out, float a, float b, long n, cudaStream_t st) {
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 1184) blocks = 1184;
+    add_noise_kernel<<<blocks, 256, 0, st>>>(x0, noise, out, a, b, n);
+    VSD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// lcm_controlnet.py:1019-1036 with the same operation order (no FMA contraction) as the fp32 reference
+__global__ void lcm_step_kernel(const float* __restrict__ eps, const float* __restrict__ x, const float* __restrict__ z,
+                                float* __restrict__ x_prev, float* __restrict__ denoised, float sqrt_a, float sqrt_1ma,
+                                float c_skip, float c_out, float sqrt_ap, float sqrt_1map, int has_noise, long n) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const float xi = x[i];
+        const float x0 = __fdiv_rn(__fsub_rn(xi, __fmul_rn(sqrt_1ma, eps[i])), sqrt_a);
+        const float den = __fadd_rn(__fmul_rn(c_out, x0), __fmul_rn(c_skip, xi));
+        denoised[i] = den;
+        x_prev[i] = has_noise ? __fadd_rn(__fmul_rn(sqrt_ap, den), __fmul_rn(sqrt_1map, z[i])) : den;
+    }
+}
+int launch_lcm_step(const float* eps, const float* x, const float* z, float* x_prev, float* denoised, float sqrt_a,
+                    float sqrt_1ma, float c_skip, float c_out, float sqrt_ap, float sqrt_1map, int has_noise, long n,
+                    cudaStream_t st) {
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 1184) blocks = 1184;
+    lcm_step_kernel<<<blocks, 256, 0, st>>>(eps, x, z, x_prev, denoised, sqrt_a, sqrt_1ma, c_skip, c_out, sqrt_ap,
+                                            sqrt_1map, has_noise, n);
+    VSD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ colour
+__device__ __forceinline__ int clip255(int v) { return min(max(v, 0), 255); }
+
+// BT.601 limited-range YUV420P -> packed RGB24, chroma replicated over each 2x2 block (oracle/imageproc.py).
+// One thread = 2 rows x 4 columns (one 32-bit Y load per row, one 16-bit U/V load, three 32-bit RGB stores/row).
+__global__ void yuv420_to_rgb_kernel(const uint8_t* __restrict__ yp, const uint8_t* __restrict__ up,
+                                     const uint8_t* __restrict__ vp, uint8_t* __restrict__ rgb, int NB, int H, int W) {
+    const int W4 = W >> 2, H2 = H >> 1;
+    const long total = (long)NB * H2 * W4;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int xq = (int)(i % W4);
+        const int yh = (int)((i / W4) % H2);
+        const int n = (int)(i / ((long)W4 * H2));
+        const uint8_t* ybase = yp + (long)n * H * W;
+        const uint8_t* ub = up + (long)n * H2 * (W >> 1) + (long)yh * (W >> 1) + xq * 2;
+        const uint8_t* vb = vp + (long)n * H2 * (W >> 1) + (long)yh * (W >> 1) + xq * 2;
+        const uchar2 u2 = *reinterpret_cast<const uchar2*>(ub);
+        const uchar2 v2 = *reinterpret_cast<const uchar2*>(vb);
+        const int d[2] = {(int)u2.x - 128, (int)u2.y - 128};
+        const int e[2] = {(int)v2.x - 128, (int)v2.y - 128};
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int row = yh * 2 + r;
+            const uchar4 y4 = *reinterpret_cast<const uchar4*>(ybase + (long)row * W + xq * 4);
+            const int yy[4] = {y4.x, y4.y, y4.z, y4.w};
+            uint8_t o[12];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int c = yy[k] - 16, dd = d[k >> 1], ee = e[k >> 1];
+                o[k * 3 + 0] = (uint8_t)clip255((298 * c + 409 * ee + 128) >> 8);
+                o[k * 3 + 1] = (uint8_t)clip255((298 * c - 100 * dd - 208 * ee + 128) >> 8);
+                o[k * 3 + 2] = (uint8_t)clip255((298 * c + 516 * dd + 128) >> 8);
+            }
+            uint32_t* dst = reinterpret_cast<uint32_t*>(rgb + ((long)n * H + row) * W * 3 + xq * 12);
+            dst[0] = o[0] | (o[1] << 8) | (o[2] << 16) | ((uint32_t)o[3] << 24);
+            dst[1] = o[4] | (o[5] << 8) | (o[6] << 16) | ((uint32_t)o[7] << 24);
+            dst[2] = o[8] | (o[9] << 8) | (o[10] << 16) | ((uint32_t)o[11] << 24);
+        }
+    }
+}
+
+int launch_yuv420_to_rgb(const uint8_t* y, const uint8_t* u, const uint8_t* v, uint8_t* rgb, int NB, int H, int W,
+                         cudaStream_t st) {
+    VSD_REQUIRE(H % 2 == 0 && W % 4 == 0, "YUV420 conversion needs even height and width % 4 == 0");
+    const long total = (long)NB * (H / 2) * (W / 4);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    yuv420_to_rgb_kernel<<<blocks, 256, 0, st>>>(y, u, v, rgb, NB, H, W);
+    VSD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Decoder tail + VaeImageProcessor.postprocess + RGB24 -> YUV420P (oracle/imageproc.py), one thread per 2x2 block.
+//   img: fp32 NHWC, ldi floats per pixel (3 used). taesd_denorm=1 applies the decoder's x*2-1 first.
+//   u8 = rint_half_even( clamp(x/2 + 0.5, 0, 1) * 255 ), as separate fp32 operations.
+__global__ void pack_rgb_yuv420_kernel(const float* __restrict__ img, int ldi, uint8_t* __restrict__ rgb,
+                                       uint8_t* __restrict__ yp, uint8_t* __restrict__ up, uint8_t* __restrict__ vp,
+                                       int NB, int H, int W, int taesd_denorm) {
+    const int W2 = W >> 1, H2 = H >> 1;
+    const long total = (long)NB * H2 * W2;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int xh = (int)(i % W2);
+        const int yh = (int)((i / W2) % H2);
+        const int n = (int)(i / ((long)W2 * H2));
+        int sum[3] = {0, 0, 0};
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int row = yh * 2 + r, col = xh * 2 + c;
+                const long pix = ((long)n * H + row) * W + col;
+                int q[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    float v = img[pix * ldi + k];
+                    if (taesd_denorm) v = __fsub_rn(__fmul_rn(v, 2.0f), 1.0f);
+                    v = __fadd_rn(__fmul_rn(v, 0.5f), 0.5f);
+                    v = fminf(fmaxf(v, 0.0f), 1.0f);
+                    q[k] = __float2int_rn(__fmul_rn(v, 255.0f));
+                    sum[k] += q[k];
+                }
+                if (rgb) {
+                    uint8_t* d = rgb + pix * 3;
+                    d[0] = (uint8_t)q[0]; d[1] = (uint8_t)q[1]; d[2] = (uint8_t)q[2];
+                }
+                if (yp) yp[pix] = (uint8_t)clip255(((66 * q[0] + 129 * q[1] + 25 * q[2] + 128) >> 8) + 16);
+            }
+        }
+        if (up) {
+            const int mr = (sum[0] + 2) >> 2, mg = (sum[1] + 2) >> 2, mb = (sum[2] + 2) >> 2;
+            const long ci = ((long)n * H2 + yh) * W2 + xh;
+            up[ci] = (uint8_t)clip255(((-38 * mr - 74 * mg + 112 * mb + 128) >> 8) + 128);
+            vp[ci] = (uint8_t)clip255(((112 * mr - 94 * mg - 18 * mb + 128) >> 8) + 128);
+        }
+    }
+}
+
+int launch_pack_rgb_yuv420(const float* img, int ldi, uint8_t* rgb, uint8_t* y, uint8_t* u, uint8_t* v, int NB, int H,
+                           int W, int taesd_denorm, cudaStream_t st) {
+    VSD_REQUIRE(H % 2 == 0 && W % 2 == 0, "pack needs even dimensions");
+    const long total = (long)NB * (H / 2) * (W / 2);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    pack_rgb_yuv420_kernel<<<blocks, 256, 0, st>>>(img, ldi, rgb, y, u, v, NB, H, W, taesd_denorm);
+    VSD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace vsd

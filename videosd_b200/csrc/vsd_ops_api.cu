@@ -87,4 +87,72 @@ int vsd_op_conv_gemm(const void* x, int nb, int h, int w, int c, int ldx, int ta
     return launch_gemm_op(op, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int vsd_op_attention(const void* q, int ldq, const void* k, int ldk, const void* vt, int ldvt, void* out, int ldo,
+                     int batch, int heads, int d, int nq, int nk, int q_rows_per_img, int k_rows_per_img,
+                     int vt_cols_per_img, int vt_rows, void* stream) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    AttnOp op;
+    rc = build_attn_op(&op, reinterpret_cast<const bf16*>(q), ldq, reinterpret_cast<const bf16*>(k), ldk,
+                       reinterpret_cast<const bf16*>(vt), ldvt, reinterpret_cast<bf16*>(out), ldo, batch, heads, d, nq,
+                       nk, q_rows_per_img, k_rows_per_img, vt_cols_per_img, vt_rows);
+    if (rc) return rc;
+    return launch_attn_op(op, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int vsd_op_groupnorm(const void* x, int ldx, void* y, int ldy, const float* gamma, const float* beta, int nb, int hw,
+                     int c, int groups, float eps, int silu, void* stream) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    rc = ensure_ws((size_t)groupnorm_ws_floats(nb, hw, c, groups) * 4 + 1024);
+    if (rc) return rc;
+    return launch_groupnorm(reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<bf16*>(y), ldy, gamma, beta, nb, hw,
+                            c, groups, eps, silu, g_ws, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int vsd_op_layernorm(const void* x, int ldx, void* y, int ldy, const float* gamma, const float* beta, int rows, int c,
+                     float eps, void* stream) {
+    return launch_layernorm(reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<bf16*>(y), ldy, gamma, beta, rows, c,
+                            eps, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int vsd_op_upsample_nearest(const void* x, int ldx, void* y, int ldy, int nb, int hi, int wi, int ho, int wo, int c,
+                            void* stream) {
+    return launch_upsample_nearest(reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<bf16*>(y), ldy, nb, hi, wi,
+                                   ho, wo, c, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int vsd_op_im2col_s2(const void* x, int ldx, void* y, int nb, int hi, int wi, int c, int ho, int wo, void* stream) {
+    return launch_im2col_s2(reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<bf16*>(y), nb, hi, wi, c, ho, wo,
+                            reinterpret_cast<cudaStream_t>(stream));
+}
+
+int vsd_op_conv3x3_small_cin(const void* x, int x_kind, int nb, int h, int w, int cin, const float* wt,
+                             const float* bias, void* y, int ldy, int cout, int relu, void* stream) {
+    return launch_conv3x3_small_cin(x, x_kind, nb, h, w, cin, wt, bias, reinterpret_cast<bf16*>(y), ldy, cout, relu,
+                                    reinterpret_cast<cudaStream_t>(stream));
+}
+
+int vsd_op_add_noise(const float* x0, const float* noise, float* out, float sqrt_alpha, float sqrt_one_minus_alpha,
+                     long n, void* stream) {
+    return launch_add_noise(x0, noise, out, sqrt_alpha, sqrt_one_minus_alpha, n, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int vsd_op_lcm_step(const float* eps, const float* x, const float* z, float* x_prev, float* denoised, float sqrt_a,
+                    float sqrt_1ma, float c_skip, float c_out, float sqrt_ap, float sqrt_1map, int has_noise, long n,
+                    void* stream) {
+    return launch_lcm_step(eps, x, z, x_prev, denoised, sqrt_a, sqrt_1ma, c_skip, c_out, sqrt_ap, sqrt_1map, has_noise, n,
+                           reinterpret_cast<cudaStream_t>(stream));
+}
+
+int vsd_op_yuv420_to_rgb(const uint8_t* y, const uint8_t* u, const uint8_t* v, uint8_t* rgb, int nb, int h, int w,
+                         void* stream) {
+    return launch_yuv420_to_rgb(y, u, v, rgb, nb, h, w, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int vsd_op_pack_rgb_yuv420(const float* img, int ldi, uint8_t* rgb, uint8_t* y, uint8_t* u, uint8_t* v, int nb, int h,
+                           int w, int taesd_denorm, void* stream) {
+    return launch_pack_rgb_yuv420(img, ldi, rgb, y, u, v, nb, h, w, taesd_denorm, reinterpret_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

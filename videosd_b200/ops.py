@@ -32,3 +32,119 @@ def conv_gemm(x, weight_ohwi, taps, bias=None, rowvec=None, residual=None, act=0
                                  _p(rowvec), _p(residual), c_int(ldr), c_int(act), c_int(block_n), c_int(splits),
                                  cur_stream()), "vsd_op_conv_gemm")
     return out
+
+
+def attn_dk_pad(d):
+    return (d + 63) // 64 * 64
+
+
+def pad_heads(x, heads, d):
+    """(rows, heads*d) -> (rows, heads*dk_pad) with per-head zero padding (what the padded Q/K projections emit)."""
+    rows = x.shape[0]
+    dk = attn_dk_pad(d)
+    out = torch.zeros((rows, heads, dk), device=x.device, dtype=x.dtype)
+    out[:, :, :d] = x.view(rows, heads, d)
+    return out.view(rows, heads * dk)
+
+
+def attention(q_pad, k_pad, vt, batch, heads, d, nq, nk, q_rows_per_img=None, k_rows_per_img=None,
+              vt_cols_per_img=None, out=None):
+    """q_pad/k_pad: bf16 (batch*rows, heads*dk_pad); vt: bf16 (heads*d, batch*cols). Returns (batch*nq, heads*d)."""
+    q_rows_per_img = nq if q_rows_per_img is None else q_rows_per_img
+    k_rows_per_img = nk if k_rows_per_img is None else k_rows_per_img
+    vt_cols_per_img = nk if vt_cols_per_img is None else vt_cols_per_img
+    if out is None:
+        out = torch.empty((batch * nq, heads * d), device=q_pad.device, dtype=torch.bfloat16)
+    check(lib().vsd_op_attention(_p(q_pad), c_int(q_pad.stride(0)), _p(k_pad), c_int(k_pad.stride(0)), _p(vt),
+                                 c_int(vt.stride(0)), _p(out), c_int(out.stride(0)), c_int(batch), c_int(heads),
+                                 c_int(d), c_int(nq), c_int(nk), c_int(q_rows_per_img), c_int(k_rows_per_img),
+                                 c_int(vt_cols_per_img), c_int(vt.shape[0]), cur_stream()), "vsd_op_attention")
+    return out
+
+
+def groupnorm(x, gamma, beta, groups=32, eps=1e-5, silu=False, out=None):
+    """x: bf16 NHWC (nb,h,w,c)."""
+    nb, h, w, c = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib().vsd_op_groupnorm(_p(x), c_int(x.stride(2)), _p(out), c_int(out.stride(2)), _p(gamma), _p(beta),
+                                 c_int(nb), c_int(h * w), c_int(c), c_int(groups), c_float(eps), c_int(1 if silu else 0),
+                                 cur_stream()), "vsd_op_groupnorm")
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5):
+    """x: bf16 (rows, c)."""
+    rows, c = x.shape
+    out = torch.empty_like(x)
+    check(lib().vsd_op_layernorm(_p(x), c_int(x.stride(0)), _p(out), c_int(out.stride(0)), _p(gamma), _p(beta),
+                                 c_int(rows), c_int(c), c_float(eps), cur_stream()), "vsd_op_layernorm")
+    return out
+
+
+def upsample_nearest(x, ho, wo):
+    nb, hi, wi, c = x.shape
+    out = torch.empty((nb, ho, wo, c), device=x.device, dtype=x.dtype)
+    check(lib().vsd_op_upsample_nearest(_p(x), c_int(x.stride(2)), _p(out), c_int(out.stride(2)), c_int(nb), c_int(hi),
+                                        c_int(wi), c_int(ho), c_int(wo), c_int(c), cur_stream()), "vsd_op_upsample_nearest")
+    return out
+
+
+def im2col_s2(x):
+    nb, hi, wi, c = x.shape
+    ho, wo = (hi - 1) // 2 + 1, (wi - 1) // 2 + 1
+    out = torch.empty((nb, ho, wo, 9 * c), device=x.device, dtype=x.dtype)
+    check(lib().vsd_op_im2col_s2(_p(x), c_int(x.stride(2)), _p(out), c_int(nb), c_int(hi), c_int(wi), c_int(c), c_int(ho),
+                                 c_int(wo), cur_stream()), "vsd_op_im2col_s2")
+    return out
+
+
+def conv3x3_small_cin(x, x_kind, weight_ohwi_f32, bias, relu=False):
+    """x: (nb,h,w,cin) fp32 (kind 0/2) or u8 (kind 1). weight: fp32 (cout,3,3,cin)."""
+    nb, h, w, cin = x.shape
+    cout = weight_ohwi_f32.shape[0]
+    out = torch.empty((nb, h, w, cout), device=x.device, dtype=torch.bfloat16)
+    check(lib().vsd_op_conv3x3_small_cin(_p(x), c_int(x_kind), c_int(nb), c_int(h), c_int(w), c_int(cin),
+                                         _p(weight_ohwi_f32), _p(bias), _p(out), c_int(cout), c_int(cout),
+                                         c_int(1 if relu else 0), cur_stream()), "vsd_op_conv3x3_small_cin")
+    return out
+
+
+def add_noise(x0, noise, sqrt_alpha, sqrt_one_minus_alpha):
+    out = torch.empty_like(x0)
+    check(lib().vsd_op_add_noise(_p(x0), _p(noise), _p(out), c_float(sqrt_alpha), c_float(sqrt_one_minus_alpha),
+                                 ctypes.c_long(x0.numel()), cur_stream()), "vsd_op_add_noise")
+    return out
+
+
+def lcm_step(eps, x, z, sc):
+    """sc: dict with sqrt_alpha, sqrt_beta, c_skip, c_out, sqrt_alpha_prev, sqrt_beta_prev (python floats)."""
+    x_prev = torch.empty_like(x)
+    den = torch.empty_like(x)
+    check(lib().vsd_op_lcm_step(_p(eps), _p(x), _p(z), _p(x_prev), _p(den), c_float(sc["sqrt_alpha"]),
+                                c_float(sc["sqrt_beta"]), c_float(sc["c_skip"]), c_float(sc["c_out"]),
+                                c_float(sc["sqrt_alpha_prev"]), c_float(sc["sqrt_beta_prev"]),
+                                c_int(0 if z is None else 1), ctypes.c_long(x.numel()), cur_stream()), "vsd_op_lcm_step")
+    return x_prev, den
+
+
+def yuv420_to_rgb(y, u, v):
+    """y: u8 (nb,h,w); u,v: u8 (nb,h/2,w/2) -> (nb,h,w,3) u8."""
+    nb, h, w = y.shape
+    rgb = torch.empty((nb, h, w, 3), device=y.device, dtype=torch.uint8)
+    check(lib().vsd_op_yuv420_to_rgb(_p(y), _p(u), _p(v), _p(rgb), c_int(nb), c_int(h), c_int(w), cur_stream()),
+          "vsd_op_yuv420_to_rgb")
+    return rgb
+
+
+def pack_rgb_yuv420(img, taesd_denorm=False, want_rgb=True):
+    """img: fp32 (nb,h,w,ld>=3) -> rgb (nb,h,w,3) u8, y, u, v planes."""
+    nb, h, w, ld = img.shape
+    dev = img.device
+    rgb = torch.empty((nb, h, w, 3), device=dev, dtype=torch.uint8) if want_rgb else None
+    y = torch.empty((nb, h, w), device=dev, dtype=torch.uint8)
+    u = torch.empty((nb, h // 2, w // 2), device=dev, dtype=torch.uint8)
+    v = torch.empty((nb, h // 2, w // 2), device=dev, dtype=torch.uint8)
+    check(lib().vsd_op_pack_rgb_yuv420(_p(img), c_int(ld), _p(rgb), _p(y), _p(u), _p(v), c_int(nb), c_int(h), c_int(w),
+                                       c_int(1 if taesd_denorm else 0), cur_stream()), "vsd_op_pack_rgb_yuv420")
+    return rgb, y, u, v
