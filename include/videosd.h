@@ -87,6 +87,61 @@ int vsd_op_yuv420_to_rgb(const uint8_t* y, const uint8_t* u, const uint8_t* v, u
 int vsd_op_pack_rgb_yuv420(const float* img, int ldi, uint8_t* rgb, uint8_t* y, uint8_t* u, uint8_t* v, int nb, int h,
                            int w, int taesd_denorm, void* stream);
 
+/* ------------------------------------------------------------------ engine (per-frame path) */
+
+/* One context per GPU (the reference creates one VideoSDPipeline Ray actor per GPU, videopipeline.py:11-32).
+ * Calls on a context must be serialised by the caller (server.py keeps <= 1 in-flight infer per GPU, :132-137). */
+typedef struct vsd_ctx vsd_ctx;
+
+vsd_ctx* vsd_create(int device);             /* NULL on failure (see vsd_last_error) */
+void vsd_destroy(vsd_ctx* ctx);
+
+/* Weights by diffusers state-dict name, prefixed "unet." or "vae.", fp32 host data in
+ * PyTorch layout (conv: [Cout][Cin][kh][kw], linear: [out][in]). Replaces from_pretrained in
+ * videopipeline.py:49-72. Converted to bf16 and repacked for the tensor-core kernels on load. */
+int vsd_load_weight(vsd_ctx* ctx, const char* name, const float* host_f32, const int64_t* shape, int ndim);
+int vsd_num_weights(vsd_ctx* ctx);
+
+/* Working size: `batch` frames of height x width (multiples of 8; infer(height=, width=) at videopipeline.py:75-88).
+ * Must be called after the weights are loaded; invalidates schedule, contexts and noise. */
+int vsd_configure(vsd_ctx* ctx, int batch, int height, int width);
+
+/* LCM schedule (LCMScheduler_X.set_timesteps, lcm_controlnet.py:905-938, computed by the host):
+ *   timesteps[steps]; scalars[steps][6] = sqrt(abar_t), sqrt(1-abar_t), c_skip, c_out, sqrt(abar_prev),
+ *   sqrt(1-abar_prev) (:995-1036); add_noise coefficients at timesteps[0] (:1046-1071); the 256-d guidance
+ *   embedding (:347-368); has_step_noise = len(timesteps) > 1 (:1032). Builds the launch plan. */
+int vsd_set_schedule(vsd_ctx* ctx, int steps, const int* timesteps, const float* scalars, float add_noise_a,
+                     float add_noise_b, const float* w_embedding256, int has_step_noise);
+
+/* Prompt context (CLIP last_hidden_state, 77 x 768 fp32, host) for batch slot `slot`; projects it through every
+ * cross-attention to_k / to_v once (the reference recomputes them every step of every frame, lcm_controlnet.py:449). */
+int vsd_set_context(vsd_ctx* ctx, int slot, const float* context_77x768);
+
+/* Noise tensors, NHWC fp32 host: init [batch][h/8][w/8][4] (:331) and per-step [steps][batch][h/8][w/8][4] (:1033). */
+int vsd_set_noise(vsd_ctx* ctx, const float* init_noise_nhwc, const float* step_noise_nhwc);
+
+/* One frame batch, host planes in / host planes out, synchronous. YUV420P: y [batch][h][w], u, v [batch][h/2][w/2].
+ * Replaces frame.to_image() -> infer -> VideoFrame.from_image (server.py:104-117). */
+int vsd_infer_yuv420(vsd_ctx* ctx, const uint8_t* y, const uint8_t* u, const uint8_t* v, uint8_t* out_y,
+                     uint8_t* out_u, uint8_t* out_v);
+/* Packed RGB24 in / out ([batch][h][w][3]); the PIL-compatible path of VideoSDPipeline.infer. */
+int vsd_infer_rgb(vsd_ctx* ctx, const uint8_t* rgb_in, uint8_t* rgb_out);
+
+/* Split form of vsd_infer_yuv420 (asynchronous on the context's stream; vsd_sync waits). */
+int vsd_upload_yuv420(vsd_ctx* ctx, const uint8_t* y, const uint8_t* u, const uint8_t* v);
+int vsd_run_yuv420(vsd_ctx* ctx);
+int vsd_download_yuv420(vsd_ctx* ctx, uint8_t* y, uint8_t* u, uint8_t* v);
+int vsd_sync(vsd_ctx* ctx);
+void* vsd_stream(vsd_ctx* ctx);               /* cudaStream_t of the context */
+long vsd_launches_per_frame(vsd_ctx* ctx, int yuv);
+long vsd_arena_peak_bytes(vsd_ctx* ctx);
+
+/* Debug taps for the parity tests: fp32 NHWC device buffers copied to the host.
+ * what: "init_latents", "noisy", "image" ([batch][h][w][4], 3 used), or with index = step: "eps", "latents", "denoised". */
+int vsd_debug_read(vsd_ctx* ctx, const char* what, int index, float* host, long nfloats);
+int vsd_debug_unet(vsd_ctx* ctx, const float* latents_nhwc, int step, float* eps_nhwc);
+int vsd_debug_run_eager(vsd_ctx* ctx, int yuv);
+
 #ifdef __cplusplus
 }
 #endif

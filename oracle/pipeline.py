@@ -23,10 +23,13 @@ def frame_noise(batch, h8, w8, num_timesteps):
 
 
 @torch.no_grad()
-def lcm_img2img(unet, vae, rgb_u8, context, steps=4, strength=0.5, guidance_scale=7.5, noise=None, taps=None):
+def lcm_img2img(unet, vae, rgb_u8, context, steps=4, strength=0.5, guidance_scale=7.5, noise=None, taps=None,
+                device="cpu"):
     """rgb_u8: (B,H,W,3) u8 (already cropped/resized to the working size). context: (B,77,768) fp32.
-    Returns dict with 'image' (B,3,H,W) fp32, 'rgb' (B,H,W,3) u8, 'latents' (list per step), 'denoised'."""
-    x = imageproc.preprocess(rgb_u8)                                  # :457
+    Returns dict with 'image' (B,3,H,W) fp32, 'rgb' (B,H,W,3) u8, 'latents' (list per step), 'denoised'.
+    `device` only moves the fp32 module math (tests run the checker on the GPU for speed); RNG stays on the CPU."""
+    x = imageproc.preprocess(rgb_u8).to(device)                       # :457
+    context = context.to(device)
     B, _, H, W = x.shape
     sched = LCMSchedulerOracle()
     timesteps = sched.set_timesteps(strength, steps, 50)              # :493
@@ -35,14 +38,17 @@ def lcm_img2img(unet, vae, rgb_u8, context, steps=4, strength=0.5, guidance_scal
     if noise is None:
         noise = frame_noise(B, h8, w8, len(timesteps))
     init_noise, step_noise = noise
+    init_noise = init_noise.to(device)
+    step_noise = [z.to(device) for z in step_noise]
     latents = sched.add_noise(init_latents, init_noise, timesteps[:1].repeat(B))   # :334
     w = torch.tensor(guidance_scale).repeat(B)
-    w_emb = w_embedding(w, 256)                                        # :517-520
+    w_emb = w_embedding(w, 256).to(device)                             # :517-520
     out = {"timesteps": timesteps.tolist(), "init_latents": init_latents, "noisy_latents": latents, "latents": [],
-           "eps": [], "denoised_steps": []}
+           "eps": [], "denoised_steps": [], "latents_in": []}
     denoised = None
     for i, t in enumerate(timesteps):                                  # :532-582
-        ts = torch.full((B,), int(t), dtype=torch.long)
+        ts = torch.full((B,), int(t), dtype=torch.long, device=device)
+        out["latents_in"].append(latents)
         eps = unet(latents, ts, w_emb, context)
         latents, denoised = sched.step(eps, i, latents, step_noise[i] if step_noise else None)
         out["eps"].append(eps)

@@ -29,10 +29,31 @@ def build_unet(seed=1234):
     return net
 
 
+def _calibrate_taesd(net, seed):
+    """Rescales the two output convolutions so that a random-init TAESD behaves like a trained one in magnitude:
+    latents of unit scale (so the input frame matters next to the injected noise) and a decoded image that spans
+    [0, 1] (so the uint8 output is not a near-black frame and PSNR is a meaningful test). Deterministic."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        x = torch.rand((1, 3, 64, 64), generator=g) * 2 - 1
+        enc_out = net.encoder.layers[-1]
+        z = net.encode(x)
+        s = 1.0 / float(z.std())
+        enc_out.weight.mul_(s)
+        enc_out.bias.sub_(float(z.mean())).mul_(s)
+        zz = torch.randn((1, 4, 16, 16), generator=g) * 1.5
+        dec_out = net.decoder.layers[-1]
+        raw = (net.decode(zz) + 1) / 2  # layers(...) before the final *2-1
+        k = 0.25 / float(raw.std())
+        dec_out.weight.mul_(k)
+        dec_out.bias.mul_(k).add_(0.5 - float(raw.mean()) * k)
+
+
 def build_taesd(seed=4321):
     prev = torch.random.get_rng_state()
     torch.manual_seed(seed)
     net = TAESD().eval()
+    _calibrate_taesd(net, seed + 1)
     torch.random.set_rng_state(prev)
     for p in net.parameters():
         p.requires_grad_(False)

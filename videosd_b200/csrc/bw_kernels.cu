@@ -350,6 +350,32 @@ int launch_conv3x3_small_cin(const void* x, int x_kind, int NB, int H, int W, in
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------ time-embedding GEMV
+__global__ void gemv_f32_kernel(const float* __restrict__ W, const float* __restrict__ x, const float* __restrict__ b,
+                                float* __restrict__ y, int out, int in, int silu_in, int silu_out) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= out) return;
+    float acc = 0.f;
+    for (int k = lane; k < in; k += 32) {
+        float xv = x[k];
+        if (silu_in) xv = xv / (1.0f + expf(-xv));
+        acc = fmaf(W[(long)row * in + k], xv, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        if (b) acc += b[row];
+        if (silu_out) acc = acc / (1.0f + expf(-acc));
+        y[row] = acc;
+    }
+}
+int launch_gemv_f32(const float* W, const float* x, const float* b, float* y, int out, int in, int silu_in, int silu_out,
+                    cudaStream_t st) {
+    gemv_f32_kernel<<<(out + 7) / 8, 256, 0, st>>>(W, x, b, y, out, in, silu_in, silu_out);
+    VSD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------ LCM scheduler
 // lcm_controlnet.py:1046-1071: x_t = sqrt(abar)*x0 + sqrt(1-abar)*noise
 __global__ void add_noise_kernel(const float* __restrict__ x0, const float* __restrict__ noise, float* __restrict__ out,

@@ -54,6 +54,10 @@ __device__ __forceinline__ void epilogue_store32(const GemmParams& p, float (&v)
                 if (j < ncols) v[j] += __bfloat162float(r[j]);
         }
     }
+    if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
     if (p.out_f32) {
         float* o = reinterpret_cast<float*>(p.out) + grow * p.ldo + col;
         if (full && ((p.ldo & 3) == 0) && ((col & 3) == 0)) {
@@ -333,31 +337,27 @@ static int pow2_at_least(int v) {
     return p;
 }
 
-// Pick the pixel rectangle covered by one 128-row tile.
+// Pick the pixel rectangle (BW x BH x BN, powers of two, product 128) covered by one 128-row tile: the shape
+// that needs the fewest tiles; ties go to the widest rectangle (longest contiguous TMA rows).
 static void pick_tile_rect(int NB, int H, int W, int* BW, int* BH, int* BN) {
-    int bw = 1;
-    while (bw * 2 <= W && bw * 2 <= 128) bw <<= 1;       // largest power of two <= min(W, 128)
-    // prefer an exact divisor of W if one exists that is at least half as wide (no wasted columns)
-    int best = bw;
-    for (int c = bw; c >= 1; c >>= 1) {
-        if (W % c == 0) {
-            if (c * 2 >= bw || c >= 32) best = c;
-            break;
+    long best_tiles = -1;
+    int bbw = 128, bbh = 1, bbn = 1;
+    for (int bw = 128; bw >= 1; bw >>= 1) {
+        for (int bh = 128 / bw; bh >= 1; bh >>= 1) {
+            const int bn = 128 / (bw * bh);
+            const long tiles = (long)((W + bw - 1) / bw) * ((H + bh - 1) / bh) * ((NB + bn - 1) / bn);
+            if (best_tiles < 0 || tiles < best_tiles) {
+                best_tiles = tiles; bbw = bw; bbh = bh; bbn = bn;
+            }
         }
     }
-    bw = best;
-    int rem = 128 / bw;
-    int bh = 1;
-    while (bh * 2 <= rem && bh < H) bh <<= 1;            // smallest power of two >= min(H, rem)
-    if (bh > rem) bh = rem;
-    int bn = rem / bh;
-    *BW = bw; *BH = bh; *BN = bn;
-    (void)NB;
+    *BW = bbw; *BH = bbh; *BN = bbn;
 }
 
 int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N, int ldw, void* out, int ldo,
-                  int out_f32, const float* bias, const float* rowvec, const bf16* residual, int ldr, int act,
+                  int out_f32, const float* bias, const float* rowvec, const bf16* residual, int ldr, int act_flags,
                   float* partial_ws, size_t partial_ws_bytes, int force_block_n, int force_splits) {
+    const int act = act_flags & 0xF;
     VSD_REQUIRE(taps == 1 || taps == 9, "taps must be 1 or 9");
     VSD_REQUIRE(a.C % 64 == 0, "input channels must be a multiple of 64 for the tcgen05 path");
     VSD_REQUIRE(a.ld >= a.C, "bad activation stride");
@@ -415,10 +415,12 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
             if (splits < 1) splits = 1;
         }
     }
+    const long rows = (long)a.NB * a.H * a.W;
+    if (force_splits <= 0)
+        while (splits > 1 && (size_t)splits * rows * N * 4 > partial_ws_bytes) --splits;  // fit the workspace
     p.kb_per_split = (p.kb_total + splits - 1) / splits;
     splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
     p.splits = splits;
-    const long rows = (long)a.NB * a.H * a.W;
     if (splits > 1) {
         VSD_REQUIRE(partial_ws != nullptr && (size_t)splits * rows * N * 4 <= partial_ws_bytes,
                     "split-K workspace too small");
@@ -438,7 +440,9 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
     op->smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + (2 * stages + 1) * 8 + 16;
 
     p.out = out; p.ldo = ldo; p.out_f32 = out_f32;
-    p.bias = bias; p.rowvec = rowvec; p.residual = residual; p.ldr = ldr; p.act = act;
+    p.bias = bias; p.rowvec = rowvec; p.residual = residual; p.ldr = ldr;
+    p.act = act;
+    p.relu = (act_flags & ACT_RELU_FLAG) ? 1 : 0;
 
     int rc = make_tmap_act(&op->mapA, a.ptr, a.C, a.W, a.H, a.NB, a.ld, p.BW, p.BH, p.BN);
     if (rc) return rc;

@@ -1,0 +1,1132 @@
+// Frame-level engine behind the C ABI (include/videosd.h, "engine" section): owns the weights (bf16, repacked
+// for the tcgen05 kernels), builds a static launch plan for one (batch, height, width, steps) configuration
+//   YUV420/RGB in -> TAESD encode -> add noise -> steps x (UNet, LCM step) -> TAESD decode -> pack RGB/YUV420
+// and replays it as one CUDA graph per frame batch. Mirrors the sequencing of
+// diffusert/lcm/lcm_controlnet.py:380-618 (ControlNet residuals = 0) with the UNet2DConditionModel /
+// AutoencoderTiny topology of SURVEY.md Appendix A. Activations are NHWC bf16; latents, scheduler math and
+// normalisation statistics are fp32.
+#include "vsd_internal.h"
+#include "../../include/videosd.h"
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+namespace vsd {
+
+// ------------------------------------------------------------------------------------------------ helpers
+static inline uint16_t f32_to_bf16_rne(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);  // NaN
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+
+static void parallel_for(long n, const std::function<void(long, long)>& fn) {
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = (int)(hw ? (hw > 16 ? 16 : hw) : 4);
+    if (n < 1 << 16) nt = 1;
+    std::vector<std::thread> th;
+    const long chunk = (n + nt - 1) / nt;
+    for (int t = 0; t < nt; ++t) {
+        const long a = t * chunk, b = std::min(n, a + chunk);
+        if (a >= b) break;
+        th.emplace_back(fn, a, b);
+    }
+    for (auto& t : th) t.join();
+}
+
+struct View {  // NHWC bf16 activation view
+    bf16* p = nullptr;
+    int nb = 0, h = 0, w = 0, c = 0, ld = 0;
+    long rows() const { return (long)nb * h * w; }
+    View slice(int c0, int cn) const { View v = *this; v.p = p + c0; v.c = cn; return v; }
+    ActView act() const { return ActView{p, nb, h, w, c, ld}; }
+    ActView act_rows() const { return ActView{p, 1, 1, (int)rows(), c, ld}; }  // as a [rows, c] matrix
+};
+
+struct DevW {
+    void* p = nullptr;
+    std::vector<int64_t> shape;
+    int is_bf16 = 0;
+};
+
+class Arena {
+  public:
+    char* base = nullptr;
+    size_t cap = 0, off = 0, peak = 0;
+    int init(size_t bytes) {
+        VSD_CHECK_CUDA(cudaMalloc(&base, bytes));
+        VSD_CHECK_CUDA(cudaMemset(base, 0, bytes));
+        cap = bytes; off = 0; peak = 0;
+        return 0;
+    }
+    void destroy() { if (base) cudaFree(base); base = nullptr; }
+    void* alloc(size_t bytes) {
+        const size_t a = (off + 255) & ~size_t(255);
+        if (a + bytes > cap) return nullptr;
+        off = a + bytes;
+        if (off > peak) peak = off;
+        return base + a;
+    }
+    size_t mark() const { return off; }
+    void release(size_t m) { off = m; }
+};
+
+typedef std::function<int(cudaStream_t)> Launch;
+
+struct StepScalars { float sqrt_a, sqrt_1ma, c_skip, c_out, sqrt_ap, sqrt_1map; int t; };
+
+struct Engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::unordered_map<std::string, DevW> w;
+    // configuration
+    int NB = 0, H = 0, W = 0, h8 = 0, w8 = 0;
+    int steps = 0, has_step_noise = 0;
+    float an_a = 0, an_b = 0;  // add_noise coefficients at timesteps[0]
+    std::vector<StepScalars> sc;
+    std::vector<float> w_emb;  // 256
+    bool configured = false, schedule_set = false, context_set = false;
+    // buffers
+    Arena arena;
+    size_t arena_static_mark = 0;
+    float* splitk_ws = nullptr; size_t splitk_bytes = 0;
+    uint8_t *d_y = nullptr, *d_u = nullptr, *d_v = nullptr, *d_rgb_in = nullptr;       // inputs
+    uint8_t *d_oy = nullptr, *d_ou = nullptr, *d_ov = nullptr, *d_rgb_out = nullptr;   // outputs
+    float *init_latents = nullptr, *noisy = nullptr, *init_noise = nullptr, *step_noise = nullptr, *image = nullptr;
+    std::vector<float*> eps, lat, den;  // per step
+    bf16* ctx_bf16 = nullptr;  // [NB][128][768]
+    // per transformer layer cross-attention K / V^T caches (filled by set_context)
+    struct XAttn { std::string prefix; int C, d, dkp; bf16* k2; bf16* v2t; };
+    std::vector<XAttn> xattn;
+    // per step: temb projections per resnet [NB][cout]
+    std::unordered_map<std::string, std::vector<float*>> temb;  // resnet prefix -> per-step device pointer
+    float *t_emb_in = nullptr, *t_h = nullptr, *t_emb = nullptr;
+    // plans
+    std::vector<Launch> plan_pre_yuv, plan_pre_rgb, plan_core, plan_post;
+    std::vector<std::vector<Launch>> plan_unet;  // per step (debug entry)
+    cudaGraphExec_t graph_yuv = nullptr, graph_rgb = nullptr;
+    long launches_per_frame_yuv = 0;
+    std::string err;
+};
+
+#define ENG_REQUIRE(cond, msg)                                              \
+    do {                                                                    \
+        if (!(cond)) {                                                      \
+            set_error(std::string("engine: ") + (msg) + " [" #cond "]");    \
+            return -1;                                                      \
+        }                                                                   \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ weights
+static bool ends_with(const std::string& s, const char* suf) {
+    const size_t n = strlen(suf);
+    return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
+}
+
+static int upload(DevW* dw, const void* host, size_t bytes) {
+    VSD_CHECK_CUDA(cudaMalloc(&dw->p, bytes));
+    VSD_CHECK_CUDA(cudaMemcpy(dw->p, host, bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// rows of `src` ([rows][cols] fp32) -> bf16 rows placed at dst_row(r) of a zeroed [dst_rows][cols] matrix
+static void scatter_rows_bf16(std::vector<uint16_t>& dst, const float* src, long rows, long cols,
+                              const std::function<long(long)>& dst_row) {
+    parallel_for(rows, [&](long a, long b) {
+        for (long r = a; r < b; ++r) {
+            const long dr = dst_row(r);
+            uint16_t* d = dst.data() + dr * cols;
+            const float* s = src + r * cols;
+            for (long c = 0; c < cols; ++c) d[c] = f32_to_bf16_rne(s[c]);
+        }
+    });
+}
+
+static int load_weight(Engine* e, const std::string& name, const float* host, const int64_t* shape, int ndim) {
+    ENG_REQUIRE(ndim >= 1 && ndim <= 4, "weight rank must be 1..4");
+    long numel = 1;
+    for (int i = 0; i < ndim; ++i) numel *= shape[i];
+    DevW dw;
+    dw.shape.assign(shape, shape + ndim);
+    std::string key = name;
+    if (ndim == 4) {
+        const long co = shape[0], ci = shape[1], kh = shape[2], kw = shape[3];
+        if (ci <= 4) {  // edge convolutions stay fp32, OHWI
+            std::vector<float> t((size_t)numel);
+            for (long o = 0; o < co; ++o)
+                for (long i = 0; i < ci; ++i)
+                    for (long y = 0; y < kh; ++y)
+                        for (long x = 0; x < kw; ++x)
+                            t[((o * kh + y) * kw + x) * ci + i] = host[((o * ci + i) * kh + y) * kw + x];
+            int rc = upload(&dw, t.data(), t.size() * 4);
+            if (rc) return rc;
+        } else {  // bf16 [Cout][kh*kw*Cin], tap-major
+            std::vector<uint16_t> t((size_t)numel);
+            parallel_for(co, [&](long a, long b) {
+                for (long o = a; o < b; ++o)
+                    for (long i = 0; i < ci; ++i)
+                        for (long y = 0; y < kh; ++y)
+                            for (long x = 0; x < kw; ++x)
+                                t[((o * kh + y) * kw + x) * ci + i] = f32_to_bf16_rne(host[((o * ci + i) * kh + y) * kw + x]);
+            });
+            dw.is_bf16 = 1;
+            int rc = upload(&dw, t.data(), t.size() * 2);
+            if (rc) return rc;
+        }
+    } else if (ndim == 2) {
+        const long out = shape[0], in = shape[1];
+        const bool is_time = name.find("time_embedding.") != std::string::npos || name.find("time_emb_proj") != std::string::npos;
+        if (is_time) {
+            int rc = upload(&dw, host, (size_t)numel * 4);
+            if (rc) return rc;
+        } else if (ends_with(name, "attn1.to_q.weight") || ends_with(name, "attn1.to_k.weight")) {
+            // fused, head-padded [2*8*dkp][C]: Q rows first, K rows second
+            const int heads = 8, d = (int)(out / heads), dkp = attn_dk_pad(d);
+            const bool is_k = ends_with(name, "attn1.to_k.weight");
+            key = name.substr(0, name.size() - strlen("to_q.weight")) + "qk.weight";
+            auto it = e->w.find(key);
+            const long rows_total = 2L * heads * dkp;
+            if (it == e->w.end()) {
+                DevW nw;
+                nw.is_bf16 = 1;
+                nw.shape = {rows_total, in};
+                VSD_CHECK_CUDA(cudaMalloc(&nw.p, (size_t)rows_total * in * 2));
+                VSD_CHECK_CUDA(cudaMemset(nw.p, 0, (size_t)rows_total * in * 2));
+                it = e->w.emplace(key, nw).first;
+            }
+            std::vector<uint16_t> t((size_t)heads * dkp * in, 0);
+            scatter_rows_bf16(t, host, out, in, [&](long r) { return (r / d) * dkp + (r % d); });
+            VSD_CHECK_CUDA(cudaMemcpy(reinterpret_cast<uint16_t*>(it->second.p) + (is_k ? (size_t)heads * dkp * in : 0),
+                                      t.data(), t.size() * 2, cudaMemcpyHostToDevice));
+            return 0;
+        } else if (ends_with(name, "attn2.to_q.weight") || ends_with(name, "attn2.to_k.weight")) {
+            const int heads = 8, d = (int)(out / heads), dkp = attn_dk_pad(d);
+            std::vector<uint16_t> t((size_t)heads * dkp * in, 0);
+            scatter_rows_bf16(t, host, out, in, [&](long r) { return (r / d) * dkp + (r % d); });
+            dw.is_bf16 = 1;
+            dw.shape = {(int64_t)heads * dkp, in};
+            int rc = upload(&dw, t.data(), t.size() * 2);
+            if (rc) return rc;
+        } else if (ends_with(name, "ff.net.0.proj.weight")) {
+            // GEGLU: interleave per 128-row tile [64 value rows | 64 gate rows]
+            const long half = out / 2;
+            ENG_REQUIRE(half % 64 == 0, "GEGLU width must be a multiple of 64");
+            std::vector<uint16_t> t((size_t)numel);
+            scatter_rows_bf16(t, host, out, in, [&](long r) {
+                const bool gate = r >= half;
+                const long j = gate ? r - half : r;
+                return (j / 64) * 128 + (gate ? 64 : 0) + (j % 64);
+            });
+            dw.is_bf16 = 1;
+            int rc = upload(&dw, t.data(), t.size() * 2);
+            if (rc) return rc;
+        } else {
+            std::vector<uint16_t> t((size_t)numel);
+            scatter_rows_bf16(t, host, out, in, [](long r) { return r; });
+            dw.is_bf16 = 1;
+            int rc = upload(&dw, t.data(), t.size() * 2);
+            if (rc) return rc;
+        }
+    } else {  // vectors: fp32
+        if (ends_with(name, "ff.net.0.proj.bias")) {
+            const long out = shape[0], half = out / 2;
+            std::vector<float> t((size_t)out);
+            for (long r = 0; r < out; ++r) {
+                const bool gate = r >= half;
+                const long j = gate ? r - half : r;
+                t[(j / 64) * 128 + (gate ? 64 : 0) + (j % 64)] = host[r];
+            }
+            int rc = upload(&dw, t.data(), t.size() * 4);
+            if (rc) return rc;
+        } else {
+            int rc = upload(&dw, host, (size_t)numel * 4);
+            if (rc) return rc;
+        }
+    }
+    auto old = e->w.find(key);
+    if (old != e->w.end()) {
+        cudaFree(old->second.p);
+        e->w.erase(old);
+    }
+    e->w.emplace(key, dw);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ plan builder
+struct Builder {
+    Engine* e;
+    std::vector<Launch>* out;
+    int rc = 0;
+    std::string fail;
+
+    const bf16* wb(const std::string& n) {
+        auto it = e->w.find(n);
+        if (it == e->w.end() || !it->second.is_bf16) { miss(n); return nullptr; }
+        return reinterpret_cast<const bf16*>(it->second.p);
+    }
+    const float* wf(const std::string& n) {
+        auto it = e->w.find(n);
+        if (it == e->w.end() || it->second.is_bf16) { miss(n); return nullptr; }
+        return reinterpret_cast<const float*>(it->second.p);
+    }
+    bool has(const std::string& n) { return e->w.find(n) != e->w.end(); }
+    void miss(const std::string& n) {
+        if (!rc) { rc = -1; fail = "missing or mistyped weight: " + n; }
+    }
+    void bad(const std::string& m) {
+        if (!rc) { rc = -1; fail = m; }
+    }
+    View alloc(int nb, int h, int w, int c) {
+        View v;
+        v.nb = nb; v.h = h; v.w = w; v.c = c; v.ld = c;
+        v.p = reinterpret_cast<bf16*>(e->arena.alloc((size_t)nb * h * w * c * 2));
+        if (!v.p) bad("activation arena exhausted");
+        return v;
+    }
+    float* alloc_f32(size_t n) {
+        float* p = reinterpret_cast<float*>(e->arena.alloc(n * 4));
+        if (!p) bad("activation arena exhausted");
+        return p;
+    }
+
+    // out = epilogue(conv/linear(a)); `a` may be any NHWC view, `o` any view with o.c == N (or N/2 for GEGLU)
+    void gemm(const ActView& a, int taps, const bf16* wt, int N, int ldw, void* outp, int ldo, int out_f32,
+              const float* bias, const float* rowvec, const bf16* res, int ldr, int act) {
+        if (rc) return;
+        GemmOp op;
+        int r = build_gemm_op(&op, a, taps, wt, N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act, e->splitk_ws,
+                              e->splitk_bytes, 0, 0);
+        if (r) { rc = r; fail = get_error(); return; }
+        out->push_back([op](cudaStream_t st) { return launch_gemm_op(op, st); });
+    }
+    void conv(const View& x, const std::string& name, int taps, const View& o, const float* rowvec, const View* res,
+              int act, bool has_bias = true) {
+        const bf16* wt = wb(name + ".weight");
+        const float* b = has_bias ? wf(name + ".bias") : nullptr;
+        if (rc) return;
+        gemm(x.act(), taps, wt, o.c, taps * x.c, o.p, o.ld, 0, b, rowvec, res ? res->p : nullptr, res ? res->ld : 0, act);
+    }
+    void groupnorm(const View& x, const std::string& name, float eps, int silu, const View& o) {
+        const float* g = wf(name + ".weight");
+        const float* b = wf(name + ".bias");
+        if (rc) return;
+        float* ws = alloc_f32((size_t)groupnorm_ws_floats(x.nb, x.h * x.w, x.c, 32));
+        if (rc) return;
+        const View xi = x, oo = o;
+        out->push_back([=](cudaStream_t st) {
+            return launch_groupnorm(xi.p, xi.ld, oo.p, oo.ld, g, b, xi.nb, xi.h * xi.w, xi.c, 32, eps, silu, ws, st);
+        });
+    }
+    void layernorm(const View& x, const std::string& name, const View& o) {
+        const float* g = wf(name + ".weight");
+        const float* b = wf(name + ".bias");
+        if (rc) return;
+        const View xi = x, oo = o;
+        out->push_back([=](cudaStream_t st) {
+            return launch_layernorm(xi.p, xi.ld, oo.p, oo.ld, g, b, (int)xi.rows(), xi.c, 1e-5f, st);
+        });
+    }
+    void attention(const bf16* q, int ldq, const bf16* k, int ldk, const bf16* vt, int ldvt, const View& o, int heads,
+                   int d, int nq, int nk, int q_rows, int k_rows, int vt_cols, int vt_rows) {
+        if (rc) return;
+        AttnOp op;
+        int r = build_attn_op(&op, q, ldq, k, ldk, vt, ldvt, o.p, o.ld, o.nb, heads, d, nq, nk, q_rows, k_rows, vt_cols,
+                              vt_rows);
+        if (r) { rc = r; fail = get_error(); return; }
+        out->push_back([op](cudaStream_t st) { return launch_attn_op(op, st); });
+    }
+
+    // ---- diffusers ResnetBlock2D (Appendix A.3)
+    void resnet(const View& x, const std::string& p, const float* temb_rowvec, const View& o) {
+        const size_t m = e->arena.mark();
+        View t1 = alloc(x.nb, x.h, x.w, x.c);
+        groupnorm(x, p + ".norm1", 1e-5f, 1, t1);
+        View h1 = alloc(x.nb, x.h, x.w, o.c);
+        conv(t1, p + ".conv1", 9, h1, temb_rowvec, nullptr, ACT_NONE);
+        View t2 = alloc(x.nb, x.h, x.w, o.c);
+        groupnorm(h1, p + ".norm2", 1e-5f, 1, t2);
+        if (x.c != o.c) {
+            View sc = alloc(x.nb, x.h, x.w, o.c);
+            conv(x, p + ".conv_shortcut", 1, sc, nullptr, nullptr, ACT_NONE);
+            conv(t2, p + ".conv2", 9, o, nullptr, &sc, ACT_NONE);
+        } else {
+            conv(t2, p + ".conv2", 9, o, nullptr, &x, ACT_NONE);
+        }
+        e->arena.release(m);
+    }
+
+    // ---- diffusers Transformer2DModel with one BasicTransformerBlock (Appendix A.4)
+    void transformer(const View& x, const std::string& p, const View& o) {
+        const size_t m = e->arena.mark();
+        const int C = x.c, heads = 8, d = C / heads, dkp = attn_dk_pad(d);
+        const int HW = x.h * x.w, NB = x.nb;
+        const long M = x.rows();
+        const std::string tb = p + ".transformer_blocks.0";
+        View g = alloc(NB, x.h, x.w, C);
+        groupnorm(x, p + ".norm", 1e-6f, 0, g);
+        View h0 = alloc(NB, x.h, x.w, C);
+        conv(g, p + ".proj_in", 1, h0, nullptr, nullptr, ACT_NONE);
+        // self attention
+        View n1 = alloc(NB, x.h, x.w, C);
+        layernorm(h0, tb + ".norm1", n1);
+        View qk = alloc(NB, x.h, x.w, 2 * heads * dkp);
+        gemm(n1.act_rows(), 1, wb(tb + ".attn1.qk.weight"), qk.c, C, qk.p, qk.ld, 0, nullptr, nullptr, nullptr, 0, ACT_NONE);
+        // V^T[C][tokens] = Wv * n1^T : weight as the row operand, activations as the column operand
+        const int cols_img = (HW + 7) / 8 * 8;
+        const int ldvt = NB * cols_img;
+        bf16* vt = reinterpret_cast<bf16*>(e->arena.alloc((size_t)C * ldvt * 2));
+        if (!vt) bad("activation arena exhausted");
+        const bf16* wv = wb(tb + ".attn1.to_v.weight");
+        if (!rc) {
+            ActView aw{wv, 1, 1, C, C, C};
+            if (cols_img == HW) {
+                gemm(aw, 1, n1.p, (int)M, n1.ld, vt, ldvt, 0, nullptr, nullptr, nullptr, 0, ACT_NONE);
+            } else {
+                for (int b = 0; b < NB; ++b)
+                    gemm(aw, 1, n1.p + (long)b * HW * n1.ld, HW, n1.ld, vt + (long)b * cols_img, ldvt, 0, nullptr, nullptr,
+                         nullptr, 0, ACT_NONE);
+            }
+        }
+        View a1 = alloc(NB, x.h, x.w, C);
+        attention(qk.p, qk.ld, qk.p + heads * dkp, qk.ld, vt, ldvt, a1, heads, d, HW, HW, HW, HW, cols_img, C);
+        View h1 = alloc(NB, x.h, x.w, C);
+        gemm(a1.act_rows(), 1, wb(tb + ".attn1.to_out.0.weight"), C, C, h1.p, h1.ld, 0, wf(tb + ".attn1.to_out.0.bias"),
+             nullptr, h0.p, h0.ld, ACT_NONE);
+        // cross attention against the cached context projections
+        View n2 = alloc(NB, x.h, x.w, C);
+        layernorm(h1, tb + ".norm2", n2);
+        View q2 = alloc(NB, x.h, x.w, heads * dkp);
+        gemm(n2.act_rows(), 1, wb(tb + ".attn2.to_q.weight"), q2.c, C, q2.p, q2.ld, 0, nullptr, nullptr, nullptr, 0, ACT_NONE);
+        const Engine::XAttn* xa = nullptr;
+        for (auto& c : e->xattn)
+            if (c.prefix == tb) xa = &c;
+        if (!xa) bad("cross-attention cache missing for " + tb);
+        View a2 = alloc(NB, x.h, x.w, C);
+        if (!rc) attention(q2.p, q2.ld, xa->k2, heads * dkp, xa->v2t, NB * 128, a2, heads, d, HW, 77, HW, 128, 128, C);
+        View h2 = alloc(NB, x.h, x.w, C);
+        gemm(a2.act_rows(), 1, wb(tb + ".attn2.to_out.0.weight"), C, C, h2.p, h2.ld, 0, wf(tb + ".attn2.to_out.0.bias"),
+             nullptr, h1.p, h1.ld, ACT_NONE);
+        // feed-forward (GEGLU fused into the first GEMM's epilogue)
+        View n3 = alloc(NB, x.h, x.w, C);
+        layernorm(h2, tb + ".norm3", n3);
+        View ff = alloc(NB, x.h, x.w, 4 * C);
+        gemm(n3.act_rows(), 1, wb(tb + ".ff.net.0.proj.weight"), 8 * C, C, ff.p, ff.ld, 0, wf(tb + ".ff.net.0.proj.bias"),
+             nullptr, nullptr, 0, ACT_GEGLU);
+        View h3 = alloc(NB, x.h, x.w, C);
+        gemm(ff.act_rows(), 1, wb(tb + ".ff.net.2.weight"), C, 4 * C, h3.p, h3.ld, 0, wf(tb + ".ff.net.2.bias"), nullptr,
+             h2.p, h2.ld, ACT_NONE);
+        conv(h3, p + ".proj_out", 1, o, nullptr, &x, ACT_NONE);
+        e->arena.release(m);
+    }
+
+    void conv_s2(const View& x, const std::string& name, const View& o, bool has_bias) {
+        const size_t m = e->arena.mark();
+        View cols = alloc(o.nb, o.h, o.w, 9 * x.c);
+        if (rc) return;
+        const View xi = x, ci = cols, oo = o;
+        out->push_back([=](cudaStream_t st) {
+            return launch_im2col_s2(xi.p, xi.ld, ci.p, xi.nb, xi.h, xi.w, xi.c, oo.h, oo.w, st);
+        });
+        const bf16* wt = wb(name + ".weight");
+        const float* b = has_bias ? wf(name + ".bias") : nullptr;
+        gemm(cols.act(), 1, wt, o.c, 9 * x.c, o.p, o.ld, 0, b, nullptr, nullptr, 0, ACT_NONE);
+        e->arena.release(m);
+    }
+    void upsample(const View& x, const View& o) {
+        if (rc) return;
+        const View xi = x, oo = o;
+        out->push_back([=](cudaStream_t st) {
+            return launch_upsample_nearest(xi.p, xi.ld, oo.p, oo.ld, xi.nb, xi.h, xi.w, oo.h, oo.w, xi.c, st);
+        });
+    }
+};
+
+static int ds(int v) { return (v - 1) / 2 + 1; }  // conv k3 s2 p1 output size
+
+// Allocates the persistent UNet tensors (skip/concat buffers) once; returns views through `S`.
+struct UNetStatic {
+    View concat[4][3];  // up block i, resnet j: [h | skip]
+    View mid_in;        // output of the last down block resnet that is not a skip... (it IS a skip; see build)
+    int hs[4], ws[4];
+};
+
+// Emits one UNet pass: eps(fp32 [NB,h8,w8,4]) = UNet(latents fp32, temb of step `si`).
+static void build_unet(Builder& B, const float* latents, float* eps_out, int si, UNetStatic& S) {
+    Engine* e = B.e;
+    const int NB = e->NB;
+    const int widths[4] = {320, 640, 1280, 1280};
+    auto temb = [&](const std::string& resnet) -> const float* {
+        auto it = e->temb.find(resnet);
+        if (it == e->temb.end()) { B.bad("time embedding projection missing for " + resnet); return nullptr; }
+        return it->second[si];
+    };
+    // skip k (push order) is consumed by up-resnet (11-k): up block i = (11-k)/3, resnet j = (11-k)%3, and lives in
+    // the second half of that resnet's concat buffer. Channel split of concat[i][j]: [h : ch][skip : cs].
+    const int up_out[4] = {1280, 1280, 640, 320};
+    const int prev_out[4] = {1280, 1280, 1280, 640};  // width of h entering up block i
+    auto skip_view = [&](int k) -> View {
+        const int r = 11 - k, i = r / 3, j = r % 3;
+        const int ch = (j == 0) ? prev_out[i] : up_out[i];
+        const View& cb = S.concat[i][j];
+        return cb.slice(ch, cb.c - ch);
+    };
+    auto h_view = [&](int i, int j) -> View {
+        const int ch = (j == 0) ? prev_out[i] : up_out[i];
+        return S.concat[i][j].slice(0, ch);
+    };
+    int k = 0;
+    // conv_in -> skip 0
+    {
+        View s0 = skip_view(k++);
+        const float* w = B.wf("unet.conv_in.weight");
+        const float* b = B.wf("unet.conv_in.bias");
+        if (!B.rc) {
+            const View o = s0;
+            B.out->push_back([=](cudaStream_t st) {
+                return launch_conv3x3_small_cin(latents, 0, o.nb, o.h, o.w, 4, w, b, o.p, o.ld, o.c, 0, st);
+            });
+        }
+    }
+    View x = skip_view(0);
+    for (int i = 0; i < 4; ++i) {
+        const std::string bp = "unet.down_blocks." + std::to_string(i);
+        for (int j = 0; j < 2; ++j) {
+            const std::string rp = bp + ".resnets." + std::to_string(j);
+            if (i < 3) {
+                const size_t m = e->arena.mark();
+                View r = B.alloc(NB, x.h, x.w, widths[i]);
+                B.resnet(x, rp, temb(rp), r);
+                View s = skip_view(k++);
+                B.transformer(r, bp + ".attentions." + std::to_string(j), s);
+                x = s;
+                e->arena.release(m);
+            } else {
+                View s = skip_view(k++);
+                B.resnet(x, rp, temb(rp), s);
+                x = s;
+            }
+        }
+        if (i < 3) {
+            View s = skip_view(k++);
+            B.conv_s2(x, bp + ".downsamplers.0.conv", s, true);
+            x = s;
+        }
+    }
+    // mid block -> h of up block 0, resnet 0
+    {
+        const size_t m = e->arena.mark();
+        View a = B.alloc(NB, x.h, x.w, 1280);
+        B.resnet(x, "unet.mid_block.resnets.0", temb("unet.mid_block.resnets.0"), a);
+        View t = B.alloc(NB, x.h, x.w, 1280);
+        B.transformer(a, "unet.mid_block.attentions.0", t);
+        B.resnet(t, "unet.mid_block.resnets.1", temb("unet.mid_block.resnets.1"), h_view(0, 0));
+        e->arena.release(m);
+    }
+    View final_h;
+    for (int i = 0; i < 4; ++i) {
+        const std::string bp = "unet.up_blocks." + std::to_string(i);
+        for (int j = 0; j < 3; ++j) {
+            const std::string rp = bp + ".resnets." + std::to_string(j);
+            const View& in = S.concat[i][j];
+            // where does this layer's result go? next resnet's h slot, or (after the last resnet) the upsampler
+            const size_t m = e->arena.mark();
+            View dst;
+            const bool last = (j == 2);
+            if (!last) dst = h_view(i, j + 1);
+            else dst = B.alloc(NB, in.h, in.w, up_out[i]);
+            if (i > 0) {
+                View r = B.alloc(NB, in.h, in.w, up_out[i]);
+                B.resnet(in, rp, temb(rp), r);
+                B.transformer(r, bp + ".attentions." + std::to_string(j), dst);
+            } else {
+                B.resnet(in, rp, temb(rp), dst);
+            }
+            if (last) {
+                if (i < 3) {
+                    const View& nxt = S.concat[i + 1][0];
+                    View up = B.alloc(NB, nxt.h, nxt.w, up_out[i]);
+                    B.upsample(dst, up);
+                    B.conv(up, bp + ".upsamplers.0.conv", 9, h_view(i + 1, 0), nullptr, nullptr, ACT_NONE);
+                } else {
+                    View g = B.alloc(NB, in.h, in.w, 320);
+                    B.groupnorm(dst, "unet.conv_norm_out", 1e-5f, 1, g);
+                    B.gemm(g.act(), 9, B.wb("unet.conv_out.weight"), 4, 9 * 320, eps_out, 4, 1, B.wf("unet.conv_out.bias"),
+                           nullptr, nullptr, 0, ACT_NONE);
+                }
+            }
+            e->arena.release(m);
+        }
+    }
+}
+
+// TAESD Block: relu(conv(relu(conv(relu(conv(x))))) + x)
+static void taesd_block(Builder& B, const View& x, const std::string& p, const View& o) {
+    const size_t m = B.e->arena.mark();
+    View a = B.alloc(x.nb, x.h, x.w, 64), b = B.alloc(x.nb, x.h, x.w, 64);
+    B.conv(x, p + ".conv.0", 9, a, nullptr, nullptr, ACT_RELU_FLAG);
+    B.conv(a, p + ".conv.2", 9, b, nullptr, nullptr, ACT_RELU_FLAG);
+    B.conv(b, p + ".conv.4", 9, o, nullptr, &x, ACT_RELU_FLAG);
+    B.e->arena.release(m);
+}
+
+static void build_taesd_encoder(Builder& B, const uint8_t* rgb, float* latents_out) {
+    Engine* e = B.e;
+    const int NB = e->NB;
+    int h = e->H, w = e->W;
+    const std::string p = "vae.encoder.layers.";
+    View x = B.alloc(NB, h, w, 64);
+    {
+        const float* wt = B.wf(p + "0.weight");
+        const float* b = B.wf(p + "0.bias");
+        if (!B.rc) {
+            const View o = x;
+            B.out->push_back([=](cudaStream_t st) {
+                return launch_conv3x3_small_cin(rgb, 1, o.nb, o.h, o.w, 3, wt, b, o.p, o.ld, 64, 0, st);
+            });
+        }
+    }
+    View y = B.alloc(NB, h, w, 64);
+    taesd_block(B, x, p + "1", y);
+    x = y;
+    int layer = 2;
+    for (int s = 0; s < 3; ++s) {
+        h = ds(h); w = ds(w);
+        View d = B.alloc(NB, h, w, 64);
+        B.conv_s2(x, p + std::to_string(layer++), d, false);
+        x = d;
+        for (int j = 0; j < 3; ++j) {
+            View o = B.alloc(NB, h, w, 64);
+            taesd_block(B, x, p + std::to_string(layer++), o);
+            x = o;
+        }
+    }
+    B.gemm(x.act(), 9, B.wb(p + "14.weight"), 4, 9 * 64, latents_out, 4, 1, B.wf(p + "14.bias"), nullptr, nullptr, 0, ACT_NONE);
+}
+
+static void build_taesd_decoder(Builder& B, const float* z, float* image_out /*[NB,H,W,4] fp32, 3 used*/) {
+    Engine* e = B.e;
+    const int NB = e->NB;
+    int h = e->h8, w = e->w8;
+    const std::string p = "vae.decoder.layers.";
+    View x = B.alloc(NB, h, w, 64);
+    {
+        const float* wt = B.wf(p + "0.weight");
+        const float* b = B.wf(p + "0.bias");
+        if (!B.rc) {
+            const View o = x;
+            B.out->push_back([=](cudaStream_t st) {
+                return launch_conv3x3_small_cin(z, 2, o.nb, o.h, o.w, 4, wt, b, o.p, o.ld, 64, 1, st);
+            });
+        }
+    }
+    int layer = 2;
+    for (int s = 0; s < 3; ++s) {
+        for (int j = 0; j < 3; ++j) {
+            View o = B.alloc(NB, h, w, 64);
+            taesd_block(B, x, p + std::to_string(layer++), o);
+            x = o;
+        }
+        layer++;  // nn.Upsample
+        h *= 2; w *= 2;
+        View up = B.alloc(NB, h, w, 64);
+        B.upsample(x, up);
+        View c = B.alloc(NB, h, w, 64);
+        B.conv(up, p + std::to_string(layer++), 9, c, nullptr, nullptr, ACT_NONE, false);
+        x = c;
+    }
+    View o = B.alloc(NB, h, w, 64);
+    taesd_block(B, x, p + std::to_string(layer++), o);
+    B.gemm(o.act(), 9, B.wb(p + std::to_string(layer) + ".weight"), 3, 9 * 64, image_out, 4, 1,
+           B.wf(p + std::to_string(layer) + ".bias"), nullptr, nullptr, 0, ACT_NONE);
+}
+
+static int run_plan(const std::vector<Launch>& plan, cudaStream_t st) {
+    for (const auto& l : plan) {
+        int rc = l(st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+static void free_graphs(Engine* e) {
+    if (e->graph_yuv) cudaGraphExecDestroy(e->graph_yuv);
+    if (e->graph_rgb) cudaGraphExecDestroy(e->graph_rgb);
+    e->graph_yuv = e->graph_rgb = nullptr;
+}
+
+static const char* kResnetPrefixes[22] = {
+    "unet.down_blocks.0.resnets.0", "unet.down_blocks.0.resnets.1", "unet.down_blocks.1.resnets.0",
+    "unet.down_blocks.1.resnets.1", "unet.down_blocks.2.resnets.0", "unet.down_blocks.2.resnets.1",
+    "unet.down_blocks.3.resnets.0", "unet.down_blocks.3.resnets.1", "unet.mid_block.resnets.0",
+    "unet.mid_block.resnets.1", "unet.up_blocks.0.resnets.0", "unet.up_blocks.0.resnets.1",
+    "unet.up_blocks.0.resnets.2", "unet.up_blocks.1.resnets.0", "unet.up_blocks.1.resnets.1",
+    "unet.up_blocks.1.resnets.2", "unet.up_blocks.2.resnets.0", "unet.up_blocks.2.resnets.1",
+    "unet.up_blocks.2.resnets.2", "unet.up_blocks.3.resnets.0", "unet.up_blocks.3.resnets.1",
+    "unet.up_blocks.3.resnets.2"};
+
+static std::vector<std::string> transformer_prefixes() {
+    std::vector<std::string> v;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 2; ++j)
+            v.push_back("unet.down_blocks." + std::to_string(i) + ".attentions." + std::to_string(j) + ".transformer_blocks.0");
+    v.push_back("unet.mid_block.attentions.0.transformer_blocks.0");
+    for (int i = 1; i < 4; ++i)
+        for (int j = 0; j < 3; ++j)
+            v.push_back("unet.up_blocks." + std::to_string(i) + ".attentions." + std::to_string(j) + ".transformer_blocks.0");
+    return v;
+}
+
+// (Re)allocates every buffer for a (batch, height, width) configuration. Plans are built by finalize().
+static int configure(Engine* e, int nb, int H, int W) {
+    ENG_REQUIRE(nb >= 1 && nb <= 64, "batch must be in [1, 64]");
+    ENG_REQUIRE(H % 8 == 0 && W % 8 == 0 && H >= 16 && W >= 16, "height and width must be multiples of 8 (>= 16)");
+    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    free_graphs(e);
+    e->arena.destroy();
+    if (e->splitk_ws) cudaFree(e->splitk_ws);
+    e->splitk_ws = nullptr;
+    e->NB = nb; e->H = H; e->W = W; e->h8 = H / 8; e->w8 = W / 8;
+    e->configured = false; e->schedule_set = false; e->context_set = false;
+    e->xattn.clear(); e->temb.clear(); e->eps.clear(); e->lat.clear(); e->den.clear();
+    const double scale = (double)nb * H * W / (512.0 * 512.0);
+    const size_t bytes = (size_t)(640.0 * 1048576.0 * scale) + (size_t)384 * 1048576;
+    int rc = e->arena.init(bytes);
+    if (rc) return rc;
+    e->splitk_bytes = (size_t)(16.0 * 1048576.0 * (scale < 1 ? 1 : scale)) + (size_t)48 * 1048576;
+    VSD_CHECK_CUDA(cudaMalloc(&e->splitk_ws, e->splitk_bytes));
+    Arena& A = e->arena;
+    const size_t px = (size_t)nb * H * W, lpx = (size_t)nb * e->h8 * e->w8;
+    e->d_y = (uint8_t*)A.alloc(px); e->d_u = (uint8_t*)A.alloc(px / 4); e->d_v = (uint8_t*)A.alloc(px / 4);
+    e->d_rgb_in = (uint8_t*)A.alloc(px * 3);
+    e->d_oy = (uint8_t*)A.alloc(px); e->d_ou = (uint8_t*)A.alloc(px / 4); e->d_ov = (uint8_t*)A.alloc(px / 4);
+    e->d_rgb_out = (uint8_t*)A.alloc(px * 3);
+    e->init_latents = (float*)A.alloc(lpx * 16); e->noisy = (float*)A.alloc(lpx * 16);
+    e->init_noise = (float*)A.alloc(lpx * 16);
+    e->step_noise = (float*)A.alloc(lpx * 16 * 16);  // up to 16 steps
+    e->image = (float*)A.alloc(px * 16);
+    e->ctx_bf16 = (bf16*)A.alloc((size_t)nb * 128 * 768 * 2);
+    e->t_emb_in = (float*)A.alloc(320 * 4); e->t_h = (float*)A.alloc(1280 * 4); e->t_emb = (float*)A.alloc(1280 * 4);
+    ENG_REQUIRE(e->t_emb != nullptr, "arena too small for the static buffers");
+    // cross-attention caches
+    for (const auto& tb : transformer_prefixes()) {
+        auto it = e->w.find(tb + ".attn2.to_q.weight");
+        ENG_REQUIRE(it != e->w.end(), "load the UNet weights before configure(): " + tb);
+        Engine::XAttn xa;
+        xa.prefix = tb;
+        xa.C = (int)it->second.shape[1];
+        xa.d = xa.C / 8;
+        xa.dkp = attn_dk_pad(xa.d);
+        xa.k2 = (bf16*)A.alloc((size_t)nb * 128 * 8 * xa.dkp * 2);
+        xa.v2t = (bf16*)A.alloc((size_t)xa.C * nb * 128 * 2);
+        ENG_REQUIRE(xa.v2t != nullptr, "arena too small for the context caches");
+        e->xattn.push_back(xa);
+    }
+    e->arena_static_mark = A.mark();
+    e->configured = true;
+    return 0;
+}
+
+// Time-embedding path (Appendix A.2 steps 1-2 and the 22 per-resnet projections), once per schedule.
+static int set_schedule(Engine* e, int steps, const int* timesteps, const float* scalars /*steps x 6*/, float an_a,
+                        float an_b, const float* w_emb256, int has_step_noise) {
+    ENG_REQUIRE(e->configured, "configure() first");
+    ENG_REQUIRE(steps >= 1 && steps <= 16, "1..16 steps");
+    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    free_graphs(e);
+    e->arena.release(e->arena_static_mark);
+    e->temb.clear(); e->eps.clear(); e->lat.clear(); e->den.clear();
+    e->steps = steps; e->an_a = an_a; e->an_b = an_b; e->has_step_noise = has_step_noise;
+    e->sc.resize(steps);
+    for (int i = 0; i < steps; ++i) {
+        const float* s = scalars + i * 6;
+        e->sc[i] = StepScalars{s[0], s[1], s[2], s[3], s[4], s[5], timesteps[i]};
+    }
+    e->w_emb.assign(w_emb256, w_emb256 + 256);
+    Arena& A = e->arena;
+    const size_t lpx = (size_t)e->NB * e->h8 * e->w8;
+    for (int i = 0; i < steps; ++i) {
+        e->eps.push_back((float*)A.alloc(lpx * 16));
+        e->lat.push_back((float*)A.alloc(lpx * 16));
+        e->den.push_back((float*)A.alloc(lpx * 16));
+    }
+    float* d_wemb = (float*)A.alloc(256 * 4);
+    float* d_sin = (float*)A.alloc(320 * 4);
+    ENG_REQUIRE(d_sin != nullptr, "arena exhausted");
+    VSD_CHECK_CUDA(cudaMemcpyAsync(d_wemb, w_emb256, 256 * 4, cudaMemcpyHostToDevice, e->stream));
+    auto need_f = [&](const std::string& n) -> const float* {
+        auto it = e->w.find(n);
+        return (it == e->w.end() || it->second.is_bf16) ? nullptr : (const float*)it->second.p;
+    };
+    const float* w_cond = need_f("unet.time_embedding.cond_proj.weight");
+    const float* w1 = need_f("unet.time_embedding.linear_1.weight");
+    const float* b1 = need_f("unet.time_embedding.linear_1.bias");
+    const float* w2 = need_f("unet.time_embedding.linear_2.weight");
+    const float* b2 = need_f("unet.time_embedding.linear_2.bias");
+    ENG_REQUIRE(w_cond && w1 && b1 && w2 && b2, "time_embedding weights missing");
+    for (int r = 0; r < 22; ++r) e->temb[kResnetPrefixes[r]] = std::vector<float*>();
+    std::vector<float> sinus(320);
+    for (int i = 0; i < steps; ++i) {
+        // Timesteps(320, flip_sin_to_cos=True, freq_shift=0): [cos | sin], fp32
+        const float t = (float)timesteps[i];
+        for (int k = 0; k < 160; ++k) {
+            const float f = expf(-logf(10000.0f) * (float)k / 160.0f);
+            const float a = t * f;
+            sinus[k] = cosf(a);
+            sinus[160 + k] = sinf(a);
+        }
+        VSD_CHECK_CUDA(cudaMemcpyAsync(d_sin, sinus.data(), 320 * 4, cudaMemcpyHostToDevice, e->stream));
+        VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+        // t_emb_in = sinusoid + cond_proj(w_emb)   (bias pointer reused as the additive term)
+        int rc = launch_gemv_f32(w_cond, d_wemb, d_sin, e->t_emb_in, 320, 256, 0, 0, e->stream);
+        if (rc) return rc;
+        rc = launch_gemv_f32(w1, e->t_emb_in, b1, e->t_h, 1280, 320, 0, 1, e->stream);
+        if (rc) return rc;
+        rc = launch_gemv_f32(w2, e->t_h, b2, e->t_emb, 1280, 1280, 0, 0, e->stream);
+        if (rc) return rc;
+        for (int r = 0; r < 22; ++r) {
+            const std::string p = kResnetPrefixes[r];
+            auto it = e->w.find(p + ".time_emb_proj.weight");
+            const float* pb = need_f(p + ".time_emb_proj.bias");
+            ENG_REQUIRE(it != e->w.end() && pb, "time_emb_proj missing: " + p);
+            const int cout = (int)it->second.shape[0];
+            float* dst = (float*)A.alloc((size_t)e->NB * cout * 4);
+            ENG_REQUIRE(dst != nullptr, "arena exhausted");
+            rc = launch_gemv_f32((const float*)it->second.p, e->t_emb, pb, dst, cout, 1280, 1, 0, e->stream);
+            if (rc) return rc;
+            for (int b = 1; b < e->NB; ++b)
+                VSD_CHECK_CUDA(cudaMemcpyAsync(dst + (size_t)b * cout, dst, (size_t)cout * 4, cudaMemcpyDeviceToDevice, e->stream));
+            e->temb[p].push_back(dst);
+        }
+    }
+    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    e->schedule_set = true;
+
+    // ---- build the launch plans on top of the static + schedule allocations
+    e->plan_pre_yuv.clear(); e->plan_pre_rgb.clear(); e->plan_core.clear(); e->plan_post.clear(); e->plan_unet.clear();
+    Builder B{e, &e->plan_pre_yuv};
+    {
+        Engine* ee = e;
+        e->plan_pre_yuv.push_back([ee](cudaStream_t st) {
+            return launch_yuv420_to_rgb(ee->d_y, ee->d_u, ee->d_v, ee->d_rgb_in, ee->NB, ee->H, ee->W, st);
+        });
+    }
+    B.out = &e->plan_core;
+    const size_t enc_mark = A.mark();
+    build_taesd_encoder(B, e->d_rgb_in, e->init_latents);
+    A.release(enc_mark);
+    {
+        Engine* ee = e;
+        const long n = (long)lpx * 4;
+        e->plan_core.push_back([ee, n](cudaStream_t st) {
+            return launch_add_noise(ee->init_latents, ee->init_noise, ee->noisy, ee->an_a, ee->an_b, n, st);
+        });
+    }
+    // persistent skip / concat buffers (shared by all steps)
+    UNetStatic S;
+    {
+        int hh = e->h8, ww = e->w8;
+        for (int i = 0; i < 4; ++i) { S.hs[i] = hh; S.ws[i] = ww; hh = ds(hh); ww = ds(ww); }
+        const int cat_c[4][3] = {{2560, 2560, 2560}, {2560, 2560, 1920}, {1920, 1280, 960}, {960, 640, 640}};
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 3; ++j) S.concat[i][j] = B.alloc(e->NB, S.hs[3 - i], S.ws[3 - i], cat_c[i][j]);
+        // up block i resnet j runs at level (3 - i); the skips consumed there were produced at that level,
+        // except the j == 2 skip of blocks 0..2, which is the *previous* level's downsampler output... check:
+        // pop order: skip 11,10 (level 3 resnets), 9 (down of level 2 -> lives at level 3) => all level 3. OK.
+    }
+    const size_t unet_mark = A.mark();
+    for (int i = 0; i < steps; ++i) {
+        A.release(unet_mark);
+        std::vector<Launch> up;
+        B.out = &up;
+        const float* lat_in = (i == 0) ? e->noisy : e->lat[i - 1];
+        build_unet(B, lat_in, e->eps[i], i, S);
+        const StepScalars s = e->sc[i];
+        Engine* ee = e;
+        const long n = (long)lpx * 4;
+        const int hn = has_step_noise;
+        float* z = e->step_noise + (size_t)i * lpx * 4;
+        float* xp = e->lat[i]; float* dn = e->den[i]; const float* ep = e->eps[i];
+        e->plan_unet.push_back(up);
+        for (auto& l : up) e->plan_core.push_back(l);
+        e->plan_core.push_back([=](cudaStream_t st) {
+            (void)ee;
+            return launch_lcm_step(ep, lat_in, z, xp, dn, s.sqrt_a, s.sqrt_1ma, s.c_skip, s.c_out, s.sqrt_ap, s.sqrt_1map, hn,
+                                   n, st);
+        });
+    }
+    A.release(unet_mark);
+    B.out = &e->plan_core;
+    build_taesd_decoder(B, e->den[steps - 1], e->image);
+    A.release(unet_mark);
+    {
+        Engine* ee = e;
+        e->plan_post.push_back([ee](cudaStream_t st) {
+            return launch_pack_rgb_yuv420(ee->image, 4, ee->d_rgb_out, ee->d_oy, ee->d_ou, ee->d_ov, ee->NB, ee->H, ee->W, 1, st);
+        });
+    }
+    if (B.rc) {
+        set_error("plan build failed: " + B.fail);
+        e->schedule_set = false;
+        return B.rc;
+    }
+    return 0;
+}
+
+// Projects a context (77 x 768 fp32, host) into every transformer layer's cross-attention K / V^T cache slot b.
+static int set_context(Engine* e, int b, const float* ctx_host) {
+    ENG_REQUIRE(e->configured, "configure() first");
+    ENG_REQUIRE(b >= 0 && b < e->NB, "context slot out of range");
+    std::vector<uint16_t> t((size_t)128 * 768, 0);
+    for (long i = 0; i < 77L * 768; ++i) t[i] = f32_to_bf16_rne(ctx_host[i]);
+    bf16* dctx = e->ctx_bf16 + (size_t)b * 128 * 768;
+    VSD_CHECK_CUDA(cudaMemcpyAsync(dctx, t.data(), t.size() * 2, cudaMemcpyHostToDevice, e->stream));
+    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    for (auto& xa : e->xattn) {
+        auto wk = e->w.find(xa.prefix + ".attn2.to_k.weight");
+        auto wv = e->w.find(xa.prefix + ".attn2.to_v.weight");
+        ENG_REQUIRE(wk != e->w.end() && wv != e->w.end(), "attn2 weights missing: " + xa.prefix);
+        GemmOp op;
+        // K2[77][8*dkp] = ctx * Wk_pad^T
+        ActView actx{dctx, 1, 1, 77, 768, 768};
+        int rc = build_gemm_op(&op, actx, 1, (const bf16*)wk->second.p, 8 * xa.dkp, 768, xa.k2 + (size_t)b * 128 * 8 * xa.dkp,
+                               8 * xa.dkp, 0, nullptr, nullptr, nullptr, 0, ACT_NONE, e->splitk_ws, e->splitk_bytes, 0, 1);
+        if (rc) return rc;
+        rc = launch_gemm_op(op, e->stream);
+        if (rc) return rc;
+        // V2^T[C][77] = Wv * ctx^T, written at column offset b*128 of the [C][NB*128] cache
+        ActView aw{wv->second.p, 1, 1, xa.C, 768, 768};
+        rc = build_gemm_op(&op, aw, 1, dctx, 77, 768, xa.v2t + (size_t)b * 128, e->NB * 128, 0, nullptr, nullptr, nullptr, 0,
+                           ACT_NONE, e->splitk_ws, e->splitk_bytes, 0, 1);
+        if (rc) return rc;
+        rc = launch_gemm_op(op, e->stream);
+        if (rc) return rc;
+    }
+    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    e->context_set = true;
+    return 0;
+}
+
+static int capture(Engine* e, bool yuv, cudaGraphExec_t* exec) {
+    cudaGraph_t g = nullptr;
+    VSD_CHECK_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = 0;
+    if (yuv) rc = run_plan(e->plan_pre_yuv, e->stream);
+    if (!rc) rc = run_plan(e->plan_core, e->stream);
+    if (!rc) rc = run_plan(e->plan_post, e->stream);
+    cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    VSD_CHECK_CUDA(ce);
+    VSD_CHECK_CUDA(cudaGraphInstantiate(exec, g, 0));
+    cudaGraphDestroy(g);
+    return 0;
+}
+
+static int run_frame(Engine* e, bool yuv) {
+    ENG_REQUIRE(e->schedule_set, "set_schedule() first");
+    ENG_REQUIRE(e->context_set, "set_context() first");
+    cudaGraphExec_t* ex = yuv ? &e->graph_yuv : &e->graph_rgb;
+    if (!*ex) {
+        int rc = capture(e, yuv, ex);
+        if (rc) return rc;
+    }
+    VSD_CHECK_CUDA(cudaGraphLaunch(*ex, e->stream));
+    return 0;
+}
+
+}  // namespace vsd
+
+using namespace vsd;
+
+extern "C" {
+
+struct vsd_ctx { Engine e; };
+
+vsd_ctx* vsd_create(int device) {
+    if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice failed"); return nullptr; }
+    if (ensure_init()) return nullptr;
+    vsd_ctx* c = new vsd_ctx();
+    c->e.device = device;
+    if (cudaStreamCreateWithFlags(&c->e.stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error("cudaStreamCreate failed");
+        delete c;
+        return nullptr;
+    }
+    return c;
+}
+
+void vsd_destroy(vsd_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->e.device);
+    cudaStreamSynchronize(c->e.stream);
+    free_graphs(&c->e);
+    for (auto& kv : c->e.w) cudaFree(kv.second.p);
+    c->e.arena.destroy();
+    if (c->e.splitk_ws) cudaFree(c->e.splitk_ws);
+    cudaStreamDestroy(c->e.stream);
+    delete c;
+}
+
+#define CTX_GUARD(c)                                             \
+    if (!(c)) { set_error("null context"); return -1; }          \
+    if (cudaSetDevice((c)->e.device) != cudaSuccess) { set_error("cudaSetDevice failed"); return -2; }
+
+int vsd_load_weight(vsd_ctx* c, const char* name, const float* host_f32, const int64_t* shape, int ndim) {
+    CTX_GUARD(c);
+    return load_weight(&c->e, name, host_f32, shape, ndim);
+}
+
+int vsd_num_weights(vsd_ctx* c) { return c ? (int)c->e.w.size() : -1; }
+
+int vsd_configure(vsd_ctx* c, int batch, int height, int width) {
+    CTX_GUARD(c);
+    return configure(&c->e, batch, height, width);
+}
+
+int vsd_set_schedule(vsd_ctx* c, int steps, const int* timesteps, const float* scalars, float add_noise_a,
+                     float add_noise_b, const float* w_embedding256, int has_step_noise) {
+    CTX_GUARD(c);
+    return set_schedule(&c->e, steps, timesteps, scalars, add_noise_a, add_noise_b, w_embedding256, has_step_noise);
+}
+
+int vsd_set_context(vsd_ctx* c, int slot, const float* context_77x768) {
+    CTX_GUARD(c);
+    return set_context(&c->e, slot, context_77x768);
+}
+
+int vsd_set_noise(vsd_ctx* c, const float* init_noise_nhwc, const float* step_noise_nhwc) {
+    CTX_GUARD(c);
+    Engine* e = &c->e;
+    ENG_REQUIRE(e->schedule_set, "set_schedule() first");
+    const size_t lpx = (size_t)e->NB * e->h8 * e->w8;
+    VSD_CHECK_CUDA(cudaMemcpyAsync(e->init_noise, init_noise_nhwc, lpx * 16, cudaMemcpyHostToDevice, e->stream));
+    if (step_noise_nhwc && e->has_step_noise)
+        VSD_CHECK_CUDA(cudaMemcpyAsync(e->step_noise, step_noise_nhwc, lpx * 16 * e->steps, cudaMemcpyHostToDevice, e->stream));
+    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int vsd_upload_yuv420(vsd_ctx* c, const uint8_t* y, const uint8_t* u, const uint8_t* v) {
+    CTX_GUARD(c);
+    Engine* e = &c->e;
+    ENG_REQUIRE(e->configured, "configure() first");
+    const size_t px = (size_t)e->NB * e->H * e->W;
+    VSD_CHECK_CUDA(cudaMemcpyAsync(e->d_y, y, px, cudaMemcpyHostToDevice, e->stream));
+    VSD_CHECK_CUDA(cudaMemcpyAsync(e->d_u, u, px / 4, cudaMemcpyHostToDevice, e->stream));
+    VSD_CHECK_CUDA(cudaMemcpyAsync(e->d_v, v, px / 4, cudaMemcpyHostToDevice, e->stream));
+    return 0;
+}
+
+int vsd_run_yuv420(vsd_ctx* c) {
+    CTX_GUARD(c);
+    return run_frame(&c->e, true);
+}
+
+int vsd_download_yuv420(vsd_ctx* c, uint8_t* y, uint8_t* u, uint8_t* v) {
+    CTX_GUARD(c);
+    Engine* e = &c->e;
+    const size_t px = (size_t)e->NB * e->H * e->W;
+    VSD_CHECK_CUDA(cudaMemcpyAsync(y, e->d_oy, px, cudaMemcpyDeviceToHost, e->stream));
+    VSD_CHECK_CUDA(cudaMemcpyAsync(u, e->d_ou, px / 4, cudaMemcpyDeviceToHost, e->stream));
+    VSD_CHECK_CUDA(cudaMemcpyAsync(v, e->d_ov, px / 4, cudaMemcpyDeviceToHost, e->stream));
+    return 0;
+}
+
+int vsd_sync(vsd_ctx* c) {
+    CTX_GUARD(c);
+    VSD_CHECK_CUDA(cudaStreamSynchronize(c->e.stream));
+    return vsd_check_pipeline_fault();
+}
+
+int vsd_infer_yuv420(vsd_ctx* c, const uint8_t* y, const uint8_t* u, const uint8_t* v, uint8_t* out_y, uint8_t* out_u,
+                     uint8_t* out_v) {
+    int rc = vsd_upload_yuv420(c, y, u, v);
+    if (rc) return rc;
+    rc = vsd_run_yuv420(c);
+    if (rc) return rc;
+    rc = vsd_download_yuv420(c, out_y, out_u, out_v);
+    if (rc) return rc;
+    VSD_CHECK_CUDA(cudaStreamSynchronize(c->e.stream));
+    return 0;
+}
+
+int vsd_infer_rgb(vsd_ctx* c, const uint8_t* rgb_in, uint8_t* rgb_out) {
+    CTX_GUARD(c);
+    Engine* e = &c->e;
+    ENG_REQUIRE(e->configured, "configure() first");
+    const size_t px = (size_t)e->NB * e->H * e->W;
+    VSD_CHECK_CUDA(cudaMemcpyAsync(e->d_rgb_in, rgb_in, px * 3, cudaMemcpyHostToDevice, e->stream));
+    int rc = run_frame(e, false);
+    if (rc) return rc;
+    VSD_CHECK_CUDA(cudaMemcpyAsync(rgb_out, e->d_rgb_out, px * 3, cudaMemcpyDeviceToHost, e->stream));
+    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+void* vsd_stream(vsd_ctx* c) { return c ? (void*)c->e.stream : nullptr; }
+
+long vsd_launches_per_frame(vsd_ctx* c, int yuv) {
+    if (!c) return -1;
+    const Engine& e = c->e;
+    long n = (long)e.plan_core.size() + (long)e.plan_post.size() + (yuv ? (long)e.plan_pre_yuv.size() : 0);
+    // split-K GEMMs launch a second (reduce) kernel; GroupNorm launches two. Count conservatively as plan entries.
+    return n;
+}
+
+long vsd_arena_peak_bytes(vsd_ctx* c) { return c ? (long)c->e.arena.peak : -1; }
+
+/* ---- debug taps used by the parity tests ---- */
+int vsd_debug_read(vsd_ctx* c, const char* what, int index, float* host, long nfloats) {
+    CTX_GUARD(c);
+    Engine* e = &c->e;
+    const std::string w = what;
+    const float* src = nullptr;
+    if (w == "init_latents") src = e->init_latents;
+    else if (w == "noisy") src = e->noisy;
+    else if (w == "image") src = e->image;
+    else if (w == "eps" && index >= 0 && index < (int)e->eps.size()) src = e->eps[index];
+    else if (w == "latents" && index >= 0 && index < (int)e->lat.size()) src = e->lat[index];
+    else if (w == "denoised" && index >= 0 && index < (int)e->den.size()) src = e->den[index];
+    ENG_REQUIRE(src != nullptr, "unknown debug tap " + w);
+    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    VSD_CHECK_CUDA(cudaMemcpy(host, src, (size_t)nfloats * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+/* Runs one UNet pass eagerly: latents (host fp32 NHWC [NB,h8,w8,4]) at schedule step `step` -> eps (host). */
+int vsd_debug_unet(vsd_ctx* c, const float* latents_nhwc, int step, float* eps_nhwc) {
+    CTX_GUARD(c);
+    Engine* e = &c->e;
+    ENG_REQUIRE(e->schedule_set && e->context_set, "schedule and context must be set");
+    ENG_REQUIRE(step >= 0 && step < e->steps, "step out of range");
+    const size_t lpx = (size_t)e->NB * e->h8 * e->w8;
+    float* dst = (step == 0) ? e->noisy : e->lat[step - 1];
+    VSD_CHECK_CUDA(cudaMemcpyAsync(dst, latents_nhwc, lpx * 16, cudaMemcpyHostToDevice, e->stream));
+    int rc = run_plan(e->plan_unet[step], e->stream);
+    if (rc) return rc;
+    VSD_CHECK_CUDA(cudaMemcpyAsync(eps_nhwc, e->eps[step], lpx * 16, cudaMemcpyDeviceToHost, e->stream));
+    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    return vsd_check_pipeline_fault();
+}
+
+/* Runs the whole frame eagerly (no CUDA graph), for debugging and for ncu launch lists. */
+int vsd_debug_run_eager(vsd_ctx* c, int yuv) {
+    CTX_GUARD(c);
+    Engine* e = &c->e;
+    ENG_REQUIRE(e->schedule_set && e->context_set, "schedule and context must be set");
+    int rc = 0;
+    if (yuv) rc = run_plan(e->plan_pre_yuv, e->stream);
+    if (!rc) rc = run_plan(e->plan_core, e->stream);
+    if (!rc) rc = run_plan(e->plan_post, e->stream);
+    if (rc) return rc;
+    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    return vsd_check_pipeline_fault();
+}
+
+}  // extern "C"

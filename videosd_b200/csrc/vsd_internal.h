@@ -36,7 +36,7 @@ int make_tmap_2d(CUtensorMap* m, const void* base, int K, int rows, int ld, int 
 
 // ---- tcgen05 implicit-GEMM convolution / linear kernel -------------------------------------------
 // out[pixel, n] = epilogue( sum_{tap, c} A[pixel + tap offset, c] * Wt[n, tap*cin + c] )
-enum { ACT_NONE = 0, ACT_GEGLU = 1 };
+enum { ACT_NONE = 0, ACT_GEGLU = 1, ACT_RELU_FLAG = 16 };  // ReLU (after the residual add) may be OR-ed in
 
 struct GemmParams {
     // A operand traversal (NHWC activation, stride-1 taps; linear layers use H=NB=1, W=rows)
@@ -58,7 +58,7 @@ struct GemmParams {
     const float* rowvec;  // [NB, N] or null (per-image broadcast, e.g. time embedding projection)
     const bf16* residual; // [rows, ldr] or null
     int ldr;
-    int act;
+    int act, relu;
     float* partial;       // [splits, rows, N] fp32 when splits > 1
 };
 
@@ -118,7 +118,12 @@ int launch_yuv420_to_rgb(const uint8_t* y, const uint8_t* u, const uint8_t* v, u
                          cudaStream_t st);
 int launch_pack_rgb_yuv420(const float* img, int ldi, uint8_t* rgb, uint8_t* y, uint8_t* u, uint8_t* v, int NB, int H,
                            int W, int taesd_denorm, cudaStream_t st);
-int launch_relu_tanh_misc(int kind, const void* in, void* out, long n, cudaStream_t st);
+// y[out] = act_out( W[out][in] * act_in(x) + b ), fp32, one warp per output (time-embedding path, M = 1)
+int launch_gemv_f32(const float* W, const float* x, const float* b, float* y, int out, int in, int silu_in, int silu_out,
+                    cudaStream_t st);
+int attn_dk_pad(int d);
+int attn_dv_pad(int d);
+int ensure_init();
 
 unsigned int read_trap_code_gemm();
 unsigned int read_trap_code_attn();

@@ -1,0 +1,155 @@
+"""Python host wrapper over the frame-level C ABI (include/videosd.h, "engine" section).
+
+PyTorch/numpy only own host buffers here; every per-frame computation happens inside libvideosd.so. One Engine per
+GPU, calls serialised by the caller (like one Ray actor per GPU in the reference, diffusert/videopipeline.py:11).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import scheduler as _sched
+from ._lib import VsdError, check, lib
+
+c_int = ctypes.c_int
+
+
+def _fptr(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+def _u8ptr(t):
+    if isinstance(t, torch.Tensor):
+        return ctypes.c_void_p(t.data_ptr())
+    return ctypes.c_void_p(t.ctypes.data)
+
+
+class Engine:
+    def __init__(self, device=0):
+        L = lib()
+        L.vsd_create.restype = ctypes.c_void_p
+        L.vsd_stream.restype = ctypes.c_void_p
+        L.vsd_launches_per_frame.restype = ctypes.c_long
+        L.vsd_arena_peak_bytes.restype = ctypes.c_long
+        self._L = L
+        self.device = device
+        self._ctx = L.vsd_create(c_int(device))
+        if not self._ctx:
+            raise VsdError("vsd_create failed: " + (L.vsd_last_error() or b"?").decode())
+        self._ctx = ctypes.c_void_p(self._ctx)
+        self._schedule = _sched.LCMSchedule()
+        self.batch = self.height = self.width = None
+        self.timesteps = None
+        self._sched_key = None
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._L.vsd_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    # ---- weights ---------------------------------------------------------------------------------------
+    def load_state_dict(self, prefix, state_dict):
+        """prefix: 'unet' or 'vae'; state_dict: name -> torch tensor (any float dtype) in PyTorch layout."""
+        for name, t in state_dict.items():
+            a = t.detach().to(torch.float32).contiguous().cpu().numpy()
+            shape = (ctypes.c_int64 * a.ndim)(*a.shape)
+            check(self._L.vsd_load_weight(self._ctx, f"{prefix}.{name}".encode(), _fptr(a), shape, c_int(a.ndim)),
+                  f"vsd_load_weight({prefix}.{name})")
+
+    # ---- configuration ---------------------------------------------------------------------------------
+    def configure(self, batch, height, width):
+        check(self._L.vsd_configure(self._ctx, c_int(batch), c_int(height), c_int(width)), "vsd_configure")
+        self.batch, self.height, self.width = batch, height, width
+        self._sched_key = None
+
+    def set_schedule(self, strength, steps, guidance_scale=7.5):
+        ts = self._schedule.timesteps(strength, steps)
+        if not ts:
+            raise ValueError(f"strength {strength} yields an empty LCM timestep table")
+        key = (tuple(ts), float(guidance_scale))
+        if key == self._sched_key:
+            return ts
+        sc = np.ascontiguousarray(self._schedule.step_scalars(ts))
+        a, b = self._schedule.add_noise_coeffs(ts[0])
+        w = np.ascontiguousarray(_sched.guidance_embedding(guidance_scale))
+        tarr = (ctypes.c_int * len(ts))(*ts)
+        check(self._L.vsd_set_schedule(self._ctx, c_int(len(ts)), tarr, _fptr(sc), ctypes.c_float(a), ctypes.c_float(b),
+                                       _fptr(w), c_int(1 if len(ts) > 1 else 0)), "vsd_set_schedule")
+        self.timesteps = ts
+        self._sched_key = key
+        return ts
+
+    def set_context(self, slot, context):
+        """context: (77, 768) float tensor/array (CLIP last_hidden_state for the prompt)."""
+        a = np.ascontiguousarray(torch.as_tensor(context).detach().to(torch.float32).cpu().numpy())
+        if a.shape != (77, 768):
+            raise ValueError(f"context must be (77, 768), got {a.shape}")
+        check(self._L.vsd_set_context(self._ctx, c_int(slot), _fptr(a)), "vsd_set_context")
+
+    def set_noise(self, init_noise_nchw, step_noise_nchw):
+        """init: (B,4,h,w); steps: list of (B,4,h,w) (empty for single-step)."""
+        init = np.ascontiguousarray(init_noise_nchw.permute(0, 2, 3, 1).contiguous().float().numpy())
+        if len(step_noise_nchw):
+            st = torch.stack(list(step_noise_nchw), 0).permute(0, 1, 3, 4, 2).contiguous().float().numpy()
+            st = np.ascontiguousarray(st)
+            check(self._L.vsd_set_noise(self._ctx, _fptr(init), _fptr(st)), "vsd_set_noise")
+        else:
+            check(self._L.vsd_set_noise(self._ctx, _fptr(init), None), "vsd_set_noise")
+
+    def set_reference_noise(self):
+        init, steps = _sched.reference_cpu_noise(self.batch, self.height // 8, self.width // 8, len(self.timesteps))
+        self.set_noise(init, steps)
+
+    # ---- frames ----------------------------------------------------------------------------------------
+    def infer_yuv420(self, y, u, v, out_y, out_u, out_v):
+        """u8 host buffers (numpy arrays or CPU torch tensors, ideally pinned); synchronous."""
+        check(self._L.vsd_infer_yuv420(self._ctx, _u8ptr(y), _u8ptr(u), _u8ptr(v), _u8ptr(out_y), _u8ptr(out_u),
+                                       _u8ptr(out_v)), "vsd_infer_yuv420")
+
+    def infer_rgb(self, rgb_in, rgb_out):
+        check(self._L.vsd_infer_rgb(self._ctx, _u8ptr(rgb_in), _u8ptr(rgb_out)), "vsd_infer_rgb")
+
+    def upload_yuv420(self, y, u, v):
+        check(self._L.vsd_upload_yuv420(self._ctx, _u8ptr(y), _u8ptr(u), _u8ptr(v)), "vsd_upload_yuv420")
+
+    def run_yuv420(self):
+        check(self._L.vsd_run_yuv420(self._ctx), "vsd_run_yuv420")
+
+    def download_yuv420(self, y, u, v):
+        check(self._L.vsd_download_yuv420(self._ctx, _u8ptr(y), _u8ptr(u), _u8ptr(v)), "vsd_download_yuv420")
+
+    def sync(self):
+        check(self._L.vsd_sync(self._ctx), "vsd_sync")
+
+    @property
+    def stream(self):
+        return self._L.vsd_stream(self._ctx)
+
+    def launches_per_frame(self, yuv=True):
+        return int(self._L.vsd_launches_per_frame(self._ctx, c_int(1 if yuv else 0)))
+
+    def arena_peak_bytes(self):
+        return int(self._L.vsd_arena_peak_bytes(self._ctx))
+
+    # ---- debug taps (parity tests) ------------------------------------------------------------------------
+    def debug_read(self, what, index=0, channels=4, spatial="latent"):
+        h, w = (self.height // 8, self.width // 8) if spatial == "latent" else (self.height, self.width)
+        a = np.empty((self.batch, h, w, channels), dtype=np.float32)
+        check(self._L.vsd_debug_read(self._ctx, what.encode(), c_int(index), _fptr(a), ctypes.c_long(a.size)),
+              f"vsd_debug_read({what})")
+        return torch.from_numpy(a).permute(0, 3, 1, 2).contiguous()  # NCHW like the oracle
+
+    def debug_unet(self, latents_nchw, step):
+        a = np.ascontiguousarray(latents_nchw.permute(0, 2, 3, 1).contiguous().float().numpy())
+        o = np.empty_like(a)
+        check(self._L.vsd_debug_unet(self._ctx, _fptr(a), c_int(step), _fptr(o)), "vsd_debug_unet")
+        return torch.from_numpy(o).permute(0, 3, 1, 2).contiguous()
+
+    def debug_run_eager(self, yuv=True):
+        check(self._L.vsd_debug_run_eager(self._ctx, c_int(1 if yuv else 0)), "vsd_debug_run_eager")
