@@ -74,7 +74,8 @@ class LCMSchedulerOracle:
 
     # lcm_controlnet.py:1046-1071
     def add_noise(self, original_samples, noise, timesteps):
-        ac = self.alphas_cumprod.to(dtype=original_samples.dtype)
+        ac = self.alphas_cumprod.to(device=original_samples.device, dtype=original_samples.dtype)
+        timesteps = timesteps.to(original_samples.device)
         sa = ac[timesteps] ** 0.5
         sb = (1 - ac[timesteps]) ** 0.5
         while sa.dim() < original_samples.dim():

@@ -1,0 +1,27 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (sm_100a); run on the B200 box with -m gpu")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import numpy as np
+
+    return np.load(os.path.join(ROOT, "tests", "golden", "reference_golden.npz"))
+
+
+@pytest.fixture(scope="session")
+def oracle_models():
+    """Seeded random-init oracle UNet / TAESD (fp32, CPU) shared by the session."""
+    from oracle.weights import build_taesd, build_unet
+
+    return build_unet(), build_taesd()

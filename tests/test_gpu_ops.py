@@ -1,0 +1,42 @@
+"""-m gpu: operator-level parity through the C ABI (ctypes), each CUDA kernel family against a plain torch fp32
+reference of the same op on the same seeded inputs. Integer / byte work (colour, uint8 pack, scheduler scalars in
+fp32 with the reference's operation order) must be bit-exact; bf16 tensor-core work within 1e-2 relative (max norm).
+The case lists live in tools/gpu_check.py so the bring-up battery and the test suite cannot drift apart."""
+import importlib.util
+import os
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def chk():
+    spec = importlib.util.spec_from_file_location("gpu_check", os.path.join(ROOT, "tools", "gpu_check.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def _run(chk, fn):
+    chk.RESULTS.clear()
+    fn()
+    bad = [r for r in chk.RESULTS if not r.get("ok")]
+    assert chk.RESULTS and not bad, bad
+
+
+def test_tcgen05_conv_gemm(chk):
+    _run(chk, chk.check_gemm)
+
+
+def test_tcgen05_attention(chk):
+    _run(chk, chk.check_attn)
+
+
+def test_groupnorm_layernorm(chk):
+    _run(chk, chk.check_norm)
+
+
+def test_colour_scheduler_edge_convs_bit_exact(chk):
+    _run(chk, chk.check_misc)

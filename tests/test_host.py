@@ -1,0 +1,131 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol, the product's scheduler /
+weight tables agree with the oracle, and the drop-in boundary keeps the reference's argument behaviour."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "videosd.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vsd_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from videosd_b200._lib import LIB_PATH, lib
+
+    assert os.path.exists(LIB_PATH), "build the library first: python -m videosd_b200.build"
+    L = lib()
+    syms = _declared_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/videosd.h but not exported"
+    L.vsd_abi_version.restype = ctypes.c_int
+    assert L.vsd_abi_version() == 1
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from videosd_b200._lib import VsdError
+    from videosd_b200.engine import Engine
+
+    with pytest.raises(VsdError):
+        Engine(0)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "videosd_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports the oracle"
+
+
+def test_product_schedule_equals_oracle():
+    from oracle.scheduler import LCMSchedulerOracle, w_embedding
+    from videosd_b200 import scheduler
+
+    s, o = scheduler.LCMSchedule(), LCMSchedulerOracle()
+    for strength, n in [(0.5, 4), (0.6, 4), (0.05, 4), (0.4, 20), (1.0, 4), (0.5, 1), (0.1, 12)]:
+        ts = s.timesteps(strength, n)
+        assert ts == o.set_timesteps(strength, n).tolist()
+        sc = s.step_scalars(ts)
+        for i in range(len(ts)):
+            d = o.step_scalars(i)
+            ref = np.array([float(d[k]) for k in ("sqrt_alpha", "sqrt_beta", "c_skip", "c_out", "sqrt_alpha_prev",
+                                                  "sqrt_beta_prev")], dtype=np.float32)
+            assert np.array_equal(sc[i], ref)
+        a, b = s.add_noise_coeffs(ts[0])
+        assert a == float(o.alphas_cumprod[ts[0]] ** 0.5) and b == float((1 - o.alphas_cumprod[ts[0]]) ** 0.5)
+    assert np.array_equal(scheduler.guidance_embedding(7.5), w_embedding(torch.tensor([7.5]), 256)[0].numpy())
+    with pytest.raises(ValueError):
+        s.timesteps(0.5, 1001)
+
+
+def test_product_noise_equals_oracle_rng_order():
+    from oracle import pipeline
+    from videosd_b200.scheduler import reference_cpu_noise
+
+    a, b = reference_cpu_noise(2, 8, 12, 4), pipeline.frame_noise(2, 8, 12, 4)
+    assert torch.equal(a[0], b[0]) and all(torch.equal(x, y) for x, y in zip(a[1], b[1]))
+
+
+def test_weight_tables_equal_oracle_modules():
+    from oracle.taesd import TAESD
+    from oracle.unet import UNetLCM
+    from videosd_b200 import weights
+
+    u = {k: tuple(v.shape) for k, v in UNetLCM().state_dict().items()}
+    assert u == {k: tuple(v) for k, v in weights.unet_param_shapes().items()}
+    t = {k: tuple(v.shape) for k, v in TAESD().state_dict().items()}
+    assert t == {k: tuple(v) for k, v in weights.taesd_param_shapes().items()}
+    sd = weights.random_state_dict(weights.taesd_param_shapes(), 1)
+    sd2 = weights.random_state_dict(weights.taesd_param_shapes(), 1)
+    assert all(torch.equal(sd[k], sd2[k]) for k in sd)
+
+
+def test_boundary_ctor_contract():
+    from videosd_b200.videopipeline import VideoSDPipeline
+
+    with pytest.raises(KeyError):           # videopipeline.py:22-26: missing model / controlnet -> KeyError re-raised
+        VideoSDPipeline(controlnet="x")
+    with pytest.raises(KeyError):
+        VideoSDPipeline(model="x")
+
+
+def test_boundary_crop_resize_matches_reference_rule():
+    from PIL import Image
+
+    from videosd_b200.videopipeline import VideoSDPipeline
+
+    img = Image.fromarray((np.random.RandomState(0).rand(480, 640, 3) * 255).astype(np.uint8))
+    out = VideoSDPipeline._fit(img, 512, 512)
+    assert out.size == (512, 512)
+    # identity when the frame already has the working size (all BASELINE configs)
+    same = VideoSDPipeline._fit(out, 512, 512)
+    assert np.array_equal(np.asarray(same), np.asarray(out))
+    wide = VideoSDPipeline._fit(img, 640, 360)
+    assert wide.size == (640, 360)
+
+
+def test_session_router_pins_and_batches():
+    from videosd_b200.parallel import SessionRouter, shard_streams
+
+    r = SessionRouter(num_gpus=2, max_batch=4)
+    owners = [r.assign(f"s{i}") for i in range(8)]
+    assert owners == [0, 1, 0, 1, 0, 1, 0, 1] and r.assign("s0") == 0
+    b = r.batches([f"s{i}" for i in range(8)] + ["s8", "s9"])
+    assert all(len(x) <= 4 for g in b.values() for x in g)
+    assert sorted(s for g in b.values() for x in g for s in x) == sorted(f"s{i}" for i in range(10))
+    r.release("s0")
+    assert r.assign("new") == 0
+    all_streams = sorted(s for k in range(4) for s in shard_streams(32, 4, k))
+    assert all_streams == list(range(32))

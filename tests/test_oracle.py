@@ -1,0 +1,155 @@
+"""CPU tests of the oracle (the checker): golden vectors produced by the reference's own code
+(tests/golden/make_reference_golden.py), structural identities and the colour spec."""
+import numpy as np
+import torch
+
+from oracle import imageproc, pipeline
+from oracle.scheduler import LCMSchedulerOracle, w_embedding
+from oracle.taesd import TAESD
+from oracle.weights import random_context
+
+
+# ------------------------------------------------------------------ golden: the reference scheduler itself
+def test_alphas_cumprod_match_reference(golden):
+    s = LCMSchedulerOracle()
+    assert np.array_equal(s.alphas_cumprod.numpy(), golden["alphas_cumprod"])
+
+
+def test_timestep_tables_match_reference(golden):
+    s = LCMSchedulerOracle()
+    for k, (strength, steps) in enumerate(golden["table_cfg"]):
+        assert s.set_timesteps(float(strength), int(steps)).tolist() == golden[f"table_{k}"].tolist()
+    # SURVEY.md Appendix C spot values
+    assert s.set_timesteps(0.5, 4).tolist() == [499, 379, 259, 139]
+    assert s.set_timesteps(0.05, 4).tolist() == [39, 19]          # fewer timesteps than steps
+    assert s.set_timesteps(0.4, 20).tolist()[:2] == [399, 379]
+
+
+def test_step_matches_reference_bit_exact(golden):
+    s = LCMSchedulerOracle()
+    s.set_timesteps(0.5, 4)
+    sample = torch.from_numpy(golden["step_sample"])
+    mo = torch.from_numpy(golden["step_model_out"])
+    for i in range(4):
+        torch.manual_seed(1000 + i)
+        prev, den = s.step(mo, i, sample)       # draws torch.randn from the global CPU RNG like the reference
+        assert np.array_equal(prev.numpy(), golden[f"step_prev_{i}"])
+        assert np.array_equal(den.numpy(), golden[f"step_den_{i}"])
+    s.set_timesteps(0.5, 1)                      # single-step: no noise, prev == denoised
+    prev, den = s.step(mo, 0, sample)
+    assert np.array_equal(prev.numpy(), golden["single_prev"]) and np.array_equal(den.numpy(), golden["single_den"])
+
+
+def test_add_noise_and_w_embedding_match_reference(golden):
+    s = LCMSchedulerOracle()
+    s.set_timesteps(0.5, 4)
+    out = s.add_noise(torch.from_numpy(golden["step_sample"]), torch.from_numpy(golden["add_noise_noise"]),
+                      s.timesteps[:1].repeat(2))
+    assert np.array_equal(out.numpy(), golden["add_noise_out"])
+    w = w_embedding(torch.tensor(7.5).repeat(2), 256)
+    assert np.array_equal(w.numpy(), golden["w_embedding"])
+    np.testing.assert_allclose(w[0, :3].numpy(), [-0.85123587, 0.84213120, 0.01187626], atol=2e-6)
+
+
+def test_scheduler_constants_appendix_c():
+    s = LCMSchedulerOracle()
+    s.set_timesteps(0.5, 4)
+    sc = s.step_scalars(0)
+    assert abs(float(sc["sqrt_alpha"]) - 0.52694350) < 1e-7 and abs(float(sc["sqrt_beta"]) - 0.84990031) < 1e-7
+    assert s.step_scalars(3)["prev_t"] == 139            # last step: prev_t = t
+    assert abs(float(s.step_scalars(3)["c_out"]) - 0.99999994) < 1e-7
+
+
+# ------------------------------------------------------------------ golden: the reference __call__ over the oracle modules
+def test_pipeline_sequencing_matches_reference_call(golden, oracle_models):
+    unet, vae = oracle_models
+    rgb = golden["pipe_rgb_in"]
+    ctx = random_context(1, seed=int(golden["pipe_ctx_seed"][0]))
+    out = pipeline.lcm_img2img(unet, vae, rgb[None], ctx, steps=4, strength=0.5)
+    assert out["timesteps"] == golden["pipe_timesteps"].tolist()
+    for i in range(4):
+        # identical modules and op order; only host thread count may reorder fp32 reductions
+        np.testing.assert_allclose(out["latents_in"][i].numpy(), golden[f"pipe_latents_in_{i}"], rtol=0, atol=2e-4)
+        np.testing.assert_allclose(out["eps"][i].numpy(), golden[f"pipe_eps_{i}"], rtol=0, atol=2e-4)
+    diff = np.abs(out["rgb"][0].astype(int) - golden["pipe_rgb_out"].astype(int))
+    assert diff.max() <= 1 and (diff > 0).mean() < 0.01
+
+
+def test_frame_noise_is_constant_per_frame():
+    a = pipeline.frame_noise(1, 8, 8, 4)
+    b = pipeline.frame_noise(1, 8, 8, 4)
+    assert torch.equal(a[0], b[0]) and all(torch.equal(x, y) for x, y in zip(a[1], b[1]))
+    assert len(pipeline.frame_noise(1, 8, 8, 1)[1]) == 0     # single timestep: no step noise drawn
+
+
+# ------------------------------------------------------------------ structure (Appendix A.6 / A.7)
+def test_parameter_counts(oracle_models):
+    unet, vae = oracle_models
+    assert sum(p.numel() for p in unet.parameters()) == 859_602_884
+    assert sum(p.numel() for p in vae.encoder.parameters()) == 1_222_532
+    assert sum(p.numel() for p in vae.decoder.parameters()) == 1_222_531
+
+
+def test_state_dict_key_names(oracle_models):
+    unet, vae = oracle_models
+    k = set(unet.state_dict().keys())
+    assert len(k) == 687
+    for name in ["conv_in.weight", "time_embedding.cond_proj.weight", "time_embedding.linear_2.bias",
+                 "down_blocks.0.attentions.1.transformer_blocks.0.attn2.to_k.weight",
+                 "down_blocks.2.downsamplers.0.conv.bias", "mid_block.attentions.0.proj_out.weight",
+                 "up_blocks.1.resnets.2.conv_shortcut.weight", "up_blocks.3.attentions.2.transformer_blocks.0.ff.net.0.proj.bias",
+                 "up_blocks.2.upsamplers.0.conv.weight", "up_blocks.0.resnets.0.time_emb_proj.weight", "conv_norm_out.bias"]:
+        assert name in k, name
+    assert "down_blocks.3.attentions.0.norm.weight" not in k and "up_blocks.0.attentions.0.norm.weight" not in k
+    assert "time_embedding.cond_proj.bias" not in k
+    assert unet.state_dict()["up_blocks.1.resnets.2.conv1.weight"].shape == (1280, 1920, 3, 3)
+    assert unet.state_dict()["up_blocks.3.resnets.0.conv1.weight"].shape == (320, 960, 3, 3)
+    tk = set(TAESD().state_dict().keys())
+    assert "encoder.layers.2.weight" in tk and "encoder.layers.2.bias" not in tk      # strided convs have no bias
+    assert "decoder.layers.6.weight" in tk and "decoder.layers.6.bias" not in tk
+    assert "encoder.layers.1.conv.4.bias" in tk and "decoder.layers.18.bias" in tk
+
+
+def test_unet_odd_latent_size_runs(oracle_models):
+    unet, _ = oracle_models
+    x = torch.randn(1, 4, 6, 10)                       # not a multiple of 8: exercises upsample-to-skip-size
+    out = unet(x, torch.tensor([499]), w_embedding(torch.tensor([7.5])), random_context(1))
+    assert out.shape == x.shape and torch.isfinite(out).all()
+
+
+# ------------------------------------------------------------------ image I/O spec (Appendix D)
+def test_preprocess_postprocess_spec():
+    u8 = np.arange(256, dtype=np.uint8).reshape(1, 16, 16, 1).repeat(3, axis=3)
+    x = imageproc.preprocess(u8)
+    assert x.shape == (1, 3, 16, 16) and x.dtype == torch.float32
+    assert float(x.min()) == -1.0 and float(x.max()) == 1.0
+    assert np.array_equal(imageproc.postprocess(x), u8)               # exact round trip for every code value
+    t = torch.tensor([-3.0, 9.0, 0.0, 1.0]).view(1, 1, 1, 4).repeat(1, 3, 1, 1)
+    assert imageproc.postprocess(t)[0, 0, :, 0].tolist() == [0, 255, 128, 255]   # clamp; 127.5 rounds half-to-even
+
+
+def test_yuv_rgb_known_answers():
+    def one(y, u, v):
+        return imageproc.yuv420_to_rgb(np.full((2, 2), y, np.uint8), np.full((1, 1), u, np.uint8),
+                                       np.full((1, 1), v, np.uint8))[0, 0].tolist()
+    assert one(16, 128, 128) == [0, 0, 0]                 # limited-range black
+    assert one(235, 128, 128) == [255, 255, 255]          # limited-range white
+    # BT.601 primaries (hand-evaluated from the integer matrices in oracle/imageproc.py)
+    assert one(82, 90, 240) == [255, 1, 0]                # (298*66 + 409*112 + 128) >> 8 = 255 ; G = 1 ; B < 0 -> 0
+    assert one(144, 54, 34) == [0, 254, 0]
+    assert one(41, 240, 110) == [0, 0, 255]
+    y, u, v = imageproc.rgb_to_yuv420(np.array([[[255, 0, 0]] * 2] * 2, np.uint8))
+    assert (int(y[0, 0]), int(u[0, 0]), int(v[0, 0])) == (82, 90, 240)
+    y, u, v = imageproc.rgb_to_yuv420(np.array([[[0, 255, 0]] * 2] * 2, np.uint8))
+    assert (int(y[0, 0]), int(u[0, 0]), int(v[0, 0])) == (144, 54, 34)
+    y, u, v = imageproc.rgb_to_yuv420(np.zeros((2, 2, 3), np.uint8))
+    assert (int(y[0, 0]), int(u[0, 0]), int(v[0, 0])) == (16, 128, 128)
+
+
+def test_yuv_rgb_round_trip_property():
+    y, u, v = imageproc.synthetic_frame(64, 96, seed=5)
+    rgb = imageproc.yuv420_to_rgb(y, u, v)
+    y2, u2, v2 = imageproc.rgb_to_yuv420(rgb)
+    assert np.abs(y2.astype(int) - y.astype(int)).max() <= 2       # integer matrices invert to within rounding
+    assert np.abs(u2.astype(int) - u.astype(int)).max() <= 2 and np.abs(v2.astype(int) - v.astype(int)).max() <= 2
+    assert y.min() >= 16 and y.max() <= 235

@@ -21,52 +21,55 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 // ------------------------------------------------------------------------------------------ GroupNorm
-// Pass 1: per (image, pixel-chunk) partial sum / sum-of-squares per group, deterministic (no global atomics).
-// blockDim.x = vpp * R (vpp = C/8 channel vectors per pixel): each thread owns one channel vector, so its
-// 8 group ids are loop-invariant.
+// Pass 1: per (image, pixel-chunk) partial sum / sum-of-squares per group. Fully deterministic: no atomics, the
+// block-level fold runs in a fixed order. blockDim.x = vpp * R (vpp = C/8 channel vectors per pixel): each thread
+// owns one channel vector, so the (at most two, since C/groups >= 8) groups it touches are loop-invariant.
 __global__ void gn_stats_kernel(const bf16* __restrict__ x, int ldx, int HW, int C, int groups, int px_per_chunk,
                                 float* __restrict__ partial /*[NB][chunks][groups][2]*/) {
-    extern __shared__ float sacc[];  // [groups][2]
+    extern __shared__ float4 spart[];  // [blockDim.x] = {sum g0, sumsq g0, sum g0+1, sumsq g0+1}
     const int vpp = C >> 3;
     const int cpg = C / groups;
     const int vi = threadIdx.x % vpp;
     const int r0 = threadIdx.x / vpp;
     const int R = blockDim.x / vpp;
     const int n = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
-    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sacc[i] = 0.f;
-    __syncthreads();
     const int p_begin = chunk * px_per_chunk;
     const int p_end = min(HW, p_begin + px_per_chunk);
     float s[8], ss[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s[j] = 0.f; ss[j] = 0.f; }
-    if (r0 < R) {
-        const bf16* base = x + ((long)n * HW) * ldx + vi * 8;
-        for (int p = p_begin + r0; p < p_end; p += R) {
-            const uint4 t = *reinterpret_cast<const uint4*>(base + (long)p * ldx);
-            float f[8];
-            unpack8(t, f);
+    const bf16* base = x + ((long)n * HW) * ldx + vi * 8;
+    for (int p = p_begin + r0; p < p_end; p += R) {
+        const uint4 t = *reinterpret_cast<const uint4*>(base + (long)p * ldx);
+        float f[8];
+        unpack8(t, f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] += f[j] * f[j]; }
-        }
-        // fold the 8 channels into (at most two) groups, then one shared atomic per group touched
-        const int g0 = (vi * 8) / cpg;
-        float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;
-        int g1 = g0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int g = (vi * 8 + j) / cpg;
-            if (g == g0) { a0 += s[j]; b0 += ss[j]; }
-            else if (g == g0 + 1) { g1 = g; a1 += s[j]; b1 += ss[j]; }
-            else { atomicAdd(&sacc[g * 2], s[j]); atomicAdd(&sacc[g * 2 + 1], ss[j]); }  // cpg < 4 (not used by SD1.5)
-        }
-        atomicAdd(&sacc[g0 * 2], a0);
-        atomicAdd(&sacc[g0 * 2 + 1], b0);
-        if (g1 != g0) { atomicAdd(&sacc[g1 * 2], a1); atomicAdd(&sacc[g1 * 2 + 1], b1); }
+        for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] += f[j] * f[j]; }
     }
+    const int g0 = (vi * 8) / cpg;
+    float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if ((vi * 8 + j) / cpg == g0) { a0 += s[j]; b0 += ss[j]; }
+        else { a1 += s[j]; b1 += ss[j]; }
+    }
+    spart[threadIdx.x] = make_float4(a0, b0, a1, b1);
     __syncthreads();
-    float* dst = partial + ((long)n * chunks + chunk) * groups * 2;
-    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) dst[i] = sacc[i];
+    if (threadIdx.x < groups) {
+        const int g = threadIdx.x;
+        const int v_lo = (g * cpg) >> 3, v_hi = ((g + 1) * cpg - 1) >> 3;
+        float a = 0.f, b = 0.f;
+        for (int r = 0; r < R; ++r) {
+            for (int v = v_lo; v <= v_hi; ++v) {
+                const float4 t = spart[r * vpp + v];
+                if ((v * 8) / cpg == g) { a += t.x; b += t.y; }
+                else { a += t.z; b += t.w; }
+            }
+        }
+        float* dst = partial + (((long)n * chunks + chunk) * groups + g) * 2;
+        dst[0] = a;
+        dst[1] = b;
+    }
 }
 
 // Pass 2: reduce the partials, build per-channel scale/shift in smem, normalise (+SiLU), bf16 out.
@@ -139,13 +142,13 @@ int groupnorm_ws_floats(int NB, int HW, int C, int groups) {
 int launch_groupnorm(const bf16* x, int ldx, bf16* y, int ldy, const float* gamma, const float* beta, int NB, int HW,
                      int C, int groups, float eps, int silu, float* partial_ws, cudaStream_t st) {
     VSD_REQUIRE(C % 8 == 0 && C % groups == 0 && ldx % 8 == 0 && ldy % 8 == 0, "GroupNorm needs C%8==0 and 16-byte rows");
-    VSD_REQUIRE(C / 8 <= 1024, "GroupNorm channel count too large");
+    VSD_REQUIRE(C / 8 <= 1024 && C / groups >= 8, "GroupNorm needs 8 <= C/groups and C <= 8192");
     int ppc, chunks;
     gn_geometry(NB, HW, &ppc, &chunks);
     const int vpp = C / 8;
     int R = 256 / vpp;
     if (R < 1) R = 1;
-    gn_stats_kernel<<<dim3(chunks, NB), vpp * R, groups * 2 * sizeof(float), st>>>(x, ldx, HW, C, groups, ppc, partial_ws);
+    gn_stats_kernel<<<dim3(chunks, NB), vpp * R, (size_t)vpp * R * sizeof(float4), st>>>(x, ldx, HW, C, groups, ppc, partial_ws);
     VSD_CHECK_CUDA(cudaGetLastError());
     const size_t smem = (size_t)(groups * 2 + 2 * C) * sizeof(float);
     gn_apply_kernel<<<dim3(chunks, NB), 256, smem, st>>>(x, ldx, y, ldy, gamma, beta, HW, C, groups, eps, silu,

@@ -529,7 +529,6 @@ static void build_unet(Builder& B, const float* latents, float* eps_out, int si,
         B.resnet(t, "unet.mid_block.resnets.1", temb("unet.mid_block.resnets.1"), h_view(0, 0));
         e->arena.release(m);
     }
-    View final_h;
     for (int i = 0; i < 4; ++i) {
         const std::string bp = "unet.up_blocks." + std::to_string(i);
         for (int j = 0; j < 3; ++j) {
@@ -923,6 +922,9 @@ static int capture(Engine* e, bool yuv, cudaGraphExec_t* exec) {
     cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
     if (rc) { if (g) cudaGraphDestroy(g); return rc; }
     VSD_CHECK_CUDA(ce);
+    size_t nodes = 0;
+    VSD_CHECK_CUDA(cudaGraphGetNodes(g, nullptr, &nodes));
+    if (yuv) e->launches_per_frame_yuv = (long)nodes;
     VSD_CHECK_CUDA(cudaGraphInstantiate(exec, g, 0));
     cudaGraphDestroy(g);
     return 0;
@@ -1074,9 +1076,9 @@ void* vsd_stream(vsd_ctx* c) { return c ? (void*)c->e.stream : nullptr; }
 long vsd_launches_per_frame(vsd_ctx* c, int yuv) {
     if (!c) return -1;
     const Engine& e = c->e;
-    long n = (long)e.plan_core.size() + (long)e.plan_post.size() + (yuv ? (long)e.plan_pre_yuv.size() : 0);
-    // split-K GEMMs launch a second (reduce) kernel; GroupNorm launches two. Count conservatively as plan entries.
-    return n;
+    if (yuv && e.launches_per_frame_yuv > 0) return e.launches_per_frame_yuv;  // kernel nodes of the captured graph
+    // before capture: plan entries (a lower bound: GroupNorm and split-K entries launch two kernels each)
+    return (long)e.plan_core.size() + (long)e.plan_post.size() + (yuv ? (long)e.plan_pre_yuv.size() : 0);
 }
 
 long vsd_arena_peak_bytes(vsd_ctx* c) { return c ? (long)c->e.arena.peak : -1; }

@@ -1,0 +1,191 @@
+"""Drop-in for the reference's frame-transform boundary, diffusert/videopipeline.py.
+
+Same surface as the reference class (`VideoSDPipeline.remote(**config)`, `await pipe.infer.remote(pil_img, **options)
+-> PIL.Image`, ctor kwargs model / controlnet / gpus / compile / device, missing model or controlnet -> KeyError
+re-raised, videopipeline.py:16-32; infer signature :75-88), but everything between the cropped/resized RGB frame and
+the output RGB frame runs in the CUDA engine (videosd_b200/engine.py -> libvideosd.so) instead of
+diffusers + PyTorch. `infer_yuv420` additionally moves the YUV420<->RGB conversions that the reference leaves to
+PyAV/libswscale in server.py:108,117 inside the boundary.
+
+Not on this path (SURVEY.md 8(f) "next" rows): the canny ControlNet branch (the reference runs it every step; here its
+residuals are zero), GPU crop/Lanczos (PIL on the host, like the reference), and the CLIP text encoder: pass
+`prompt_encoder=callable(list[str]) -> (77, 768)` in the config to plug one in; without it a deterministic
+pseudo-embedding derived from the prompt text is used (no tokenizer vocabulary exists offline).
+"""
+import asyncio
+import concurrent.futures
+import hashlib
+import itertools
+import os
+
+import numpy as np
+import torch
+from PIL import Image
+
+from . import weights as _weights
+from .engine import Engine
+
+try:  # the reference uses Ray actors; Ray is optional here
+    import ray  # noqa: F401
+
+    _HAVE_RAY = True
+except Exception:  # noqa: BLE001
+    _HAVE_RAY = False
+
+
+class _Awaitable:
+    """Result of `.remote(...)`: awaitable from an asyncio loop (like a Ray ObjectRef) and `.result()`-able."""
+
+    def __init__(self, fut):
+        self._fut = fut
+
+    def __await__(self):
+        return asyncio.wrap_future(self._fut).__await__()
+
+    def result(self, timeout=None):
+        return self._fut.result(timeout)
+
+
+class _RemoteMethod:
+    def __init__(self, handle, name):
+        self._handle, self._name = handle, name
+
+    def remote(self, *args, **kwargs):
+        h = self._handle
+        return _Awaitable(h._pool.submit(lambda: getattr(h._obj, self._name)(*args, **kwargs)))
+
+
+class _ActorHandle:
+    """Minimal stand-in for a Ray actor handle: one worker thread per instance => methods run serially,
+    exactly one in-flight infer per GPU (server.py:132-137)."""
+
+    def __init__(self, cls, args, kwargs):
+        self._pool = concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix="videosd-gpu")
+        self._obj = self._pool.submit(lambda: cls(*args, **kwargs)).result()
+
+    def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return _RemoteMethod(self, name)
+
+
+_device_counter = itertools.count()
+
+
+def _pseudo_prompt_embedding(prompt):
+    text = prompt if isinstance(prompt, str) else "\n".join(prompt)
+    seed = int.from_bytes(hashlib.sha256(text.encode()).digest()[:8], "little") % (2 ** 63)
+    return torch.randn((77, 768), generator=torch.Generator().manual_seed(seed))
+
+
+class VideoSDPipeline:
+    def __init__(self, *args, **kwargs):
+        try:
+            self.model_name = kwargs["model"]
+            self.controlnet_name = kwargs["controlnet"]
+        except KeyError:
+            print("Model name and controlnet model must be specified")
+            raise
+        if "device" in kwargs:
+            self.device = int(kwargs["device"])
+        else:
+            n = max(torch.cuda.device_count(), 1)
+            self.device = 0 if _HAVE_RAY and os.environ.get("RAY_ACTOR") else next(_device_counter) % n
+        self.prompt_encoder = kwargs.get("prompt_encoder")
+        self.noise_mode = kwargs.get("noise_mode", "reference_cuda")
+        self.engine = Engine(self.device)          # raises if the CUDA library / a B200 is missing: no fallback
+        self.load_model(self.model_name, self.controlnet_name, kwargs.get("random_init", False))
+        self._shape = None
+        self._noise_key = None
+        self._prompt_key = None
+
+    @classmethod
+    def remote(cls, *args, **kwargs):
+        return _ActorHandle(cls, args, kwargs)
+
+    def load_model(self, model_name, controlnet_model=None, random_init=False):
+        """Loads UNet + TAESD weights. `model_name` may be a local diffusers directory holding unet/ and vae/
+        safetensors; with random_init (or VIDEOSD_RANDOM_INIT=1) seeded random weights of the architecture are used
+        (benchmarks / tests; no checkpoints can be downloaded in this environment)."""
+        if os.path.isdir(str(model_name)) and os.path.isdir(os.path.join(model_name, "unet")):
+            self.engine.load_state_dict("unet", _weights.load_safetensors_dir(os.path.join(model_name, "unet")))
+            self.engine.load_state_dict("vae", _weights.load_safetensors_dir(os.path.join(model_name, "vae")))
+        elif random_init or os.environ.get("VIDEOSD_RANDOM_INIT") == "1":
+            self.engine.load_state_dict("unet", _weights.random_state_dict(_weights.unet_param_shapes(), 1234))
+            self.engine.load_state_dict("vae", _weights.random_state_dict(_weights.taesd_param_shapes(), 4321))
+        else:
+            raise FileNotFoundError(
+                f"model '{model_name}' is not a local diffusers directory (unet/, vae/ with .safetensors). "
+                "There is no network here; pass random_init=True for seeded random weights.")
+        return self.engine
+
+    # ------------------------------------------------------------------------------------------------
+    def _prepare(self, batch, height, width, strength, steps, guidance_scale, seed, prompt, prompt_embeds=None):
+        if self._shape != (batch, height, width):
+            self.engine.configure(batch, height, width)
+            self._shape = (batch, height, width)
+            self._noise_key = self._prompt_key = None
+        ts = self.engine.set_schedule(strength, steps, 7.5)   # guidance_scale from the UI is dropped by the reference (F8)
+        nkey = (seed, len(ts), self.noise_mode)
+        if nkey != self._noise_key:
+            h8, w8 = height // 8, width // 8
+            if self.noise_mode == "reference_cpu":
+                self.engine.set_reference_noise()
+            else:
+                # reference on a CUDA device: torch.manual_seed(seed) seeds the device Philox that draws the init
+                # noise in the model dtype (lcm_controlnet.py:331); step noise always comes from the re-armed CPU RNG
+                from .scheduler import reference_cpu_noise
+                g = torch.Generator(device=f"cuda:{self.device}").manual_seed(int(seed))
+                init = torch.randn((batch, 4, h8, w8), generator=g, device=f"cuda:{self.device}", dtype=torch.float16)
+                _, st = reference_cpu_noise(batch, h8, w8, len(ts))
+                # the CPU stream also yields the init draw first; step noises follow it, as in the reference
+                self.engine.set_noise(init.float().cpu(), st)
+            self._noise_key = nkey
+        pkey = prompt if isinstance(prompt, str) else tuple(prompt)
+        if prompt_embeds is not None or pkey != self._prompt_key:
+            if prompt_embeds is not None:
+                emb = torch.as_tensor(prompt_embeds).reshape(-1, 77, 768)[0]
+            elif self.prompt_encoder is not None:
+                emb = torch.as_tensor(self.prompt_encoder(prompt)).reshape(-1, 77, 768)[0]
+            else:
+                emb = _pseudo_prompt_embedding(prompt)
+            for b in range(batch):
+                self.engine.set_context(b, emb)
+            self._prompt_key = None if prompt_embeds is not None else pkey
+        return ts
+
+    @staticmethod
+    def _fit(img, width, height):
+        """Center-crop to the target aspect ratio, then Lanczos-resize (videopipeline.py:92-107)."""
+        if img.width / img.height > width / height:
+            new_w = img.height * (width / height)
+            box = ((img.width - new_w) / 2, 0, (img.width + new_w) / 2, img.height)
+        else:
+            new_h = img.width * (height / width)
+            box = (0, (img.height - new_h) / 2, img.width, (img.height + new_h) / 2)
+        img = img.crop(box)
+        return img.resize((width, height), resample=Image.Resampling.LANCZOS)
+
+    def infer(self, img, prompt=["pixar, cg"], height=360, width=640, strength=0.4, steps=20, guidance_scale=7.5,
+              ref=False, style_fidelity=0.0, controlnet=False, seed=42, controlnet_scale=1, prompt_embeds=None,
+              **_ignored):
+        width, height = int(width), int(height)
+        width -= width % 8
+        height -= height % 8
+        img = self._fit(img.convert("RGB"), width, height)
+        self._prepare(1, height, width, float(strength), int(steps), guidance_scale, int(seed), prompt, prompt_embeds)
+        rgb_in = np.ascontiguousarray(np.asarray(img, dtype=np.uint8))
+        rgb_out = np.empty_like(rgb_in)
+        self.engine.infer_rgb(rgb_in, rgb_out)
+        return Image.fromarray(rgb_out)
+
+    def infer_yuv420(self, y, u, v, prompt=["pixar, cg"], strength=0.4, steps=20, seed=42, prompt_embeds=None, **_ignored):
+        """Fast path: YUV420P planes (u8 numpy, already at the working size; (B,H,W) or (H,W)) -> planes."""
+        y, u, v = (np.ascontiguousarray(a) for a in (y, u, v))
+        if y.ndim == 2:
+            y, u, v = y[None], u[None], v[None]
+        b, h, w = y.shape
+        self._prepare(b, h, w, float(strength), int(steps), 7.5, int(seed), prompt, prompt_embeds)
+        oy, ou, ov = np.empty_like(y), np.empty_like(u), np.empty_like(v)
+        self.engine.infer_yuv420(y, u, v, oy, ou, ov)
+        return oy, ou, ov
