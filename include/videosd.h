@@ -46,6 +46,12 @@ int vsd_op_conv_gemm(const void* x, int nb, int h, int w, int c, int ldx, int ta
                      int ldo, int out_f32, const float* bias, const float* rowvec, const void* residual, int ldr,
                      int act, int block_n, int splits, void* stream);
 
+/* Bring-up variant: CTA (0,0,0) writes clock64() stamps {start, setup done, first operands landed, last MMA issued,
+ * accumulator ready, epilogue stores issued, teardown} to dbg (device int64[8]). */
+int vsd_op_conv_gemm_timed(const void* x, int nb, int h, int w, int c, int ldx, int taps, const void* wt, int n, void* out,
+                           int ldo, const float* bias, int block_n, int splits, int occ, int kb_per_stage, long long* dbg,
+                           void* stream);
+
 /* Fused flash-style attention on tcgen05 (replaces F.scaled_dot_product_attention in diffusers AttnProcessor2_0,
  * reached from lcm_controlnet.py:568-577).
  *   q, k : dev bf16 [batch*rows_per_img][heads*dk_pad], dk_pad = round_up(d, 64), per-head zero padding
@@ -101,6 +107,10 @@ void vsd_destroy(vsd_ctx* ctx);
  * videopipeline.py:49-72. Converted to bf16 and repacked for the tensor-core kernels on load. */
 int vsd_load_weight(vsd_ctx* ctx, const char* name, const float* host_f32, const int64_t* shape, int ndim);
 int vsd_num_weights(vsd_ctx* ctx);
+/* GEMM autotuner (on by default): at plan-build time each distinct GEMM shape is timed over (block_n, split-K,
+ * CTAs/SM) candidates with the L2 flushed. vsd_tuning_report dumps the choices as text. */
+int vsd_set_autotune(vsd_ctx* ctx, int enabled);
+int vsd_tuning_report(vsd_ctx* ctx, char* buf, long cap);
 
 /* Working size: `batch` frames of height x width (multiples of 8; infer(height=, width=) at videopipeline.py:75-88).
  * Must be called after the weights are loaded; invalidates schedule, contexts and noise. */

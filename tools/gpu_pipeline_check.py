@@ -57,6 +57,9 @@ def main():
     eng.set_reference_noise()
     print("timesteps", ts, "launches/frame", eng.launches_per_frame(), "arena peak MB", eng.arena_peak_bytes() / 2 ** 20, flush=True)
     rep["launches_per_frame"] = eng.launches_per_frame()
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/tuning_{H}x{W}x{B}.txt", "w") as f:
+        f.write(eng.tuning_report())
 
     unet_g, vae_g = unet.cuda(), vae.cuda()
     frames = [imageproc.synthetic_frame(H, W, seed=b, shift=17 * b) for b in range(B)]

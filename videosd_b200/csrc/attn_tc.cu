@@ -75,15 +75,19 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     const uint32_t tO = tmem_base + 128u;  // dv_pad fp32 columns
 
     if (warp == 0) {
-        if (lane == 0) {
+        // warp-uniform control flow; the elect.sync leader issues the TMA operations
+        if (elect_one()) {
             mbar_expect_tx(q_full, (uint32_t)nkc * kTileBytes);
             for (int kc = 0; kc < nkc; ++kc)
                 tma_load_2d(sQ + (size_t)kc * kTileBytes, &mapQ, q_full, h * p.dk_pad + kc * 64,
                             b * p.q_rows_per_img + qt * 128);
-            for (int j = 0; j < nblocks; ++j) {
-                const int s = j % p.stages;
-                const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
-                mbar_wait(&kv_empty[s], ph ^ 1u, 1);
+        }
+        __syncwarp();
+        int s = 0;
+        uint32_t ph = 0;
+        for (int j = 0; j < nblocks; ++j) {
+            mbar_wait(&kv_empty[s], ph ^ 1u, 1);
+            if (elect_one()) {
                 mbar_expect_tx(&kv_full[s], stage_bytes);
                 uint8_t* st = sKV + (size_t)s * stage_bytes;
                 for (int kc = 0; kc < nkc; ++kc)
@@ -94,22 +98,23 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                     tma_load_2d(sv + (size_t)a * v_tile, &mapVt, &kv_full[s], b * p.vt_cols_per_img + j * 128 + a * 64,
                                 h * p.d);
             }
+            __syncwarp();
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
-        __syncwarp();
     } else if (warp == 1) {
         const uint32_t idesc_s = umma_idesc_bf16(128, 128);
         const uint32_t idesc_o = umma_idesc_bf16(128, (uint32_t)p.dv_pad);
         mbar_wait(q_full, 0, 2);
+        int s = 0;
+        uint32_t ph = 0;
         for (int j = 0; j < nblocks; ++j) {
-            const int s = j % p.stages;
-            const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
             mbar_wait(&kv_full[s], ph, 3);
             tc_fence_after_sync();
             const uint32_t q_addr = smem_u32(sQ);
             const uint32_t k_addr = smem_u32(sKV + (size_t)s * stage_bytes);
             const uint32_t v_addr = k_addr + (uint32_t)nkc * kTileBytes;
             const uint32_t p_addr = smem_u32(sP);
-            if (lane == 0) {
+            if (elect_one()) {
                 const int nk16 = p.dk_pad >> 4;
                 for (int k = 0; k < nk16; ++k) {
                     const uint32_t off = (uint32_t)(k >> 2) * kTileBytes + (uint32_t)(k & 3) * 32u;
@@ -120,7 +125,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
             __syncwarp();
             mbar_wait(p_ready, (uint32_t)j & 1u, 4);
             tc_fence_after_sync();
-            if (lane == 0) {
+            if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const uint32_t aoff = (uint32_t)(k >> 2) * kTileBytes + (uint32_t)(k & 3) * 32u;
@@ -132,6 +137,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                 umma_commit(pv_done);
             }
             __syncwarp();
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
     } else {
         const int q = warp & 3;

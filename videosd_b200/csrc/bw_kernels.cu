@@ -83,15 +83,26 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, int ldx, bf16* __res
     float* shift = scale + C;
     const int n = blockIdx.y;
     const int cpg = C / groups;
-    if (threadIdx.x < groups) {
-        const float* src = partial + (long)n * chunks * groups * 2 + threadIdx.x * 2;
+    {
+        // 8 threads per group walk the chunk partials in a fixed interleaved order, then a fixed shuffle tree
+        const int g = threadIdx.x >> 3, j = threadIdx.x & 7;
         float a = 0.f, b = 0.f;
-        for (int c = 0; c < chunks; ++c) { a += src[(long)c * groups * 2]; b += src[(long)c * groups * 2 + 1]; }
-        const float cnt = (float)HW * (float)cpg;
-        const float mean = a / cnt;
-        const float var = fmaxf(b / cnt - mean * mean, 0.f);
-        gstat[threadIdx.x * 2] = mean;
-        gstat[threadIdx.x * 2 + 1] = rsqrtf(var + eps);
+        if (g < groups) {
+            const float* src = partial + (long)n * chunks * groups * 2 + g * 2;
+            for (int c = j; c < chunks; c += 8) { a += src[(long)c * groups * 2]; b += src[(long)c * groups * 2 + 1]; }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if (g < groups && j == 0) {
+            const float cnt = (float)HW * (float)cpg;
+            const float mean = a / cnt;
+            const float var = fmaxf(b / cnt - mean * mean, 0.f);
+            gstat[g * 2] = mean;
+            gstat[g * 2 + 1] = rsqrtf(var + eps);
+        }
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -124,10 +135,10 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, int ldx, bf16* __res
 }
 
 static void gn_geometry(int NB, int HW, int* px_per_chunk, int* chunks) {
-    int target = 256 / (NB > 0 ? NB : 1);
+    int target = 128 / (NB > 0 ? NB : 1);
     if (target < 1) target = 1;
     int ppc = (HW + target - 1) / target;
-    if (ppc < 8) ppc = 8;
+    if (ppc < 16) ppc = 16;
     *px_per_chunk = ppc;
     *chunks = (HW + ppc - 1) / ppc;
 }
@@ -142,7 +153,7 @@ int groupnorm_ws_floats(int NB, int HW, int C, int groups) {
 int launch_groupnorm(const bf16* x, int ldx, bf16* y, int ldy, const float* gamma, const float* beta, int NB, int HW,
                      int C, int groups, float eps, int silu, float* partial_ws, cudaStream_t st) {
     VSD_REQUIRE(C % 8 == 0 && C % groups == 0 && ldx % 8 == 0 && ldy % 8 == 0, "GroupNorm needs C%8==0 and 16-byte rows");
-    VSD_REQUIRE(C / 8 <= 1024 && C / groups >= 8, "GroupNorm needs 8 <= C/groups and C <= 8192");
+    VSD_REQUIRE(C / 8 <= 1024 && C / groups >= 8 && groups <= 32, "GroupNorm needs 8 <= C/groups, C <= 8192, groups <= 32");
     int ppc, chunks;
     gn_geometry(NB, HW, &ppc, &chunks);
     const int vpp = C / 8;
@@ -284,16 +295,19 @@ int launch_im2col_s2(const bf16* x, int ldx, bf16* y, int NB, int Hi, int Wi, in
 // x_kind 0: fp32 NHWC (Cin channels)          1: u8 RGB NHWC with the TAESD-encode prologue ((2*(u/255)-1)+1)/2
 //        2: fp32 NHWC with the TAESD-decode prologue tanh(z/3)*3
 // One thread = one pixel x 64 output channels (blockIdx.y selects the 64-channel slab); weights [Cout][3][3][Cin].
-__global__ void conv3x3_small_cin_kernel(const void* __restrict__ xin, int x_kind, int NB, int H, int W, int Cin,
-                                         const float* __restrict__ w, const float* __restrict__ bias,
-                                         bf16* __restrict__ y, int ldy, int Cout, int relu) {
-    __shared__ float sw[64 * 36];
+template <int CIN>
+__global__ void __launch_bounds__(128)
+conv3x3_small_cin_kernel(const void* __restrict__ xin, int x_kind, int NB, int H, int W,
+                         const float* __restrict__ w, const float* __restrict__ bias,
+                         bf16* __restrict__ y, int ldy, int Cout, int relu) {
+    constexpr int K = 9 * CIN;
+    constexpr int KP = (K + 3) & ~3;            // row padded to float4
+    __shared__ __align__(16) float sw[64 * KP];
     __shared__ float sb[64];
     const int co0 = blockIdx.y * 64;
-    const int K = 9 * Cin;
-    for (int i = threadIdx.x; i < 64 * K; i += blockDim.x) {
-        const int co = i / K;
-        sw[i] = (co0 + co < Cout) ? w[(long)(co0 + co) * K + (i - co * K)] : 0.f;
+    for (int i = threadIdx.x; i < 64 * KP; i += blockDim.x) {
+        const int co = i / KP, k = i - co * KP;
+        sw[i] = (co0 + co < Cout && k < K) ? w[(long)(co0 + co) * K + k] : 0.f;
     }
     if (threadIdx.x < 64) sb[threadIdx.x] = (bias && co0 + threadIdx.x < Cout) ? bias[co0 + threadIdx.x] : 0.f;
     __syncthreads();
@@ -302,36 +316,47 @@ __global__ void conv3x3_small_cin_kernel(const void* __restrict__ xin, int x_kin
     const int wx = (int)(pix % W);
     const int hy = (int)((pix / W) % H);
     const int n = (int)(pix / ((long)W * H));
-    float patch[36];
+    float patch[KP];
+#pragma unroll
+    for (int k = K; k < KP; ++k) patch[k] = 0.f;
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
         const int hh = hy + t / 3 - 1, ww = wx + t % 3 - 1;
         const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
         const long src = ((long)n * H + hh) * W + ww;
-        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
             float v = 0.f;
-            if (ok && c < Cin) {
+            if (ok) {
                 if (x_kind == 1) {
                     const float u8 = (float)reinterpret_cast<const uint8_t*>(xin)[src * 3 + c];
                     const float img = __fsub_rn(__fmul_rn(2.0f, __fdiv_rn(u8, 255.0f)), 1.0f);  // VaeImageProcessor
                     v = __fmul_rn(__fadd_rn(img, 1.0f), 0.5f);                                   // TAESD encode
                 } else {
-                    v = reinterpret_cast<const float*>(xin)[src * Cin + c];
+                    v = reinterpret_cast<const float*>(xin)[src * CIN + c];
                     if (x_kind == 2) v = tanhf(v / 3.0f) * 3.0f;
                 }
             }
-            if (c < Cin) patch[t * Cin + c] = v;
+            patch[t * CIN + c] = v;
         }
     }
     bf16* out = y + pix * ldy + co0;
     const int nco = min(64, Cout - co0);
+#pragma unroll 1
     for (int c8 = 0; c8 < nco; c8 += 8) {
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float a = sb[c8 + j];
-            const float* wr = sw + (c8 + j) * K;
-            for (int k = 0; k < K; ++k) a = fmaf(patch[k], wr[k], a);
+            const float4* wr = reinterpret_cast<const float4*>(sw + (c8 + j) * KP);
+#pragma unroll
+            for (int k4 = 0; k4 < KP / 4; ++k4) {
+                const float4 ww4 = wr[k4];
+                a = fmaf(patch[k4 * 4 + 0], ww4.x, a);
+                a = fmaf(patch[k4 * 4 + 1], ww4.y, a);
+                a = fmaf(patch[k4 * 4 + 2], ww4.z, a);
+                a = fmaf(patch[k4 * 4 + 3], ww4.w, a);
+            }
             acc[j] = relu ? fmaxf(a, 0.f) : a;
         }
         if (c8 + 8 <= nco) {
@@ -348,7 +373,10 @@ int launch_conv3x3_small_cin(const void* x, int x_kind, int NB, int H, int W, in
     VSD_REQUIRE(x_kind != 1 || Cin == 3, "u8 input implies 3 channels");
     const long pixels = (long)NB * H * W;
     dim3 grid((unsigned)((pixels + 127) / 128), (Cout + 63) / 64);
-    conv3x3_small_cin_kernel<<<grid, 128, 0, st>>>(x, x_kind, NB, H, W, Cin, w, bias, y, ldy, Cout, relu);
+    if (Cin == 3) conv3x3_small_cin_kernel<3><<<grid, 128, 0, st>>>(x, x_kind, NB, H, W, w, bias, y, ldy, Cout, relu);
+    else if (Cin == 4) conv3x3_small_cin_kernel<4><<<grid, 128, 0, st>>>(x, x_kind, NB, H, W, w, bias, y, ldy, Cout, relu);
+    else if (Cin == 1) conv3x3_small_cin_kernel<1><<<grid, 128, 0, st>>>(x, x_kind, NB, H, W, w, bias, y, ldy, Cout, relu);
+    else conv3x3_small_cin_kernel<2><<<grid, 128, 0, st>>>(x, x_kind, NB, H, W, w, bias, y, ldy, Cout, relu);
     VSD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -22,34 +22,64 @@ static constexpr int kGemmThreads = 192;
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-// Applies bias / per-image vector / residual to 32 consecutive accumulator columns and stores them.
+// Applies bias / per-image vector / residual / ReLU to 32 consecutive accumulator columns and stores them.
+// Every loop is fully unrolled with compile-time indices so v[] stays in registers.
+//   sbias : optional shared-memory copy of (bias [+ rowvec]) for this tile's columns (index 0 = this chunk)
+//   rpre  : optional residual values for this chunk, already loaded (4 x uint4 = 32 bf16)
 __device__ __forceinline__ void epilogue_store32(const GemmParams& p, float (&v)[32], int n_img, long grow, int col,
-                                                 int ncols) {
+                                                 int ncols, const float* sbias, bool rowvec_in_sbias,
+                                                 const uint4* rpre) {
     if (ncols <= 0) return;
     const bool full = (ncols >= 32);
-    if (p.bias) {
+    if (sbias) {
+        const float4* b4 = reinterpret_cast<const float4*>(sbias);
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (full || j < ncols) v[j] += __ldg(p.bias + col + j);
+        for (int q = 0; q < 8; ++q) {
+            const float4 t = b4[q];
+            v[q * 4] += t.x; v[q * 4 + 1] += t.y; v[q * 4 + 2] += t.z; v[q * 4 + 3] += t.w;
+        }
+    } else if (p.bias) {
+        if (full && ((col & 3) == 0)) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 t = __ldg(b4 + q);
+                v[q * 4] += t.x; v[q * 4 + 1] += t.y; v[q * 4 + 2] += t.z; v[q * 4 + 3] += t.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j < ncols) v[j] += __ldg(p.bias + col + j);
+        }
     }
-    if (p.rowvec) {
+    if (p.rowvec && !rowvec_in_sbias) {
         const float* rv = p.rowvec + (long)n_img * p.N + col;
+        if (full && ((col & 3) == 0) && ((p.N & 3) == 0)) {
+            const float4* r4 = reinterpret_cast<const float4*>(rv);
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (full || j < ncols) v[j] += __ldg(rv + j);
+            for (int q = 0; q < 8; ++q) {
+                const float4 t = __ldg(r4 + q);
+                v[q * 4] += t.x; v[q * 4 + 1] += t.y; v[q * 4 + 2] += t.z; v[q * 4 + 3] += t.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j < ncols) v[j] += __ldg(rv + j);
+        }
     }
     if (p.residual) {
         const bf16* r = p.residual + grow * p.ldr + col;
-        if (full && ((p.ldr & 7) == 0) && ((col & 7) == 0)) {
+        if (rpre || (full && ((p.ldr & 7) == 0) && ((col & 7) == 0))) {
             const uint4* r4 = reinterpret_cast<const uint4*>(r);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                uint4 t = r4[q];
-                float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y), c = unpack_bf16x2(t.z), d = unpack_bf16x2(t.w);
+                const uint4 t = rpre ? rpre[q] : r4[q];
+                const float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y), c = unpack_bf16x2(t.z), d = unpack_bf16x2(t.w);
                 v[q * 8 + 0] += a.x; v[q * 8 + 1] += a.y; v[q * 8 + 2] += b.x; v[q * 8 + 3] += b.y;
                 v[q * 8 + 4] += c.x; v[q * 8 + 5] += c.y; v[q * 8 + 6] += d.x; v[q * 8 + 7] += d.y;
             }
         } else {
+#pragma unroll
             for (int j = 0; j < 32; ++j)
                 if (j < ncols) v[j] += __bfloat162float(r[j]);
         }
@@ -65,6 +95,7 @@ __device__ __forceinline__ void epilogue_store32(const GemmParams& p, float (&v)
 #pragma unroll
             for (int q = 0; q < 8; ++q) o4[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
         } else {
+#pragma unroll
             for (int j = 0; j < 32; ++j)
                 if (j < ncols) o[j] = v[j];
         }
@@ -77,6 +108,7 @@ __device__ __forceinline__ void epilogue_store32(const GemmParams& p, float (&v)
                 o4[q] = make_uint4(pack_bf16x2(v[q * 8], v[q * 8 + 1]), pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]),
                                    pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
         } else {
+#pragma unroll
             for (int j = 0; j < 32; ++j)
                 if (j < ncols) o[j] = __float2bfloat16(v[j]);
         }
@@ -89,16 +121,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stages = p.stages;
-    const uint32_t b_bytes = (uint32_t)p.block_n * 128u;
-    uint8_t* sA = smem;
-    uint8_t* sB = smem + (size_t)stages * kABytes;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + (size_t)stages * b_bytes);
+    const int kbs = p.kb_per_stage;                       // 64-wide k-blocks carried by one pipeline stage
+    const uint32_t b_bytes = (uint32_t)p.block_n * 128u;  // one k-block of the B tile
+    const uint32_t stage_bytes = (uint32_t)kbs * ((uint32_t)kABytes + b_bytes);
+    // stage layout: [A k-block 0 .. kbs-1][B k-block 0 .. kbs-1]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
     uint64_t* empty_bar = full_bar + stages;
     uint64_t* tmem_full_bar = empty_bar + stages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    // [block_n] bias (+ time-embedding row) of this tile, 16-byte aligned for float4 reads
+    float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const bool dbg_cta = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+#define VSD_STAMP(i) do { if (dbg_cta) p.dbg[i] = clock64(); } while (0)
+    if (threadIdx.x == 0) VSD_STAMP(0);
 
     const int mt = blockIdx.x;
     const int tw = mt % p.tiles_w;
@@ -125,50 +163,77 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) VSD_STAMP(1);
 
     if (warp == 0) {
-        if (lane == 0) {
+        // One elected thread runs the whole producer loop (single active thread => ptxas keeps the loop state in
+        // uniform registers and issues UTMALDG directly).
+        if (elect_one()) {
             const int kpt = p.cin >> 6;  // 64-channel blocks per tap
-            int it = 0;
-            for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
-                const int s = it % stages;
-                const uint32_t ph = (uint32_t)(it / stages) & 1u;
+            int tap = kb_begin / kpt;
+            int cb = kb_begin - tap * kpt;
+            int s = 0, dbg_it = 0;
+            uint32_t ph = 0;
+            for (int kb = kb_begin; kb < kb_end;) {
+                const int nkb = min(kbs, kb_end - kb);
                 mbar_wait(&empty_bar[s], ph ^ 1u, 1);
-                mbar_expect_tx(&full_bar[s], (uint32_t)kABytes + b_bytes);
-                const int tap = kb / kpt;
-                const int cb = kb - tap * kpt;
-                int dy = 0, dx = 0;
-                if (p.taps == 9) {
-                    dy = tap / 3 - 1;
-                    dx = tap - (tap / 3) * 3 - 1;
+                if (dbg_cta && dbg_it < 16) p.dbg[16 + 2 * dbg_it] = clock64();
+                uint8_t* sa = smem + (size_t)s * stage_bytes;
+                uint8_t* sb = sa + (size_t)kbs * kABytes;
+                mbar_expect_tx(&full_bar[s], (uint32_t)nkb * ((uint32_t)kABytes + b_bytes));
+                for (int j = 0; j < nkb; ++j, ++kb) {
+                    int dy = 0, dx = 0;
+                    if (p.taps == 9) {
+                        const int ty = (tap * 11) >> 5;  // tap / 3 for tap in [0, 9)
+                        dy = ty - 1;
+                        dx = tap - ty * 3 - 1;
+                    }
+                    tma_load_4d(sa + (size_t)j * kABytes, &mapA, &full_bar[s], cb * 64, w0 + dx, h0 + dy, n0);
+                    tma_load_2d(sb + (size_t)j * b_bytes, &mapB, &full_bar[s], kb * 64, col0);
+                    if (++cb == kpt) { cb = 0; ++tap; }
                 }
-                tma_load_4d(sA + (size_t)s * kABytes, &mapA, &full_bar[s], cb * 64, w0 + dx, h0 + dy, n0);
-                tma_load_2d(sB + (size_t)s * b_bytes, &mapB, &full_bar[s], kb * 64, col0);
+                if (dbg_cta && dbg_it < 16) p.dbg[16 + 2 * dbg_it + 1] = clock64();
+                ++dbg_it;
+                if (++s == stages) { s = 0; ph ^= 1u; }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         const uint32_t idesc = umma_idesc_bf16(kBlockM, (uint32_t)p.block_n);
-        int it = 0;
-        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
-            const int s = it % stages;
-            const uint32_t ph = (uint32_t)(it / stages) & 1u;
+        int s = 0, dbg_it = 0;
+        uint32_t ph = 0;
+        bool first = true;
+        for (int kb = kb_begin; kb < kb_end;) {
+            const int nkb = min(kbs, kb_end - kb);
             mbar_wait(&full_bar[s], ph, 2);
             tc_fence_after_sync();
-            if (lane == 0) {
-                const uint32_t a_addr = smem_u32(sA + (size_t)s * kABytes);
-                const uint32_t b_addr = smem_u32(sB + (size_t)s * b_bytes);
+            if (lane == 0 && first) VSD_STAMP(2);
+            if (lane == 0 && dbg_cta && dbg_it < 16) p.dbg[64 + 2 * dbg_it] = clock64();
+            {
+                const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint32_t b_addr = a_addr + (uint32_t)kbs * kABytes;
+                if (elect_one()) {   // one elected lane issues; ptxas keeps descriptors in uniform registers
+                    for (int j = 0; j < nkb; ++j) {
 #pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k) {
-                    umma_bf16(tmem_base, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                              (it > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            umma_bf16(tmem_base, umma_desc_sw128(a_addr + j * kABytes + k * 32),
+                                      umma_desc_sw128(b_addr + j * b_bytes + k * 32), idesc,
+                                      (first && j == 0 && k == 0) ? 0u : 1u);
+                        }
+                    }
+                    umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
                 }
-                umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+                __syncwarp();
+                if (lane == 0 && dbg_cta && dbg_it < 16) p.dbg[64 + 2 * dbg_it + 1] = clock64();
             }
-            __syncwarp();
+            ++dbg_it;
+            first = false;
+            kb += nkb;
+            if (++s == stages) { s = 0; ph ^= 1u; }
         }
-        if (lane == 0) umma_commit(tmem_full_bar);
+        if (elect_one()) umma_commit(tmem_full_bar);
         __syncwarp();
+        if (lane == 0) VSD_STAMP(3);
     } else {
         const int q = warp & 3;
         const int r = q * 32 + lane;
@@ -179,8 +244,33 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         const bool row_ok = (n_img < p.NB) && (hh < p.H) && (ww < p.W);
         const long grow = ((long)n_img * p.H + hh) * p.W + ww;
         const long rows_total = (long)p.NB * p.H * p.W;
+        // While the main loop runs: stage bias (+ the per-image time-embedding row when the tile lies inside one
+        // image) in shared memory and prefetch the first residual chunk.
+        const bool rowvec_in_sbias = (p.rowvec != nullptr) && (p.BN == 1);
+        const bool use_sbias = (p.splits == 1) && (p.bias != nullptr || rowvec_in_sbias);
+        if (use_sbias) {
+            for (int i = threadIdx.x - 64; i < p.block_n; i += 128) {
+                const int col = col0 + i;
+                float bv = 0.f;
+                if (col < p.N) {
+                    if (p.bias) bv = __ldg(p.bias + col);
+                    if (rowvec_in_sbias) bv += __ldg(p.rowvec + (long)n0 * p.N + col);
+                }
+                sbias[i] = bv;
+            }
+        }
+        const bool res_vec = (p.residual != nullptr) && row_ok && ((p.ldr & 7) == 0) && ((col0 & 7) == 0) &&
+                             (p.splits == 1) && (p.act != ACT_GEGLU);
+        uint4 rnext[4];
+        if (res_vec && col0 + 32 <= p.N) {
+            const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + grow * p.ldr + col0);
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) rnext[q4] = r4[q4];
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue warps only: sbias is complete
         mbar_wait(tmem_full_bar, 0, 3);
         tc_fence_after_sync();
+        if (threadIdx.x == 64) VSD_STAMP(4);
         const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
         if (p.splits > 1) {
             float* dst = p.partial + ((long)split * rows_total + grow) * p.N;
@@ -198,7 +288,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                             d4[j] = make_float4(__uint_as_float(u[4 * j]), __uint_as_float(u[4 * j + 1]),
                                                 __uint_as_float(u[4 * j + 2]), __uint_as_float(u[4 * j + 3]));
                     } else {
-                        for (int j = 0; j < ncols; ++j) dst[col + j] = __uint_as_float(u[j]);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < ncols) dst[col + j] = __uint_as_float(u[j]);
                     }
                 }
             }
@@ -212,11 +304,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 tmem_ld32(tbase + half + c, g);
                 tmem_ld_wait();
                 float v[32];
+                const float4* bu = reinterpret_cast<const float4*>(sbias + c);
+                const float4* bg = reinterpret_cast<const float4*>(sbias + half + c);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float uv = __uint_as_float(u[j]) + __ldg(p.bias + col0 + c + j);
-                    const float gv = __uint_as_float(g[j]) + __ldg(p.bias + col0 + half + c + j);
-                    v[j] = uv * gelu_erf(gv);
+                for (int q4 = 0; q4 < 8; ++q4) {
+                    const float4 tu = bu[q4], tg = bg[q4];
+                    v[q4 * 4 + 0] = (__uint_as_float(u[q4 * 4 + 0]) + tu.x) * gelu_erf(__uint_as_float(g[q4 * 4 + 0]) + tg.x);
+                    v[q4 * 4 + 1] = (__uint_as_float(u[q4 * 4 + 1]) + tu.y) * gelu_erf(__uint_as_float(g[q4 * 4 + 1]) + tg.y);
+                    v[q4 * 4 + 2] = (__uint_as_float(u[q4 * 4 + 2]) + tu.z) * gelu_erf(__uint_as_float(g[q4 * 4 + 2]) + tg.z);
+                    v[q4 * 4 + 3] = (__uint_as_float(u[q4 * 4 + 3]) + tu.w) * gelu_erf(__uint_as_float(g[q4 * 4 + 3]) + tg.w);
                 }
                 if (row_ok) {
                     bf16* o = reinterpret_cast<bf16*>(p.out) + grow * p.ldo + ocol0 + c;
@@ -231,18 +327,35 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             for (int c = 0; c < p.block_n; c += 32) {
                 uint32_t u[32];
                 tmem_ld32(tbase + c, u);
+                const int col = col0 + c;
+                const int ncols = min(32, p.N - col);
+                uint4 rcur[4];
+                const bool have_pre = res_vec && ncols == 32;
+                if (have_pre) {
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) rcur[q4] = rnext[q4];
+                    if (c + 32 < p.block_n && col + 64 <= p.N) {   // prefetch the next chunk's residual
+                        const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + grow * p.ldr + col + 32);
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) rnext[q4] = r4[q4];
+                    }
+                }
                 tmem_ld_wait();
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]);
-                const int col = col0 + c;
-                if (row_ok) epilogue_store32(p, v, n_img, grow, col, min(32, p.N - col));
+                if (row_ok)
+                    epilogue_store32(p, v, n_img, grow, col, ncols, use_sbias ? sbias + c : nullptr, rowvec_in_sbias,
+                                     have_pre ? rcur : nullptr);
             }
         }
     }
+    if (threadIdx.x == 64) VSD_STAMP(5);
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (threadIdx.x == 32) VSD_STAMP(6);
+#undef VSD_STAMP
 }
 
 // Sums split-K partials and applies the same epilogue. One thread per (row, 32-column chunk).
@@ -270,7 +383,7 @@ __global__ void splitk_reduce_kernel(const GemmParams p, long rows) {
         }
     }
     const int n_img = (int)(grow / ((long)p.H * p.W));
-    epilogue_store32(p, v, n_img, grow, col, ncols);
+    epilogue_store32(p, v, n_img, grow, col, ncols, nullptr, false, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -356,7 +469,8 @@ static void pick_tile_rect(int NB, int H, int W, int* BW, int* BH, int* BN) {
 
 int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N, int ldw, void* out, int ldo,
                   int out_f32, const float* bias, const float* rowvec, const bf16* residual, int ldr, int act_flags,
-                  float* partial_ws, size_t partial_ws_bytes, int force_block_n, int force_splits) {
+                  float* partial_ws, size_t partial_ws_bytes, int force_block_n, int force_splits, int force_occupancy,
+                  int force_kb_per_stage) {
     const int act = act_flags & 0xF;
     VSD_REQUIRE(taps == 1 || taps == 9, "taps must be 1 or 9");
     VSD_REQUIRE(a.C % 64 == 0, "input channels must be a multiple of 64 for the tcgen05 path");
@@ -431,13 +545,21 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
     // Tiles up to 160 columns run two CTAs per SM (one CTA's epilogue overlaps the other's main loop);
     // wider tiles take the whole SM with a deeper ring.
     const int stage_bytes = kABytes + bn * 128;
-    const int smem_budget = (bn > 160) ? g_max_smem : (g_max_smem / 2 - 1024);
-    int stages = (smem_budget - 2048) / stage_bytes;
+    int occ = force_occupancy > 0 ? force_occupancy : ((bn > 160) ? 1 : 2);
+    if (occ == 2 && 2 * (kABytes + bn * 128) + 4096 > g_max_smem / 2) occ = 1;   // not even two stages fit twice
+    const int smem_budget = (occ == 1) ? g_max_smem : (g_max_smem / 2 - 1024);
+    // Each barrier round trip (TMA -> full -> MMA -> commit -> empty -> TMA) costs several hundred cycles, so a
+    // stage carries kb_per_stage 64-wide k-blocks; keep >= 3 stages in flight when the budget allows.
+    int kbs = force_kb_per_stage > 0 ? force_kb_per_stage : 2;
+    while (kbs > 1 && ((smem_budget - 3072) / (kbs * stage_bytes) < (force_kb_per_stage > 0 ? 2 : 3) || kbs > p.kb_per_split)) --kbs;
+    int stages = (smem_budget - 3072) / (kbs * stage_bytes);
     if (stages > 8) stages = 8;
-    if (stages > p.kb_per_split) stages = p.kb_per_split;
+    const int stage_iters = (p.kb_per_split + kbs - 1) / kbs;
+    if (stages > stage_iters) stages = stage_iters;
     if (stages < 1) stages = 1;
     p.stages = stages;
-    op->smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + (2 * stages + 1) * 8 + 16;
+    p.kb_per_stage = kbs;
+    op->smem_bytes = stages * kbs * stage_bytes + 1024 /*align slack*/ + (2 * stages + 1) * 8 + 64 + bn * 4;
 
     p.out = out; p.ldo = ldo; p.out_f32 = out_f32;
     p.bias = bias; p.rowvec = rowvec; p.residual = residual; p.ldr = ldr;

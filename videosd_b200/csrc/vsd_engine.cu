@@ -112,6 +112,12 @@ struct Engine {
     std::vector<Launch> plan_pre_yuv, plan_pre_rgb, plan_core, plan_post;
     std::vector<std::vector<Launch>> plan_unet;  // per step (debug entry)
     cudaGraphExec_t graph_yuv = nullptr, graph_rgb = nullptr;
+    // GEMM autotuner: (block_n, splits, occupancy) per distinct shape, timed with L2 flushed
+    int autotune = 1;
+    struct Tuned { int bn, splits, occ, kbs; float us; };
+    std::unordered_map<std::string, Tuned> tuned;
+    void* flush_buf = nullptr; size_t flush_bytes = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     long launches_per_frame_yuv = 0;
     std::string err;
 };
@@ -259,6 +265,70 @@ static int load_weight(Engine* e, const std::string& name, const float* host, co
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ GEMM autotuner
+static int time_gemm(Engine* e, const GemmOp& op, float* us) {
+    float best = 1e30f;
+    for (int rep = 0; rep < 2; ++rep) {
+        VSD_CHECK_CUDA(cudaMemsetAsync(e->flush_buf, rep, e->flush_bytes, e->stream));   // evict L2: weights come from HBM
+        VSD_CHECK_CUDA(cudaEventRecord(e->ev0, e->stream));
+        int rc = launch_gemm_op(op, e->stream);
+        if (rc) return rc;
+        VSD_CHECK_CUDA(cudaEventRecord(e->ev1, e->stream));
+        VSD_CHECK_CUDA(cudaEventSynchronize(e->ev1));
+        float ms = 0.f;
+        VSD_CHECK_CUDA(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+        if (ms * 1e3f < best) best = ms * 1e3f;
+    }
+    *us = best;
+    return 0;
+}
+
+static int tune_gemm(Engine* e, const ActView& a, int taps, const bf16* wt, int N, int ldw, void* outp, int ldo,
+                     int out_f32, const float* bias, const float* rowvec, const bf16* res, int ldr, int act,
+                     Engine::Tuned* result) {
+    if (!e->flush_buf) {
+        e->flush_bytes = (size_t)192 << 20;
+        VSD_CHECK_CUDA(cudaMalloc(&e->flush_buf, e->flush_bytes));
+        VSD_CHECK_CUDA(cudaEventCreate(&e->ev0));
+        VSD_CHECK_CUDA(cudaEventCreate(&e->ev1));
+    }
+    const bool geglu = (act & 0xF) == ACT_GEGLU;
+    const int bns[8] = {32, 64, 96, 128, 160, 192, 224, 256};
+    const int kbss[3] = {1, 2, 4};
+    const int sps[8] = {1, 2, 3, 4, 6, 8, 12, 16};
+    const int kb_total = taps * (a.C / 64);
+    Engine::Tuned best{0, 1, 0, 1, 1e30f};
+    for (int bi = 0; bi < 8; ++bi) {
+        const int bn = bns[bi];
+        if (geglu && bn != 128) continue;
+        if (bn != 32 && bn > ((N + 31) / 32) * 32) continue;
+        for (int si = 0; si < 8; ++si) {
+            const int sp = sps[si];
+            if (sp > 1 && (geglu || kb_total / sp < 2)) continue;
+            for (int occ = 1; occ <= 2; ++occ) {
+                for (int ki = 0; ki < 3; ++ki) {
+                    const int kbs = kbss[ki];
+                    GemmOp op;
+                    if (build_gemm_op(&op, a, taps, wt, N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act,
+                                      e->splitk_ws, e->splitk_bytes, bn, sp, occ, kbs))
+                        continue;   // does not fit (workspace / smem): skip
+                    if (op.p.splits != sp || op.p.kb_per_stage != kbs) continue;
+                    const long ctas = (long)op.grid.x * op.grid.y * op.grid.z;
+                    if (sp > 1 && ctas > 4 * 148) continue;
+                    if (occ == 2 && op.smem_bytes > 114 * 1024) continue;   // would not actually co-reside
+                    float us = 0.f;
+                    int rc = time_gemm(e, op, &us);
+                    if (rc) return rc;
+                    if (us < best.us) best = Engine::Tuned{bn, sp, occ, kbs, us};
+                }
+            }
+        }
+    }
+    if (best.bn == 0) { set_error("autotune found no valid GEMM configuration"); return -1; }
+    *result = best;
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ plan builder
 struct Builder {
     Engine* e;
@@ -301,8 +371,22 @@ struct Builder {
               const float* bias, const float* rowvec, const bf16* res, int ldr, int act) {
         if (rc) return;
         GemmOp op;
+        int fbn = 0, fsp = 0, focc = 0, fkbs = 0;
+        if (e->autotune) {
+            char key[160];
+            snprintf(key, sizeof(key), "%dx%dx%dx%d|t%d|n%d|a%d|f%d|r%d", a.NB, a.H, a.W, a.C, taps, N, act, out_f32,
+                     res ? 1 : 0);
+            auto it = e->tuned.find(key);
+            if (it == e->tuned.end()) {
+                Engine::Tuned t;
+                int r = tune_gemm(e, a, taps, wt, N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act, &t);
+                if (r) { rc = r; fail = get_error(); return; }
+                it = e->tuned.emplace(key, t).first;
+            }
+            fbn = it->second.bn; fsp = it->second.splits; focc = it->second.occ; fkbs = it->second.kbs;
+        }
         int r = build_gemm_op(&op, a, taps, wt, N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act, e->splitk_ws,
-                              e->splitk_bytes, 0, 0);
+                              e->splitk_bytes, fbn, fsp, focc, fkbs);
         if (r) { rc = r; fail = get_error(); return; }
         out->push_back([op](cudaStream_t st) { return launch_gemm_op(op, st); });
     }
@@ -971,6 +1055,9 @@ void vsd_destroy(vsd_ctx* c) {
     for (auto& kv : c->e.w) cudaFree(kv.second.p);
     c->e.arena.destroy();
     if (c->e.splitk_ws) cudaFree(c->e.splitk_ws);
+    if (c->e.flush_buf) cudaFree(c->e.flush_buf);
+    if (c->e.ev0) cudaEventDestroy(c->e.ev0);
+    if (c->e.ev1) cudaEventDestroy(c->e.ev1);
     cudaStreamDestroy(c->e.stream);
     delete c;
 }
@@ -985,6 +1072,30 @@ int vsd_load_weight(vsd_ctx* c, const char* name, const float* host_f32, const i
 }
 
 int vsd_num_weights(vsd_ctx* c) { return c ? (int)c->e.w.size() : -1; }
+
+int vsd_set_autotune(vsd_ctx* c, int enabled) {
+    if (!c) return -1;
+    c->e.autotune = enabled ? 1 : 0;
+    return 0;
+}
+
+/* Writes "key bn splits occ us" lines of the tuned GEMM shapes into buf; returns the number of entries. */
+int vsd_tuning_report(vsd_ctx* c, char* buf, long cap) {
+    if (!c) return -1;
+    std::string s;
+    for (auto& kv : c->e.tuned) {
+        char line[256];
+        snprintf(line, sizeof(line), "%s bn=%d splits=%d occ=%d kbs=%d us=%.2f\n", kv.first.c_str(), kv.second.bn,
+                 kv.second.splits, kv.second.occ, kv.second.kbs, kv.second.us);
+        s += line;
+    }
+    if (buf && cap > 0) {
+        const size_t n = std::min((size_t)cap - 1, s.size());
+        memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return (int)c->e.tuned.size();
+}
 
 int vsd_configure(vsd_ctx* c, int batch, int height, int width) {
     CTX_GUARD(c);

@@ -48,7 +48,7 @@ struct GemmParams {
     int N;                // rows of the weight matrix (GEMM N)
     int block_n;          // multiple of 32, <= 256
     int tmem_cols;        // power of two >= block_n
-    int stages;
+    int stages, kb_per_stage;
     // K split
     int kb_total, kb_per_split, splits;
     // epilogue
@@ -60,6 +60,7 @@ struct GemmParams {
     int ldr;
     int act, relu;
     float* partial;       // [splits, rows, N] fp32 when splits > 1
+    long long* dbg;       // optional: CTA (0,0,0) writes clock64() phase stamps here (bring-up only)
 };
 
 struct GemmOp {
@@ -76,7 +77,8 @@ struct ActView {
 };
 int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N, int ldw, void* out, int ldo,
                   int out_f32, const float* bias, const float* rowvec, const bf16* residual, int ldr, int act,
-                  float* partial_ws, size_t partial_ws_bytes, int force_block_n, int force_splits);
+                  float* partial_ws, size_t partial_ws_bytes, int force_block_n, int force_splits,
+                  int force_occupancy = 0, int force_kb_per_stage = 0);
 int launch_gemm_op(const GemmOp& op, cudaStream_t st);
 int gemm_init();  // sets func attributes; call once per process after a device is selected
 

@@ -87,6 +87,23 @@ int vsd_op_conv_gemm(const void* x, int nb, int h, int w, int c, int ldx, int ta
     return launch_gemm_op(op, reinterpret_cast<cudaStream_t>(stream));
 }
 
+/* bring-up: same as vsd_op_conv_gemm but CTA (0,0,0) records 7 clock64() phase stamps into dbg (device int64[8]) */
+int vsd_op_conv_gemm_timed(const void* x, int nb, int h, int w, int c, int ldx, int taps, const void* wt, int n, void* out,
+                           int ldo, const float* bias, int block_n, int splits, int occ, int kb_per_stage, long long* dbg,
+                           void* stream) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    rc = ensure_ws((size_t)16 * nb * h * w * n * 4 + 1024);
+    if (rc) return rc;
+    GemmOp op;
+    ActView a{x, nb, h, w, c, ldx};
+    rc = build_gemm_op(&op, a, taps, reinterpret_cast<const bf16*>(wt), n, taps * c, out, ldo, 0, bias, nullptr, nullptr, 0,
+                       0, g_ws, g_ws_bytes, block_n, splits, occ, kb_per_stage);
+    if (rc) return rc;
+    op.p.dbg = dbg;
+    return launch_gemm_op(op, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int vsd_op_attention(const void* q, int ldq, const void* k, int ldk, const void* vt, int ldvt, void* out, int ldo,
                      int batch, int heads, int d, int nq, int nk, int q_rows_per_img, int k_rows_per_img,
                      int vt_cols_per_img, int vt_rows, void* stream) {

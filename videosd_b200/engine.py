@@ -134,6 +134,14 @@ class Engine:
     def launches_per_frame(self, yuv=True):
         return int(self._L.vsd_launches_per_frame(self._ctx, c_int(1 if yuv else 0)))
 
+    def set_autotune(self, enabled):
+        check(self._L.vsd_set_autotune(self._ctx, c_int(1 if enabled else 0)), "vsd_set_autotune")
+
+    def tuning_report(self):
+        buf = ctypes.create_string_buffer(1 << 18)
+        self._L.vsd_tuning_report(self._ctx, buf, ctypes.c_long(len(buf)))
+        return buf.value.decode()
+
     def arena_peak_bytes(self):
         return int(self._L.vsd_arena_peak_bytes(self._ctx))
 
