@@ -111,6 +111,7 @@ int vsd_num_weights(vsd_ctx* ctx);
  * CTAs/SM) candidates with the L2 flushed. vsd_tuning_report dumps the choices as text. */
 int vsd_set_autotune(vsd_ctx* ctx, int enabled);
 int vsd_tuning_report(vsd_ctx* ctx, char* buf, long cap);
+int vsd_tuning_load(vsd_ctx* ctx, const char* text);   /* returns the number of entries loaded */
 
 /* Working size: `batch` frames of height x width (multiples of 8; infer(height=, width=) at videopipeline.py:75-88).
  * Must be called after the weights are loaded; invalidates schedule, contexts and noise. */

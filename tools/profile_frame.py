@@ -23,7 +23,13 @@ def main():
     eng.load_state_dict("unet", weights.random_state_dict(weights.unet_param_shapes(), 1234))
     eng.load_state_dict("vae", weights.random_state_dict(weights.taesd_param_shapes(), 4321))
     eng.configure(B, H, W)
+    cache = f"gpurun_out/tune_cache_{size}.txt"
+    if os.path.exists(cache):        # produced by an earlier run outside the profiler
+        print("tuning cache entries loaded:", eng.tuning_load(open(cache).read()), flush=True)
     eng.set_schedule(0.5, 4)
+    if "--save-tuning" in sys.argv:
+        os.makedirs("gpurun_out", exist_ok=True)
+        open(cache, "w").write(eng.tuning_report())
     ctx = torch.randn((77, 768), generator=torch.Generator().manual_seed(7))
     for b in range(B):
         eng.set_context(b, ctx)

@@ -12,6 +12,7 @@
 // warp 0: TMA producer | warp 1: MMA issue + TMEM alloc | warps 2..5: softmax / correction / epilogue
 #include "tc_common.cuh"
 #include "vsd_internal.h"
+#include <algorithm>
 
 namespace vsd {
 
@@ -50,6 +51,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    pdl_launch_dependents();
     const int nblocks = (p.nk + 127) >> 7;
 
     if (warp == 0 && lane == 0) {
@@ -76,6 +78,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
 
     if (warp == 0) {
         // warp-uniform control flow; the elect.sync leader issues the TMA operations
+        pdl_wait();   // Q / K / V^T are produced by the preceding projection kernels
         if (elect_one()) {
             mbar_expect_tx(q_full, (uint32_t)nkc * kTileBytes);
             for (int kc = 0; kc < nkc; ++kc)
@@ -144,6 +147,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         const int r = q * 32 + lane;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
         float m_run = -INFINITY, l_run = 0.f;
+        pdl_wait();   // the output buffer may still be read by an earlier kernel
         for (int j = 0; j < nblocks; ++j) {
             mbar_wait(s_full, (uint32_t)j & 1u, 5);
             tc_fence_after_sync();
@@ -275,6 +279,8 @@ int build_attn_op(AttnOp* op, const bf16* q, int ldq, const bf16* k, int ldk, co
     op->smem_bytes = fixed + stages * stage_bytes;
     const int cols = 128 + op->dv_pad;
     op->tmem_cols = cols <= 256 ? 256 : 512;
+    // TMEM over-subscription guard under programmatic dependent launch (see build_gemm_op)
+    if (op->smem_bytes < op->tmem_cols * 450) op->smem_bytes = std::min(op->tmem_cols * 450, g_attn_max_smem);
     int rc = make_tmap_2d(&op->mapQ, q, heads * op->dk_pad, batch * q_rows_per_img, ldq, 128);
     if (rc) return rc;
     rc = make_tmap_2d(&op->mapK, k, heads * op->dk_pad, batch * k_rows_per_img, ldk, 128);
@@ -291,8 +297,7 @@ int launch_attn_op(const AttnOp& op, cudaStream_t st) {
     p.nq = op.nq; p.nk = op.nk;
     p.q_rows_per_img = op.q_rows_per_img; p.k_rows_per_img = op.k_rows_per_img; p.vt_cols_per_img = op.vt_cols_per_img;
     p.out = op.out; p.ldo = op.ldo; p.scale_log2e = op.scale_log2e; p.stages = op.stages; p.tmem_cols = op.tmem_cols;
-    attention_kernel<<<op.grid, kAttnThreads, op.smem_bytes, st>>>(op.mapQ, op.mapK, op.mapVt, p);
-    VSD_CHECK_CUDA(cudaGetLastError());
+    VSD_CHECK_CUDA(launch_k(attention_kernel, op.grid, dim3(kAttnThreads), (size_t)op.smem_bytes, st, op.mapQ, op.mapK, op.mapVt, p));
     return 0;
 }
 

@@ -26,6 +26,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // owns one channel vector, so the (at most two, since C/groups >= 8) groups it touches are loop-invariant.
 __global__ void gn_stats_kernel(const bf16* __restrict__ x, int ldx, int HW, int C, int groups, int px_per_chunk,
                                 float* __restrict__ partial /*[NB][chunks][groups][2]*/) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float4 spart[];  // [blockDim.x] = {sum g0, sumsq g0, sum g0+1, sumsq g0+1}
     const int vpp = C >> 3;
     const int cpg = C / groups;
@@ -39,6 +41,7 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x, int ldx, int HW, int
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s[j] = 0.f; ss[j] = 0.f; }
     const bf16* base = x + ((long)n * HW) * ldx + vi * 8;
+#pragma unroll 4
     for (int p = p_begin + r0; p < p_end; p += R) {
         const uint4 t = *reinterpret_cast<const uint4*>(base + (long)p * ldx);
         float f[8];
@@ -77,6 +80,8 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, int ldx, bf16* __res
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C,
                                 int groups, float eps, int silu, const float* __restrict__ partial, int chunks,
                                 int px_per_block) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float sm[];  // [groups*2] then [C] scale, [C] shift
     float* gstat = sm;
     float* scale = sm + groups * 2;
@@ -118,6 +123,7 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, int ldx, bf16* __res
     const long total = (long)(p_end - p_begin) * vpp;
     const bf16* xb = x + ((long)n * HW + p_begin) * ldx;
     bf16* yb = y + ((long)n * HW + p_begin) * ldy;
+#pragma unroll 2
     for (long i = threadIdx.x; i < total; i += blockDim.x) {
         const int p = (int)(i / vpp);
         const int vi = (int)(i - (long)p * vpp);
@@ -134,19 +140,23 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, int ldx, bf16* __res
     }
 }
 
-static void gn_geometry(int NB, int HW, int* px_per_chunk, int* chunks) {
-    int target = 128 / (NB > 0 ? NB : 1);
-    if (target < 1) target = 1;
-    int ppc = (HW + target - 1) / target;
-    if (ppc < 16) ppc = 16;
+// Blocks of ~1024 channel-vectors (small tensors are latency-bound: spread them over many SMs), at most 128 chunks
+// per image so the per-block partial reduction stays short.
+static void gn_geometry(int NB, int HW, int C, int* px_per_chunk, int* chunks) {
+    const long vecs = (long)HW * (C / 8);
+    long want = (vecs + 1023) / 1024;
+    const long cap = NB >= 4 ? 64 : 128;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    int ppc = (int)((HW + want - 1) / want);
+    if (ppc < 1) ppc = 1;
     *px_per_chunk = ppc;
     *chunks = (HW + ppc - 1) / ppc;
 }
 
 int groupnorm_ws_floats(int NB, int HW, int C, int groups) {
     int ppc, chunks;
-    gn_geometry(NB, HW, &ppc, &chunks);
-    (void)C;
+    gn_geometry(NB, HW, C, &ppc, &chunks);
     return NB * chunks * groups * 2;
 }
 
@@ -155,15 +165,15 @@ int launch_groupnorm(const bf16* x, int ldx, bf16* y, int ldy, const float* gamm
     VSD_REQUIRE(C % 8 == 0 && C % groups == 0 && ldx % 8 == 0 && ldy % 8 == 0, "GroupNorm needs C%8==0 and 16-byte rows");
     VSD_REQUIRE(C / 8 <= 1024 && C / groups >= 8 && groups <= 32, "GroupNorm needs 8 <= C/groups, C <= 8192, groups <= 32");
     int ppc, chunks;
-    gn_geometry(NB, HW, &ppc, &chunks);
+    gn_geometry(NB, HW, C, &ppc, &chunks);
     const int vpp = C / 8;
     int R = 256 / vpp;
     if (R < 1) R = 1;
-    gn_stats_kernel<<<dim3(chunks, NB), vpp * R, (size_t)vpp * R * sizeof(float4), st>>>(x, ldx, HW, C, groups, ppc, partial_ws);
+    VSD_CHECK_CUDA(launch_k(gn_stats_kernel, dim3(chunks, NB), dim3(vpp * R), (size_t)vpp * R * sizeof(float4), st, x, ldx, HW, C, groups, ppc, partial_ws));
     VSD_CHECK_CUDA(cudaGetLastError());
     const size_t smem = (size_t)(groups * 2 + 2 * C) * sizeof(float);
-    gn_apply_kernel<<<dim3(chunks, NB), 256, smem, st>>>(x, ldx, y, ldy, gamma, beta, HW, C, groups, eps, silu,
-                                                          partial_ws, chunks, ppc);
+    VSD_CHECK_CUDA(launch_k(gn_apply_kernel, dim3(chunks, NB), dim3(256), smem, st, x, ldx, y, ldy, gamma, beta, HW, C, groups, eps, silu,
+                                                          partial_ws, chunks, ppc));
     VSD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -174,6 +184,8 @@ template <int MAXV>
 __global__ void layernorm_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy,
                                  const float* __restrict__ gamma, const float* __restrict__ beta, int rows, int C,
                                  float eps) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -222,9 +234,9 @@ int launch_layernorm(const bf16* x, int ldx, bf16* y, int ldy, const float* gamm
     VSD_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && C <= 2048, "LayerNorm needs C%8==0, C<=2048");
     const int warps = 8;
     dim3 grid((rows + warps - 1) / warps);
-    if (C <= 512) layernorm_kernel<2><<<grid, warps * 32, 0, st>>>(x, ldx, y, ldy, gamma, beta, rows, C, eps);
-    else if (C <= 1280) layernorm_kernel<5><<<grid, warps * 32, 0, st>>>(x, ldx, y, ldy, gamma, beta, rows, C, eps);
-    else layernorm_kernel<8><<<grid, warps * 32, 0, st>>>(x, ldx, y, ldy, gamma, beta, rows, C, eps);
+    if (C <= 512) VSD_CHECK_CUDA(launch_k(layernorm_kernel<2>, dim3(grid), dim3(warps * 32), 0, st, x, ldx, y, ldy, gamma, beta, rows, C, eps));
+    else if (C <= 1280) VSD_CHECK_CUDA(launch_k(layernorm_kernel<5>, dim3(grid), dim3(warps * 32), 0, st, x, ldx, y, ldy, gamma, beta, rows, C, eps));
+    else VSD_CHECK_CUDA(launch_k(layernorm_kernel<8>, dim3(grid), dim3(warps * 32), 0, st, x, ldx, y, ldy, gamma, beta, rows, C, eps));
     VSD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -233,6 +245,8 @@ int launch_layernorm(const bf16* x, int ldx, bf16* y, int ldy, const float* gamm
 // torch F.interpolate(mode="nearest"): src = min(floor(dst * in/out), in-1)
 __global__ void upsample_nearest_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy, int NB,
                                         int Hi, int Wi, int Ho, int Wo, int C) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int vpp = C >> 3;
     const long total = (long)NB * Ho * Wo * vpp;
     const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
@@ -255,7 +269,7 @@ int launch_upsample_nearest(const bf16* x, int ldx, bf16* y, int ldy, int NB, in
     const long total = (long)NB * Ho * Wo * (C / 8);
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    upsample_nearest_kernel<<<blocks, 256, 0, st>>>(x, ldx, y, ldy, NB, Hi, Wi, Ho, Wo, C);
+    VSD_CHECK_CUDA(launch_k(upsample_nearest_kernel, dim3(blocks), dim3(256), 0, st, x, ldx, y, ldy, NB, Hi, Wi, Ho, Wo, C));
     VSD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -263,6 +277,8 @@ int launch_upsample_nearest(const bf16* x, int ldx, bf16* y, int ldy, int NB, in
 // 3x3 stride-2 pad-1 patches -> rows of a [NB*Ho*Wo][9*C] matrix (tap-major), feeding the tcgen05 GEMM.
 __global__ void im2col_s2_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int NB, int Hi, int Wi,
                                  int C, int Ho, int Wo) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int vpp = C >> 3;
     const long total = (long)NB * Ho * Wo * 9 * vpp;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -285,7 +301,7 @@ int launch_im2col_s2(const bf16* x, int ldx, bf16* y, int NB, int Hi, int Wi, in
     const long total = (long)NB * Ho * Wo * 9 * (C / 8);
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    im2col_s2_kernel<<<blocks, 256, 0, st>>>(x, ldx, y, NB, Hi, Wi, C, Ho, Wo);
+    VSD_CHECK_CUDA(launch_k(im2col_s2_kernel, dim3(blocks), dim3(256), 0, st, x, ldx, y, NB, Hi, Wi, C, Ho, Wo));
     VSD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -300,6 +316,8 @@ __global__ void __launch_bounds__(128)
 conv3x3_small_cin_kernel(const void* __restrict__ xin, int x_kind, int NB, int H, int W,
                          const float* __restrict__ w, const float* __restrict__ bias,
                          bf16* __restrict__ y, int ldy, int Cout, int relu) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int K = 9 * CIN;
     constexpr int KP = (K + 3) & ~3;            // row padded to float4
     __shared__ __align__(16) float sw[64 * KP];
@@ -373,10 +391,10 @@ int launch_conv3x3_small_cin(const void* x, int x_kind, int NB, int H, int W, in
     VSD_REQUIRE(x_kind != 1 || Cin == 3, "u8 input implies 3 channels");
     const long pixels = (long)NB * H * W;
     dim3 grid((unsigned)((pixels + 127) / 128), (Cout + 63) / 64);
-    if (Cin == 3) conv3x3_small_cin_kernel<3><<<grid, 128, 0, st>>>(x, x_kind, NB, H, W, w, bias, y, ldy, Cout, relu);
-    else if (Cin == 4) conv3x3_small_cin_kernel<4><<<grid, 128, 0, st>>>(x, x_kind, NB, H, W, w, bias, y, ldy, Cout, relu);
-    else if (Cin == 1) conv3x3_small_cin_kernel<1><<<grid, 128, 0, st>>>(x, x_kind, NB, H, W, w, bias, y, ldy, Cout, relu);
-    else conv3x3_small_cin_kernel<2><<<grid, 128, 0, st>>>(x, x_kind, NB, H, W, w, bias, y, ldy, Cout, relu);
+    if (Cin == 3) VSD_CHECK_CUDA(launch_k(conv3x3_small_cin_kernel<3>, dim3(grid), dim3(128), 0, st, x, x_kind, NB, H, W, w, bias, y, ldy, Cout, relu));
+    else if (Cin == 4) VSD_CHECK_CUDA(launch_k(conv3x3_small_cin_kernel<4>, dim3(grid), dim3(128), 0, st, x, x_kind, NB, H, W, w, bias, y, ldy, Cout, relu));
+    else if (Cin == 1) VSD_CHECK_CUDA(launch_k(conv3x3_small_cin_kernel<1>, dim3(grid), dim3(128), 0, st, x, x_kind, NB, H, W, w, bias, y, ldy, Cout, relu));
+    else VSD_CHECK_CUDA(launch_k(conv3x3_small_cin_kernel<2>, dim3(grid), dim3(128), 0, st, x, x_kind, NB, H, W, w, bias, y, ldy, Cout, relu));
     VSD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -384,6 +402,8 @@ int launch_conv3x3_small_cin(const void* x, int x_kind, int NB, int H, int W, in
 // ------------------------------------------------------------------------------------------ time-embedding GEMV
 __global__ void gemv_f32_kernel(const float* __restrict__ W, const float* __restrict__ x, const float* __restrict__ b,
                                 float* __restrict__ y, int out, int in, int silu_in, int silu_out) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= out) return;
@@ -402,7 +422,7 @@ __global__ void gemv_f32_kernel(const float* __restrict__ W, const float* __rest
 }
 int launch_gemv_f32(const float* W, const float* x, const float* b, float* y, int out, int in, int silu_in, int silu_out,
                     cudaStream_t st) {
-    gemv_f32_kernel<<<(out + 7) / 8, 256, 0, st>>>(W, x, b, y, out, in, silu_in, silu_out);
+    VSD_CHECK_CUDA(launch_k(gemv_f32_kernel, dim3((out + 7) / 8), dim3(256), 0, st, W, x, b, y, out, in, silu_in, silu_out));
     VSD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -411,13 +431,15 @@ int launch_gemv_f32(const float* W, const float* x, const float* b, float* y, in
 // lcm_controlnet.py:1046-1071: x_t = sqrt(abar)*x0 + sqrt(1-abar)*noise
 __global__ void add_noise_kernel(const float* __restrict__ x0, const float* __restrict__ noise, float* __restrict__ out,
                                  float a, float b, long n) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
         out[i] = __fadd_rn(__fmul_rn(a, x0[i]), __fmul_rn(b, noise[i]));
 }
 int launch_add_noise(const float* x0, const float* noise, float* out, float a, float b, long n, cudaStream_t st) {
     int blocks = (int)((n + 255) / 256);
     if (blocks > 1184) blocks = 1184;
-    add_noise_kernel<<<blocks, 256, 0, st>>>(x0, noise, out, a, b, n);
+    VSD_CHECK_CUDA(launch_k(add_noise_kernel, dim3(blocks), dim3(256), 0, st, x0, noise, out, a, b, n));
     VSD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -426,6 +448,8 @@ int launch_add_noise(const float* x0, const float* noise, float* out, float a, f
 __global__ void lcm_step_kernel(const float* __restrict__ eps, const float* __restrict__ x, const float* __restrict__ z,
                                 float* __restrict__ x_prev, float* __restrict__ denoised, float sqrt_a, float sqrt_1ma,
                                 float c_skip, float c_out, float sqrt_ap, float sqrt_1map, int has_noise, long n) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
         const float xi = x[i];
         const float x0 = __fdiv_rn(__fsub_rn(xi, __fmul_rn(sqrt_1ma, eps[i])), sqrt_a);
@@ -439,8 +463,8 @@ int launch_lcm_step(const float* eps, const float* x, const float* z, float* x_p
                     cudaStream_t st) {
     int blocks = (int)((n + 255) / 256);
     if (blocks > 1184) blocks = 1184;
-    lcm_step_kernel<<<blocks, 256, 0, st>>>(eps, x, z, x_prev, denoised, sqrt_a, sqrt_1ma, c_skip, c_out, sqrt_ap,
-                                            sqrt_1map, has_noise, n);
+    VSD_CHECK_CUDA(launch_k(lcm_step_kernel, dim3(blocks), dim3(256), 0, st, eps, x, z, x_prev, denoised, sqrt_a, sqrt_1ma, c_skip, c_out, sqrt_ap,
+                                            sqrt_1map, has_noise, n));
     VSD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -452,6 +476,8 @@ __device__ __forceinline__ int clip255(int v) { return min(max(v, 0), 255); }
 // One thread = 2 rows x 4 columns (one 32-bit Y load per row, one 16-bit U/V load, three 32-bit RGB stores/row).
 __global__ void yuv420_to_rgb_kernel(const uint8_t* __restrict__ yp, const uint8_t* __restrict__ up,
                                      const uint8_t* __restrict__ vp, uint8_t* __restrict__ rgb, int NB, int H, int W) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int W4 = W >> 2, H2 = H >> 1;
     const long total = (long)NB * H2 * W4;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -492,7 +518,7 @@ int launch_yuv420_to_rgb(const uint8_t* y, const uint8_t* u, const uint8_t* v, u
     const long total = (long)NB * (H / 2) * (W / 4);
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    yuv420_to_rgb_kernel<<<blocks, 256, 0, st>>>(y, u, v, rgb, NB, H, W);
+    VSD_CHECK_CUDA(launch_k(yuv420_to_rgb_kernel, dim3(blocks), dim3(256), 0, st, y, u, v, rgb, NB, H, W));
     VSD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -503,6 +529,8 @@ int launch_yuv420_to_rgb(const uint8_t* y, const uint8_t* u, const uint8_t* v, u
 __global__ void pack_rgb_yuv420_kernel(const float* __restrict__ img, int ldi, uint8_t* __restrict__ rgb,
                                        uint8_t* __restrict__ yp, uint8_t* __restrict__ up, uint8_t* __restrict__ vp,
                                        int NB, int H, int W, int taesd_denorm) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int W2 = W >> 1, H2 = H >> 1;
     const long total = (long)NB * H2 * W2;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -548,7 +576,7 @@ int launch_pack_rgb_yuv420(const float* img, int ldi, uint8_t* rgb, uint8_t* y, 
     const long total = (long)NB * (H / 2) * (W / 2);
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    pack_rgb_yuv420_kernel<<<blocks, 256, 0, st>>>(img, ldi, rgb, y, u, v, NB, H, W, taesd_denorm);
+    VSD_CHECK_CUDA(launch_k(pack_rgb_yuv420_kernel, dim3(blocks), dim3(256), 0, st, img, ldi, rgb, y, u, v, NB, H, W, taesd_denorm));
     VSD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -137,6 +137,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const bool dbg_cta = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
 #define VSD_STAMP(i) do { if (dbg_cta) p.dbg[i] = clock64(); } while (0)
     if (threadIdx.x == 0) VSD_STAMP(0);
+    pdl_launch_dependents();   // the next kernel may begin its own prologue / weight prefetch now
 
     const int mt = blockIdx.x;
     const int tw = mt % p.tiles_w;
@@ -174,13 +175,34 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             int cb = kb_begin - tap * kpt;
             int s = 0, dbg_it = 0;
             uint32_t ph = 0;
+            // Stages of the first ring pass: the constant operand (weights) is fetched before waiting for the
+            // producer kernel of the activations (programmatic dependent launch), the other one right after.
+            const int total_iters = (kb_end - kb_begin + kbs - 1) / kbs;
+            const int npre = (p.a_static || p.b_static) ? min(stages, total_iters) : 0;
+            {
+                int kb = kb_begin;
+                for (int it = 0; it < npre; ++it) {
+                    const int nkb = min(kbs, kb_end - kb);
+                    uint8_t* sa = smem + (size_t)it * stage_bytes;
+                    uint8_t* sb = sa + (size_t)kbs * kABytes;
+                    mbar_expect_tx(&full_bar[it], (uint32_t)nkb * ((uint32_t)kABytes + b_bytes));
+                    for (int j = 0; j < nkb; ++j, ++kb) {
+                        if (p.b_static) tma_load_2d(sb + (size_t)j * b_bytes, &mapB, &full_bar[it], kb * 64, col0);
+                        else tma_load_4d(sa + (size_t)j * kABytes, &mapA, &full_bar[it], kb * 64, w0, h0, n0);  // taps == 1
+                    }
+                }
+            }
+            pdl_wait();
             for (int kb = kb_begin; kb < kb_end;) {
                 const int nkb = min(kbs, kb_end - kb);
-                mbar_wait(&empty_bar[s], ph ^ 1u, 1);
+                const bool pre = dbg_it < npre;
+                if (!pre) {
+                    mbar_wait(&empty_bar[s], ph ^ 1u, 1);
+                    mbar_expect_tx(&full_bar[s], (uint32_t)nkb * ((uint32_t)kABytes + b_bytes));
+                }
                 if (dbg_cta && dbg_it < 16) p.dbg[16 + 2 * dbg_it] = clock64();
                 uint8_t* sa = smem + (size_t)s * stage_bytes;
                 uint8_t* sb = sa + (size_t)kbs * kABytes;
-                mbar_expect_tx(&full_bar[s], (uint32_t)nkb * ((uint32_t)kABytes + b_bytes));
                 for (int j = 0; j < nkb; ++j, ++kb) {
                     int dy = 0, dx = 0;
                     if (p.taps == 9) {
@@ -188,8 +210,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         dy = ty - 1;
                         dx = tap - ty * 3 - 1;
                     }
-                    tma_load_4d(sa + (size_t)j * kABytes, &mapA, &full_bar[s], cb * 64, w0 + dx, h0 + dy, n0);
-                    tma_load_2d(sb + (size_t)j * b_bytes, &mapB, &full_bar[s], kb * 64, col0);
+                    if (!(pre && p.a_static))
+                        tma_load_4d(sa + (size_t)j * kABytes, &mapA, &full_bar[s], cb * 64, w0 + dx, h0 + dy, n0);
+                    if (!(pre && p.b_static))
+                        tma_load_2d(sb + (size_t)j * b_bytes, &mapB, &full_bar[s], kb * 64, col0);
                     if (++cb == kpt) { cb = 0; ++tap; }
                 }
                 if (dbg_cta && dbg_it < 16) p.dbg[16 + 2 * dbg_it + 1] = clock64();
@@ -259,6 +283,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 sbias[i] = bv;
             }
         }
+        pdl_wait();   // bias / time-embedding rows above are constants; everything below depends on earlier kernels
         const bool res_vec = (p.residual != nullptr) && row_ok && ((p.ldr & 7) == 0) && ((col0 & 7) == 0) &&
                              (p.splits == 1) && (p.act != ACT_GEGLU);
         uint4 rnext[4];
@@ -358,32 +383,60 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #undef VSD_STAMP
 }
 
-// Sums split-K partials and applies the same epilogue. One thread per (row, 32-column chunk).
+// Sums split-K partials (fixed order => deterministic) and applies the epilogue. One thread per (row, 4 columns):
+// many threads with one float4 per split each keep plenty of loads in flight for this latency-bound pass.
 __global__ void splitk_reduce_kernel(const GemmParams p, long rows) {
-    const int chunks = (p.N + 31) / 32;
+    pdl_launch_dependents();
+    pdl_wait();
+    const int groups4 = (p.N + 3) >> 2;
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= rows * chunks) return;
-    const long grow = idx / chunks;
-    const int col = (int)(idx - grow * chunks) * 32;
-    const int ncols = min(32, p.N - col);
-    float v[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = 0.f;
-    for (int s = 0; s < p.splits; ++s) {
-        const float* src = p.partial + ((long)s * rows + grow) * p.N + col;
-        if (ncols == 32 && ((p.N & 3) == 0)) {
-            const float4* s4 = reinterpret_cast<const float4*>(src);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float4 t = s4[j];
-                v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
-            }
-        } else {
-            for (int j = 0; j < ncols; ++j) v[j] += src[j];
+    if (idx >= rows * groups4) return;
+    const long grow = idx / groups4;
+    const int col = (int)(idx - grow * groups4) * 4;
+    const int ncols = min(4, p.N - col);
+    const bool vec = (ncols == 4) && ((p.N & 3) == 0);
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* src = p.partial + grow * p.N + col;
+    const long split_stride = rows * p.N;
+    if (vec) {
+#pragma unroll 8
+        for (int s = 0; s < p.splits; ++s) {
+            const float4 t = *reinterpret_cast<const float4*>(src + (long)s * split_stride);
+            v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
         }
+    } else {
+        for (int s = 0; s < p.splits; ++s)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j < ncols) v[j] += src[(long)s * split_stride + j];
     }
     const int n_img = (int)(grow / ((long)p.H * p.W));
-    epilogue_store32(p, v, n_img, grow, col, ncols, nullptr, false, nullptr);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (j < ncols) {
+            if (p.bias) v[j] += __ldg(p.bias + col + j);
+            if (p.rowvec) v[j] += __ldg(p.rowvec + (long)n_img * p.N + col + j);
+            if (p.residual) v[j] += __bfloat162float(p.residual[grow * p.ldr + col + j]);
+            if (p.relu) v[j] = fmaxf(v[j], 0.f);
+        }
+    }
+    if (p.out_f32) {
+        float* o = reinterpret_cast<float*>(p.out) + grow * p.ldo + col;
+        if (vec && ((p.ldo & 3) == 0)) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j < ncols) o[j] = v[j];
+        }
+    } else {
+        bf16* o = reinterpret_cast<bf16*>(p.out) + grow * p.ldo + col;
+        if (vec && ((p.ldo & 3) == 0)) *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+        else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j < ncols) o[j] = __float2bfloat16(v[j]);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -560,11 +613,18 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
     p.stages = stages;
     p.kb_per_stage = kbs;
     op->smem_bytes = stages * kbs * stage_bytes + 1024 /*align slack*/ + (2 * stages + 1) * 8 + 64 + bn * 4;
+    // With programmatic dependent launch CTAs of different kernels co-reside on an SM. TMEM is not part of the block
+    // scheduler's accounting, so bound the CTAs per SM through shared memory: smem >= tmem_cols * 450 B guarantees that
+    // the co-resident CTAs' TMEM columns sum to <= 512 (otherwise tcgen05.alloc of a CTA the others wait on could spin).
+    if (op->smem_bytes < p.tmem_cols * 450) op->smem_bytes = p.tmem_cols * 450;
 
     p.out = out; p.ldo = ldo; p.out_f32 = out_f32;
     p.bias = bias; p.rowvec = rowvec; p.residual = residual; p.ldr = ldr;
     p.act = act;
     p.relu = (act_flags & ACT_RELU_FLAG) ? 1 : 0;
+    p.a_static = (act_flags & ACT_A_STATIC_FLAG) ? 1 : 0;
+    p.b_static = (act_flags & (ACT_A_STATIC_FLAG | ACT_NO_STATIC_FLAG)) ? 0 : 1;
+    if (p.a_static && taps != 1) p.a_static = 0;
 
     int rc = make_tmap_act(&op->mapA, a.ptr, a.C, a.W, a.H, a.NB, a.ld, p.BW, p.BH, p.BN);
     if (rc) return rc;
@@ -575,8 +635,7 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
 }
 
 int launch_gemm_op(const GemmOp& op, cudaStream_t st) {
-    conv_gemm_kernel<<<op.grid, kGemmThreads, op.smem_bytes, st>>>(op.mapA, op.mapB, op.p);
-    VSD_CHECK_CUDA(cudaGetLastError());
+    VSD_CHECK_CUDA(launch_k(conv_gemm_kernel, op.grid, dim3(kGemmThreads), (size_t)op.smem_bytes, st, op.mapA, op.mapB, op.p));
     if (op.p.splits > 1) {
         const long rows = (long)op.p.NB * op.p.H * op.p.W;
         return launch_splitk_reduce(op.p, rows, st);
@@ -585,10 +644,9 @@ int launch_gemm_op(const GemmOp& op, cudaStream_t st) {
 }
 
 int launch_splitk_reduce(const GemmParams& p, long rows, cudaStream_t st) {
-    const long work = rows * ((p.N + 31) / 32);
-    const int threads = 128;
-    splitk_reduce_kernel<<<(unsigned)((work + threads - 1) / threads), threads, 0, st>>>(p, rows);
-    VSD_CHECK_CUDA(cudaGetLastError());
+    const long work = rows * ((p.N + 3) / 4);
+    const int threads = 256;
+    VSD_CHECK_CUDA(launch_k(splitk_reduce_kernel, dim3((unsigned)((work + threads - 1) / threads)), dim3(threads), 0, st, p, rows));
     return 0;
 }
 

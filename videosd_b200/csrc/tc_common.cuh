@@ -28,6 +28,12 @@ __device__ __forceinline__ uint32_t elect_one() {
     return pred;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of this library is launched with programmaticStreamSerialization: it may start while its
+// predecessor still runs, so it must not read or write mutable global memory before pdl_wait().
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -471,11 +471,11 @@ struct Builder {
         if (!rc) {
             ActView aw{wv, 1, 1, C, C, C};
             if (cols_img == HW) {
-                gemm(aw, 1, n1.p, (int)M, n1.ld, vt, ldvt, 0, nullptr, nullptr, nullptr, 0, ACT_NONE);
+                gemm(aw, 1, n1.p, (int)M, n1.ld, vt, ldvt, 0, nullptr, nullptr, nullptr, 0, ACT_NONE | ACT_A_STATIC_FLAG);
             } else {
                 for (int b = 0; b < NB; ++b)
                     gemm(aw, 1, n1.p + (long)b * HW * n1.ld, HW, n1.ld, vt + (long)b * cols_img, ldvt, 0, nullptr, nullptr,
-                         nullptr, 0, ACT_NONE);
+                         nullptr, 0, ACT_NONE | ACT_A_STATIC_FLAG);
             }
         }
         View a1 = alloc(NB, x.h, x.w, C);
@@ -1077,6 +1077,27 @@ int vsd_set_autotune(vsd_ctx* c, int enabled) {
     if (!c) return -1;
     c->e.autotune = enabled ? 1 : 0;
     return 0;
+}
+
+/* Pre-populates the autotuner cache from vsd_tuning_report text (e.g. saved by an earlier process). */
+int vsd_tuning_load(vsd_ctx* c, const char* text) {
+    if (!c || !text) return -1;
+    int n = 0;
+    const char* p = text;
+    while (*p) {
+        char key[200];
+        Engine::Tuned t{0, 1, 0, 1, 0.f};
+        int consumed = 0;
+        if (sscanf(p, "%199s bn=%d splits=%d occ=%d kbs=%d us=%f%n", key, &t.bn, &t.splits, &t.occ, &t.kbs, &t.us, &consumed) >= 5 &&
+            t.bn > 0) {
+            c->e.tuned[key] = t;
+            ++n;
+        }
+        const char* nl = strchr(p, '\n');
+        if (!nl) break;
+        p = nl + 1;
+    }
+    return n;
 }
 
 /* Writes "key bn splits occ us" lines of the tuned GEMM shapes into buf; returns the number of entries. */

@@ -30,13 +30,32 @@ const char* get_error();
         }                                                                                  \
     } while (0)
 
+// ---- kernel launch with programmatic dependent launch (PDL) enabled; VSD_PDL=0 in the environment disables it
+int pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled();
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---- tensor maps (driver entry point resolved at run time; the library does not link libcuda)
 int make_tmap_act(CUtensorMap* m, const void* base, int C, int W, int H, int N, int ld, int boxW, int boxH, int boxN);
 int make_tmap_2d(CUtensorMap* m, const void* base, int K, int rows, int ld, int box_rows);
 
 // ---- tcgen05 implicit-GEMM convolution / linear kernel -------------------------------------------
 // out[pixel, n] = epilogue( sum_{tap, c} A[pixel + tap offset, c] * Wt[n, tap*cin + c] )
-enum { ACT_NONE = 0, ACT_GEGLU = 1, ACT_RELU_FLAG = 16 };  // ReLU (after the residual add) may be OR-ed in
+enum { ACT_NONE = 0, ACT_GEGLU = 1, ACT_RELU_FLAG = 16,
+       ACT_A_STATIC_FLAG = 32,   // the row operand is the constant one (swapped-operand V^T projection)
+       ACT_NO_STATIC_FLAG = 64 };  // neither operand is constant  // ReLU (after the residual add) may be OR-ed in
 
 struct GemmParams {
     // A operand traversal (NHWC activation, stride-1 taps; linear layers use H=NB=1, W=rows)
@@ -60,6 +79,7 @@ struct GemmParams {
     int ldr;
     int act, relu;
     float* partial;       // [splits, rows, N] fp32 when splits > 1
+    int a_static, b_static;  // operand is constant (weights): its first stages may be fetched before pdl_wait()
     long long* dbg;       // optional: CTA (0,0,0) writes clock64() phase stamps here (bring-up only)
 };
 

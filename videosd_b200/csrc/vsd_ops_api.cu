@@ -3,6 +3,7 @@
 // the caller (torch tensors' data_ptr()). The frame-level API lives in vsd_engine.cu.
 #include "vsd_internal.h"
 #include "../../include/videosd.h"
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -11,6 +12,15 @@ namespace vsd {
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 const char* get_error() { return g_err.c_str(); }
+
+int pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("VSD_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v;
+}
 
 static std::mutex g_init_mu;
 static std::vector<int> g_inited_devices;

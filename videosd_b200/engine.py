@@ -142,6 +142,9 @@ class Engine:
         self._L.vsd_tuning_report(self._ctx, buf, ctypes.c_long(len(buf)))
         return buf.value.decode()
 
+    def tuning_load(self, text):
+        return int(self._L.vsd_tuning_load(self._ctx, text.encode()))
+
     def arena_peak_bytes(self):
         return int(self._L.vsd_arena_peak_bytes(self._ctx))
 
