@@ -101,6 +101,10 @@ typedef struct vsd_ctx vsd_ctx;
 
 vsd_ctx* vsd_create(int device);             /* NULL on failure (see vsd_last_error) */
 void vsd_destroy(vsd_ctx* ctx);
+/* Additional lane on the parent's GPU: own stream / buffers / CUDA graph, shares the parent's weights read-only.
+ * Lanes keep several frames in flight on one GPU (co-located sessions, or one stream pipelined); the reference
+ * allows at most one in-flight frame per GPU (server.py:132-137). The parent must outlive its lanes. */
+vsd_ctx* vsd_create_lane(vsd_ctx* parent);
 
 /* Weights by diffusers state-dict name, prefixed "unet." or "vae.", fp32 host data in
  * PyTorch layout (conv: [Cout][Cin][kh][kw], linear: [out][in]). Replaces from_pretrained in
@@ -152,6 +156,8 @@ long vsd_arena_peak_bytes(vsd_ctx* ctx);
 int vsd_debug_read(vsd_ctx* ctx, const char* what, int index, float* host, long nfloats);
 int vsd_debug_unet(vsd_ctx* ctx, const float* latents_nhwc, int step, float* eps_nhwc);
 int vsd_debug_run_eager(vsd_ctx* ctx, int yuv);
+/* Times each tagged section of the launch plan as its own CUDA graph ("tag kernels microseconds" lines). */
+int vsd_debug_profile_sections(vsd_ctx* ctx, int depth, int reps, char* buf, long cap);
 
 #ifdef __cplusplus
 }

@@ -49,6 +49,14 @@ def main():
             eng.run_yuv420()
             eng.sync()
     print("launches/frame", eng.launches_per_frame())
+    for i, a in enumerate(sys.argv):
+        if a == "--sections":
+            depth = int(sys.argv[i + 1])
+            rows = eng.debug_profile_sections(depth, 10)
+            tot = sum(r[2] for r in rows)
+            print(f"SECTIONS depth={depth} sum={tot/1e3:.3f} ms")
+            for t, n, us in rows:
+                print(f"  {t:70s} kernels={n:4d} {us:9.2f} us")
 
 
 if __name__ == "__main__":

@@ -149,15 +149,34 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const int kb_begin = split * p.kb_per_split;
     const int kb_end = min(kb_begin + p.kb_per_split, p.kb_total);
 
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&mapA);
-        tma_prefetch_desc(&mapB);
-        for (int s = 0; s < stages; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+    // Stage bookkeeping shared by the early prefetch and the producer loop
+    const int total_iters = (kb_end - kb_begin + kbs - 1) / kbs;
+    const int npre = (p.a_static || p.b_static) ? min(stages, total_iters) : 0;
+    if (warp == 0) {
+        if (elect_one()) {
+            tma_prefetch_desc(&mapA);
+            tma_prefetch_desc(&mapB);
+            for (int s = 0; s < stages; ++s) {
+                mbar_init(&full_bar[s], 1);
+                mbar_init(&empty_bar[s], 1);
+            }
+            mbar_init(tmem_full_bar, 1);
+            fence_barrier_init();
+            // The constant operand (weights) of the first ring pass is requested right away: before the TMEM
+            // allocation / CTA barrier below and before waiting for the producer kernel of the activations (PDL).
+            int kb = kb_begin;
+            for (int it = 0; it < npre; ++it) {
+                const int nkb = min(kbs, kb_end - kb);
+                uint8_t* sa = smem + (size_t)it * stage_bytes;
+                uint8_t* sb = sa + (size_t)kbs * kABytes;
+                mbar_expect_tx(&full_bar[it], (uint32_t)nkb * ((uint32_t)kABytes + b_bytes));
+                for (int j = 0; j < nkb; ++j, ++kb) {
+                    if (p.b_static) tma_load_2d(sb + (size_t)j * b_bytes, &mapB, &full_bar[it], kb * 64, col0);
+                    else tma_load_4d(sa + (size_t)j * kABytes, &mapA, &full_bar[it], kb * 64, w0, h0, n0);  // taps == 1
+                }
+            }
         }
-        mbar_init(tmem_full_bar, 1);
-        fence_barrier_init();
+        __syncwarp();
     }
     if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     tc_fence_before_sync();
@@ -175,23 +194,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             int cb = kb_begin - tap * kpt;
             int s = 0, dbg_it = 0;
             uint32_t ph = 0;
-            // Stages of the first ring pass: the constant operand (weights) is fetched before waiting for the
-            // producer kernel of the activations (programmatic dependent launch), the other one right after.
-            const int total_iters = (kb_end - kb_begin + kbs - 1) / kbs;
-            const int npre = (p.a_static || p.b_static) ? min(stages, total_iters) : 0;
-            {
-                int kb = kb_begin;
-                for (int it = 0; it < npre; ++it) {
-                    const int nkb = min(kbs, kb_end - kb);
-                    uint8_t* sa = smem + (size_t)it * stage_bytes;
-                    uint8_t* sb = sa + (size_t)kbs * kABytes;
-                    mbar_expect_tx(&full_bar[it], (uint32_t)nkb * ((uint32_t)kABytes + b_bytes));
-                    for (int j = 0; j < nkb; ++j, ++kb) {
-                        if (p.b_static) tma_load_2d(sb + (size_t)j * b_bytes, &mapB, &full_bar[it], kb * 64, col0);
-                        else tma_load_4d(sa + (size_t)j * kABytes, &mapA, &full_bar[it], kb * 64, w0, h0, n0);  // taps == 1
-                    }
-                }
-            }
             pdl_wait();
             for (int kb = kb_begin; kb < kb_end;) {
                 const int nkb = min(kbs, kb_end - kb);

@@ -78,7 +78,19 @@ class Arena {
     void release(size_t m) { off = m; }
 };
 
-typedef std::function<int(cudaStream_t)> Launch;
+struct Launch {
+    std::function<int(cudaStream_t)> fn;
+    std::string tag;   // dotted scope, e.g. "step0.unet.down0.attn1.ff1" (used by the section profiler)
+    int operator()(cudaStream_t st) const { return fn(st); }
+};
+static thread_local std::string g_scope;   // current tag while a plan is being built
+struct Scope {
+    std::string saved;
+    explicit Scope(const std::string& name) : saved(g_scope) { g_scope = g_scope.empty() ? name : g_scope + "." + name; }
+    ~Scope() { g_scope = saved; }
+};
+template <typename F>
+static Launch mk(F f, const char* op) { return Launch{std::function<int(cudaStream_t)>(f), g_scope + "." + op}; }
 
 struct StepScalars { float sqrt_a, sqrt_1ma, c_skip, c_out, sqrt_ap, sqrt_1map; int t; };
 
@@ -86,6 +98,7 @@ struct Engine {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::unordered_map<std::string, DevW> w;
+    bool owns_weights = true;   // false for a lane created with vsd_create_lane (weights belong to the parent)
     // configuration
     int NB = 0, H = 0, W = 0, h8 = 0, w8 = 0;
     int steps = 0, has_step_noise = 0;
@@ -117,6 +130,7 @@ struct Engine {
     struct Tuned { int bn, splits, occ, kbs; float us; };
     std::unordered_map<std::string, Tuned> tuned;
     void* flush_buf = nullptr; size_t flush_bytes = 0;
+    unsigned int* gn_sync = nullptr;   // grid-barrier state for the fused GroupNorm kernel (never reused memory)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     long launches_per_frame_yuv = 0;
     std::string err;
@@ -330,6 +344,14 @@ static int tune_gemm(Engine* e, const ActView& a, int taps, const bf16* wt, int 
 }
 
 // ------------------------------------------------------------------------------------------------ plan builder
+// "unet.down_blocks.0.resnets.1" -> "down_blocks0_resnets1" (one dot-free component for the profiler scopes)
+static std::string short_name(const std::string& p) {
+    std::string r;
+    size_t start = p.find('.') == std::string::npos ? 0 : p.find('.') + 1;
+    for (size_t i = start; i < p.size(); ++i) r += (p[i] == '.') ? '_' : p[i];
+    return r;
+}
+
 struct Builder {
     Engine* e;
     std::vector<Launch>* out;
@@ -388,7 +410,7 @@ struct Builder {
         int r = build_gemm_op(&op, a, taps, wt, N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act, e->splitk_ws,
                               e->splitk_bytes, fbn, fsp, focc, fkbs);
         if (r) { rc = r; fail = get_error(); return; }
-        out->push_back([op](cudaStream_t st) { return launch_gemm_op(op, st); });
+        out->push_back(mk([op](cudaStream_t st) { return launch_gemm_op(op, st); }, "gemm"));
     }
     void conv(const View& x, const std::string& name, int taps, const View& o, const float* rowvec, const View* res,
               int act, bool has_bias = true) {
@@ -404,18 +426,19 @@ struct Builder {
         float* ws = alloc_f32((size_t)groupnorm_ws_floats(x.nb, x.h * x.w, x.c, 32));
         if (rc) return;
         const View xi = x, oo = o;
-        out->push_back([=](cudaStream_t st) {
-            return launch_groupnorm(xi.p, xi.ld, oo.p, oo.ld, g, b, xi.nb, xi.h * xi.w, xi.c, 32, eps, silu, ws, st);
-        });
+        unsigned int* sync = e->gn_sync;
+        out->push_back(mk([=](cudaStream_t st) {
+            return launch_groupnorm(xi.p, xi.ld, oo.p, oo.ld, g, b, xi.nb, xi.h * xi.w, xi.c, 32, eps, silu, ws, sync, st);
+        }, "gn"));
     }
     void layernorm(const View& x, const std::string& name, const View& o) {
         const float* g = wf(name + ".weight");
         const float* b = wf(name + ".bias");
         if (rc) return;
         const View xi = x, oo = o;
-        out->push_back([=](cudaStream_t st) {
+        out->push_back(mk([=](cudaStream_t st) {
             return launch_layernorm(xi.p, xi.ld, oo.p, oo.ld, g, b, (int)xi.rows(), xi.c, 1e-5f, st);
-        });
+        }, "ln"));
     }
     void attention(const bf16* q, int ldq, const bf16* k, int ldk, const bf16* vt, int ldvt, const View& o, int heads,
                    int d, int nq, int nk, int q_rows, int k_rows, int vt_cols, int vt_rows) {
@@ -424,11 +447,12 @@ struct Builder {
         int r = build_attn_op(&op, q, ldq, k, ldk, vt, ldvt, o.p, o.ld, o.nb, heads, d, nq, nk, q_rows, k_rows, vt_cols,
                               vt_rows);
         if (r) { rc = r; fail = get_error(); return; }
-        out->push_back([op](cudaStream_t st) { return launch_attn_op(op, st); });
+        out->push_back(mk([op](cudaStream_t st) { return launch_attn_op(op, st); }, "attn"));
     }
 
     // ---- diffusers ResnetBlock2D (Appendix A.3)
     void resnet(const View& x, const std::string& p, const float* temb_rowvec, const View& o) {
+        Scope sc_(short_name(p));
         const size_t m = e->arena.mark();
         View t1 = alloc(x.nb, x.h, x.w, x.c);
         groupnorm(x, p + ".norm1", 1e-5f, 1, t1);
@@ -448,6 +472,7 @@ struct Builder {
 
     // ---- diffusers Transformer2DModel with one BasicTransformerBlock (Appendix A.4)
     void transformer(const View& x, const std::string& p, const View& o) {
+        Scope sc_(short_name(p));
         const size_t m = e->arena.mark();
         const int C = x.c, heads = 8, d = C / heads, dkp = attn_dk_pad(d);
         const int HW = x.h * x.w, NB = x.nb;
@@ -515,9 +540,9 @@ struct Builder {
         View cols = alloc(o.nb, o.h, o.w, 9 * x.c);
         if (rc) return;
         const View xi = x, ci = cols, oo = o;
-        out->push_back([=](cudaStream_t st) {
+        out->push_back(mk([=](cudaStream_t st) {
             return launch_im2col_s2(xi.p, xi.ld, ci.p, xi.nb, xi.h, xi.w, xi.c, oo.h, oo.w, st);
-        });
+        }, "im2col"));
         const bf16* wt = wb(name + ".weight");
         const float* b = has_bias ? wf(name + ".bias") : nullptr;
         gemm(cols.act(), 1, wt, o.c, 9 * x.c, o.p, o.ld, 0, b, nullptr, nullptr, 0, ACT_NONE);
@@ -526,9 +551,9 @@ struct Builder {
     void upsample(const View& x, const View& o) {
         if (rc) return;
         const View xi = x, oo = o;
-        out->push_back([=](cudaStream_t st) {
+        out->push_back(mk([=](cudaStream_t st) {
             return launch_upsample_nearest(xi.p, xi.ld, oo.p, oo.ld, xi.nb, xi.h, xi.w, oo.h, oo.w, xi.c, st);
-        });
+        }, "upsample"));
     }
 };
 
@@ -573,9 +598,9 @@ static void build_unet(Builder& B, const float* latents, float* eps_out, int si,
         const float* b = B.wf("unet.conv_in.bias");
         if (!B.rc) {
             const View o = s0;
-            B.out->push_back([=](cudaStream_t st) {
+            B.out->push_back(mk([=](cudaStream_t st) {
                 return launch_conv3x3_small_cin(latents, 0, o.nb, o.h, o.w, 4, w, b, o.p, o.ld, o.c, 0, st);
-            });
+            }, "conv_in"));
         }
     }
     View x = skip_view(0);
@@ -670,9 +695,9 @@ static void build_taesd_encoder(Builder& B, const uint8_t* rgb, float* latents_o
         const float* b = B.wf(p + "0.bias");
         if (!B.rc) {
             const View o = x;
-            B.out->push_back([=](cudaStream_t st) {
+            B.out->push_back(mk([=](cudaStream_t st) {
                 return launch_conv3x3_small_cin(rgb, 1, o.nb, o.h, o.w, 3, wt, b, o.p, o.ld, 64, 0, st);
-            });
+            }, "conv_rgb"));
         }
     }
     View y = B.alloc(NB, h, w, 64);
@@ -704,9 +729,9 @@ static void build_taesd_decoder(Builder& B, const float* z, float* image_out /*[
         const float* b = B.wf(p + "0.bias");
         if (!B.rc) {
             const View o = x;
-            B.out->push_back([=](cudaStream_t st) {
+            B.out->push_back(mk([=](cudaStream_t st) {
                 return launch_conv3x3_small_cin(z, 2, o.nb, o.h, o.w, 4, wt, b, o.p, o.ld, 64, 1, st);
-            });
+            }, "conv_z"));
         }
     }
     int layer = 2;
@@ -896,20 +921,23 @@ static int set_schedule(Engine* e, int steps, const int* timesteps, const float*
     Builder B{e, &e->plan_pre_yuv};
     {
         Engine* ee = e;
-        e->plan_pre_yuv.push_back([ee](cudaStream_t st) {
+        e->plan_pre_yuv.push_back(mk([ee](cudaStream_t st) {
             return launch_yuv420_to_rgb(ee->d_y, ee->d_u, ee->d_v, ee->d_rgb_in, ee->NB, ee->H, ee->W, st);
-        });
+        }, "yuv2rgb"));
     }
     B.out = &e->plan_core;
     const size_t enc_mark = A.mark();
-    build_taesd_encoder(B, e->d_rgb_in, e->init_latents);
+    {
+        Scope sc_("taesd_enc");
+        build_taesd_encoder(B, e->d_rgb_in, e->init_latents);
+    }
     A.release(enc_mark);
     {
         Engine* ee = e;
         const long n = (long)lpx * 4;
-        e->plan_core.push_back([ee, n](cudaStream_t st) {
+        e->plan_core.push_back(mk([ee, n](cudaStream_t st) {
             return launch_add_noise(ee->init_latents, ee->init_noise, ee->noisy, ee->an_a, ee->an_b, n, st);
-        });
+        }, "add_noise"));
     }
     // persistent skip / concat buffers (shared by all steps)
     UNetStatic S;
@@ -929,7 +957,10 @@ static int set_schedule(Engine* e, int steps, const int* timesteps, const float*
         std::vector<Launch> up;
         B.out = &up;
         const float* lat_in = (i == 0) ? e->noisy : e->lat[i - 1];
-        build_unet(B, lat_in, e->eps[i], i, S);
+        {
+            Scope sc_("step" + std::to_string(i));
+            build_unet(B, lat_in, e->eps[i], i, S);
+        }
         const StepScalars s = e->sc[i];
         Engine* ee = e;
         const long n = (long)lpx * 4;
@@ -938,21 +969,24 @@ static int set_schedule(Engine* e, int steps, const int* timesteps, const float*
         float* xp = e->lat[i]; float* dn = e->den[i]; const float* ep = e->eps[i];
         e->plan_unet.push_back(up);
         for (auto& l : up) e->plan_core.push_back(l);
-        e->plan_core.push_back([=](cudaStream_t st) {
+        e->plan_core.push_back(mk([=](cudaStream_t st) {
             (void)ee;
             return launch_lcm_step(ep, lat_in, z, xp, dn, s.sqrt_a, s.sqrt_1ma, s.c_skip, s.c_out, s.sqrt_ap, s.sqrt_1map, hn,
                                    n, st);
-        });
+        }, "lcm_step"));
     }
     A.release(unet_mark);
     B.out = &e->plan_core;
-    build_taesd_decoder(B, e->den[steps - 1], e->image);
+    {
+        Scope sc_("taesd_dec");
+        build_taesd_decoder(B, e->den[steps - 1], e->image);
+    }
     A.release(unet_mark);
     {
         Engine* ee = e;
-        e->plan_post.push_back([ee](cudaStream_t st) {
+        e->plan_post.push_back(mk([ee](cudaStream_t st) {
             return launch_pack_rgb_yuv420(ee->image, 4, ee->d_rgb_out, ee->d_oy, ee->d_ou, ee->d_ov, ee->NB, ee->H, ee->W, 1, st);
-        });
+        }, "pack"));
     }
     if (B.rc) {
         set_error("plan build failed: " + B.fail);
@@ -1039,6 +1073,11 @@ vsd_ctx* vsd_create(int device) {
     if (ensure_init()) return nullptr;
     vsd_ctx* c = new vsd_ctx();
     c->e.device = device;
+    if (cudaMalloc(&c->e.gn_sync, 64) != cudaSuccess || cudaMemset(c->e.gn_sync, 0, 64) != cudaSuccess) {
+        set_error("cudaMalloc failed");
+        delete c;
+        return nullptr;
+    }
     if (cudaStreamCreateWithFlags(&c->e.stream, cudaStreamNonBlocking) != cudaSuccess) {
         set_error("cudaStreamCreate failed");
         delete c;
@@ -1047,15 +1086,31 @@ vsd_ctx* vsd_create(int device) {
     return c;
 }
 
+/* A lane: its own stream, buffers, launch plan and CUDA graph, sharing the parent's weights (read-only). Several
+ * lanes on one GPU keep more than one frame in flight (sessions pinned to the same GPU, or one stream pipelined).
+ * The parent must outlive its lanes and must have all weights loaded before lanes are created. */
+vsd_ctx* vsd_create_lane(vsd_ctx* parent) {
+    if (!parent) { set_error("null parent"); return nullptr; }
+    vsd_ctx* c = vsd_create(parent->e.device);
+    if (!c) return nullptr;
+    c->e.w = parent->e.w;
+    c->e.owns_weights = false;
+    c->e.tuned = parent->e.tuned;
+    c->e.autotune = parent->e.autotune;
+    return c;
+}
+
 void vsd_destroy(vsd_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->e.device);
     cudaStreamSynchronize(c->e.stream);
     free_graphs(&c->e);
-    for (auto& kv : c->e.w) cudaFree(kv.second.p);
+    if (c->e.owns_weights)
+        for (auto& kv : c->e.w) cudaFree(kv.second.p);
     c->e.arena.destroy();
     if (c->e.splitk_ws) cudaFree(c->e.splitk_ws);
     if (c->e.flush_buf) cudaFree(c->e.flush_buf);
+    if (c->e.gn_sync) cudaFree(c->e.gn_sync);
     if (c->e.ev0) cudaEventDestroy(c->e.ev0);
     if (c->e.ev1) cudaEventDestroy(c->e.ev1);
     cudaStreamDestroy(c->e.stream);
@@ -1068,6 +1123,7 @@ void vsd_destroy(vsd_ctx* c) {
 
 int vsd_load_weight(vsd_ctx* c, const char* name, const float* host_f32, const int64_t* shape, int ndim) {
     CTX_GUARD(c);
+    if (!c->e.owns_weights) { set_error("weights of a lane belong to its parent context"); return -1; }
     return load_weight(&c->e, name, host_f32, shape, ndim);
 }
 
@@ -1247,6 +1303,69 @@ int vsd_debug_unet(vsd_ctx* c, const float* latents_nhwc, int step, float* eps_n
     VSD_CHECK_CUDA(cudaMemcpyAsync(eps_nhwc, e->eps[step], lpx * 16, cudaMemcpyDeviceToHost, e->stream));
     VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
     return vsd_check_pipeline_fault();
+}
+
+/* Section profiler: groups consecutive plan entries by the first `depth` components of their tag, captures each
+ * group as its own CUDA graph and times `reps` replays with events. Writes "tag launches us" lines into buf. */
+int vsd_debug_profile_sections(vsd_ctx* c, int depth, int reps, char* buf, long cap) {
+    CTX_GUARD(c);
+    Engine* e = &c->e;
+    ENG_REQUIRE(e->schedule_set && e->context_set, "schedule and context must be set");
+    std::vector<const Launch*> all;
+    for (auto& l : e->plan_pre_yuv) all.push_back(&l);
+    for (auto& l : e->plan_core) all.push_back(&l);
+    for (auto& l : e->plan_post) all.push_back(&l);
+    auto key = [&](const std::string& t) {
+        size_t pos = 0;
+        for (int d = 0; d < depth; ++d) {
+            size_t nx = t.find('.', pos);
+            if (nx == std::string::npos) return t;
+            pos = nx + 1;
+        }
+        return t.substr(0, pos ? pos - 1 : 0);
+    };
+    cudaEvent_t e0, e1;
+    VSD_CHECK_CUDA(cudaEventCreate(&e0));
+    VSD_CHECK_CUDA(cudaEventCreate(&e1));
+    std::string out;
+    size_t i = 0;
+    while (i < all.size()) {
+        const std::string k = key(all[i]->tag);
+        size_t j = i;
+        while (j < all.size() && key(all[j]->tag) == k) ++j;
+        cudaGraph_t g = nullptr;
+        cudaGraphExec_t ex = nullptr;
+        VSD_CHECK_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = 0;
+        for (size_t q = i; q < j && !rc; ++q) rc = (*all[q])(e->stream);
+        cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
+        if (rc) return rc;
+        VSD_CHECK_CUDA(ce);
+        size_t nodes = 0;
+        cudaGraphGetNodes(g, nullptr, &nodes);
+        VSD_CHECK_CUDA(cudaGraphInstantiate(&ex, g, 0));
+        VSD_CHECK_CUDA(cudaGraphLaunch(ex, e->stream));   // warm
+        VSD_CHECK_CUDA(cudaEventRecord(e0, e->stream));
+        for (int r = 0; r < reps; ++r) VSD_CHECK_CUDA(cudaGraphLaunch(ex, e->stream));
+        VSD_CHECK_CUDA(cudaEventRecord(e1, e->stream));
+        VSD_CHECK_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        char line[256];
+        snprintf(line, sizeof(line), "%s %zu %.2f\n", k.c_str(), nodes, ms * 1000.f / reps);
+        out += line;
+        cudaGraphExecDestroy(ex);
+        cudaGraphDestroy(g);
+        i = j;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (buf && cap > 0) {
+        const size_t n = std::min((size_t)cap - 1, out.size());
+        memcpy(buf, out.data(), n);
+        buf[n] = 0;
+    }
+    return 0;
 }
 
 /* Runs the whole frame eagerly (no CUDA graph), for debugging and for ncu launch lists. */

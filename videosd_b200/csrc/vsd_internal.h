@@ -122,7 +122,8 @@ int attn_init();
 
 // ---- bandwidth kernels ---------------------------------------------------------------------------
 int launch_groupnorm(const bf16* x, int ldx, bf16* y, int ldy, const float* gamma, const float* beta, int NB, int HW,
-                     int C, int groups, float eps, int silu, float* partial_ws, cudaStream_t st);
+                     int C, int groups, float eps, int silu, float* partial_ws, unsigned int* sync /*2 zeroed words or null*/,
+                     cudaStream_t st);
 int groupnorm_ws_floats(int NB, int HW, int C, int groups);
 int launch_layernorm(const bf16* x, int ldx, bf16* y, int ldy, const float* gamma, const float* beta, int rows, int C,
                      float eps, cudaStream_t st);
@@ -149,5 +150,6 @@ int ensure_init();
 
 unsigned int read_trap_code_gemm();
 unsigned int read_trap_code_attn();
+unsigned int read_trap_code_bw();
 
 }  // namespace vsd

@@ -72,9 +72,10 @@ int vsd_abi_version(void) { return VSD_ABI_VERSION; }
 int vsd_check_pipeline_fault(void) {
     unsigned int a = read_trap_code_gemm();
     unsigned int b = read_trap_code_attn();
-    if (a || b) {
-        char buf[160];
-        snprintf(buf, sizeof(buf), "tensor-core pipeline wait timed out: gemm=0x%08x attn=0x%08x", a, b);
+    unsigned int c = read_trap_code_bw();
+    if (a || b || c) {
+        char buf[200];
+        snprintf(buf, sizeof(buf), "device-side wait timed out: gemm=0x%08x attn=0x%08x groupnorm-barrier=0x%08x", a, b, c);
         set_error(buf);
         return -5;
     }
@@ -133,8 +134,13 @@ int vsd_op_groupnorm(const void* x, int ldx, void* y, int ldy, const float* gamm
     if (rc) return rc;
     rc = ensure_ws((size_t)groupnorm_ws_floats(nb, hw, c, groups) * 4 + 1024);
     if (rc) return rc;
+    static unsigned int* sync = nullptr;   // grid-barrier state of the fused kernel (zeroed once, self-resetting)
+    if (!sync) {
+        VSD_CHECK_CUDA(cudaMalloc(&sync, 64));
+        VSD_CHECK_CUDA(cudaMemset(sync, 0, 64));
+    }
     return launch_groupnorm(reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<bf16*>(y), ldy, gamma, beta, nb, hw,
-                            c, groups, eps, silu, g_ws, reinterpret_cast<cudaStream_t>(stream));
+                            c, groups, eps, silu, g_ws, sync, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int vsd_op_layernorm(const void* x, int ldx, void* y, int ldy, const float* gamma, const float* beta, int rows, int c,

@@ -25,15 +25,18 @@ def _u8ptr(t):
 
 
 class Engine:
-    def __init__(self, device=0):
+    def __init__(self, device=0, parent=None):
+        """parent: another Engine on the same GPU whose (already loaded) weights this lane shares."""
         L = lib()
         L.vsd_create.restype = ctypes.c_void_p
+        L.vsd_create_lane.restype = ctypes.c_void_p
         L.vsd_stream.restype = ctypes.c_void_p
         L.vsd_launches_per_frame.restype = ctypes.c_long
         L.vsd_arena_peak_bytes.restype = ctypes.c_long
         self._L = L
         self.device = device
-        self._ctx = L.vsd_create(c_int(device))
+        self._parent = parent   # keeps the weight owner alive
+        self._ctx = L.vsd_create_lane(parent._ctx) if parent is not None else L.vsd_create(c_int(device))
         if not self._ctx:
             raise VsdError("vsd_create failed: " + (L.vsd_last_error() or b"?").decode())
         self._ctx = ctypes.c_void_p(self._ctx)
@@ -162,5 +165,68 @@ class Engine:
         check(self._L.vsd_debug_unet(self._ctx, _fptr(a), c_int(step), _fptr(o)), "vsd_debug_unet")
         return torch.from_numpy(o).permute(0, 3, 1, 2).contiguous()
 
+    def debug_profile_sections(self, depth=2, reps=10):
+        buf = ctypes.create_string_buffer(1 << 20)
+        check(self._L.vsd_debug_profile_sections(self._ctx, c_int(depth), c_int(reps), buf, ctypes.c_long(len(buf))),
+              "vsd_debug_profile_sections")
+        return [(t, int(n), float(us)) for t, n, us in (ln.split() for ln in buf.value.decode().splitlines() if ln.strip())]
+
     def debug_run_eager(self, yuv=True):
         check(self._L.vsd_debug_run_eager(self._ctx, c_int(1 if yuv else 0)), "vsd_debug_run_eager")
+
+
+class LanePool:
+    """N lanes on one GPU sharing one copy of the weights; frames are handed to lanes round-robin so up to N frames
+    are in flight (CUDA kernels of independent frames overlap and fill the SMs that a single batch-1 frame leaves
+    idle). Configuration calls are broadcast to every lane."""
+
+    def __init__(self, device=0, lanes=2):
+        self.lanes = [Engine(device)]
+        self._n = lanes
+        self._next = 0
+
+    def load_state_dict(self, prefix, sd):
+        self.lanes[0].load_state_dict(prefix, sd)
+
+    def finalize(self):
+        """Call after all weights are loaded: creates the additional lanes."""
+        while len(self.lanes) < self._n:
+            self.lanes.append(Engine(self.lanes[0].device, parent=self.lanes[0]))
+
+    def configure(self, batch, height, width):
+        self.finalize()
+        for e in self.lanes:
+            e.configure(batch, height, width)
+
+    def set_schedule(self, strength, steps, guidance_scale=7.5):
+        ts = None
+        for i, e in enumerate(self.lanes):
+            if i:
+                e.tuning_load(self.lanes[0].tuning_report())   # tune once
+            ts = e.set_schedule(strength, steps, guidance_scale)
+        return ts
+
+    def set_context(self, slot, context):
+        for e in self.lanes:
+            e.set_context(slot, context)
+
+    def set_reference_noise(self):
+        for e in self.lanes:
+            e.set_reference_noise()
+
+    def set_noise(self, init, steps):
+        for e in self.lanes:
+            e.set_noise(init, steps)
+
+    def next_lane(self):
+        e = self.lanes[self._next]
+        self._next = (self._next + 1) % len(self.lanes)
+        return e
+
+    def sync(self):
+        for e in self.lanes:
+            e.sync()
+
+    def close(self):
+        for e in reversed(self.lanes):
+            e.close()
