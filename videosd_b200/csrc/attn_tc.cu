@@ -9,14 +9,15 @@
 // Layouts (produced by the projection GEMMs, so no transposes happen here):
 //   Q, K : [rows][heads * dk_pad] bf16, each head zero-padded from d to dk_pad (multiple of 64)
 //   V^T  : [heads * d][keys]      bf16 (the V projection is computed with swapped operands)
-// warp 0: TMA producer | warp 1: MMA issue + TMEM alloc | warps 2..5: softmax / correction / epilogue
+// warp 0: TMA producer | warp 1: MMA issue + TMEM alloc | warps 2..9: softmax / correction / epilogue
+// (row r of the tile is shared by warps w and w+4: TMEM lane quarter = warp % 4, each takes 64 of the 128 keys)
 #include "tc_common.cuh"
 #include "vsd_internal.h"
 #include <algorithm>
 
 namespace vsd {
 
-static constexpr int kAttnThreads = 192;
+static constexpr int kAttnThreads = 320;   // TMA warp, MMA warp, 8 softmax warps (two threads per query row)
 static constexpr int kTileBytes = 128 * 128;  // one [128 rows][64 bf16] swizzled tile
 
 struct AttnParams {
@@ -28,6 +29,12 @@ struct AttnParams {
     float scale_log2e;
     int stages, tmem_cols;
 };
+
+__device__ __forceinline__ float ex2_approx(float x) {   // one MUFU op; ex2(-inf) = 0
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
@@ -48,6 +55,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     uint64_t* kv_full = bars + 4;
     uint64_t* kv_empty = kv_full + p.stages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_empty + p.stages);
+    float* sx = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));  // [2][128] row exchange
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -60,7 +68,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         tma_prefetch_desc(&mapVt);
         mbar_init(q_full, 1);
         mbar_init(s_full, 1);
-        mbar_init(p_ready, 128);
+        mbar_init(p_ready, 256);
         mbar_init(pv_done, 1);
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&kv_full[s], 1);
@@ -144,6 +152,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         }
     } else {
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;          // which 64 keys of the 128-key block this thread handles
         const int r = q * 32 + lane;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
         float m_run = -INFINITY, l_run = 0.f;
@@ -151,27 +160,36 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         for (int j = 0; j < nblocks; ++j) {
             mbar_wait(s_full, (uint32_t)j & 1u, 5);
             tc_fence_after_sync();
-            const int kbase = j * 128;
-            // pass 1: block row max over the valid keys
+            const int kbase = j * 128 + half * 64;
+            const bool full_blk = (kbase + 64 <= p.nk);   // warp-uniform: no key masking needed
+            // pass 1: row max over this thread's 64 keys, then combine with the partner thread of the row
             float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < 128; c += 32) {
-                uint32_t u[32];
-                tmem_ld32(tS + lane_off + c, u);
-                tmem_ld_wait();
 #pragma unroll
-                for (int jj = 0; jj < 32; ++jj)
-                    if (kbase + c + jj < p.nk) mx = fmaxf(mx, __uint_as_float(u[jj]));
+            for (int c = 0; c < 64; c += 32) {
+                uint32_t u[32];
+                tmem_ld32(tS + lane_off + half * 64 + c, u);
+                tmem_ld_wait();
+                if (full_blk) {
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) mx = fmaxf(mx, __uint_as_float(u[jj]));
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj)
+                        if (kbase + c + jj < p.nk) mx = fmaxf(mx, __uint_as_float(u[jj]));
+                }
             }
+            sx[half * 128 + r] = mx;
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            mx = fmaxf(mx, sx[(half ^ 1) * 128 + r]);
             const float m_new = fmaxf(m_run, mx);
-            const float alpha = exp2f((m_run - m_new) * p.scale_log2e);  // 0 on the first block
+            const float alpha = ex2_approx((m_run - m_new) * p.scale_log2e);  // 0 on the first block
             if (j > 0) {
                 // O and the P buffer belong to the previous P*V until it retires
                 mbar_wait(pv_done, (uint32_t)(j - 1) & 1u, 6);
                 tc_fence_after_sync();
                 if (__any_sync(0xffffffffu, alpha != 1.0f)) {
 #pragma unroll 1
-                    for (int c = 0; c < p.dv_pad; c += 16) {
+                    for (int c = half * 16; c < p.dv_pad; c += 32) {   // the two threads of a row interleave 16-col chunks
                         uint32_t o[16];
                         tmem_ld16(tO + lane_off + c, o);
                         tmem_ld_wait();
@@ -183,29 +201,38 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                 }
             }
             l_run *= alpha;
-            // pass 2: probabilities -> bf16 P tile in the swizzled K-major layout
+            // pass 2: probabilities -> bf16, one 128-byte row of P tile atom `half` (swizzled K-major layout)
             float lsum = 0.f;
             const float mscaled = m_new * p.scale_log2e;
-#pragma unroll 1
-            for (int c = 0; c < 128; c += 32) {
+            uint8_t* prow = sP + (size_t)half * kTileBytes + (size_t)r * 128;
+#pragma unroll
+            for (int c = 0; c < 64; c += 32) {
                 uint32_t u[32];
-                tmem_ld32(tS + lane_off + c, u);
+                tmem_ld32(tS + lane_off + half * 64 + c, u);
                 tmem_ld_wait();
                 float pv[32];
+                if (full_blk) {
 #pragma unroll
-                for (int jj = 0; jj < 32; ++jj) {
-                    float e = exp2f(__uint_as_float(u[jj]) * p.scale_log2e - mscaled);
-                    e = (kbase + c + jj < p.nk) ? e : 0.f;
-                    lsum += e;
-                    pv[jj] = e;
+                    for (int jj = 0; jj < 32; ++jj) {
+                        const float e = ex2_approx(fmaf(__uint_as_float(u[jj]), p.scale_log2e, -mscaled));
+                        lsum += e;
+                        pv[jj] = e;
+                    }
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) {
+                        float e = ex2_approx(fmaf(__uint_as_float(u[jj]), p.scale_log2e, -mscaled));
+                        e = (kbase + c + jj < p.nk) ? e : 0.f;
+                        lsum += e;
+                        pv[jj] = e;
+                    }
                 }
-                uint8_t* tile = sP + (size_t)(c >> 6) * kTileBytes + (size_t)r * 128;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int chunk = ((c & 63) >> 3) + i;  // 16-byte chunk inside the 128-byte row
-                    uint4 w = make_uint4(pack_bf16x2(pv[i * 8], pv[i * 8 + 1]), pack_bf16x2(pv[i * 8 + 2], pv[i * 8 + 3]),
-                                         pack_bf16x2(pv[i * 8 + 4], pv[i * 8 + 5]), pack_bf16x2(pv[i * 8 + 6], pv[i * 8 + 7]));
-                    *reinterpret_cast<uint4*>(tile + ((chunk ^ (r & 7)) << 4)) = w;
+                    const int chunk = (c >> 3) + i;  // 16-byte chunk inside the 128-byte row
+                    const uint4 w = make_uint4(pack_bf16x2(pv[i * 8], pv[i * 8 + 1]), pack_bf16x2(pv[i * 8 + 2], pv[i * 8 + 3]),
+                                               pack_bf16x2(pv[i * 8 + 4], pv[i * 8 + 5]), pack_bf16x2(pv[i * 8 + 6], pv[i * 8 + 7]));
+                    *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) = w;
                 }
             }
             l_run += lsum;
@@ -216,12 +243,14 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         }
         mbar_wait(pv_done, (uint32_t)(nblocks - 1) & 1u, 7);
         tc_fence_after_sync();
-        const float inv_l = 1.0f / l_run;
+        sx[half * 128 + r] = l_run;
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        const float inv_l = 1.0f / (l_run + sx[(half ^ 1) * 128 + r]);
         const int qrow = qt * 128 + r;
         const bool row_ok = qrow < p.nq;
         bf16* orow = p.out + ((long)b * p.nq + qrow) * p.ldo + h * p.d;
 #pragma unroll 1
-        for (int c = 0; c < p.d; c += 16) {
+        for (int c = half * 16; c < p.d; c += 32) {
             uint32_t o[16];
             tmem_ld16(tO + lane_off + c, o);
             tmem_ld_wait();
@@ -269,7 +298,7 @@ int build_attn_op(AttnOp* op, const bf16* q, int ldq, const bf16* k, int ldk, co
     VSD_REQUIRE((ldo % 8) == 0 && ((heads * d) <= ldo), "attention output stride");
     const int nkc = op->dk_pad / 64;
     const int stage_bytes = nkc * kTileBytes + 2 * op->dv_pad * 128;
-    const int fixed = nkc * kTileBytes + 2 * kTileBytes + 1024 + 256;
+    const int fixed = nkc * kTileBytes + 2 * kTileBytes + 1024 + 256 + 1024 + 32;   // + row-exchange scratch
     int stages = 2;
     if (fixed + stages * stage_bytes > g_attn_max_smem) stages = 1;
     VSD_REQUIRE(fixed + stages * stage_bytes <= g_attn_max_smem, "attention tile does not fit shared memory");

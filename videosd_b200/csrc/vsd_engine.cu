@@ -8,6 +8,7 @@
 #include "vsd_internal.h"
 #include "../../include/videosd.h"
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <memory>
@@ -320,6 +321,8 @@ static int tune_gemm(Engine* e, const ActView& a, int taps, const bf16* wt, int 
             const int sp = sps[si];
             if (sp > 1 && (geglu || kb_total / sp < 2)) continue;
             for (int occ = 1; occ <= 2; ++occ) {
+                static const int only_occ = getenv("VSD_TUNE_OCC") ? atoi(getenv("VSD_TUNE_OCC")) : 0;   // experiment knob
+                if (only_occ && occ != only_occ) continue;
                 for (int ki = 0; ki < 3; ++ki) {
                     const int kbs = kbss[ki];
                     GemmOp op;
