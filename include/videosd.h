@@ -66,6 +66,7 @@ int vsd_op_attention(const void* q, int ldq, const void* k, int ldk, const void*
  * Transformer2DModel). x, y: dev bf16 [nb*hw][ld]. */
 int vsd_op_groupnorm(const void* x, int ldx, void* y, int ldy, const float* gamma, const float* beta, int nb, int hw,
                      int c, int groups, float eps, int silu, void* stream);
+int vsd_debug_set_gn_stamps(long long* dev_buf);   /* bring-up: clock64 phase stamps of the fused GroupNorm kernel */
 /* LayerNorm over the last dimension (BasicTransformerBlock.norm1/2/3). */
 int vsd_op_layernorm(const void* x, int ldx, void* y, int ldy, const float* gamma, const float* beta, int rows, int c,
                      float eps, void* stream);

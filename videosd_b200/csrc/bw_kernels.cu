@@ -133,7 +133,7 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, int ldx, bf16* __res
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float v = f[j] * scale[vi * 8 + j] + shift[vi * 8 + j];
-            if (silu) v = v / (1.0f + __expf(-v));
+            if (silu) v = __fdividef(v, 1.0f + __expf(-v));
             f[j] = v;
         }
         *reinterpret_cast<uint4*>(yb + (long)p * ldy + vi * 8) = pack8(f);
@@ -148,39 +148,17 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, int ldx, bf16* __res
 // then normalises its chunk from shared memory: one launch and one read of x instead of two launches and two reads.
 static __device__ unsigned int g_bw_fault = 0;
 
-__device__ __forceinline__ void grid_barrier(unsigned int* sync, unsigned int nblocks) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        volatile unsigned int* gen_p = sync + 1;
-        const unsigned int gen = *gen_p;   // read the generation before arriving
-        __threadfence();
-        const unsigned int old = atomicAdd(sync, 1u);
-        if (old == nblocks - 1) {
-            sync[0] = 0;
-            __threadfence();
-            atomicAdd(sync + 1, 1u);
-        } else {
-            const long long t0 = clock64();
-            while (*gen_p == gen) {
-                __nanosleep(32);
-                if (clock64() - t0 > 2000000000LL) { atomicExch(&g_bw_fault, 0x90000001u); break; }
-            }
-        }
-        __threadfence();
-    }
-    __syncthreads();
-}
-
 __global__ void gn_fused_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C, int groups,
-                                float eps, int silu, int px_per_chunk, float* __restrict__ partial, unsigned int* sync) {
+                                float eps, int silu, int px_per_chunk, float* __restrict__ partial, unsigned int* sync,
+                                long long* dbg) {
     extern __shared__ __align__(16) uint8_t gsm[];
+    const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+    if (dbg_on) dbg[0] = clock64();
     const int vpp = C >> 3;
     const int cpg = C / groups;
-    float* gstat = reinterpret_cast<float*>(gsm);            // [groups*2]
-    float* scale = gstat + 64;                               // [C]
-    float* shift = scale + C;                                // [C]
-    float4* spart = reinterpret_cast<float4*>(shift + C);    // [blockDim.x]
+    float* gstat = reinterpret_cast<float*>(gsm);            // [groups*2] mean, rstd
+    float4* spart = reinterpret_cast<float4*>(gstat + 64);   // [blockDim.x]
     uint4* chunk = reinterpret_cast<uint4*>(spart + blockDim.x);   // [px_per_chunk * vpp]
     const int vi = threadIdx.x % vpp;
     const int r0 = threadIdx.x / vpp;
@@ -188,9 +166,16 @@ __global__ void gn_fused_kernel(const bf16* __restrict__ x, int ldx, bf16* __res
     const int n = blockIdx.y, ck = blockIdx.x, chunks = gridDim.x;
     const int p_begin = ck * px_per_chunk;
     const int p_end = min(HW, p_begin + px_per_chunk);
-    // per-channel affine parameters are constants: fetch them before waiting for the producer of x
-    for (int c = threadIdx.x; c < C; c += blockDim.x) { scale[c] = gamma[c]; shift[c] = beta[c]; }
+    // this thread's 8 channels' affine parameters are constants: fetch them before waiting for the producer of x
+    float ga[8], be[8];
+    {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
+        ga[0] = g0.x; ga[1] = g0.y; ga[2] = g0.z; ga[3] = g0.w; ga[4] = g1.x; ga[5] = g1.y; ga[6] = g1.z; ga[7] = g1.w;
+        be[0] = b0.x; be[1] = b0.y; be[2] = b0.z; be[3] = b0.w; be[4] = b1.x; be[5] = b1.y; be[6] = b1.z; be[7] = b1.w;
+    }
     pdl_wait();
+    if (dbg_on) dbg[1] = clock64();
     float s[8], ss[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s[j] = 0.f; ss[j] = 0.f; }
@@ -227,21 +212,40 @@ __global__ void gn_fused_kernel(const bf16* __restrict__ x, int ldx, bf16* __res
         dst[0] = a;
         dst[1] = b;
     }
-    grid_barrier(sync, gridDim.x * gridDim.y);
-    pdl_launch_dependents();   // only now: every block of this grid is resident, successors cannot starve it
-    {
-        // 8 threads per group walk the chunk partials in a fixed interleaved order, then a fixed shuffle tree;
-        // blockDim may be smaller than 8 * groups, so groups are visited in rounds (uniform trip count).
-        const int gpr = blockDim.x >> 3;   // groups per round
+    if (dbg_on) dbg[2] = clock64();
+    // ---- grid barrier (sense reversal; every block is co-resident, see launch_groupnorm). The LAST block to arrive
+    // reduces all partials in a fixed order and publishes (mean, rstd) per (image, group) before releasing the others,
+    // so the statistics are computed once instead of by every block (which also hammered the same L2 lines).
+    __shared__ unsigned int s_last, s_gen;
+    float* stats_out = partial + (long)gridDim.y * chunks * groups * 2;   // [NB][groups][2]
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        volatile unsigned int* gen_p = sync + 1;
+        s_gen = *gen_p;                      // read the generation before arriving
+        __threadfence();                     // this block's partials are visible before the arrival
+        const unsigned int old = atomicAdd(sync, 1u);
+        s_last = (old == gridDim.x * gridDim.y - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        const int gpr = blockDim.x >> 3;     // (image, group) items per round, 8 threads each
         const int j = threadIdx.x & 7;
-        for (int g0r = 0; g0r < groups; g0r += gpr) {
-            const int g = g0r + (threadIdx.x >> 3);
-            const bool ok = (g < groups) && ((threadIdx.x >> 3) < gpr);
-            float a = 0.f, b = 0.f;
-            if (ok) {
-                const float* src = partial + (long)n * chunks * groups * 2 + g * 2;
-                for (int c = j; c < chunks; c += 8) { a += __ldcg(src + (long)c * groups * 2); b += __ldcg(src + (long)c * groups * 2 + 1); }
+        const int items = (int)gridDim.y * groups;
+        for (int i0 = 0; i0 < items; i0 += gpr) {
+            const int item = i0 + (threadIdx.x >> 3);
+            const bool ok = (item < items) && ((threadIdx.x >> 3) < gpr);
+            const int in = ok ? item / groups : 0, ig = ok ? item % groups : 0;
+            const float2* src = reinterpret_cast<const float2*>(partial + (long)in * chunks * groups * 2) + ig;
+            float2 v[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int c = j + 8 * k;
+                v[k] = (ok && c < chunks) ? __ldcg(src + (long)c * groups) : make_float2(0.f, 0.f);
             }
+            float a = 0.f, b = 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) { a += v[k].x; b += v[k].y; }
 #pragma unroll
             for (int o = 4; o > 0; o >>= 1) {
                 a += __shfl_xor_sync(0xffffffffu, a, o);
@@ -251,34 +255,52 @@ __global__ void gn_fused_kernel(const bf16* __restrict__ x, int ldx, bf16* __res
                 const float cnt = (float)HW * (float)cpg;
                 const float mean = a / cnt;
                 const float var = fmaxf(b / cnt - mean * mean, 0.f);
-                gstat[g * 2] = mean;
-                gstat[g * 2 + 1] = rsqrtf(var + eps);
+                stats_out[item * 2] = mean;
+                stats_out[item * 2 + 1] = rsqrtf(var + eps);
             }
         }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            sync[0] = 0;
+            __threadfence();
+            atomicAdd(sync + 1, 1u);         // release
+        }
+    } else if (threadIdx.x == 0) {
+        volatile unsigned int* gen_p = sync + 1;
+        const long long t0 = clock64();
+        while (*gen_p == s_gen) {
+            if (clock64() - t0 > 2000000000LL) { atomicExch(&g_bw_fault, 0x90000001u); break; }
+        }
+        __threadfence();
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const int g = c / cpg;
-        const float a = gstat[g * 2 + 1] * scale[c];
-        shift[c] = shift[c] - gstat[g * 2] * a;
-        scale[c] = a;
-    }
+    if (dbg_on) dbg[3] = clock64();
+    pdl_launch_dependents();   // only now: every block of this grid is resident, successors cannot starve it
+    if (threadIdx.x < groups * 2) gstat[threadIdx.x] = __ldcg(stats_out + (long)n * groups * 2 + threadIdx.x);
     __syncthreads();
-    bf16* yb = y + ((long)n * HW) * ldy + vi * 8;
+    if (dbg_on) dbg[4] = clock64();
+    // fold statistics and affine parameters of this thread's 8 channels into one multiply-add each
     float sc[8], sh[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { sc[j] = scale[vi * 8 + j]; sh[j] = shift[vi * 8 + j]; }
+    for (int j = 0; j < 8; ++j) {
+        const int g = (vi * 8 + j) / cpg;
+        sc[j] = gstat[g * 2 + 1] * ga[j];
+        sh[j] = be[j] - gstat[g * 2] * sc[j];
+    }
+    bf16* yb = y + ((long)n * HW) * ldy + vi * 8;
     for (int p = p_begin + r0; p < p_end; p += R) {
         float f[8];
         unpack8(chunk[(p - p_begin) * vpp + vi], f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            float v = f[j] * sc[j] + sh[j];
-            if (silu) v = v / (1.0f + __expf(-v));
+            float v = fmaf(f[j], sc[j], sh[j]);
+            if (silu) v = __fdividef(v, 1.0f + __expf(-v));
             f[j] = v;
         }
         *reinterpret_cast<uint4*>(yb + (long)p * ldy) = pack8(f);
     }
+    if (dbg_on) dbg[5] = clock64();
 }
 
 unsigned int read_trap_code_bw() {
@@ -287,6 +309,8 @@ unsigned int read_trap_code_bw() {
     if (v) cudaMemcpyToSymbol(g_bw_fault, &z, sizeof(z));
     return v;
 }
+
+long long* g_gn_dbg = nullptr;   // bring-up: phase stamps of block (0,0) of the fused kernel
 
 static void gn_geometry(int NB, int HW, int C, int* px_per_chunk, int* chunks) {
     const long vecs = (long)HW * (C / 8);
@@ -304,7 +328,7 @@ static void gn_geometry(int NB, int HW, int C, int* px_per_chunk, int* chunks) {
 int groupnorm_ws_floats(int NB, int HW, int C, int groups) {
     int ppc, chunks;
     gn_geometry(NB, HW, C, &ppc, &chunks);
-    return NB * chunks * groups * 2;
+    return NB * chunks * groups * 2 + NB * groups * 2;   // chunk partials + final (mean, rstd) per (image, group)
 }
 
 int launch_groupnorm(const bf16* x, int ldx, bf16* y, int ldy, const float* gamma, const float* beta, int NB, int HW,
@@ -318,7 +342,7 @@ int launch_groupnorm(const bf16* x, int ldx, bf16* y, int ldy, const float* gamm
     if (R < 1) R = 1;
     {
         // fused single-kernel path when the chunk fits shared memory and the whole grid is co-resident
-        const size_t fsmem = (size_t)(64 + 2 * C) * 4 + (size_t)vpp * R * 16 + (size_t)ppc * vpp * 16;
+        const size_t fsmem = (size_t)64 * 4 + (size_t)vpp * R * 16 + (size_t)ppc * vpp * 16;
         static bool attr_set = false;
         if (!attr_set) {
             VSD_CHECK_CUDA(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -329,7 +353,7 @@ int launch_groupnorm(const bf16* x, int ldx, bf16* y, int ldy, const float* gamm
         // blocks) are all resident and no lane can starve another's late blocks. Larger tensors use two kernels.
         if (sync != nullptr && fsmem <= 48 * 1024 && (long)chunks * NB <= 128 && groups <= 32 && vpp * R <= 320) {
             VSD_CHECK_CUDA(launch_k(gn_fused_kernel, dim3(chunks, NB), dim3(vpp * R), fsmem, st, x, ldx, y, ldy, gamma, beta, HW,
-                                    C, groups, eps, silu, ppc, partial_ws, sync));
+                                    C, groups, eps, silu, ppc, partial_ws, sync, g_gn_dbg));
             return 0;
         }
     }

@@ -151,5 +151,6 @@ int ensure_init();
 unsigned int read_trap_code_gemm();
 unsigned int read_trap_code_attn();
 unsigned int read_trap_code_bw();
+extern long long* g_gn_dbg;   // bring-up: phase stamps of the fused GroupNorm kernel
 
 }  // namespace vsd

@@ -143,6 +143,9 @@ int vsd_op_groupnorm(const void* x, int ldx, void* y, int ldy, const float* gamm
                             c, groups, eps, silu, g_ws, sync, reinterpret_cast<cudaStream_t>(stream));
 }
 
+/* bring-up: route the fused GroupNorm's phase stamps (clock64 x6) to a device buffer (NULL disables) */
+int vsd_debug_set_gn_stamps(long long* dev_buf) { vsd::g_gn_dbg = dev_buf; return 0; }
+
 int vsd_op_layernorm(const void* x, int ldx, void* y, int ldy, const float* gamma, const float* beta, int rows, int c,
                      float eps, void* stream) {
     return launch_layernorm(reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<bf16*>(y), ldy, gamma, beta, rows, c,
