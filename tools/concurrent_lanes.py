@@ -9,22 +9,17 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from videosd_b200 import weights  # noqa: E402
-from videosd_b200.engine import Engine  # noqa: E402
+from videosd_b200.engine import LanePool  # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 H = W = 512
 usd = weights.random_state_dict(weights.unet_param_shapes(), 1234)
 vsd = weights.random_state_dict(weights.taesd_param_shapes(), 4321)
 ctx = torch.randn((77, 768), generator=torch.Generator().manual_seed(7))
-engs = []
-for i in range(N):
-    e = Engine(0)
-    e.load_state_dict("unet", usd); e.load_state_dict("vae", vsd)
-    e.configure(1, H, W)
-    if engs:
-        e.tuning_load(engs[0].tuning_report())
-    e.set_schedule(0.5, 4); e.set_context(0, ctx); e.set_reference_noise()
-    engs.append(e)
+pool = LanePool(0, N)
+pool.load_state_dict("unet", usd); pool.load_state_dict("vae", vsd)
+pool.configure(1, H, W); pool.set_schedule(0.5, 4); pool.set_context(0, ctx); pool.set_reference_noise()
+engs = pool.lanes
 rs = np.random.RandomState(0)
 y = rs.randint(16, 235, (1, H, W)).astype(np.uint8); u = rs.randint(16, 240, (1, H // 2, W // 2)).astype(np.uint8); v = u.copy()
 for e in engs:

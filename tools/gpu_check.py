@@ -73,14 +73,15 @@ def ref_conv(x_nhwc, w_ohwi, taps, bias=None, rowvec=None, residual=None):
 
 
 def gemm_case(name, nb, h, w, c, n, taps, bias=False, rowvec=False, residual=False, out_f32=False, block_n=0, splits=0,
-              tol=1e-2):
+              tol=1e-2, halo=False):
     def fn():
         x = randn((nb, h, w, c), 1).bfloat16()
         wt = randn((n, taps * c), 2, scale=(taps * c) ** -0.5).bfloat16()
         b = randn((n,), 3) if bias else None
         rv = randn((nb, n), 4) if rowvec else None
         res = randn((nb, h, w, n), 5).bfloat16() if residual else None
-        y = ops.conv_gemm(x, wt, taps, bias=b, rowvec=rv, residual=res, out_f32=out_f32, block_n=block_n, splits=splits)
+        y = ops.conv_gemm(x, wt, taps, bias=b, rowvec=rv, residual=res, out_f32=out_f32, block_n=block_n, splits=splits,
+                          halo=halo)
         torch.cuda.synchronize()
         ref = ref_conv(x, wt, taps, b, rv, res)
         record(name, rel_err(y, ref), tol, {"shape": [nb, h, w, c, n, taps], "block_n": block_n, "splits": splits})
@@ -111,6 +112,18 @@ def check_gemm():
     gemm_case("conv3x3_odd_23x40_128_n3", 1, 23, 40, 128, 3, 9, bias=True, out_f32=True)
     gemm_case("conv3x3_512x512_64_64", 1, 512, 512, 64, 64, 9, bias=True)
     gemm_case("conv3x3_96x96_b4_320", 4, 96, 96, 320, 320, 9, bias=True)
+
+    # 3x3 halo mode (8x16 tiles, three column-shifted halo tiles per channel block)
+    gemm_case("halo_16x8_64_64", 1, 16, 8, 64, 64, 9, bias=True, halo=True, block_n=64)
+    gemm_case("halo_64x64_320_320_all", 1, 64, 64, 320, 320, 9, bias=True, rowvec=True, residual=True, halo=True)
+    gemm_case("halo_64x64_320_320_bn160", 1, 64, 64, 320, 320, 9, bias=True, halo=True, block_n=160)
+    gemm_case("halo_32x32_640_640_split3", 1, 32, 32, 640, 640, 9, bias=True, halo=True, block_n=128, splits=3)
+    gemm_case("halo_16x16_1280_1280_split6", 1, 16, 16, 1280, 1280, 9, bias=True, rowvec=True, halo=True, block_n=128, splits=6)
+    gemm_case("halo_odd_45x80_64", 1, 45, 80, 64, 64, 9, bias=True, halo=True)
+    gemm_case("halo_odd_23x40_128_n3", 1, 23, 40, 128, 3, 9, bias=True, out_f32=True, halo=True)
+    gemm_case("halo_512x512_64_64", 1, 512, 512, 64, 64, 9, bias=True, halo=True)
+    gemm_case("halo_96x96_b4_320", 4, 96, 96, 320, 320, 9, bias=True, halo=True)
+    gemm_case("halo_b3_16x16_64", 3, 16, 16, 64, 64, 9, bias=True, halo=True)
 
     def geglu():
         m, c = 4096, 320
@@ -149,20 +162,21 @@ def bench_gemm():
         ("conv3 96x96x4 320->320", 4, 96, 96, 320, 320, 9),
         ("lin 8192x8192x8192", 1, 1, 8192, 8192, 8192, 1),
     ]
-    for name, nb, h, w, c, n, taps in cases:
+    for name, nb, h, w, c, n, taps in cases + [(nm + " HALO", a, b_, c_, d, e, f) for (nm, a, b_, c_, d, e, f) in cases if f == 9 and b_ >= 16]:
         try:
             x = randn((nb, h, w, c), 1).bfloat16()
             wt = randn((n, taps * c), 2, scale=(taps * c) ** -0.5).bfloat16()
             out = torch.empty((nb, h, w, n), device=DEV, dtype=torch.bfloat16)
+            hl = name.endswith("HALO")
             for _ in range(3):
-                ops.conv_gemm(x, wt, taps, out=out)
+                ops.conv_gemm(x, wt, taps, out=out, halo=hl)
             torch.cuda.synchronize()
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             iters = 20
             e0.record()
             for _ in range(iters):
-                ops.conv_gemm(x, wt, taps, out=out)
+                ops.conv_gemm(x, wt, taps, out=out, halo=hl)
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / iters

@@ -19,6 +19,7 @@ static constexpr int kBlockM = 128;
 static constexpr int kBlockK = 64;
 static constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB per stage
 static constexpr int kGemmThreads = 192;
+static constexpr int kHaloABytes = 18 * 1024;          // halo mode: 18 image rows x 8 pixels x 128 B
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
@@ -123,8 +124,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const int stages = p.stages;
     const int kbs = p.kb_per_stage;                       // 64-wide k-blocks carried by one pipeline stage
     const uint32_t b_bytes = (uint32_t)p.block_n * 128u;  // one k-block of the B tile
-    const uint32_t stage_bytes = (uint32_t)kbs * ((uint32_t)kABytes + b_bytes);
-    // stage layout: [A k-block 0 .. kbs-1][B k-block 0 .. kbs-1]
+    // stage layout: [A k-block 0 .. kbs-1][B k-block 0 .. kbs-1]; halo mode: [A halo tile 8 x 18 px][B tap dy=-1,0,1]
+    const bool halo = p.halo != 0;
+    const uint32_t a_stage = halo ? (uint32_t)kHaloABytes : (uint32_t)kbs * kABytes;
+    const uint32_t stage_bytes = halo ? ((uint32_t)kHaloABytes + 3u * b_bytes) : (uint32_t)kbs * ((uint32_t)kABytes + b_bytes);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
     uint64_t* empty_bar = full_bar + stages;
     uint64_t* tmem_full_bar = empty_bar + stages;
@@ -150,8 +153,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const int kb_end = min(kb_begin + p.kb_per_split, p.kb_total);
 
     // Stage bookkeeping shared by the early prefetch and the producer loop
-    const int total_iters = (kb_end - kb_begin + kbs - 1) / kbs;
-    const int npre = (p.a_static || p.b_static) ? min(stages, total_iters) : 0;
+    const int total_iters = halo ? (kb_end - kb_begin) : (kb_end - kb_begin + kbs - 1) / kbs;
+    const int npre = ((p.a_static && !halo) || p.b_static) ? min(stages, total_iters) : 0;
     if (warp == 0) {
         if (elect_one()) {
             tma_prefetch_desc(&mapA);
@@ -165,14 +168,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             // The constant operand (weights) of the first ring pass is requested right away: before the TMEM
             // allocation / CTA barrier below and before waiting for the producer kernel of the activations (PDL).
             int kb = kb_begin;
-            for (int it = 0; it < npre; ++it) {
-                const int nkb = min(kbs, kb_end - kb);
-                uint8_t* sa = smem + (size_t)it * stage_bytes;
-                uint8_t* sb = sa + (size_t)kbs * kABytes;
-                mbar_expect_tx(&full_bar[it], (uint32_t)nkb * ((uint32_t)kABytes + b_bytes));
-                for (int j = 0; j < nkb; ++j, ++kb) {
-                    if (p.b_static) tma_load_2d(sb + (size_t)j * b_bytes, &mapB, &full_bar[it], kb * 64, col0);
-                    else tma_load_4d(sa + (size_t)j * kABytes, &mapA, &full_bar[it], kb * 64, w0, h0, n0);  // taps == 1
+            if (halo) {
+                const int kpt = p.cin >> 6;
+                for (int it = 0; it < npre; ++it, ++kb) {   // iteration = (channel block, column shift)
+                    uint8_t* sb = smem + (size_t)it * stage_bytes + a_stage;
+                    const int cb = kb / 3, dxi = kb - cb * 3;
+                    mbar_expect_tx(&full_bar[it], stage_bytes);
+                    for (int dyi = 0; dyi < 3; ++dyi)
+                        tma_load_2d(sb + (size_t)dyi * b_bytes, &mapB, &full_bar[it], ((dyi * 3 + dxi) * kpt + cb) * 64, col0);
+                }
+            } else {
+                for (int it = 0; it < npre; ++it) {
+                    const int nkb = min(kbs, kb_end - kb);
+                    uint8_t* sa = smem + (size_t)it * stage_bytes;
+                    uint8_t* sb = sa + a_stage;
+                    mbar_expect_tx(&full_bar[it], (uint32_t)nkb * ((uint32_t)kABytes + b_bytes));
+                    for (int j = 0; j < nkb; ++j, ++kb) {
+                        if (p.b_static) tma_load_2d(sb + (size_t)j * b_bytes, &mapB, &full_bar[it], kb * 64, col0);
+                        else tma_load_4d(sa + (size_t)j * kABytes, &mapA, &full_bar[it], kb * 64, w0, h0, n0);  // taps == 1
+                    }
                 }
             }
         }
@@ -195,6 +209,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             int s = 0, dbg_it = 0;
             uint32_t ph = 0;
             pdl_wait();
+            if (halo) {
+                // iteration = (64-channel block cb, column shift dx): ONE 8 x 18-pixel halo tile serves the three
+                // row taps (dy = -1, 0, +1) as 1024-byte-aligned offsets; three weight tiles (one per dy) ride along.
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
+                    const bool pre = dbg_it < npre;
+                    if (!pre) {
+                        mbar_wait(&empty_bar[s], ph ^ 1u, 1);
+                        mbar_expect_tx(&full_bar[s], stage_bytes);
+                    }
+                    uint8_t* sa = smem + (size_t)s * stage_bytes;
+                    uint8_t* sb = sa + a_stage;
+                    const int cbh = kb / 3, dxi = kb - cbh * 3;
+                    tma_load_4d(sa, &mapA, &full_bar[s], cbh * 64, w0 + dxi - 1, h0 - 1, n0);
+                    if (!pre)
+                        for (int dyi = 0; dyi < 3; ++dyi)
+                            tma_load_2d(sb + (size_t)dyi * b_bytes, &mapB, &full_bar[s], ((dyi * 3 + dxi) * kpt + cbh) * 64, col0);
+                    ++dbg_it;
+                    if (++s == stages) { s = 0; ph ^= 1u; }
+                }
+            } else
             for (int kb = kb_begin; kb < kb_end;) {
                 const int nkb = min(kbs, kb_end - kb);
                 const bool pre = dbg_it < npre;
@@ -204,7 +238,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 }
                 if (dbg_cta && dbg_it < 16) p.dbg[16 + 2 * dbg_it] = clock64();
                 uint8_t* sa = smem + (size_t)s * stage_bytes;
-                uint8_t* sb = sa + (size_t)kbs * kABytes;
+                uint8_t* sb = sa + a_stage;
                 for (int j = 0; j < nkb; ++j, ++kb) {
                     int dy = 0, dx = 0;
                     if (p.taps == 9) {
@@ -230,19 +264,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         uint32_t ph = 0;
         bool first = true;
         for (int kb = kb_begin; kb < kb_end;) {
-            const int nkb = min(kbs, kb_end - kb);
+            const int nkb = halo ? 3 : min(kbs, kb_end - kb);   // halo: three row taps per stage
             mbar_wait(&full_bar[s], ph, 2);
             tc_fence_after_sync();
             if (lane == 0 && first) VSD_STAMP(2);
             if (lane == 0 && dbg_cta && dbg_it < 16) p.dbg[64 + 2 * dbg_it] = clock64();
             {
                 const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-                const uint32_t b_addr = a_addr + (uint32_t)kbs * kABytes;
+                const uint32_t b_addr = a_addr + a_stage;
+                const uint32_t a_step = halo ? 1024u : (uint32_t)kABytes;   // halo: next row tap = next 8-pixel image row
                 if (elect_one()) {   // one elected lane issues; ptxas keeps descriptors in uniform registers
                     for (int j = 0; j < nkb; ++j) {
 #pragma unroll
                         for (int k = 0; k < kBlockK / 16; ++k) {
-                            umma_bf16(tmem_base, umma_desc_sw128(a_addr + j * kABytes + k * 32),
+                            umma_bf16(tmem_base, umma_desc_sw128(a_addr + j * a_step + k * 32),
                                       umma_desc_sw128(b_addr + j * b_bytes + k * 32), idesc,
                                       (first && j == 0 && k == 0) ? 0u : 1u);
                         }
@@ -254,7 +289,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             }
             ++dbg_it;
             first = false;
-            kb += nkb;
+            kb += halo ? 1 : nkb;
             if (++s == stages) { s = 0; ph ^= 1u; }
         }
         if (elect_one()) umma_commit(tmem_full_bar);
@@ -525,7 +560,7 @@ static void pick_tile_rect(int NB, int H, int W, int* BW, int* BH, int* BN) {
 int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N, int ldw, void* out, int ldo,
                   int out_f32, const float* bias, const float* rowvec, const bf16* residual, int ldr, int act_flags,
                   float* partial_ws, size_t partial_ws_bytes, int force_block_n, int force_splits, int force_occupancy,
-                  int force_kb_per_stage) {
+                  int force_kb_per_stage, int force_halo) {
     const int act = act_flags & 0xF;
     VSD_REQUIRE(taps == 1 || taps == 9, "taps must be 1 or 9");
     VSD_REQUIRE(a.C % 64 == 0, "input channels must be a multiple of 64 for the tcgen05 path");
@@ -533,13 +568,18 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
     GemmParams& p = op->p;
     p = GemmParams{};
     p.taps = taps; p.cin = a.C; p.H = a.H; p.W = a.W; p.NB = a.NB;
-    pick_tile_rect(a.NB, a.H, a.W, &p.BW, &p.BH, &p.BN);
+    // Halo mode for 3x3 convolutions: 8 x 16 pixel tiles; per 64-channel block three column-shifted 8 x 18 halo
+    // tiles replace nine 128-pixel tap tiles (2.7x less activation traffic into the SM).
+    const bool halo = (taps == 9) && (a.H >= 16) && (a.W >= 8) && (force_halo != 0) && (force_halo > 0);
+    p.halo = halo ? 1 : 0;
+    if (halo) { p.BW = 8; p.BH = 16; p.BN = 1; }
+    else pick_tile_rect(a.NB, a.H, a.W, &p.BW, &p.BH, &p.BN);
     p.tiles_w = (a.W + p.BW - 1) / p.BW;
     p.tiles_h = (a.H + p.BH - 1) / p.BH;
     p.tiles_n = (a.NB + p.BN - 1) / p.BN;
     p.N = N;
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-    p.kb_total = taps * (a.C / 64);
+    p.kb_total = halo ? 3 * (a.C / 64) : taps * (a.C / 64);   // halo: iterations of (channel block, column shift)
 
     // N tile: prefer a divisor of N that keeps the grid near a multiple of the SM count.
     int bn = 0;
@@ -602,19 +642,23 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
     const int stage_bytes = kABytes + bn * 128;
     int occ = force_occupancy > 0 ? force_occupancy : ((bn > 160) ? 1 : 2);
     if (occ == 2 && 2 * (kABytes + bn * 128) + 4096 > g_max_smem / 2) occ = 1;   // not even two stages fit twice
+    if (halo && occ == 2 && force_occupancy <= 0 && 2 * (kHaloABytes + 3 * bn * 128) + 4096 > g_max_smem / 2) occ = 1;
     const int smem_budget = (occ == 1) ? g_max_smem : (g_max_smem / 2 - 1024);
     // Each barrier round trip (TMA -> full -> MMA -> commit -> empty -> TMA) costs several hundred cycles, so a
     // stage carries kb_per_stage 64-wide k-blocks; keep >= 3 stages in flight when the budget allows.
     int kbs = force_kb_per_stage > 0 ? force_kb_per_stage : 2;
+    if (halo) kbs = 1;
     while (kbs > 1 && ((smem_budget - 3072) / (kbs * stage_bytes) < (force_kb_per_stage > 0 ? 2 : 3) || kbs > p.kb_per_split)) --kbs;
-    int stages = (smem_budget - 3072) / (kbs * stage_bytes);
+    const int stage_total = halo ? (kHaloABytes + 3 * bn * 128) : kbs * stage_bytes;
+    int stages = (smem_budget - 3072) / stage_total;
+    if (halo) VSD_REQUIRE(stages >= 2, "halo tile does not leave room for two pipeline stages");
     if (stages > 8) stages = 8;
     const int stage_iters = (p.kb_per_split + kbs - 1) / kbs;
     if (stages > stage_iters) stages = stage_iters;
     if (stages < 1) stages = 1;
     p.stages = stages;
     p.kb_per_stage = kbs;
-    op->smem_bytes = stages * kbs * stage_bytes + 1024 /*align slack*/ + (2 * stages + 1) * 8 + 64 + bn * 4;
+    op->smem_bytes = stages * stage_total + 1024 /*align slack*/ + (2 * stages + 1) * 8 + 64 + bn * 4;
     // With programmatic dependent launch CTAs of different kernels co-reside on an SM. TMEM is not part of the block
     // scheduler's accounting, so bound the CTAs per SM through shared memory: smem >= tmem_cols * 450 B guarantees that
     // the co-resident CTAs' TMEM columns sum to <= 512 (otherwise tcgen05.alloc of a CTA the others wait on could spin).
@@ -628,9 +672,10 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
     p.b_static = (act_flags & (ACT_A_STATIC_FLAG | ACT_NO_STATIC_FLAG)) ? 0 : 1;
     if (p.a_static && taps != 1) p.a_static = 0;
 
-    int rc = make_tmap_act(&op->mapA, a.ptr, a.C, a.W, a.H, a.NB, a.ld, p.BW, p.BH, p.BN);
+    int rc = halo ? make_tmap_act(&op->mapA, a.ptr, a.C, a.W, a.H, a.NB, a.ld, 8, 18, 1)
+                  : make_tmap_act(&op->mapA, a.ptr, a.C, a.W, a.H, a.NB, a.ld, p.BW, p.BH, p.BN);
     if (rc) return rc;
-    rc = make_tmap_2d(&op->mapB, wt, p.kb_total * 64, N, ldw, bn);
+    rc = make_tmap_2d(&op->mapB, wt, taps * a.C, N, ldw, bn);
     if (rc) return rc;
     op->grid = dim3(m_tiles, n_tiles, splits);
     return 0;

@@ -128,7 +128,7 @@ struct Engine {
     cudaGraphExec_t graph_yuv = nullptr, graph_rgb = nullptr;
     // GEMM autotuner: (block_n, splits, occupancy) per distinct shape, timed with L2 flushed
     int autotune = 1;
-    struct Tuned { int bn, splits, occ, kbs; float us; };
+    struct Tuned { int bn, splits, occ, kbs, halo; float us; };
     std::unordered_map<std::string, Tuned> tuned;
     void* flush_buf = nullptr; size_t flush_bytes = 0;
     unsigned int* gn_sync = nullptr;   // grid-barrier state for the fused GroupNorm kernel (never reused memory)
@@ -312,7 +312,7 @@ static int tune_gemm(Engine* e, const ActView& a, int taps, const bf16* wt, int 
     const int kbss[3] = {1, 2, 4};
     const int sps[8] = {1, 2, 3, 4, 6, 8, 12, 16};
     const int kb_total = taps * (a.C / 64);
-    Engine::Tuned best{0, 1, 0, 1, 1e30f};
+    Engine::Tuned best{0, 1, 0, 1, 0, 1e30f};
     for (int bi = 0; bi < 8; ++bi) {
         const int bn = bns[bi];
         if (geglu && bn != 128) continue;
@@ -323,20 +323,22 @@ static int tune_gemm(Engine* e, const ActView& a, int taps, const bf16* wt, int 
             for (int occ = 1; occ <= 2; ++occ) {
                 static const int only_occ = getenv("VSD_TUNE_OCC") ? atoi(getenv("VSD_TUNE_OCC")) : 0;   // experiment knob
                 if (only_occ && occ != only_occ) continue;
-                for (int ki = 0; ki < 3; ++ki) {
-                    const int kbs = kbss[ki];
+                for (int ki = 0; ki < 4; ++ki) {
+                    const int use_halo = (ki == 3) ? 1 : 0;             // 4th variant: 3x3 halo mode
+                    if (use_halo && (taps != 9 || a.H < 16 || a.W < 8)) continue;
+                    const int kbs = use_halo ? 1 : kbss[ki];
                     GemmOp op;
                     if (build_gemm_op(&op, a, taps, wt, N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act,
-                                      e->splitk_ws, e->splitk_bytes, bn, sp, occ, kbs))
+                                      e->splitk_ws, e->splitk_bytes, bn, sp, occ, kbs, use_halo))
                         continue;   // does not fit (workspace / smem): skip
-                    if (op.p.splits != sp || op.p.kb_per_stage != kbs) continue;
+                    if (op.p.splits != sp || op.p.kb_per_stage != kbs || op.p.halo != use_halo) continue;
                     const long ctas = (long)op.grid.x * op.grid.y * op.grid.z;
                     if (sp > 1 && ctas > 4 * 148) continue;
                     if (occ == 2 && op.smem_bytes > 114 * 1024) continue;   // would not actually co-reside
                     float us = 0.f;
                     int rc = time_gemm(e, op, &us);
                     if (rc) return rc;
-                    if (us < best.us) best = Engine::Tuned{bn, sp, occ, kbs, us};
+                    if (us < best.us) best = Engine::Tuned{bn, sp, occ, kbs, use_halo, us};
                 }
             }
         }
@@ -396,7 +398,7 @@ struct Builder {
               const float* bias, const float* rowvec, const bf16* res, int ldr, int act) {
         if (rc) return;
         GemmOp op;
-        int fbn = 0, fsp = 0, focc = 0, fkbs = 0;
+        int fbn = 0, fsp = 0, focc = 0, fkbs = 0, fhalo = 0;
         if (e->autotune) {
             char key[160];
             snprintf(key, sizeof(key), "%dx%dx%dx%d|t%d|n%d|a%d|f%d|r%d", a.NB, a.H, a.W, a.C, taps, N, act, out_f32,
@@ -408,10 +410,10 @@ struct Builder {
                 if (r) { rc = r; fail = get_error(); return; }
                 it = e->tuned.emplace(key, t).first;
             }
-            fbn = it->second.bn; fsp = it->second.splits; focc = it->second.occ; fkbs = it->second.kbs;
+            fbn = it->second.bn; fsp = it->second.splits; focc = it->second.occ; fkbs = it->second.kbs; fhalo = it->second.halo;
         }
         int r = build_gemm_op(&op, a, taps, wt, N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act, e->splitk_ws,
-                              e->splitk_bytes, fbn, fsp, focc, fkbs);
+                              e->splitk_bytes, fbn, fsp, focc, fkbs, fhalo);
         if (r) { rc = r; fail = get_error(); return; }
         out->push_back(mk([op](cudaStream_t st) { return launch_gemm_op(op, st); }, "gemm"));
     }
@@ -1145,9 +1147,10 @@ int vsd_tuning_load(vsd_ctx* c, const char* text) {
     const char* p = text;
     while (*p) {
         char key[200];
-        Engine::Tuned t{0, 1, 0, 1, 0.f};
+        Engine::Tuned t{0, 1, 0, 1, 0, 0.f};
         int consumed = 0;
-        if (sscanf(p, "%199s bn=%d splits=%d occ=%d kbs=%d us=%f%n", key, &t.bn, &t.splits, &t.occ, &t.kbs, &t.us, &consumed) >= 5 &&
+        if (sscanf(p, "%199s bn=%d splits=%d occ=%d kbs=%d halo=%d us=%f%n", key, &t.bn, &t.splits, &t.occ, &t.kbs, &t.halo, &t.us,
+                   &consumed) >= 6 &&
             t.bn > 0) {
             c->e.tuned[key] = t;
             ++n;
@@ -1165,8 +1168,8 @@ int vsd_tuning_report(vsd_ctx* c, char* buf, long cap) {
     std::string s;
     for (auto& kv : c->e.tuned) {
         char line[256];
-        snprintf(line, sizeof(line), "%s bn=%d splits=%d occ=%d kbs=%d us=%.2f\n", kv.first.c_str(), kv.second.bn,
-                 kv.second.splits, kv.second.occ, kv.second.kbs, kv.second.us);
+        snprintf(line, sizeof(line), "%s bn=%d splits=%d occ=%d kbs=%d halo=%d us=%.2f\n", kv.first.c_str(), kv.second.bn,
+                 kv.second.splits, kv.second.occ, kv.second.kbs, kv.second.halo, kv.second.us);
         s += line;
     }
     if (buf && cap > 0) {

@@ -68,6 +68,7 @@ struct GemmParams {
     int block_n;          // multiple of 32, <= 256
     int tmem_cols;        // power of two >= block_n
     int stages, kb_per_stage;
+    int halo;             // 3x3 conv halo mode (8x16 tiles, column-shifted 8x18 activation tiles shared by 3 row taps)
     // K split
     int kb_total, kb_per_split, splits;
     // epilogue
@@ -98,7 +99,7 @@ struct ActView {
 int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N, int ldw, void* out, int ldo,
                   int out_f32, const float* bias, const float* rowvec, const bf16* residual, int ldr, int act,
                   float* partial_ws, size_t partial_ws_bytes, int force_block_n, int force_splits,
-                  int force_occupancy = 0, int force_kb_per_stage = 0);
+                  int force_occupancy = 0, int force_kb_per_stage = 0, int force_halo = 0);
 int launch_gemm_op(const GemmOp& op, cudaStream_t st);
 int gemm_init();  // sets func attributes; call once per process after a device is selected
 

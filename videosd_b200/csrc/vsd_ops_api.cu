@@ -92,8 +92,11 @@ int vsd_op_conv_gemm(const void* x, int nb, int h, int w, int c, int ldx, int ta
     if (rc) return rc;
     GemmOp op;
     ActView a{x, nb, h, w, c, ldx};
+    // test knob: act bit 8 requests the 3x3 halo mode
+    const int want_halo = (act & 256) ? 1 : 0;
+    act &= ~256;
     rc = build_gemm_op(&op, a, taps, reinterpret_cast<const bf16*>(wt), n, taps * c, out, ldo, out_f32, bias, rowvec,
-                       reinterpret_cast<const bf16*>(residual), ldr, act, g_ws, g_ws_bytes, block_n, splits);
+                       reinterpret_cast<const bf16*>(residual), ldr, act, g_ws, g_ws_bytes, block_n, splits, 0, 0, want_halo);
     if (rc) return rc;
     return launch_gemm_op(op, reinterpret_cast<cudaStream_t>(stream));
 }
