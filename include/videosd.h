@@ -80,6 +80,13 @@ int vsd_op_im2col_s2(const void* x, int ldx, void* y, int nb, int hi, int wi, in
  * wt: dev fp32 [cout][3][3][cin]. y: dev bf16. */
 int vsd_op_conv3x3_small_cin(const void* x, int x_kind, int nb, int h, int w, int cin, const float* wt,
                              const float* bias, void* y, int ldy, int cout, int relu, void* stream);
+/* Sobel edge map -> ControlNet control image (diffusert/lcm/canny_gpu.py:27-44 + lcm_controlnet.py:218-248).
+ * rgb: dev u8 [nb][h][w][3]; mag: dev fp32 scratch [nb][h][w]; maxbits: dev u32 [nb]; control: dev fp32 [nb][h][w][3]. */
+int vsd_op_sobel_control(const uint8_t* rgb, float* mag, unsigned int* maxbits, float* control, int nb, int h, int w,
+                         float low, float high, void* stream);
+/* Direct 3x3 conv (pad 1, stride 1|2) + optional SiLU for narrow layers (ControlNetConditioningEmbedding). bf16 NHWC. */
+int vsd_op_conv3x3_direct(const void* x, int ldx, int nb, int hi, int wi, int cin, const void* wt, const float* bias, void* y,
+                          int ldy, int cout, int stride, int silu, void* stream);
 /* LCMScheduler_X.add_noise (lcm_controlnet.py:1046-1071) and .step (:948-1043) on fp32 latents. */
 int vsd_op_add_noise(const float* x0, const float* noise, float* out, float sqrt_alpha, float sqrt_one_minus_alpha,
                      long n, void* stream);
@@ -128,6 +135,11 @@ int vsd_configure(vsd_ctx* ctx, int batch, int height, int width);
  *   embedding (:347-368); has_step_noise = len(timesteps) > 1 (:1032). Builds the launch plan. */
 int vsd_set_schedule(vsd_ctx* ctx, int steps, const int* timesteps, const float* scalars, float add_noise_a,
                      float add_noise_b, const float* w_embedding256, int has_step_noise);
+
+/* ControlNet branch (the reference runs it before every UNet pass, lcm_controlnet.py:558-566,
+ * on the Sobel edge map of the frame, videopipeline.py:109). Needs "controlnet.*" weights (diffusers ControlNetModel names).
+ * scales13 = logspace(-1,0,13) * controlnet_scale (guess mode). Toggling `enabled` requires vsd_set_schedule again. */
+int vsd_set_controlnet(vsd_ctx* ctx, int enabled, const float* scales13);
 
 /* Prompt context (CLIP last_hidden_state, 77 x 768 fp32, host) for batch slot `slot`; projects it through every
  * cross-attention to_k / to_v once (the reference recomputes them every step of every frame, lcm_controlnet.py:449). */

@@ -6,6 +6,7 @@ of diffusert/videopipeline.py:75-128, with the reference's RNG order on a CPU de
              init noise  = randn(B,4,h,w)                            (lcm_controlnet.py:331, generator not forwarded)
              step i noise = randn(B,4,h,w) inside scheduler.step     (:1033), drawn on every step incl. the last
 """
+import numpy as np
 import torch
 
 from . import imageproc
@@ -24,10 +25,11 @@ def frame_noise(batch, h8, w8, num_timesteps):
 
 @torch.no_grad()
 def lcm_img2img(unet, vae, rgb_u8, context, steps=4, strength=0.5, guidance_scale=7.5, noise=None, taps=None,
-                device="cpu"):
+                device="cpu", controlnet=None, controlnet_scale=1.0):
     """rgb_u8: (B,H,W,3) u8 (already cropped/resized to the working size). context: (B,77,768) fp32.
     Returns dict with 'image' (B,3,H,W) fp32, 'rgb' (B,H,W,3) u8, 'latents' (list per step), 'denoised'.
     `device` only moves the fp32 module math (tests run the checker on the GPU for speed); RNG stays on the CPU."""
+    rgb_u8 = np.asarray(rgb_u8)
     x = imageproc.preprocess(rgb_u8).to(device)                       # :457
     context = context.to(device)
     B, _, H, W = x.shape
@@ -45,11 +47,20 @@ def lcm_img2img(unet, vae, rgb_u8, context, steps=4, strength=0.5, guidance_scal
     w_emb = w_embedding(w, 256).to(device)                             # :517-520
     out = {"timesteps": timesteps.tolist(), "init_latents": init_latents, "noisy_latents": latents, "latents": [],
            "eps": [], "denoised_steps": [], "latents_in": []}
+    control = None
+    if controlnet is not None:                                         # videopipeline.py:109, lcm_controlnet.py:459-469
+        from .controlnet import control_image_tensor, sobel_edges
+        control = torch.cat([control_image_tensor(sobel_edges(rgb_u8[b])) for b in range(B)], 0).to(device)
+        out["control"] = control
     denoised = None
     for i, t in enumerate(timesteps):                                  # :532-582
         ts = torch.full((B,), int(t), dtype=torch.long, device=device)
         out["latents_in"].append(latents)
-        eps = unet(latents, ts, w_emb, context)
+        if controlnet is not None:                                     # :553-566, guess_mode=True, keep = 1.0
+            down_res, mid_res = controlnet(latents, ts, context, control, conditioning_scale=controlnet_scale, guess_mode=True)
+            eps = unet(latents, ts, w_emb, context, down_res, mid_res)
+        else:
+            eps = unet(latents, ts, w_emb, context)
         latents, denoised = sched.step(eps, i, latents, step_noise[i] if step_noise else None)
         out["eps"].append(eps)
         out["latents"].append(latents)

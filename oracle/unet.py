@@ -243,7 +243,9 @@ class UNetLCM(nn.Module):
     def time_embed(self, timesteps, timestep_cond):
         return self.time_embedding(timestep_sinusoid(timesteps, self.widths[0]), timestep_cond)
 
-    def forward(self, sample, timesteps, timestep_cond, encoder_hidden_states):
+    def forward(self, sample, timesteps, timestep_cond, encoder_hidden_states, down_residuals=None, mid_residual=None):
+        """down_residuals / mid_residual: ControlNet outputs added to the 12 skips and to the mid-block output
+        (diffusers UNet2DConditionModel.forward: down_block_additional_residuals / mid_block_additional_residual)."""
         emb = self.time_embed(timesteps, timestep_cond)
         # nearest-2x only reproduces the skip sizes when H, W are multiples of 2^3 (forward_upsample_size)
         need_sizes = any(s % 8 != 0 for s in sample.shape[-2:])
@@ -253,6 +255,10 @@ class UNetLCM(nn.Module):
             x, outs = blk(x, emb, encoder_hidden_states)
             skips += outs
         x = self.mid_block(x, emb, encoder_hidden_states)
+        if down_residuals is not None:
+            skips = [s_ + r_ for s_, r_ in zip(skips, down_residuals)]
+        if mid_residual is not None:
+            x = x + mid_residual
         for i, blk in enumerate(self.up_blocks):
             n = len(blk.resnets)
             size = None

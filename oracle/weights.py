@@ -64,3 +64,18 @@ def random_context(batch=1, seed=7):
     """Stand-in for CLIPTextModel.last_hidden_state (B,77,768): the pipeline accepts prompt_embeds
     (lcm_controlnet.py:394, :143); no tokenizer vocabulary is available offline."""
     return torch.randn((batch, 77, 768), generator=torch.Generator().manual_seed(seed))
+
+
+def build_controlnet(seed=9876):
+    """Seeded random init; the (in real checkpoints zero-initialised) output convolutions keep their random values so
+    that the ControlNet actually perturbs the UNet in the parity tests."""
+    from .controlnet import ControlNetOracle
+
+    prev = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    net = ControlNetOracle().eval()
+    _perturb_norms(net, torch.Generator().manual_seed(seed + 1))
+    torch.random.set_rng_state(prev)
+    for p in net.parameters():
+        p.requires_grad_(False)
+    return net

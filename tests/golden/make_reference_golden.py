@@ -9,6 +9,9 @@ the base classes / helpers the file imports, then:
   2. runs the reference's own `LatentConsistencyModelPipeline_controlnet.__call__` control flow (prompt_embeds path,
      ControlNet stub returning zero residuals) over the oracle's restated UNet / TAESD modules with
      the RNG reset of diffusert/videopipeline.py:126                      -> pins oracle/pipeline.py sequencing + RNG order
+  3. runs the reference's own `SobelOperator` (lcm/canny_gpu.py, importable as is) and the same `__call__` with the
+     oracle's restated ControlNetModel plugged in (conditioning scale 0.7, guess mode, per-step keep)
+                                                                          -> pins oracle/controlnet.py sobel_edges + the ControlNet call sequencing
 
 What this does NOT pin: the arithmetic inside UNet2DConditionModel / AutoencoderTiny / VaeImageProcessor, which lives in
 the absent third-party package (those restatements are checked by parameter-count and key-name identities only).
@@ -246,6 +249,60 @@ def main():
     for i, (lat, ts, eps) in enumerate(ua.calls):
         out[f"pipe_latents_in_{i}"] = lat.numpy()
         out[f"pipe_eps_{i}"] = eps.numpy()
+    # ---------------------------------------------------------------- 3. Sobel operator + __call__ with a real ControlNet
+    # (SURVEY.md 8(f) next-row #1). canny_gpu.py is importable as is (torch / torchvision / PIL only).
+    spec = importlib.util.spec_from_file_location("ref_canny_gpu", "/root/reference/diffusert/lcm/canny_gpu.py")
+    canny = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(canny)
+    sobel = canny.SobelOperator(device="cpu")
+    y2, u2, v2 = imageproc.synthetic_frame(96, 128, seed=9)
+    rgb2 = imageproc.yuv420_to_rgb(y2, u2, v2)
+    out["sobel_rgb_in"] = rgb2
+    out["sobel_out"] = np.array(sobel(PIL.Image.fromarray(rgb2), 0.11, 0.8))        # videopipeline.py:109
+    out["sobel_out_64"] = np.array(sobel(img, 0.11, 0.8))
+
+    from oracle.weights import build_controlnet
+    cn = build_controlnet()
+
+    class ControlNetAdapter(diffusers.ControlNetModel):
+        """diffusers ControlNetModel call signature (lcm_controlnet.py:558-566) over the oracle's restated module."""
+
+        def __init__(self, net):
+            super().__init__()
+            self.net = net
+            self.calls = []
+
+        def forward(self, sample, ts, encoder_hidden_states=None, controlnet_cond=None, conditioning_scale=1.0,
+                    guess_mode=False, return_dict=False):
+            self.calls.append((float(conditioning_scale), bool(guess_mode), controlnet_cond.clone()))
+            return self.net(sample, ts, encoder_hidden_states, controlnet_cond, conditioning_scale, guess_mode)
+
+    class UNetAdapterCN(UNetAdapter):
+        def forward(self, sample, ts, timestep_cond=None, encoder_hidden_states=None, cross_attention_kwargs=None,
+                    down_block_additional_residuals=None, mid_block_additional_residual=None, return_dict=False):
+            o = self.net(sample, ts, timestep_cond, encoder_hidden_states, down_block_additional_residuals,
+                         mid_block_additional_residual)
+            self.calls.append((sample.clone(), ts.clone(), o.clone()))
+            return (o,)
+
+    ua2 = UNetAdapterCN(unet)
+    cna = ControlNetAdapter(cn)
+    pipe2 = ref.LatentConsistencyModelPipeline_controlnet(
+        vae=VaeAdapter(vae), text_encoder=None, tokenizer=None, controlnet=cna, unet=ua2, scheduler=None,
+        safety_checker=None, feature_extractor=None)
+    canny_image = sobel(img, 0.11, 0.8)
+    np.random.seed(42)
+    torch.manual_seed(42).set_state(cpu_state)
+    res2 = pipe2(prompt=None, prompt_embeds=ctx, height=H, width=W, num_inference_steps=4, image=img,
+                 control_image=canny_image, controlnet_conditioning_scale=0.7, generator=None, strength=0.5)
+    out["cn_scale"] = np.array([0.7])
+    out["cn_rgb_out"] = np.array(res2.images[0])
+    out["cn_control"] = cna.calls[0][2].numpy()
+    out["cn_call_scales"] = np.array([c[0] for c in cna.calls])
+    out["cn_guess_mode"] = np.array([c[1] for c in cna.calls])
+    for i, (lat, ts, eps) in enumerate(ua2.calls):
+        out[f"cn_latents_in_{i}"] = lat.numpy()
+        out[f"cn_eps_{i}"] = eps.numpy()
     np.savez_compressed(os.path.join(HERE, "reference_golden.npz"), **out)
     print("wrote reference_golden.npz:", {k: getattr(v, "shape", None) for k, v in out.items() if k.startswith("pipe")})
 

@@ -151,3 +151,51 @@ def test_dropin_boundary_pil_in_pil_out(setup):
     assert out.size == (256, 256) and out.mode == "RGB"
     assert np.array_equal(np.asarray(out), np.asarray(out2))          # same (frame, options) -> same output
     assert np.asarray(out).std() > 1.0
+
+
+def test_controlnet_branch_frame_and_reference_golden(setup, golden):
+    """SURVEY.md 8(f) next-row #1: Sobel control image + ControlNet residuals every step (guess mode, scale 0.7)."""
+    from oracle import imageproc, pipeline
+    from oracle.weights import build_controlnet, random_context
+
+    eng, ug, vg = setup
+    cn = build_controlnet()
+    eng.load_state_dict("controlnet", cn.state_dict())
+    cg = cn.cuda()
+    try:
+        # (a) committed vectors from the reference's own __call__ with the ControlNet plugged in (64x64)
+        rgb = np.ascontiguousarray(golden["pipe_rgb_in"])
+        eng.configure(1, 64, 64)
+        eng.set_controlnet(True, float(golden["cn_scale"][0]))
+        assert eng.set_schedule(0.5, 4) == golden["pipe_timesteps"].tolist()
+        eng.set_context(0, random_context(1, seed=int(golden["pipe_ctx_seed"][0]))[0])
+        eng.set_reference_noise()
+        out = np.empty_like(rgb)
+        eng.infer_rgb(rgb, out)           # also fills the control front end used by debug_unet below
+        assert psnr(out, golden["cn_rgb_out"]) >= 40.0
+        for i in range(4):
+            eps = eng.debug_unet(torch.from_numpy(golden[f"cn_latents_in_{i}"]), i)
+            assert rel(eps, torch.from_numpy(golden[f"cn_eps_{i}"])) < 2e-2, i
+        # (b) 256x256 frame against the oracle, and the scale really matters
+        H = W = 256
+        ctx = random_context(1, seed=5)
+        eng.configure(1, H, W)
+        eng.set_controlnet(True, 1.3)
+        eng.set_schedule(0.5, 4)
+        eng.set_context(0, ctx[0])
+        eng.set_reference_noise()
+        y, u, v = imageproc.synthetic_frame(H, W, seed=21)
+        rgb = imageproc.yuv420_to_rgb(y, u, v)[None]
+        ref = pipeline.lcm_img2img(ug, vg, rgb, ctx, steps=4, strength=0.5, device="cuda", controlnet=cg, controlnet_scale=1.3)
+        out = np.empty_like(rgb)
+        eng.infer_rgb(np.ascontiguousarray(rgb), out)
+        for i in range(4):
+            assert rel(eng.debug_read("latents", i), ref["latents"][i]) < 2e-2, i
+        assert psnr(out, ref["rgb"]) >= 40.0
+        eng.set_controlnet(True, 0.2)     # scale change only: no plan rebuild, different result
+        out2 = np.empty_like(rgb)
+        eng.infer_rgb(np.ascontiguousarray(rgb), out2)
+        assert not np.array_equal(out, out2)
+    finally:
+        eng.set_controlnet(False, 1.0)
+        cn.cpu()

@@ -87,6 +87,9 @@ def test_weight_tables_equal_oracle_modules():
     assert u == {k: tuple(v) for k, v in weights.unet_param_shapes().items()}
     t = {k: tuple(v.shape) for k, v in TAESD().state_dict().items()}
     assert t == {k: tuple(v) for k, v in weights.taesd_param_shapes().items()}
+    from oracle.controlnet import ControlNetOracle
+    c = {k: tuple(v.shape) for k, v in ControlNetOracle().state_dict().items()}
+    assert c == {k: tuple(v) for k, v in weights.controlnet_param_shapes().items()}
     sd = weights.random_state_dict(weights.taesd_param_shapes(), 1)
     sd2 = weights.random_state_dict(weights.taesd_param_shapes(), 1)
     assert all(torch.equal(sd[k], sd2[k]) for k in sd)

@@ -153,3 +153,31 @@ def test_yuv_rgb_round_trip_property():
     assert np.abs(y2.astype(int) - y.astype(int)).max() <= 2       # integer matrices invert to within rounding
     assert np.abs(u2.astype(int) - u.astype(int)).max() <= 2 and np.abs(v2.astype(int) - v.astype(int)).max() <= 2
     assert y.min() >= 16 and y.max() <= 235
+
+
+# ------------------------------------------------------------------ ControlNet row
+def test_controlnet_structure_and_reference_golden(golden, oracle_models):
+    from oracle.controlnet import sobel_edges
+    from oracle.weights import build_controlnet
+
+    cn = build_controlnet()
+    assert sum(p.numel() for p in cn.parameters()) == 361_279_120          # Appendix A.6
+    keys = set(cn.state_dict().keys())
+    for k in ["controlnet_cond_embedding.conv_in.weight", "controlnet_cond_embedding.blocks.5.bias",
+              "controlnet_cond_embedding.conv_out.weight", "controlnet_down_blocks.11.weight", "controlnet_mid_block.bias",
+              "down_blocks.2.attentions.1.transformer_blocks.0.attn2.to_v.weight", "mid_block.resnets.1.conv2.bias"]:
+        assert k in keys, k
+    assert "time_embedding.cond_proj.weight" not in keys and not any(k.startswith("up_blocks") for k in keys)
+    # Sobel: bit-exact against the output of the reference's own SobelOperator (lcm/canny_gpu.py)
+    assert np.array_equal(np.array(sobel_edges(golden["sobel_rgb_in"])), golden["sobel_out"])
+    assert np.array_equal(np.array(sobel_edges(golden["pipe_rgb_in"])), golden["sobel_out_64"])
+    # the reference __call__ with the ControlNet plugged in: conditioning scale passed through, guess mode on every step
+    assert golden["cn_call_scales"].tolist() == [0.7] * 4 and golden["cn_guess_mode"].all()
+    unet, vae = oracle_models
+    out = pipeline.lcm_img2img(unet, vae, golden["pipe_rgb_in"][None], random_context(1, seed=int(golden["pipe_ctx_seed"][0])),
+                               steps=4, strength=0.5, controlnet=cn, controlnet_scale=float(golden["cn_scale"][0]))
+    np.testing.assert_allclose(out["control"].numpy(), golden["cn_control"], rtol=0, atol=0)
+    for i in range(4):
+        np.testing.assert_allclose(out["latents_in"][i].numpy(), golden[f"cn_latents_in_{i}"], rtol=0, atol=2e-4)
+        np.testing.assert_allclose(out["eps"][i].numpy(), golden[f"cn_eps_{i}"], rtol=0, atol=2e-4)
+    assert np.abs(out["rgb"][0].astype(int) - golden["cn_rgb_out"].astype(int)).max() <= 1

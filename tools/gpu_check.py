@@ -376,6 +376,34 @@ def check_misc():
     run("colour", colour)
 
 
+def check_controlnet():
+    import numpy as np
+
+    def sobel():
+        gold = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
+                                    "reference_golden.npz"))
+        rgb = torch.from_numpy(gold["sobel_rgb_in"])[None].to(DEV)
+        ctl = ops.sobel_control(rgb)
+        got = (ctl[0, :, :, 0] * 255).round().cpu().numpy().astype(int)
+        ref = gold["sobel_out"].astype(int)      # produced by the reference's SobelOperator
+        d = np.abs(got - ref)
+        record("sobel_vs_reference_golden_maxdiff", float(d.max()), 1.0, {"mismatch_frac": float((d > 0).mean())})
+        record("sobel_vs_reference_golden_mismatch_frac", float((d > 0).mean()), 1e-3)
+        assert torch.equal(ctl[..., 0], ctl[..., 1]) and torch.equal(ctl[..., 0], ctl[..., 2])
+    run("sobel", sobel)
+
+    def direct():
+        for (h, w, cin, cout, stride) in [(64, 64, 16, 16, 1), (64, 96, 16, 32, 2), (33, 47, 32, 96, 2), (32, 32, 96, 96, 1), (32, 32, 96, 256, 2)]:
+            x = randn((2, h, w, cin), 201).bfloat16()
+            wt = randn((cout, 9 * cin), 202, scale=(9 * cin) ** -0.5).bfloat16()
+            b = randn((cout,), 203)
+            y = ops.conv3x3_direct(x, wt, b, stride, True)
+            ref = torch.nn.functional.silu(torch.nn.functional.conv2d(
+                x.float().permute(0, 3, 1, 2), wt.float().view(cout, 3, 3, cin).permute(0, 3, 1, 2), b, stride=stride, padding=1)).permute(0, 2, 3, 1)
+            record(f"direct_conv_{h}x{w}_{cin}_{cout}_s{stride}", rel_err(y, ref), 5e-3)
+    run("direct_conv", direct)
+
+
 def main():
     which = sys.argv[1:] or ["gemm"]
     tag = "_".join(which)

@@ -40,17 +40,27 @@ def main():
     H, W = parts[0], parts[1]
     B = parts[2] if len(parts) > 2 else 1
     do_time = "--no-time" not in sys.argv
+    use_cn = "--controlnet" in sys.argv
+    cn_scale = 0.7
     rep = {"H": H, "W": W, "B": B}
     t0 = time.time()
     unet, vae = build_unet(), build_taesd()
+    cn = None
+    if use_cn:
+        from oracle.weights import build_controlnet
+        cn = build_controlnet()
     ctx = random_context(B)
     print(f"oracle built in {time.time()-t0:.1f}s", flush=True)
     eng = Engine(0)
     t0 = time.time()
     eng.load_state_dict("unet", unet.state_dict())
     eng.load_state_dict("vae", vae.state_dict())
+    if use_cn:
+        eng.load_state_dict("controlnet", cn.state_dict())
     print(f"weights loaded in {time.time()-t0:.1f}s", flush=True)
     eng.configure(B, H, W)
+    if use_cn:
+        eng.set_controlnet(True, cn_scale)
     ts = eng.set_schedule(0.5, 4)
     for b in range(B):
         eng.set_context(b, ctx[b])
@@ -62,14 +72,19 @@ def main():
         f.write(eng.tuning_report())
 
     unet_g, vae_g = unet.cuda(), vae.cuda()
+    cn_g = cn.cuda() if use_cn else None
     frames = [imageproc.synthetic_frame(H, W, seed=b, shift=17 * b) for b in range(B)]
     y = np.stack([f[0] for f in frames]); u = np.stack([f[1] for f in frames]); v = np.stack([f[2] for f in frames])
     rgb = np.stack([imageproc.yuv420_to_rgb(*f) for f in frames])
     t0 = time.time()
-    ref = pipeline.lcm_img2img(unet_g, vae_g, rgb, ctx, steps=4, strength=0.5, device="cuda")
+    ref = pipeline.lcm_img2img(unet_g, vae_g, rgb, ctx, steps=4, strength=0.5, device="cuda", controlnet=cn_g,
+                               controlnet_scale=cn_scale)
     torch.cuda.synchronize()
     print(f"oracle (fp32 on GPU) frame in {time.time()-t0:.2f}s", flush=True)
 
+    if use_cn:   # the control front end runs inside the frame plan: run one frame so its buffers are valid
+        _y = np.empty_like(y); _u = np.empty_like(u); _v = np.empty_like(v)
+        eng.infer_yuv420(y, u, v, _y, _u, _v)
     # ---- teacher-forced per-step parity: same input latents to both UNets
     sched = LCMSchedulerOracle(); sched.set_timesteps(0.5, 4)
     _, step_noise = pipeline.frame_noise(B, H // 8, W // 8, 4)

@@ -503,7 +503,8 @@ template <int CIN>
 __global__ void __launch_bounds__(128)
 conv3x3_small_cin_kernel(const void* __restrict__ xin, int x_kind, int NB, int H, int W,
                          const float* __restrict__ w, const float* __restrict__ bias,
-                         bf16* __restrict__ y, int ldy, int Cout, int relu) {
+                         bf16* __restrict__ y, int ldy, int Cout, int relu /*0 none, 1 ReLU, 2 SiLU*/,
+                         const bf16* __restrict__ res, int ldr) {
     pdl_launch_dependents();
     pdl_wait();
     constexpr int K = 9 * CIN;
@@ -563,7 +564,8 @@ conv3x3_small_cin_kernel(const void* __restrict__ xin, int x_kind, int NB, int H
                 a = fmaf(patch[k4 * 4 + 2], ww4.z, a);
                 a = fmaf(patch[k4 * 4 + 3], ww4.w, a);
             }
-            acc[j] = relu ? fmaxf(a, 0.f) : a;
+            if (res) a += __bfloat162float(res[pix * ldr + co0 + c8 + j]);
+            acc[j] = relu == 1 ? fmaxf(a, 0.f) : (relu == 2 ? __fdividef(a, 1.0f + __expf(-a)) : a);
         }
         if (c8 + 8 <= nco) {
             *reinterpret_cast<uint4*>(out + c8) = pack8(acc);
@@ -574,16 +576,158 @@ conv3x3_small_cin_kernel(const void* __restrict__ xin, int x_kind, int NB, int H
 }
 
 int launch_conv3x3_small_cin(const void* x, int x_kind, int NB, int H, int W, int Cin, const float* w, const float* bias,
-                             bf16* y, int ldy, int Cout, int relu, cudaStream_t st) {
+                             bf16* y, int ldy, int Cout, int relu, cudaStream_t st, const bf16* res, int ldr) {
     VSD_REQUIRE(Cin >= 1 && Cin <= 4 && ldy % 8 == 0 && Cout % 8 == 0, "small-Cin conv: Cin<=4, Cout%8==0");
     VSD_REQUIRE(x_kind != 1 || Cin == 3, "u8 input implies 3 channels");
     const long pixels = (long)NB * H * W;
     dim3 grid((unsigned)((pixels + 127) / 128), (Cout + 63) / 64);
-    if (Cin == 3) VSD_CHECK_CUDA(launch_k(conv3x3_small_cin_kernel<3>, dim3(grid), dim3(128), 0, st, x, x_kind, NB, H, W, w, bias, y, ldy, Cout, relu));
-    else if (Cin == 4) VSD_CHECK_CUDA(launch_k(conv3x3_small_cin_kernel<4>, dim3(grid), dim3(128), 0, st, x, x_kind, NB, H, W, w, bias, y, ldy, Cout, relu));
-    else if (Cin == 1) VSD_CHECK_CUDA(launch_k(conv3x3_small_cin_kernel<1>, dim3(grid), dim3(128), 0, st, x, x_kind, NB, H, W, w, bias, y, ldy, Cout, relu));
-    else VSD_CHECK_CUDA(launch_k(conv3x3_small_cin_kernel<2>, dim3(grid), dim3(128), 0, st, x, x_kind, NB, H, W, w, bias, y, ldy, Cout, relu));
+    if (Cin == 3) VSD_CHECK_CUDA(launch_k(conv3x3_small_cin_kernel<3>, dim3(grid), dim3(128), 0, st, x, x_kind, NB, H, W, w, bias, y, ldy, Cout, relu, res, ldr));
+    else if (Cin == 4) VSD_CHECK_CUDA(launch_k(conv3x3_small_cin_kernel<4>, dim3(grid), dim3(128), 0, st, x, x_kind, NB, H, W, w, bias, y, ldy, Cout, relu, res, ldr));
+    else if (Cin == 1) VSD_CHECK_CUDA(launch_k(conv3x3_small_cin_kernel<1>, dim3(grid), dim3(128), 0, st, x, x_kind, NB, H, W, w, bias, y, ldy, Cout, relu, res, ldr));
+    else VSD_CHECK_CUDA(launch_k(conv3x3_small_cin_kernel<2>, dim3(grid), dim3(128), 0, st, x, x_kind, NB, H, W, w, bias, y, ldy, Cout, relu, res, ldr));
     VSD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ ControlNet front end
+// Sobel edge map of the (already resized) input frame: diffusert/lcm/canny_gpu.py:27-44.
+//   gray = PIL convert("L") = (19595 R + 38470 G + 7471 B + 0x8000) >> 16 ; ToTensor: /255
+//   magnitude = sqrt(gx^2 + gy^2) of the two 3x3 Sobel cross-correlations (zero padding); per-image maximum.
+__global__ void sobel_mag_kernel(const uint8_t* __restrict__ rgb, float* __restrict__ mag, unsigned int* __restrict__ maxbits,
+                                 int NB, int H, int W) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long total = (long)NB * H * W;
+    float local_max = 0.f;
+    int local_n = -1;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W), y = (int)((i / W) % H), n = (int)(i / ((long)W * H));
+        float g[3][3];
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int yy = y + dy, xx = x + dx;
+                float v = 0.f;
+                if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+                    const uint8_t* p = rgb + (((long)n * H + yy) * W + xx) * 3;
+                    const unsigned int l = (19595u * p[0] + 38470u * p[1] + 7471u * p[2] + 0x8000u) >> 16;
+                    v = __fdiv_rn((float)l, 255.0f);
+                }
+                g[dy + 1][dx + 1] = v;
+            }
+        const float gx = (g[0][2] - g[0][0]) + 2.0f * (g[1][2] - g[1][0]) + (g[2][2] - g[2][0]);
+        const float gy = (g[2][0] - g[0][0]) + 2.0f * (g[2][1] - g[0][1]) + (g[2][2] - g[0][2]);
+        const float m = sqrtf(gx * gx + gy * gy);
+        mag[i] = m;
+        if (n != local_n) {   // flush when the grid-stride loop crosses an image boundary
+            if (local_n >= 0) atomicMax(maxbits + local_n, __float_as_uint(local_max));
+            local_n = n;
+            local_max = 0.f;
+        }
+        local_max = fmaxf(local_max, m);
+    }
+    if (local_n >= 0) atomicMax(maxbits + local_n, __float_as_uint(local_max));   // non-negative floats order like uints
+}
+
+// edge / max -> double threshold -> ToPILImage (x255, truncate) -> control image: 3 equal channels, u8/255 (fp32 NHWC3)
+__global__ void sobel_threshold_kernel(const float* __restrict__ mag, const unsigned int* __restrict__ maxbits,
+                                       float* __restrict__ control, int NB, int H, int W, float low, float high) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long total = (long)NB * H * W;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int n = (int)(i / ((long)W * H));
+        float e = __fdiv_rn(mag[i], __uint_as_float(maxbits[n]));
+        if (e >= high) e = 1.0f;
+        if (e <= low) e = 0.0f;
+        const float q = __fdiv_rn((float)(unsigned char)(__fmul_rn(e, 255.0f)), 255.0f);
+        control[i * 3 + 0] = q; control[i * 3 + 1] = q; control[i * 3 + 2] = q;
+    }
+}
+
+int launch_sobel_control(const uint8_t* rgb, float* mag, unsigned int* maxbits, float* control, int NB, int H, int W,
+                         float low, float high, cudaStream_t st) {
+    VSD_CHECK_CUDA(cudaMemsetAsync(maxbits, 0, sizeof(unsigned int) * NB, st));
+    const long total = (long)NB * H * W;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    VSD_CHECK_CUDA(launch_k(sobel_mag_kernel, dim3(blocks), dim3(256), 0, st, rgb, mag, maxbits, NB, H, W));
+    VSD_CHECK_CUDA(launch_k(sobel_threshold_kernel, dim3(blocks), dim3(256), 0, st, (const float*)mag, (const unsigned int*)maxbits,
+                            control, NB, H, W, low, high));
+    return 0;
+}
+
+// Direct 3x3 convolution (pad 1, stride 1 or 2) + SiLU for the narrow layers of the ControlNet conditioning embedding
+// (16/32/96 channels: not multiples of 64, and run once per frame). bf16 NHWC in/out, weights bf16 [Cout][9][Cin].
+// One thread = one output pixel x 16 output channels; the 16 filters live in shared memory as fp32.
+__global__ void __launch_bounds__(128)
+conv3x3_direct_kernel(const bf16* __restrict__ x, int ldx, int NB, int Hi, int Wi, int Cin, const bf16* __restrict__ w,
+                      const float* __restrict__ bias, bf16* __restrict__ y, int ldy, int Ho, int Wo, int Cout, int stride,
+                      int silu) {
+    extern __shared__ float swd[];   // [16][9*Cin]
+    pdl_launch_dependents();
+    const int K = 9 * Cin;
+    const int co0 = blockIdx.y * 16;
+    for (int i = threadIdx.x; i < 16 * K; i += blockDim.x) {
+        const int co = i / K;
+        swd[i] = (co0 + co < Cout) ? __bfloat162float(w[(long)(co0 + co) * K + (i - co * K)]) : 0.f;
+    }
+    __syncthreads();
+    pdl_wait();
+    const long pix = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= (long)NB * Ho * Wo) return;
+    const int wo = (int)(pix % Wo), ho = (int)((pix / Wo) % Ho), n = (int)(pix / ((long)Wo * Ho));
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = (bias && co0 + j < Cout) ? bias[co0 + j] : 0.f;
+    for (int t = 0; t < 9; ++t) {
+        const int hi = ho * stride + t / 3 - 1, wi = wo * stride + t % 3 - 1;
+        if (hi < 0 || hi >= Hi || wi < 0 || wi >= Wi) continue;
+        const bf16* src = x + (((long)n * Hi + hi) * Wi + wi) * ldx;
+        for (int c = 0; c < Cin; c += 8) {
+            float f[8];
+            unpack8(*reinterpret_cast<const uint4*>(src + c), f);
+            const float* wr = swd + t * Cin + c;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float4 w0 = *reinterpret_cast<const float4*>(wr + j * K), w1 = *reinterpret_cast<const float4*>(wr + j * K + 4);
+                acc[j] = fmaf(f[0], w0.x, acc[j]); acc[j] = fmaf(f[1], w0.y, acc[j]);
+                acc[j] = fmaf(f[2], w0.z, acc[j]); acc[j] = fmaf(f[3], w0.w, acc[j]);
+                acc[j] = fmaf(f[4], w1.x, acc[j]); acc[j] = fmaf(f[5], w1.y, acc[j]);
+                acc[j] = fmaf(f[6], w1.z, acc[j]); acc[j] = fmaf(f[7], w1.w, acc[j]);
+            }
+        }
+    }
+    bf16* out = y + pix * ldy + co0;
+    float o8[8];
+#pragma unroll
+    for (int h8 = 0; h8 < 2; ++h8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float a = acc[h8 * 8 + j];
+            o8[j] = silu ? __fdividef(a, 1.0f + __expf(-a)) : a;
+        }
+        if (co0 + h8 * 8 + 8 <= Cout) *reinterpret_cast<uint4*>(out + h8 * 8) = pack8(o8);
+    }
+}
+
+int launch_conv3x3_direct(const bf16* x, int ldx, int NB, int Hi, int Wi, int Cin, const bf16* w, const float* bias, bf16* y,
+                          int ldy, int Cout, int stride, int silu, cudaStream_t st) {
+    VSD_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && (stride == 1 || stride == 2),
+                "direct conv: channels % 8 == 0, stride 1 or 2");
+    const int Ho = (Hi - 1) / stride + 1, Wo = (Wi - 1) / stride + 1;
+    const size_t smem = (size_t)16 * 9 * Cin * sizeof(float);
+    VSD_REQUIRE(smem <= 96 * 1024, "direct conv: too many input channels");
+    static bool attr_set = false;
+    if (!attr_set) {
+        VSD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_set = true;
+    }
+    const long pixels = (long)NB * Ho * Wo;
+    dim3 grid((unsigned)((pixels + 127) / 128), (Cout + 15) / 16);
+    VSD_CHECK_CUDA(launch_k(conv3x3_direct_kernel, grid, dim3(128), smem, st, x, ldx, NB, Hi, Wi, Cin, w, bias, y, ldy, Ho, Wo,
+                            Cout, stride, silu));
     return 0;
 }
 

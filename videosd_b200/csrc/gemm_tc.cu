@@ -68,6 +68,11 @@ __device__ __forceinline__ void epilogue_store32(const GemmParams& p, float (&v)
                 if (j < ncols) v[j] += __ldg(rv + j);
         }
     }
+    if (p.out_scale) {
+        const float sc = __ldg(p.out_scale);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= sc;
+    }
     if (p.residual) {
         const bf16* r = p.residual + grow * p.ldr + col;
         if (rpre || (full && ((p.ldr & 7) == 0) && ((col & 7) == 0))) {
@@ -453,6 +458,7 @@ __global__ void splitk_reduce_kernel(const GemmParams p, long rows) {
         if (j < ncols) {
             if (p.bias) v[j] += __ldg(p.bias + col + j);
             if (p.rowvec) v[j] += __ldg(p.rowvec + (long)n_img * p.N + col + j);
+            if (p.out_scale) v[j] *= __ldg(p.out_scale);
             if (p.residual) v[j] += __bfloat162float(p.residual[grow * p.ldr + col + j]);
             if (p.relu) v[j] = fmaxf(v[j], 0.f);
         }

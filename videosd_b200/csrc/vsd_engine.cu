@@ -132,6 +132,9 @@ struct Engine {
     std::unordered_map<std::string, Tuned> tuned;
     void* flush_buf = nullptr; size_t flush_bytes = 0;
     unsigned int* gn_sync = nullptr;   // grid-barrier state for the fused GroupNorm kernel (never reused memory)
+    // ControlNet: canny/Sobel-conditioned residuals added to the UNet skips every step
+    bool cn_enabled = false;
+    float* cn_scales = nullptr;        // device [13]: logspace(-1,0,13) * conditioning scale (guess mode)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     long launches_per_frame_yuv = 0;
     std::string err;
@@ -395,7 +398,7 @@ struct Builder {
 
     // out = epilogue(conv/linear(a)); `a` may be any NHWC view, `o` any view with o.c == N (or N/2 for GEGLU)
     void gemm(const ActView& a, int taps, const bf16* wt, int N, int ldw, void* outp, int ldo, int out_f32,
-              const float* bias, const float* rowvec, const bf16* res, int ldr, int act) {
+              const float* bias, const float* rowvec, const bf16* res, int ldr, int act, const float* out_scale = nullptr) {
         if (rc) return;
         GemmOp op;
         int fbn = 0, fsp = 0, focc = 0, fkbs = 0, fhalo = 0;
@@ -415,6 +418,7 @@ struct Builder {
         int r = build_gemm_op(&op, a, taps, wt, N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act, e->splitk_ws,
                               e->splitk_bytes, fbn, fsp, focc, fkbs, fhalo);
         if (r) { rc = r; fail = get_error(); return; }
+        op.p.out_scale = out_scale;
         out->push_back(mk([op](cudaStream_t st) { return launch_gemm_op(op, st); }, "gemm"));
     }
     void conv(const View& x, const std::string& name, int taps, const View& o, const float* rowvec, const View* res,
@@ -572,7 +576,8 @@ struct UNetStatic {
 };
 
 // Emits one UNet pass: eps(fp32 [NB,h8,w8,4]) = UNet(latents fp32, temb of step `si`).
-static void build_unet(Builder& B, const float* latents, float* eps_out, int si, UNetStatic& S) {
+static void build_unet(Builder& B, const float* latents, float* eps_out, int si, UNetStatic& S,
+                       const std::function<void(const std::function<View(int)>&, const View&)>& after_mid = nullptr) {
     Engine* e = B.e;
     const int NB = e->NB;
     const int widths[4] = {320, 640, 1280, 1280};
@@ -643,6 +648,7 @@ static void build_unet(Builder& B, const float* latents, float* eps_out, int si,
         B.resnet(t, "unet.mid_block.resnets.1", temb("unet.mid_block.resnets.1"), h_view(0, 0));
         e->arena.release(m);
     }
+    if (after_mid) after_mid(skip_view, h_view(0, 0));   // ControlNet residuals are added to the 12 skips and the mid output here
     for (int i = 0; i < 4; ++i) {
         const std::string bp = "unet.up_blocks." + std::to_string(i);
         for (int j = 0; j < 3; ++j) {
@@ -760,6 +766,131 @@ static void build_taesd_decoder(Builder& B, const float* z, float* image_out /*[
            B.wf(p + std::to_string(layer) + ".bias"), nullptr, nullptr, 0, ACT_NONE);
 }
 
+// ------------------------------------------------------------------------------------------------ ControlNet
+// diffusers ControlNetModel, called by the reference before every UNet pass
+// (lcm_controlnet.py:558-566) on the Sobel edge map of the input frame (videopipeline.py:109, lcm/canny_gpu.py).
+struct CNStatic {
+    View feat[12];   // conv_in(+cond) output and the 11 down-block outputs (inputs of the 1x1 "zero" convolutions)
+    View mid;        // mid-block output
+    View cond;       // conditioning embedding [NB, h8, w8, 320], computed once per frame
+    float* control = nullptr;        // [NB, H, W, 3] fp32 control image in [0, 1]
+    float* mag = nullptr;            // [NB, H, W] Sobel magnitude
+    unsigned int* maxbits = nullptr; // [NB] per-image maximum (float bits)
+};
+
+// Once per frame: Sobel edge map of the RGB frame -> ControlNetConditioningEmbedding (3->16->16->32->32->96->96->256->320).
+static void build_control_frontend(Builder& B, const uint8_t* rgb, CNStatic& C) {
+    Engine* e = B.e;
+    const int NB = e->NB, H = e->H, W = e->W;
+    {
+        const CNStatic c = C;
+        B.out->push_back(mk([=](cudaStream_t st) {
+            return launch_sobel_control(rgb, c.mag, c.maxbits, c.control, NB, H, W, 0.11f, 0.8f, st);
+        }, "sobel"));
+    }
+    const std::string p = "controlnet.controlnet_cond_embedding.";
+    const size_t m = e->arena.mark();
+    View x = B.alloc(NB, H, W, 16);
+    {
+        const float* wt = B.wf(p + "conv_in.weight");
+        const float* b = B.wf(p + "conv_in.bias");
+        if (!B.rc) {
+            const View o = x;
+            const float* ctl = C.control;
+            B.out->push_back(mk([=](cudaStream_t st) {
+                return launch_conv3x3_small_cin(ctl, 0, o.nb, o.h, o.w, 3, wt, b, o.p, o.ld, 16, 2 /*SiLU*/, st);
+            }, "cond_conv_in"));
+        }
+    }
+    const int widths[4] = {16, 32, 96, 256};
+    int h = H, w = W;
+    for (int i = 0; i < 3; ++i) {
+        for (int half = 0; half < 2; ++half) {
+            const int cin = widths[i], cout = half ? widths[i + 1] : widths[i], stride = half ? 2 : 1;
+            const int ho = (h - 1) / stride + 1, wo = (w - 1) / stride + 1;
+            View y = B.alloc(NB, ho, wo, cout);
+            const std::string name = p + "blocks." + std::to_string(i * 2 + half);
+            const bf16* wt = B.wb(name + ".weight");
+            const float* b = B.wf(name + ".bias");
+            if (!B.rc) {
+                const View xi = x, yo = y;
+                B.out->push_back(mk([=](cudaStream_t st) {
+                    return launch_conv3x3_direct(xi.p, xi.ld, xi.nb, xi.h, xi.w, xi.c, wt, b, yo.p, yo.ld, yo.c, stride, 1, st);
+                }, "cond_conv"));
+            }
+            x = y; h = ho; w = wo;
+        }
+    }
+    if (!B.rc && (h != e->h8 || w != e->w8)) B.bad("conditioning embedding does not reach the latent resolution");
+    B.conv(x, p + "conv_out", 9, C.cond, nullptr, nullptr, ACT_NONE);
+    e->arena.release(m);
+}
+
+// One ControlNet pass at schedule step `si`: fills C.feat[0..11] and C.mid (pre zero-conv features).
+static void build_controlnet(Builder& B, const float* latents, int si, CNStatic& C) {
+    Engine* e = B.e;
+    const int widths[4] = {320, 640, 1280, 1280};
+    auto temb = [&](const std::string& resnet) -> const float* {
+        auto it = e->temb.find(resnet);
+        if (it == e->temb.end()) { B.bad("time embedding projection missing for " + resnet); return nullptr; }
+        return it->second[si];
+    };
+    int k = 0;
+    {   // conv_in(latents) + conditioning embedding
+        const float* w = B.wf("controlnet.conv_in.weight");
+        const float* b = B.wf("controlnet.conv_in.bias");
+        if (!B.rc) {
+            const View o = C.feat[0], cd = C.cond;
+            B.out->push_back(mk([=](cudaStream_t st) {
+                return launch_conv3x3_small_cin(latents, 0, o.nb, o.h, o.w, 4, w, b, o.p, o.ld, o.c, 0, st, cd.p, cd.ld);
+            }, "conv_in"));
+        }
+        k = 1;
+    }
+    View x = C.feat[0];
+    for (int i = 0; i < 4; ++i) {
+        const std::string bp = "controlnet.down_blocks." + std::to_string(i);
+        for (int j = 0; j < 2; ++j) {
+            const std::string rp = bp + ".resnets." + std::to_string(j);
+            if (i < 3) {
+                const size_t m = e->arena.mark();
+                View r = B.alloc(x.nb, x.h, x.w, widths[i]);
+                B.resnet(x, rp, temb(rp), r);
+                B.transformer(r, bp + ".attentions." + std::to_string(j), C.feat[k]);
+                e->arena.release(m);
+            } else {
+                B.resnet(x, rp, temb(rp), C.feat[k]);
+            }
+            x = C.feat[k++];
+        }
+        if (i < 3) {
+            B.conv_s2(x, bp + ".downsamplers.0.conv", C.feat[k], true);
+            x = C.feat[k++];
+        }
+    }
+    const size_t m = e->arena.mark();
+    View a = B.alloc(x.nb, x.h, x.w, 1280);
+    B.resnet(x, "controlnet.mid_block.resnets.0", temb("controlnet.mid_block.resnets.0"), a);
+    View t = B.alloc(x.nb, x.h, x.w, 1280);
+    B.transformer(a, "controlnet.mid_block.attentions.0", t);
+    B.resnet(t, "controlnet.mid_block.resnets.1", temb("controlnet.mid_block.resnets.1"), C.mid);
+    e->arena.release(m);
+}
+
+// skip_k += scale_k * (zero_conv_k(feat_k) + b_k), in place (lcm_controlnet.py:568-577: down_block_additional_residuals)
+static void build_controlnet_residuals(Builder& B, CNStatic& C, const std::function<View(int)>& skip_view, const View& mid_out) {
+    Engine* e = B.e;
+    Scope sc_("cn_residuals");
+    for (int k = 0; k < 12; ++k) {
+        const std::string n = "controlnet.controlnet_down_blocks." + std::to_string(k);
+        const View dst = skip_view(k);
+        B.gemm(C.feat[k].act(), 1, B.wb(n + ".weight"), dst.c, C.feat[k].c, dst.p, dst.ld, 0, B.wf(n + ".bias"), nullptr, dst.p, dst.ld,
+               ACT_NONE, e->cn_scales + k);
+    }
+    B.gemm(C.mid.act(), 1, B.wb("controlnet.controlnet_mid_block.weight"), mid_out.c, C.mid.c, mid_out.p, mid_out.ld, 0,
+           B.wf("controlnet.controlnet_mid_block.bias"), nullptr, mid_out.p, mid_out.ld, ACT_NONE, e->cn_scales + 12);
+}
+
 static int run_plan(const std::vector<Launch>& plan, cudaStream_t st) {
     for (const auto& l : plan) {
         int rc = l(st);
@@ -784,17 +915,22 @@ static const char* kResnetPrefixes[22] = {
     "unet.up_blocks.2.resnets.2", "unet.up_blocks.3.resnets.0", "unet.up_blocks.3.resnets.1",
     "unet.up_blocks.3.resnets.2"};
 
-static std::vector<std::string> transformer_prefixes() {
+static std::vector<std::string> transformer_prefixes(bool with_controlnet) {
     std::vector<std::string> v;
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 2; ++j)
-            v.push_back("unet.down_blocks." + std::to_string(i) + ".attentions." + std::to_string(j) + ".transformer_blocks.0");
-    v.push_back("unet.mid_block.attentions.0.transformer_blocks.0");
-    for (int i = 1; i < 4; ++i)
-        for (int j = 0; j < 3; ++j)
-            v.push_back("unet.up_blocks." + std::to_string(i) + ".attentions." + std::to_string(j) + ".transformer_blocks.0");
+    for (int m = 0; m < (with_controlnet ? 2 : 1); ++m) {
+        const std::string root = m == 0 ? "unet." : "controlnet.";
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 2; ++j)
+                v.push_back(root + "down_blocks." + std::to_string(i) + ".attentions." + std::to_string(j) + ".transformer_blocks.0");
+        v.push_back(root + "mid_block.attentions.0.transformer_blocks.0");
+        if (m == 0)
+            for (int i = 1; i < 4; ++i)
+                for (int j = 0; j < 3; ++j)
+                    v.push_back(root + "up_blocks." + std::to_string(i) + ".attentions." + std::to_string(j) + ".transformer_blocks.0");
+    }
     return v;
 }
+static bool has_controlnet_weights(const Engine* e) { return e->w.find("controlnet.conv_in.weight") != e->w.end(); }
 
 // (Re)allocates every buffer for a (batch, height, width) configuration. Plans are built by finalize().
 static int configure(Engine* e, int nb, int H, int W) {
@@ -828,7 +964,7 @@ static int configure(Engine* e, int nb, int H, int W) {
     e->t_emb_in = (float*)A.alloc(320 * 4); e->t_h = (float*)A.alloc(1280 * 4); e->t_emb = (float*)A.alloc(1280 * 4);
     ENG_REQUIRE(e->t_emb != nullptr, "arena too small for the static buffers");
     // cross-attention caches
-    for (const auto& tb : transformer_prefixes()) {
+    for (const auto& tb : transformer_prefixes(has_controlnet_weights(e))) {
         auto it = e->w.find(tb + ".attn2.to_q.weight");
         ENG_REQUIRE(it != e->w.end(), "load the UNet weights before configure(): " + tb);
         Engine::XAttn xa;
@@ -884,6 +1020,21 @@ static int set_schedule(Engine* e, int steps, const int* timesteps, const float*
     const float* b2 = need_f("unet.time_embedding.linear_2.bias");
     ENG_REQUIRE(w_cond && w1 && b1 && w2 && b2, "time_embedding weights missing");
     for (int r = 0; r < 22; ++r) e->temb[kResnetPrefixes[r]] = std::vector<float*>();
+    const bool use_cn = e->cn_enabled;
+    if (use_cn) ENG_REQUIRE(has_controlnet_weights(e), "ControlNet enabled but no controlnet.* weights are loaded");
+    std::vector<std::string> cn_resnets;
+    if (use_cn) {
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 2; ++j) cn_resnets.push_back("controlnet.down_blocks." + std::to_string(i) + ".resnets." + std::to_string(j));
+        cn_resnets.push_back("controlnet.mid_block.resnets.0");
+        cn_resnets.push_back("controlnet.mid_block.resnets.1");
+        for (auto& n : cn_resnets) e->temb[n] = std::vector<float*>();
+    }
+    const float* cw1 = use_cn ? need_f("controlnet.time_embedding.linear_1.weight") : nullptr;
+    const float* cb1 = use_cn ? need_f("controlnet.time_embedding.linear_1.bias") : nullptr;
+    const float* cw2 = use_cn ? need_f("controlnet.time_embedding.linear_2.weight") : nullptr;
+    const float* cb2 = use_cn ? need_f("controlnet.time_embedding.linear_2.bias") : nullptr;
+    if (use_cn) ENG_REQUIRE(cw1 && cb1 && cw2 && cb2, "controlnet.time_embedding weights missing");
     std::vector<float> sinus(320);
     for (int i = 0; i < steps; ++i) {
         // Timesteps(320, flip_sin_to_cos=True, freq_shift=0): [cos | sin], fp32
@@ -916,6 +1067,25 @@ static int set_schedule(Engine* e, int steps, const int* timesteps, const float*
             for (int b = 1; b < e->NB; ++b)
                 VSD_CHECK_CUDA(cudaMemcpyAsync(dst + (size_t)b * cout, dst, (size_t)cout * 4, cudaMemcpyDeviceToDevice, e->stream));
             e->temb[p].push_back(dst);
+        }
+        if (use_cn) {   // the ControlNet has its own time MLP (no guidance conditioning): emb = L2(SiLU(L1(sinusoid)))
+            rc = launch_gemv_f32(cw1, d_sin, cb1, e->t_h, 1280, 320, 0, 1, e->stream);
+            if (rc) return rc;
+            rc = launch_gemv_f32(cw2, e->t_h, cb2, e->t_emb, 1280, 1280, 0, 0, e->stream);
+            if (rc) return rc;
+            for (auto& p : cn_resnets) {
+                auto it = e->w.find(p + ".time_emb_proj.weight");
+                const float* pb = need_f(p + ".time_emb_proj.bias");
+                ENG_REQUIRE(it != e->w.end() && pb, "time_emb_proj missing: " + p);
+                const int cout = (int)it->second.shape[0];
+                float* dst = (float*)A.alloc((size_t)e->NB * cout * 4);
+                ENG_REQUIRE(dst != nullptr, "arena exhausted");
+                rc = launch_gemv_f32((const float*)it->second.p, e->t_emb, pb, dst, cout, 1280, 1, 0, e->stream);
+                if (rc) return rc;
+                for (int b = 1; b < e->NB; ++b)
+                    VSD_CHECK_CUDA(cudaMemcpyAsync(dst + (size_t)b * cout, dst, (size_t)cout * 4, cudaMemcpyDeviceToDevice, e->stream));
+                e->temb[p].push_back(dst);
+            }
         }
     }
     VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
@@ -956,6 +1126,25 @@ static int set_schedule(Engine* e, int steps, const int* timesteps, const float*
         // except the j == 2 skip of blocks 0..2, which is the *previous* level's downsampler output... check:
         // pop order: skip 11,10 (level 3 resnets), 9 (down of level 2 -> lives at level 3) => all level 3. OK.
     }
+    CNStatic CN;
+    if (use_cn) {
+        const int cn_c[12] = {320, 320, 320, 320, 640, 640, 640, 1280, 1280, 1280, 1280, 1280};
+        const int cn_l[12] = {0, 0, 0, 1, 1, 1, 2, 2, 2, 3, 3, 3};
+        for (int k = 0; k < 12; ++k) CN.feat[k] = B.alloc(e->NB, S.hs[cn_l[k]], S.ws[cn_l[k]], cn_c[k]);
+        CN.mid = B.alloc(e->NB, S.hs[3], S.ws[3], 1280);
+        CN.cond = B.alloc(e->NB, e->h8, e->w8, 320);
+        const size_t px = (size_t)e->NB * e->H * e->W;
+        CN.control = B.alloc_f32(px * 3);
+        CN.mag = B.alloc_f32(px);
+        CN.maxbits = reinterpret_cast<unsigned int*>(B.alloc_f32(64));
+        B.out = &e->plan_core;
+        const size_t fm = A.mark();
+        {
+            Scope sc_("control");
+            build_control_frontend(B, e->d_rgb_in, CN);
+        }
+        A.release(fm);
+    }
     const size_t unet_mark = A.mark();
     for (int i = 0; i < steps; ++i) {
         A.release(unet_mark);
@@ -964,7 +1153,17 @@ static int set_schedule(Engine* e, int steps, const int* timesteps, const float*
         const float* lat_in = (i == 0) ? e->noisy : e->lat[i - 1];
         {
             Scope sc_("step" + std::to_string(i));
-            build_unet(B, lat_in, e->eps[i], i, S);
+            if (use_cn) {
+                {
+                    Scope sc2_("cn");
+                    build_controlnet(B, lat_in, i, CN);
+                }
+                build_unet(B, lat_in, e->eps[i], i, S, [&](const std::function<View(int)>& skip_view, const View& mid_out) {
+                    build_controlnet_residuals(B, CN, skip_view, mid_out);
+                });
+            } else {
+                build_unet(B, lat_in, e->eps[i], i, S);
+            }
         }
         const StepScalars s = e->sc[i];
         Engine* ee = e;
@@ -1116,6 +1315,7 @@ void vsd_destroy(vsd_ctx* c) {
     if (c->e.splitk_ws) cudaFree(c->e.splitk_ws);
     if (c->e.flush_buf) cudaFree(c->e.flush_buf);
     if (c->e.gn_sync) cudaFree(c->e.gn_sync);
+    if (c->e.cn_scales) cudaFree(c->e.cn_scales);
     if (c->e.ev0) cudaEventDestroy(c->e.ev0);
     if (c->e.ev1) cudaEventDestroy(c->e.ev1);
     cudaStreamDestroy(c->e.stream);
@@ -1189,6 +1389,29 @@ int vsd_set_schedule(vsd_ctx* c, int steps, const int* timesteps, const float* s
                      float add_noise_b, const float* w_embedding256, int has_step_noise) {
     CTX_GUARD(c);
     return set_schedule(&c->e, steps, timesteps, scalars, add_noise_a, add_noise_b, w_embedding256, has_step_noise);
+}
+
+/* ControlNet on/off and its 13 per-residual scales (guess mode: logspace(-1, 0, 13) * controlnet_scale, computed by the
+ * host like diffusers does). Toggling `enabled` invalidates the schedule (call vsd_set_schedule again). */
+int vsd_set_controlnet(vsd_ctx* c, int enabled, const float* scales13) {
+    CTX_GUARD(c);
+    Engine* e = &c->e;
+    if (enabled) ENG_REQUIRE(has_controlnet_weights(e), "no controlnet.* weights are loaded");
+    if (!e->cn_scales) {
+        VSD_CHECK_CUDA(cudaMalloc(&e->cn_scales, 16 * sizeof(float)));
+        VSD_CHECK_CUDA(cudaMemset(e->cn_scales, 0, 16 * sizeof(float)));
+    }
+    if (scales13) {
+        VSD_CHECK_CUDA(cudaMemcpyAsync(e->cn_scales, scales13, 13 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    }
+    if ((enabled != 0) != e->cn_enabled) {
+        VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+        free_graphs(e);
+        e->cn_enabled = enabled != 0;
+        e->schedule_set = false;
+    }
+    return 0;
 }
 
 int vsd_set_context(vsd_ctx* c, int slot, const float* context_77x768) {

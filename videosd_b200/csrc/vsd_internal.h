@@ -78,6 +78,7 @@ struct GemmParams {
     const float* rowvec;  // [NB, N] or null (per-image broadcast, e.g. time embedding projection)
     const bf16* residual; // [rows, ldr] or null
     int ldr;
+    const float* out_scale;  // optional device scalar: out = (acc + bias) * scale + residual (ControlNet conditioning scale)
     int act, relu;
     float* partial;       // [splits, rows, N] fp32 when splits > 1
     int a_static, b_static;  // operand is constant (weights): its first stages may be fetched before pdl_wait()
@@ -133,7 +134,12 @@ int launch_upsample_nearest(const bf16* x, int ldx, bf16* y, int ldy, int NB, in
 int launch_im2col_s2(const bf16* x, int ldx, bf16* y, int NB, int Hi, int Wi, int C, int Ho, int Wo, cudaStream_t st);
 int launch_splitk_reduce(const GemmParams& p, long rows, cudaStream_t st);
 int launch_conv3x3_small_cin(const void* x, int x_kind, int NB, int H, int W, int Cin, const float* w, const float* bias,
-                             bf16* y, int ldy, int Cout, int relu, cudaStream_t st);
+                             bf16* y, int ldy, int Cout, int relu /*0 none, 1 ReLU, 2 SiLU*/, cudaStream_t st,
+                             const bf16* res = nullptr, int ldr = 0);
+int launch_sobel_control(const uint8_t* rgb, float* mag, unsigned int* maxbits, float* control, int NB, int H, int W,
+                         float low, float high, cudaStream_t st);
+int launch_conv3x3_direct(const bf16* x, int ldx, int NB, int Hi, int Wi, int Cin, const bf16* w, const float* bias, bf16* y,
+                          int ldy, int Cout, int stride, int silu, cudaStream_t st);
 int launch_add_noise(const float* x0, const float* noise, float* out, float a, float b, long n, cudaStream_t st);
 int launch_lcm_step(const float* eps, const float* x, const float* z, float* x_prev, float* denoised, float sqrt_a,
                     float sqrt_1ma, float c_skip, float c_out, float sqrt_ap, float sqrt_1map, int has_noise, long n,

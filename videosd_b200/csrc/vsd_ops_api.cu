@@ -172,6 +172,17 @@ int vsd_op_conv3x3_small_cin(const void* x, int x_kind, int nb, int h, int w, in
                                     reinterpret_cast<cudaStream_t>(stream));
 }
 
+int vsd_op_sobel_control(const uint8_t* rgb, float* mag, unsigned int* maxbits, float* control, int nb, int h, int w,
+                         float low, float high, void* stream) {
+    return launch_sobel_control(rgb, mag, maxbits, control, nb, h, w, low, high, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int vsd_op_conv3x3_direct(const void* x, int ldx, int nb, int hi, int wi, int cin, const void* wt, const float* bias, void* y,
+                          int ldy, int cout, int stride, int silu, void* stream) {
+    return launch_conv3x3_direct(reinterpret_cast<const bf16*>(x), ldx, nb, hi, wi, cin, reinterpret_cast<const bf16*>(wt), bias,
+                                 reinterpret_cast<bf16*>(y), ldy, cout, stride, silu, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int vsd_op_add_noise(const float* x0, const float* noise, float* out, float sqrt_alpha, float sqrt_one_minus_alpha,
                      long n, void* stream) {
     return launch_add_noise(x0, noise, out, sqrt_alpha, sqrt_one_minus_alpha, n, reinterpret_cast<cudaStream_t>(stream));

@@ -88,6 +88,14 @@ class Engine:
         self._sched_key = key
         return ts
 
+    def set_controlnet(self, enabled, scale=1.0):
+        """Enable the canny ControlNet branch with conditioning scale `scale` (guess mode, as the reference calls it)."""
+        sc = np.ascontiguousarray((torch.logspace(-1, 0, 13) * float(scale)).numpy().astype(np.float32))
+        check(self._L.vsd_set_controlnet(self._ctx, c_int(1 if enabled else 0), _fptr(sc)), "vsd_set_controlnet")
+        if bool(enabled) != getattr(self, "_cn_enabled", False):
+            self._cn_enabled = bool(enabled)
+            self._sched_key = None      # the launch plan must be rebuilt
+
     def set_context(self, slot, context):
         """context: (77, 768) float tensor/array (CLIP last_hidden_state for the prompt)."""
         a = np.ascontiguousarray(torch.as_tensor(context).detach().to(torch.float32).cpu().numpy())
@@ -205,6 +213,14 @@ class LanePool:
                 e.tuning_load(self.lanes[0].tuning_report())   # tune once
             ts = e.set_schedule(strength, steps, guidance_scale)
         return ts
+
+    def set_controlnet(self, enabled, scale=1.0):
+        """Enable the canny ControlNet branch with conditioning scale `scale` (guess mode, as the reference calls it)."""
+        sc = np.ascontiguousarray((torch.logspace(-1, 0, 13) * float(scale)).numpy().astype(np.float32))
+        check(self._L.vsd_set_controlnet(self._ctx, c_int(1 if enabled else 0), _fptr(sc)), "vsd_set_controlnet")
+        if bool(enabled) != getattr(self, "_cn_enabled", False):
+            self._cn_enabled = bool(enabled)
+            self._sched_key = None      # the launch plan must be rebuilt
 
     def set_context(self, slot, context):
         for e in self.lanes:

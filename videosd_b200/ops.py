@@ -148,3 +148,27 @@ def pack_rgb_yuv420(img, taesd_denorm=False, want_rgb=True):
     check(lib().vsd_op_pack_rgb_yuv420(_p(img), c_int(ld), _p(rgb), _p(y), _p(u), _p(v), c_int(nb), c_int(h), c_int(w),
                                        c_int(1 if taesd_denorm else 0), cur_stream()), "vsd_op_pack_rgb_yuv420")
     return rgb, y, u, v
+
+
+def sobel_control(rgb_u8, low=0.11, high=0.8):
+    """rgb_u8: u8 (nb,h,w,3) -> control image fp32 (nb,h,w,3) in [0,1]."""
+    nb, h, w, _ = rgb_u8.shape
+    dev = rgb_u8.device
+    mag = torch.empty((nb, h, w), device=dev, dtype=torch.float32)
+    mx = torch.zeros((nb,), device=dev, dtype=torch.int32)
+    ctl = torch.empty((nb, h, w, 3), device=dev, dtype=torch.float32)
+    check(lib().vsd_op_sobel_control(_p(rgb_u8), _p(mag), _p(mx), _p(ctl), c_int(nb), c_int(h), c_int(w), c_float(low),
+                                     c_float(high), cur_stream()), "vsd_op_sobel_control")
+    return ctl
+
+
+def conv3x3_direct(x, weight_ohwi, bias, stride=1, silu=True):
+    """x: bf16 (nb,h,w,cin); weight: bf16 (cout, 9*cin)."""
+    nb, h, w, cin = x.shape
+    cout = weight_ohwi.shape[0]
+    ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+    y = torch.empty((nb, ho, wo, cout), device=x.device, dtype=torch.bfloat16)
+    check(lib().vsd_op_conv3x3_direct(_p(x), c_int(x.stride(2)), c_int(nb), c_int(h), c_int(w), c_int(cin), _p(weight_ohwi),
+                                      _p(bias), _p(y), c_int(cout), c_int(cout), c_int(stride), c_int(1 if silu else 0),
+                                      cur_stream()), "vsd_op_conv3x3_direct")
+    return y

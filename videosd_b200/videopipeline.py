@@ -92,9 +92,13 @@ class VideoSDPipeline:
             n = max(torch.cuda.device_count(), 1)
             self.device = 0 if _HAVE_RAY and os.environ.get("RAY_ACTOR") else next(_device_counter) % n
         self.prompt_encoder = kwargs.get("prompt_encoder")
+        # The reference runs the canny ControlNet before every UNet pass; the north star's hot path excludes it, so it is
+        # opt-in here: use_controlnet=True adds ~35 % FLOPs per step.
+        self.use_controlnet = bool(kwargs.get("use_controlnet", False))
         self.noise_mode = kwargs.get("noise_mode", "reference_cuda")
         self.engine = Engine(self.device)          # raises if the CUDA library / a B200 is missing: no fallback
         self.load_model(self.model_name, self.controlnet_name, kwargs.get("random_init", False))
+        self._cn_scale = None
         self._shape = None
         self._noise_key = None
         self._prompt_key = None
@@ -110,9 +114,14 @@ class VideoSDPipeline:
         if os.path.isdir(str(model_name)) and os.path.isdir(os.path.join(model_name, "unet")):
             self.engine.load_state_dict("unet", _weights.load_safetensors_dir(os.path.join(model_name, "unet")))
             self.engine.load_state_dict("vae", _weights.load_safetensors_dir(os.path.join(model_name, "vae")))
+            if self.use_controlnet:
+                self.engine.load_state_dict("controlnet", _weights.load_safetensors_dir(str(controlnet_model)))
         elif random_init or os.environ.get("VIDEOSD_RANDOM_INIT") == "1":
             self.engine.load_state_dict("unet", _weights.random_state_dict(_weights.unet_param_shapes(), 1234))
             self.engine.load_state_dict("vae", _weights.random_state_dict(_weights.taesd_param_shapes(), 4321))
+            if self.use_controlnet:
+                self.engine.load_state_dict("controlnet",
+                                            _weights.random_state_dict(_weights.controlnet_param_shapes(), 9876))
         else:
             raise FileNotFoundError(
                 f"model '{model_name}' is not a local diffusers directory (unet/, vae/ with .safetensors). "
@@ -120,11 +129,15 @@ class VideoSDPipeline:
         return self.engine
 
     # ------------------------------------------------------------------------------------------------
-    def _prepare(self, batch, height, width, strength, steps, guidance_scale, seed, prompt, prompt_embeds=None):
+    def _prepare(self, batch, height, width, strength, steps, guidance_scale, seed, prompt, prompt_embeds=None,
+                 controlnet_scale=1.0):
         if self._shape != (batch, height, width):
             self.engine.configure(batch, height, width)
             self._shape = (batch, height, width)
             self._noise_key = self._prompt_key = None
+        if self.use_controlnet and self._cn_scale != float(controlnet_scale):
+            self.engine.set_controlnet(True, float(controlnet_scale))   # lcm_controlnet.py:553-556 (keep = 1.0)
+            self._cn_scale = float(controlnet_scale)
         ts = self.engine.set_schedule(strength, steps, 7.5)   # guidance_scale from the UI is dropped by the reference (F8)
         nkey = (seed, len(ts), self.noise_mode)
         if nkey != self._noise_key:
@@ -173,19 +186,21 @@ class VideoSDPipeline:
         width -= width % 8
         height -= height % 8
         img = self._fit(img.convert("RGB"), width, height)
-        self._prepare(1, height, width, float(strength), int(steps), guidance_scale, int(seed), prompt, prompt_embeds)
+        self._prepare(1, height, width, float(strength), int(steps), guidance_scale, int(seed), prompt, prompt_embeds,
+                      controlnet_scale)
         rgb_in = np.ascontiguousarray(np.asarray(img, dtype=np.uint8))
         rgb_out = np.empty_like(rgb_in)
         self.engine.infer_rgb(rgb_in, rgb_out)
         return Image.fromarray(rgb_out)
 
-    def infer_yuv420(self, y, u, v, prompt=["pixar, cg"], strength=0.4, steps=20, seed=42, prompt_embeds=None, **_ignored):
+    def infer_yuv420(self, y, u, v, prompt=["pixar, cg"], strength=0.4, steps=20, seed=42, prompt_embeds=None,
+                     controlnet_scale=1, **_ignored):
         """Fast path: YUV420P planes (u8 numpy, already at the working size; (B,H,W) or (H,W)) -> planes."""
         y, u, v = (np.ascontiguousarray(a) for a in (y, u, v))
         if y.ndim == 2:
             y, u, v = y[None], u[None], v[None]
         b, h, w = y.shape
-        self._prepare(b, h, w, float(strength), int(steps), 7.5, int(seed), prompt, prompt_embeds)
+        self._prepare(b, h, w, float(strength), int(steps), 7.5, int(seed), prompt, prompt_embeds, controlnet_scale)
         oy, ou, ov = np.empty_like(y), np.empty_like(u), np.empty_like(v)
         self.engine.infer_yuv420(y, u, v, oy, ou, ov)
         return oy, ou, ov

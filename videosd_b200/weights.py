@@ -76,6 +76,42 @@ def unet_param_shapes():
     return o
 
 
+def controlnet_param_shapes():
+    """diffusers ControlNetModel (lllyasviel/control_v11p_sd15_canny), SURVEY.md Appendix A.8."""
+    w = (320, 640, 1280, 1280)
+    o = {}
+    o["conv_in.weight"] = (320, 4, 3, 3); o["conv_in.bias"] = (320,)
+    o["time_embedding.linear_1.weight"] = (1280, 320); o["time_embedding.linear_1.bias"] = (1280,)
+    o["time_embedding.linear_2.weight"] = (1280, 1280); o["time_embedding.linear_2.bias"] = (1280,)
+    e = "controlnet_cond_embedding"
+    o[f"{e}.conv_in.weight"] = (16, 3, 3, 3); o[f"{e}.conv_in.bias"] = (16,)
+    ws = (16, 32, 96, 256)
+    for i in range(3):
+        o[f"{e}.blocks.{2*i}.weight"] = (ws[i], ws[i], 3, 3); o[f"{e}.blocks.{2*i}.bias"] = (ws[i],)
+        o[f"{e}.blocks.{2*i+1}.weight"] = (ws[i + 1], ws[i], 3, 3); o[f"{e}.blocks.{2*i+1}.bias"] = (ws[i + 1],)
+    o[f"{e}.conv_out.weight"] = (320, 256, 3, 3); o[f"{e}.conv_out.bias"] = (320,)
+    cin = 320
+    chans = [320]
+    for i, c in enumerate(w):
+        for j in range(2):
+            _resnet(f"down_blocks.{i}.resnets.{j}", cin if j == 0 else c, c, o)
+            if i < 3:
+                _transformer(f"down_blocks.{i}.attentions.{j}", c, o)
+            chans.append(c)
+        if i < 3:
+            o[f"down_blocks.{i}.downsamplers.0.conv.weight"] = (c, c, 3, 3)
+            o[f"down_blocks.{i}.downsamplers.0.conv.bias"] = (c,)
+            chans.append(c)
+        cin = c
+    _resnet("mid_block.resnets.0", 1280, 1280, o)
+    _transformer("mid_block.attentions.0", 1280, o)
+    _resnet("mid_block.resnets.1", 1280, 1280, o)
+    for k, c in enumerate(chans):
+        o[f"controlnet_down_blocks.{k}.weight"] = (c, c, 1, 1); o[f"controlnet_down_blocks.{k}.bias"] = (c,)
+    o["controlnet_mid_block.weight"] = (1280, 1280, 1, 1); o["controlnet_mid_block.bias"] = (1280,)
+    return o
+
+
 def taesd_param_shapes():
     o = {}
 
