@@ -84,6 +84,12 @@ int vsd_op_conv3x3_small_cin(const void* x, int x_kind, int nb, int h, int w, in
  * rgb: dev u8 [nb][h][w][3]; mag: dev fp32 scratch [nb][h][w]; maxbits: dev u32 [nb]; control: dev fp32 [nb][h][w][3]. */
 int vsd_op_sobel_control(const uint8_t* rgb, float* mag, unsigned int* maxbits, float* control, int nb, int h, int w,
                          float low, float high, void* stream);
+/* Center crop + Lanczos resize, bit-identical to PIL Image.crop + resize(LANCZOS) (diffusert/videopipeline.py:92-107).
+ * src: dev u8 [nb][in_h][in_w][3]; tmp: dev u8 scratch [nb][ch][w][3]; out: dev u8 [nb][h][w][3]; *_bounds: dev i32 [n][2]
+ * (first tap, tap count); *_coeffs: dev i32 [n][ksize], 22-bit fixed point (videosd_b200/resample.py). */
+int vsd_op_crop_resize(const uint8_t* src, int in_w, int in_h, int x0, int y0, int cw, int ch, uint8_t* tmp, uint8_t* out, int w,
+                       int h, const int* h_bounds, const int* h_coeffs, int h_ksize, const int* v_bounds, const int* v_coeffs,
+                       int v_ksize, int nb, void* stream);
 /* Direct 3x3 conv (pad 1, stride 1|2) + optional SiLU for narrow layers (ControlNetConditioningEmbedding). bf16 NHWC. */
 int vsd_op_conv3x3_direct(const void* x, int ldx, int nb, int hi, int wi, int cin, const void* wt, const float* bias, void* y,
                           int ldy, int cout, int stride, int silu, void* stream);
@@ -154,6 +160,14 @@ int vsd_infer_yuv420(vsd_ctx* ctx, const uint8_t* y, const uint8_t* u, const uin
                      uint8_t* out_u, uint8_t* out_v);
 /* Packed RGB24 in / out ([batch][h][w][3]); the PIL-compatible path of VideoSDPipeline.infer. */
 int vsd_infer_rgb(vsd_ctx* ctx, const uint8_t* rgb_in, uint8_t* rgb_out);
+
+/* GPU center-crop + Lanczos resize (videopipeline.py:92-107 does PIL crop + resize(LANCZOS) on
+ * the CPU). The host passes Pillow-compatible windows / 22-bit coefficients (videosd_b200/resample.py); results are
+ * bit-identical to Pillow. Geometry: input frames in_w x in_h, crop (x0, y0, cw, ch) -> working size. */
+int vsd_set_resize(vsd_ctx* ctx, int in_w, int in_h, int x0, int y0, int cw, int ch, const int* h_bounds, const int* h_coeffs,
+                   int h_ksize, const int* v_bounds, const int* v_coeffs, int v_ksize);
+int vsd_infer_rgb_resized(vsd_ctx* ctx, const uint8_t* rgb_src, uint8_t* rgb_out);
+int vsd_debug_read_rgb_in(vsd_ctx* ctx, uint8_t* host);
 
 /* Split form of vsd_infer_yuv420 (asynchronous on the context's stream; vsd_sync waits). */
 int vsd_upload_yuv420(vsd_ctx* ctx, const uint8_t* y, const uint8_t* u, const uint8_t* v);

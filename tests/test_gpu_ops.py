@@ -40,3 +40,11 @@ def test_groupnorm_layernorm(chk):
 
 def test_colour_scheduler_edge_convs_bit_exact(chk):
     _run(chk, chk.check_misc)
+
+
+def test_sobel_and_controlnet_embedding_convs(chk):
+    _run(chk, chk.check_controlnet)
+
+
+def test_crop_lanczos_resize_bit_exact_vs_pillow(chk):
+    _run(chk, chk.check_resize)

@@ -151,6 +151,13 @@ def test_dropin_boundary_pil_in_pil_out(setup):
     assert out.size == (256, 256) and out.mode == "RGB"
     assert np.array_equal(np.asarray(out), np.asarray(out2))          # same (frame, options) -> same output
     assert np.asarray(out).std() > 1.0
+    # the 640x480 frame went through the GPU crop + Lanczos kernels: the working-size frame the engine saw must be
+    # bit-identical to the reference's PIL crop + resize (videopipeline.py:92-107), and so must the whole output
+    fitted = VideoSDPipeline._fit(img, 256, 256)
+    eng = handle._obj.engine
+    assert np.array_equal(eng.debug_read_rgb_in()[0], np.asarray(fitted))
+    out3 = handle.infer.remote(fitted, **opts).result(timeout=600)    # already working size: plain upload path
+    assert np.array_equal(np.asarray(out3), np.asarray(out))
 
 
 def test_controlnet_branch_frame_and_reference_golden(setup, golden):

@@ -119,6 +119,27 @@ def test_boundary_crop_resize_matches_reference_rule():
     assert wide.size == (640, 360)
 
 
+def test_lanczos_tables_reproduce_pillow_bit_exactly():
+    """The GPU resize applies host-computed windows / 22-bit coefficients; the same arithmetic in numpy must equal PIL."""
+    from PIL import Image
+
+    from videosd_b200 import resample
+    from videosd_b200.videopipeline import VideoSDPipeline
+
+    for (iw, ih, w, h) in [(640, 480, 512, 512), (1280, 720, 640, 360), (320, 240, 512, 512), (641, 479, 256, 256),
+                           (640, 512, 512, 512), (512, 512, 512, 512)]:
+        src = np.random.RandomState(iw).randint(0, 256, (ih, iw, 3)).astype(np.uint8)
+        src[::5] = 255
+        src[2::9] = 0
+        ref = np.asarray(VideoSDPipeline._fit(Image.fromarray(src), w, h))
+        got = resample.resize_reference_numpy(src, w, h)
+        assert np.array_equal(got, ref), (iw, ih, w, h)
+    plan = resample.resize_plan(512, 512, 512, 512)
+    assert plan["identity"] and plan["crop"] == (0, 0, 512, 512)
+    b, k, ks = resample.lanczos_coeffs(480, 512)
+    assert ks == 7 and b.shape == (512, 2) and (k.sum(axis=1) - (1 << 22)).__abs__().max() <= 8   # rows sum to ~1.0
+
+
 def test_session_router_pins_and_batches():
     from videosd_b200.parallel import SessionRouter, shard_streams
 

@@ -404,6 +404,60 @@ def check_controlnet():
     run("direct_conv", direct)
 
 
+def check_resize():
+    """Center crop + Lanczos on the GPU vs Pillow itself (the reference's own CPU path, videopipeline.py:92-107)."""
+    import numpy as np
+    from PIL import Image
+
+    from videosd_b200.videopipeline import VideoSDPipeline
+
+    def vs_pil():
+        geos = [(640, 480, 512, 512), (1280, 720, 640, 360), (640, 480, 768, 768), (320, 240, 512, 512), (500, 375, 512, 384),
+                (641, 479, 256, 256), (640, 512, 512, 512), (1920, 1080, 512, 512), (512, 640, 512, 512), (300, 300, 512, 512)]
+        for (iw, ih, w, h) in geos:
+            rs = np.random.RandomState(iw + ih)
+            src = rs.randint(0, 256, (2, ih, iw, 3)).astype(np.uint8)
+            src[1, ::7] = 255; src[1, 3::11] = 0          # hard edges: exercises the clamp on ringing
+            got = ops.crop_resize(torch.from_numpy(src).to(DEV), w, h).cpu().numpy()
+            ref = np.stack([np.asarray(VideoSDPipeline._fit(Image.fromarray(s), w, h)) for s in src])
+            d = np.abs(got.astype(int) - ref.astype(int))
+            record(f"crop_lanczos_{iw}x{ih}_to_{w}x{h}_maxdiff", float(d.max()), 0.0)
+    run("crop_resize_vs_pil", vs_pil)
+
+    def timing():
+        src = torch.randint(0, 256, (1, 720, 1280, 3), dtype=torch.uint8, device=DEV)
+        for _ in range(3):
+            ops.crop_resize(src, 512, 512)
+        torch.cuda.synchronize()
+        from videosd_b200 import resample
+        plan = resample.resize_plan(1280, 720, 512, 512)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # time only the kernels: tables resident, as in the engine
+        from ctypes import c_int
+        from videosd_b200._lib import _p, check, cur_stream, lib
+        x0, y0, cw, ch = plan["crop"]
+        (hb, hk, hks), (vb, vk, vks) = plan["h"], plan["v"]
+        t = lambda z: torch.from_numpy(z.astype("int32")).contiguous().to(DEV)  # noqa: E731
+        hb, hk, vb, vk = t(hb), t(hk), t(vb), t(vk)
+        tmp = torch.empty((1, ch, 512, 3), device=DEV, dtype=torch.uint8)
+        out = torch.empty((1, 512, 512, 3), device=DEV, dtype=torch.uint8)
+        a.record()
+        for _ in range(50):
+            check(lib().vsd_op_crop_resize(_p(src), c_int(1280), c_int(720), c_int(x0), c_int(y0), c_int(cw), c_int(ch), _p(tmp), _p(out),
+                                           c_int(512), c_int(512), _p(hb), _p(hk), c_int(hks), _p(vb), _p(vk), c_int(vks), c_int(1),
+                                           cur_stream()), "crop_resize")
+        b.record()
+        torch.cuda.synchronize()
+        us = a.elapsed_time(b) / 50 * 1e3
+        t0 = time.time()
+        img = Image.fromarray(src[0].cpu().numpy())
+        for _ in range(10):
+            VideoSDPipeline._fit(img, 512, 512)
+        cpu_us = (time.time() - t0) / 10 * 1e6
+        record("crop_lanczos_720p_to_512_us", us, 1e9, {"pil_cpu_us": cpu_us})
+    run("crop_resize_timing", timing)
+
+
 def main():
     which = sys.argv[1:] or ["gemm"]
     tag = "_".join(which)

@@ -589,6 +589,85 @@ int launch_conv3x3_small_cin(const void* x, int x_kind, int NB, int H, int W, in
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------ crop + Lanczos resize
+// Pillow's two-pass 8-bit resampling (ImagingResample) with host-computed windows and 22-bit fixed-point coefficients
+// (videosd_b200/resample.py): out = clip8((1 << 21) + sum_i px[xmin + i] * k[i]) >> 22. Horizontal pass reads the crop
+// rectangle of the source frame and writes a uint8 intermediate; the vertical pass writes the working-size frame.
+__global__ void resample_h_kernel(const uint8_t* __restrict__ src, int in_w, int in_h, int x0, int y0, int ch,
+                                  uint8_t* __restrict__ tmp, int W, const int* __restrict__ bounds,
+                                  const int* __restrict__ kk, int ksize, int NB) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long total = (long)NB * ch * W;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int xx = (int)(i % W), y = (int)((i / W) % ch), n = (int)(i / ((long)W * ch));
+        const int xmin = bounds[xx * 2], cnt = bounds[xx * 2 + 1];
+        const int* k = kk + (long)xx * ksize;
+        const uint8_t* p = src + (((long)n * in_h + y0 + y) * in_w + x0 + xmin) * 3;
+        int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+        for (int j = 0; j < cnt; ++j) {
+            const int c = k[j];
+            a0 += p[j * 3 + 0] * c; a1 += p[j * 3 + 1] * c; a2 += p[j * 3 + 2] * c;
+        }
+        uint8_t* o = tmp + i * 3;
+        o[0] = (uint8_t)min(max(a0 >> 22, 0), 255); o[1] = (uint8_t)min(max(a1 >> 22, 0), 255); o[2] = (uint8_t)min(max(a2 >> 22, 0), 255);
+    }
+}
+
+__global__ void resample_v_kernel(const uint8_t* __restrict__ tmp, int ch, uint8_t* __restrict__ out, int H, int W,
+                                  const int* __restrict__ bounds, const int* __restrict__ kk, int ksize, int NB) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long total = (long)NB * H * W;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int xx = (int)(i % W), yy = (int)((i / W) % H), n = (int)(i / ((long)W * H));
+        const int ymin = bounds[yy * 2], cnt = bounds[yy * 2 + 1];
+        const int* k = kk + (long)yy * ksize;
+        const uint8_t* p = tmp + (((long)n * ch + ymin) * W + xx) * 3;
+        int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+        for (int j = 0; j < cnt; ++j) {
+            const int c = k[j];
+            const uint8_t* q = p + (long)j * W * 3;
+            a0 += q[0] * c; a1 += q[1] * c; a2 += q[2] * c;
+        }
+        uint8_t* o = out + i * 3;
+        o[0] = (uint8_t)min(max(a0 >> 22, 0), 255); o[1] = (uint8_t)min(max(a1 >> 22, 0), 255); o[2] = (uint8_t)min(max(a2 >> 22, 0), 255);
+    }
+}
+
+// src [NB][in_h][in_w][3] --crop (x0,y0,cw,ch)--> horizontal (if cw != W) --> tmp [NB][ch][W][3] --> vertical (if ch != H) --> out
+int launch_crop_resize(const uint8_t* src, int in_w, int in_h, int x0, int y0, int cw, int ch, uint8_t* tmp, uint8_t* out,
+                       int W, int H, const int* hb, const int* hk, int hks, const int* vb, const int* vk, int vks, int NB,
+                       cudaStream_t st) {
+    const bool need_h = cw != W, need_v = ch != H;
+    const long t1 = (long)NB * ch * W, t2 = (long)NB * H * W;
+    int b1 = (int)((t1 + 255) / 256), b2 = (int)((t2 + 255) / 256);
+    if (b1 > 148 * 16) b1 = 148 * 16;
+    if (b2 > 148 * 16) b2 = 148 * 16;
+    if (!need_h && !need_v) {   // pure crop: row-wise device copy
+        for (int n = 0; n < NB; ++n)
+            VSD_CHECK_CUDA(cudaMemcpy2DAsync(out + (long)n * H * W * 3, (size_t)W * 3, src + (((long)n * in_h + y0) * in_w + x0) * 3,
+                                             (size_t)in_w * 3, (size_t)W * 3, (size_t)H, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+    if (need_h) {
+        uint8_t* dst = need_v ? tmp : out;
+        VSD_CHECK_CUDA(launch_k(resample_h_kernel, dim3(b1), dim3(256), 0, st, src, in_w, in_h, x0, y0, ch, dst, W, hb, hk, hks, NB));
+    }
+    if (need_v) {
+        if (need_h) {
+            VSD_CHECK_CUDA(launch_k(resample_v_kernel, dim3(b2), dim3(256), 0, st, (const uint8_t*)tmp, ch, out, H, W, vb, vk, vks, NB));
+        } else {
+            // no horizontal pass: the vertical pass reads the crop rectangle directly; stage it contiguously first
+            for (int n = 0; n < NB; ++n)
+                VSD_CHECK_CUDA(cudaMemcpy2DAsync(tmp + (long)n * ch * W * 3, (size_t)W * 3, src + (((long)n * in_h + y0) * in_w + x0) * 3,
+                                                 (size_t)in_w * 3, (size_t)W * 3, (size_t)ch, cudaMemcpyDeviceToDevice, st));
+            VSD_CHECK_CUDA(launch_k(resample_v_kernel, dim3(b2), dim3(256), 0, st, (const uint8_t*)tmp, ch, out, H, W, vb, vk, vks, NB));
+        }
+    }
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------ ControlNet front end
 // Sobel edge map of the (already resized) input frame: diffusert/lcm/canny_gpu.py:27-44.
 //   gray = PIL convert("L") = (19595 R + 38470 G + 7471 B + 0x8000) >> 16 ; ToTensor: /255

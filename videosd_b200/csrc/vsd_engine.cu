@@ -133,6 +133,9 @@ struct Engine {
     void* flush_buf = nullptr; size_t flush_bytes = 0;
     unsigned int* gn_sync = nullptr;   // grid-barrier state for the fused GroupNorm kernel (never reused memory)
     // ControlNet: canny/Sobel-conditioned residuals added to the UNet skips every step
+    // GPU center-crop + Lanczos resize of arbitrary-size input frames
+    struct Resize { int in_w = 0, in_h = 0, x0 = 0, y0 = 0, cw = 0, ch = 0, hks = 0, vks = 0;
+                    int *hb = nullptr, *hk = nullptr, *vb = nullptr, *vk = nullptr; uint8_t *src = nullptr, *tmp = nullptr; } rz;
     bool cn_enabled = false;
     float* cn_scales = nullptr;        // device [13]: logspace(-1,0,13) * conditioning scale (guess mode)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -932,12 +935,20 @@ static std::vector<std::string> transformer_prefixes(bool with_controlnet) {
 }
 static bool has_controlnet_weights(const Engine* e) { return e->w.find("controlnet.conv_in.weight") != e->w.end(); }
 
+static void free_resize(Engine* e) {
+    void* ptrs[6] = {e->rz.hb, e->rz.hk, e->rz.vb, e->rz.vk, e->rz.src, e->rz.tmp};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    e->rz = Engine::Resize();
+}
+
 // (Re)allocates every buffer for a (batch, height, width) configuration. Plans are built by finalize().
 static int configure(Engine* e, int nb, int H, int W) {
     ENG_REQUIRE(nb >= 1 && nb <= 64, "batch must be in [1, 64]");
     ENG_REQUIRE(H % 8 == 0 && W % 8 == 0 && H >= 16 && W >= 16, "height and width must be multiples of 8 (>= 16)");
     VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
     free_graphs(e);
+    free_resize(e);
     e->arena.destroy();
     if (e->splitk_ws) cudaFree(e->splitk_ws);
     e->splitk_ws = nullptr;
@@ -1314,6 +1325,7 @@ void vsd_destroy(vsd_ctx* c) {
     c->e.arena.destroy();
     if (c->e.splitk_ws) cudaFree(c->e.splitk_ws);
     if (c->e.flush_buf) cudaFree(c->e.flush_buf);
+    free_resize(&c->e);
     if (c->e.gn_sync) cudaFree(c->e.gn_sync);
     if (c->e.cn_scales) cudaFree(c->e.cn_scales);
     if (c->e.ev0) cudaEventDestroy(c->e.ev0);
@@ -1485,6 +1497,57 @@ int vsd_infer_rgb(vsd_ctx* c, const uint8_t* rgb_in, uint8_t* rgb_out) {
     if (rc) return rc;
     VSD_CHECK_CUDA(cudaMemcpyAsync(rgb_out, e->d_rgb_out, px * 3, cudaMemcpyDeviceToHost, e->stream));
     VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int vsd_set_resize(vsd_ctx* c, int in_w, int in_h, int x0, int y0, int cw, int ch, const int* h_bounds, const int* h_coeffs,
+                   int h_ksize, const int* v_bounds, const int* v_coeffs, int v_ksize) {
+    CTX_GUARD(c);
+    Engine* e = &c->e;
+    ENG_REQUIRE(e->configured, "configure() first");
+    ENG_REQUIRE(in_w > 0 && in_h > 0 && cw > 0 && ch > 0 && x0 >= 0 && y0 >= 0 && x0 + cw <= in_w && y0 + ch <= in_h,
+                "crop rectangle outside the input frame");
+    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    free_resize(e);
+    Engine::Resize& r = e->rz;
+    r.in_w = in_w; r.in_h = in_h; r.x0 = x0; r.y0 = y0; r.cw = cw; r.ch = ch; r.hks = h_ksize; r.vks = v_ksize;
+    const size_t hb_b = (size_t)e->W * 2 * 4, hk_b = (size_t)e->W * h_ksize * 4, vb_b = (size_t)e->H * 2 * 4, vk_b = (size_t)e->H * v_ksize * 4;
+    VSD_CHECK_CUDA(cudaMalloc(&r.hb, hb_b)); VSD_CHECK_CUDA(cudaMalloc(&r.hk, hk_b));
+    VSD_CHECK_CUDA(cudaMalloc(&r.vb, vb_b)); VSD_CHECK_CUDA(cudaMalloc(&r.vk, vk_b));
+    VSD_CHECK_CUDA(cudaMalloc(&r.src, (size_t)e->NB * in_w * in_h * 3));
+    VSD_CHECK_CUDA(cudaMalloc(&r.tmp, (size_t)e->NB * ch * e->W * 3));
+    VSD_CHECK_CUDA(cudaMemcpy(r.hb, h_bounds, hb_b, cudaMemcpyHostToDevice));
+    VSD_CHECK_CUDA(cudaMemcpy(r.hk, h_coeffs, hk_b, cudaMemcpyHostToDevice));
+    VSD_CHECK_CUDA(cudaMemcpy(r.vb, v_bounds, vb_b, cudaMemcpyHostToDevice));
+    VSD_CHECK_CUDA(cudaMemcpy(r.vk, v_coeffs, vk_b, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+/* Arbitrary-size packed RGB24 frames in ([batch][in_h][in_w][3], the geometry given to vsd_set_resize), working-size frames
+ * out: center crop + Lanczos resize on the GPU (videopipeline.py:92-107), then the same path as vsd_infer_rgb. */
+int vsd_infer_rgb_resized(vsd_ctx* c, const uint8_t* rgb_src, uint8_t* rgb_out) {
+    CTX_GUARD(c);
+    Engine* e = &c->e;
+    ENG_REQUIRE(e->rz.src != nullptr, "vsd_set_resize() first");
+    const Engine::Resize& r = e->rz;
+    VSD_CHECK_CUDA(cudaMemcpyAsync(r.src, rgb_src, (size_t)e->NB * r.in_w * r.in_h * 3, cudaMemcpyHostToDevice, e->stream));
+    int rc = launch_crop_resize(r.src, r.in_w, r.in_h, r.x0, r.y0, r.cw, r.ch, r.tmp, e->d_rgb_in, e->W, e->H, r.hb, r.hk, r.hks,
+                                r.vb, r.vk, r.vks, e->NB, e->stream);
+    if (rc) return rc;
+    rc = run_frame(e, false);
+    if (rc) return rc;
+    const size_t px = (size_t)e->NB * e->H * e->W;
+    VSD_CHECK_CUDA(cudaMemcpyAsync(rgb_out, e->d_rgb_out, px * 3, cudaMemcpyDeviceToHost, e->stream));
+    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+/* bring-up / tests: the resized working-size input frame(s) of the last vsd_infer_rgb_resized call */
+int vsd_debug_read_rgb_in(vsd_ctx* c, uint8_t* host) {
+    CTX_GUARD(c);
+    Engine* e = &c->e;
+    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    VSD_CHECK_CUDA(cudaMemcpy(host, e->d_rgb_in, (size_t)e->NB * e->H * e->W * 3, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -136,6 +136,9 @@ int launch_splitk_reduce(const GemmParams& p, long rows, cudaStream_t st);
 int launch_conv3x3_small_cin(const void* x, int x_kind, int NB, int H, int W, int Cin, const float* w, const float* bias,
                              bf16* y, int ldy, int Cout, int relu /*0 none, 1 ReLU, 2 SiLU*/, cudaStream_t st,
                              const bf16* res = nullptr, int ldr = 0);
+int launch_crop_resize(const uint8_t* src, int in_w, int in_h, int x0, int y0, int cw, int ch, uint8_t* tmp, uint8_t* out,
+                       int W, int H, const int* hb, const int* hk, int hks, const int* vb, const int* vk, int vks, int NB,
+                       cudaStream_t st);
 int launch_sobel_control(const uint8_t* rgb, float* mag, unsigned int* maxbits, float* control, int NB, int H, int W,
                          float low, float high, cudaStream_t st);
 int launch_conv3x3_direct(const bf16* x, int ldx, int NB, int Hi, int Wi, int Cin, const bf16* w, const float* bias, bf16* y,

@@ -177,6 +177,14 @@ int vsd_op_sobel_control(const uint8_t* rgb, float* mag, unsigned int* maxbits, 
     return launch_sobel_control(rgb, mag, maxbits, control, nb, h, w, low, high, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int vsd_op_crop_resize(const uint8_t* src, int in_w, int in_h, int x0, int y0, int cw, int ch, uint8_t* tmp, uint8_t* out, int w,
+                       int h, const int* h_bounds, const int* h_coeffs, int h_ksize, const int* v_bounds, const int* v_coeffs,
+                       int v_ksize, int nb, void* stream) {
+    if (ensure_init()) return 1;
+    return launch_crop_resize(src, in_w, in_h, x0, y0, cw, ch, tmp, out, w, h, h_bounds, h_coeffs, h_ksize, v_bounds, v_coeffs,
+                              v_ksize, nb, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int vsd_op_conv3x3_direct(const void* x, int ldx, int nb, int hi, int wi, int cin, const void* wt, const float* bias, void* y,
                           int ldy, int cout, int stride, int silu, void* stream) {
     return launch_conv3x3_direct(reinterpret_cast<const bf16*>(x), ldx, nb, hi, wi, cin, reinterpret_cast<const bf16*>(wt), bias,

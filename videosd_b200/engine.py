@@ -126,6 +126,26 @@ class Engine:
     def infer_rgb(self, rgb_in, rgb_out):
         check(self._L.vsd_infer_rgb(self._ctx, _u8ptr(rgb_in), _u8ptr(rgb_out)), "vsd_infer_rgb")
 
+    def set_resize(self, in_w, in_h):
+        """Prepare the GPU center-crop + Lanczos resize from in_w x in_h frames to the configured working size."""
+        from . import resample
+        plan = resample.resize_plan(in_w, in_h, self.width, self.height)
+        x0, y0, cw, ch = plan["crop"]
+        (hb, hk, hks), (vb, vk, vks) = plan["h"], plan["v"]
+        ip = lambda a: np.ascontiguousarray(a, dtype=np.int32).ctypes.data_as(ctypes.POINTER(ctypes.c_int))  # noqa: E731
+        check(self._L.vsd_set_resize(self._ctx, c_int(in_w), c_int(in_h), c_int(x0), c_int(y0), c_int(cw), c_int(ch), ip(hb),
+                                     ip(hk), c_int(hks), ip(vb), ip(vk), c_int(vks)), "vsd_set_resize")
+        self._resize_key = (in_w, in_h, self.width, self.height, self.batch)
+
+    def infer_rgb_resized(self, rgb_src, rgb_out):
+        """rgb_src: u8 (batch, in_h, in_w, 3) host; rgb_out: u8 (batch, height, width, 3) host."""
+        check(self._L.vsd_infer_rgb_resized(self._ctx, _u8ptr(rgb_src), _u8ptr(rgb_out)), "vsd_infer_rgb_resized")
+
+    def debug_read_rgb_in(self):
+        a = np.empty((self.batch, self.height, self.width, 3), dtype=np.uint8)
+        check(self._L.vsd_debug_read_rgb_in(self._ctx, _u8ptr(a)), "vsd_debug_read_rgb_in")
+        return a
+
     def upload_yuv420(self, y, u, v):
         check(self._L.vsd_upload_yuv420(self._ctx, _u8ptr(y), _u8ptr(u), _u8ptr(v)), "vsd_upload_yuv420")
 

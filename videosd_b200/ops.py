@@ -162,6 +162,24 @@ def sobel_control(rgb_u8, low=0.11, high=0.8):
     return ctl
 
 
+def crop_resize(rgb_u8, width, height):
+    """rgb_u8: u8 (nb,in_h,in_w,3) on the device -> center-cropped, Lanczos-resized u8 (nb,height,width,3)."""
+    from . import resample
+    nb, in_h, in_w, _ = rgb_u8.shape
+    dev = rgb_u8.device
+    plan = resample.resize_plan(in_w, in_h, width, height)
+    x0, y0, cw, ch = plan["crop"]
+    (hb, hk, hks), (vb, vk, vks) = plan["h"], plan["v"]
+    t = lambda a: torch.from_numpy(a.astype("int32")).contiguous().to(dev)  # noqa: E731
+    hb, hk, vb, vk = t(hb), t(hk), t(vb), t(vk)
+    tmp = torch.empty((nb, ch, width, 3), device=dev, dtype=torch.uint8)
+    out = torch.empty((nb, height, width, 3), device=dev, dtype=torch.uint8)
+    check(lib().vsd_op_crop_resize(_p(rgb_u8), c_int(in_w), c_int(in_h), c_int(x0), c_int(y0), c_int(cw), c_int(ch), _p(tmp), _p(out),
+                                   c_int(width), c_int(height), _p(hb), _p(hk), c_int(hks), _p(vb), _p(vk), c_int(vks), c_int(nb),
+                                   cur_stream()), "vsd_op_crop_resize")
+    return out
+
+
 def conv3x3_direct(x, weight_ohwi, bias, stride=1, silu=True):
     """x: bf16 (nb,h,w,cin); weight: bf16 (cout, 9*cin)."""
     nb, h, w, cin = x.shape

@@ -185,12 +185,19 @@ class VideoSDPipeline:
         width, height = int(width), int(height)
         width -= width % 8
         height -= height % 8
-        img = self._fit(img.convert("RGB"), width, height)
+        img = img.convert("RGB")
         self._prepare(1, height, width, float(strength), int(steps), guidance_scale, int(seed), prompt, prompt_embeds,
                       controlnet_scale)
         rgb_in = np.ascontiguousarray(np.asarray(img, dtype=np.uint8))
-        rgb_out = np.empty_like(rgb_in)
-        self.engine.infer_rgb(rgb_in, rgb_out)
+        rgb_out = np.empty((height, width, 3), dtype=np.uint8)
+        if (img.width, img.height) == (width, height):
+            self.engine.infer_rgb(rgb_in, rgb_out)
+        else:
+            # center crop + Lanczos resize on the GPU, bit-identical to the reference's PIL calls (videopipeline.py:92-107)
+            key = (img.width, img.height, width, height, 1)
+            if getattr(self.engine, "_resize_key", None) != key:
+                self.engine.set_resize(img.width, img.height)
+            self.engine.infer_rgb_resized(rgb_in, rgb_out)
         return Image.fromarray(rgb_out)
 
     def infer_yuv420(self, y, u, v, prompt=["pixar, cg"], strength=0.4, steps=20, seed=42, prompt_embeds=None,
