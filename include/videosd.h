@@ -167,6 +167,10 @@ int vsd_infer_rgb(vsd_ctx* ctx, const uint8_t* rgb_in, uint8_t* rgb_out);
 int vsd_set_resize(vsd_ctx* ctx, int in_w, int in_h, int x0, int y0, int cw, int ch, const int* h_bounds, const int* h_coeffs,
                    int h_ksize, const int* v_bounds, const int* v_coeffs, int v_ksize);
 int vsd_infer_rgb_resized(vsd_ctx* ctx, const uint8_t* rgb_src, uint8_t* rgb_out);
+/* YUV420P planes at the source geometry in (even in_w, in_h), working-size planes out: colour conversion at the source size
+ * (frame.to_image(), server.py:104-108), then crop + Lanczos, the frame, and the pack to YUV420P. */
+int vsd_infer_yuv420_resized(vsd_ctx* ctx, const uint8_t* y, const uint8_t* u, const uint8_t* v, uint8_t* out_y, uint8_t* out_u,
+                             uint8_t* out_v);
 int vsd_debug_read_rgb_in(vsd_ctx* ctx, uint8_t* host);
 
 /* Split form of vsd_infer_yuv420 (asynchronous on the context's stream; vsd_sync waits). */

@@ -158,6 +158,19 @@ def test_dropin_boundary_pil_in_pil_out(setup):
     assert np.array_equal(eng.debug_read_rgb_in()[0], np.asarray(fitted))
     out3 = handle.infer.remote(fitted, **opts).result(timeout=600)    # already working size: plain upload path
     assert np.array_equal(np.asarray(out3), np.asarray(out))
+    # YUV420P planes at the webcam size: colour conversion at the source size, then the same crop + resize
+    from oracle import imageproc
+    rs = np.random.RandomState(3)
+    y = rs.randint(16, 236, (480, 640)).astype(np.uint8)
+    u, v = rs.randint(16, 241, (240, 320)).astype(np.uint8), rs.randint(16, 241, (240, 320)).astype(np.uint8)
+    kw = {k: opts[k] for k in ("prompt", "strength", "steps", "seed")}
+    oy, ou, ov = handle.infer_yuv420.remote(y, u, v, height=256, width=256, **kw).result(timeout=600)
+    rgb_src = imageproc.yuv420_to_rgb(y, u, v)                         # frame.to_image() as specified by the oracle
+    want = np.asarray(VideoSDPipeline._fit(Image.fromarray(rgb_src), 256, 256))
+    assert np.array_equal(eng.debug_read_rgb_in()[0], want)
+    ref = handle.infer.remote(Image.fromarray(want), **opts).result(timeout=600)
+    ry, ru, rv = imageproc.rgb_to_yuv420(np.asarray(ref))
+    assert oy.shape == (1, 256, 256) and np.array_equal(oy[0], ry) and np.array_equal(ou[0], ru) and np.array_equal(ov[0], rv)
 
 
 def test_controlnet_branch_frame_and_reference_golden(setup, golden):

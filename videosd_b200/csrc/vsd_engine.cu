@@ -135,7 +135,7 @@ struct Engine {
     // ControlNet: canny/Sobel-conditioned residuals added to the UNet skips every step
     // GPU center-crop + Lanczos resize of arbitrary-size input frames
     struct Resize { int in_w = 0, in_h = 0, x0 = 0, y0 = 0, cw = 0, ch = 0, hks = 0, vks = 0;
-                    int *hb = nullptr, *hk = nullptr, *vb = nullptr, *vk = nullptr; uint8_t *src = nullptr, *tmp = nullptr; } rz;
+                    int *hb = nullptr, *hk = nullptr, *vb = nullptr, *vk = nullptr; uint8_t *src = nullptr, *tmp = nullptr, *yuv = nullptr; } rz;
     bool cn_enabled = false;
     float* cn_scales = nullptr;        // device [13]: logspace(-1,0,13) * conditioning scale (guess mode)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -936,7 +936,7 @@ static std::vector<std::string> transformer_prefixes(bool with_controlnet) {
 static bool has_controlnet_weights(const Engine* e) { return e->w.find("controlnet.conv_in.weight") != e->w.end(); }
 
 static void free_resize(Engine* e) {
-    void* ptrs[6] = {e->rz.hb, e->rz.hk, e->rz.vb, e->rz.vk, e->rz.src, e->rz.tmp};
+    void* ptrs[7] = {e->rz.hb, e->rz.hk, e->rz.vb, e->rz.vk, e->rz.src, e->rz.tmp, e->rz.yuv};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     e->rz = Engine::Resize();
@@ -1516,6 +1516,7 @@ int vsd_set_resize(vsd_ctx* c, int in_w, int in_h, int x0, int y0, int cw, int c
     VSD_CHECK_CUDA(cudaMalloc(&r.vb, vb_b)); VSD_CHECK_CUDA(cudaMalloc(&r.vk, vk_b));
     VSD_CHECK_CUDA(cudaMalloc(&r.src, (size_t)e->NB * in_w * in_h * 3));
     VSD_CHECK_CUDA(cudaMalloc(&r.tmp, (size_t)e->NB * ch * e->W * 3));
+    if (in_w % 2 == 0 && in_h % 2 == 0) VSD_CHECK_CUDA(cudaMalloc(&r.yuv, (size_t)e->NB * in_w * in_h * 3 / 2));
     VSD_CHECK_CUDA(cudaMemcpy(r.hb, h_bounds, hb_b, cudaMemcpyHostToDevice));
     VSD_CHECK_CUDA(cudaMemcpy(r.hk, h_coeffs, hk_b, cudaMemcpyHostToDevice));
     VSD_CHECK_CUDA(cudaMemcpy(r.vb, v_bounds, vb_b, cudaMemcpyHostToDevice));
@@ -1538,6 +1539,31 @@ int vsd_infer_rgb_resized(vsd_ctx* c, const uint8_t* rgb_src, uint8_t* rgb_out) 
     if (rc) return rc;
     const size_t px = (size_t)e->NB * e->H * e->W;
     VSD_CHECK_CUDA(cudaMemcpyAsync(rgb_out, e->d_rgb_out, px * 3, cudaMemcpyDeviceToHost, e->stream));
+    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+/* Same with YUV420P planes at the source geometry ([batch][in_h][in_w], [batch][in_h/2][in_w/2] x2): colour conversion at the
+ * source size (what frame.to_image() does, server.py:104-108), crop + Lanczos, frame, working-size YUV420P planes out. */
+int vsd_infer_yuv420_resized(vsd_ctx* c, const uint8_t* y, const uint8_t* u, const uint8_t* v, uint8_t* out_y, uint8_t* out_u,
+                             uint8_t* out_v) {
+    CTX_GUARD(c);
+    Engine* e = &c->e;
+    ENG_REQUIRE(e->rz.src != nullptr, "vsd_set_resize() first");
+    ENG_REQUIRE(e->rz.yuv != nullptr, "YUV420 input needs even source width and height");
+    const Engine::Resize& r = e->rz;
+    const size_t spx = (size_t)e->NB * r.in_w * r.in_h;
+    uint8_t *dy = r.yuv, *du = r.yuv + spx, *dv = r.yuv + spx + spx / 4;
+    VSD_CHECK_CUDA(cudaMemcpyAsync(dy, y, spx, cudaMemcpyHostToDevice, e->stream));
+    VSD_CHECK_CUDA(cudaMemcpyAsync(du, u, spx / 4, cudaMemcpyHostToDevice, e->stream));
+    VSD_CHECK_CUDA(cudaMemcpyAsync(dv, v, spx / 4, cudaMemcpyHostToDevice, e->stream));
+    int rc = launch_yuv420_to_rgb(dy, du, dv, r.src, e->NB, r.in_h, r.in_w, e->stream);
+    if (!rc) rc = launch_crop_resize(r.src, r.in_w, r.in_h, r.x0, r.y0, r.cw, r.ch, r.tmp, e->d_rgb_in, e->W, e->H, r.hb, r.hk, r.hks,
+                                     r.vb, r.vk, r.vks, e->NB, e->stream);
+    if (!rc) rc = run_frame(e, false);
+    if (rc) return rc;
+    rc = vsd_download_yuv420(c, out_y, out_u, out_v);
+    if (rc) return rc;
     VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
     return 0;
 }

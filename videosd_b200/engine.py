@@ -70,6 +70,7 @@ class Engine:
         check(self._L.vsd_configure(self._ctx, c_int(batch), c_int(height), c_int(width)), "vsd_configure")
         self.batch, self.height, self.width = batch, height, width
         self._sched_key = None
+        self._resize_key = None      # vsd_configure drops the resize tables / staging buffers
 
     def set_schedule(self, strength, steps, guidance_scale=7.5):
         ts = self._schedule.timesteps(strength, steps)
@@ -140,6 +141,11 @@ class Engine:
     def infer_rgb_resized(self, rgb_src, rgb_out):
         """rgb_src: u8 (batch, in_h, in_w, 3) host; rgb_out: u8 (batch, height, width, 3) host."""
         check(self._L.vsd_infer_rgb_resized(self._ctx, _u8ptr(rgb_src), _u8ptr(rgb_out)), "vsd_infer_rgb_resized")
+
+    def infer_yuv420_resized(self, y, u, v, out_y, out_u, out_v):
+        """y/u/v: u8 planes at the set_resize() source geometry; out_*: u8 planes at the working size."""
+        check(self._L.vsd_infer_yuv420_resized(self._ctx, _u8ptr(y), _u8ptr(u), _u8ptr(v), _u8ptr(out_y), _u8ptr(out_u),
+                                               _u8ptr(out_v)), "vsd_infer_yuv420_resized")
 
     def debug_read_rgb_in(self):
         a = np.empty((self.batch, self.height, self.width, 3), dtype=np.uint8)

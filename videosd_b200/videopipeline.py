@@ -201,13 +201,23 @@ class VideoSDPipeline:
         return Image.fromarray(rgb_out)
 
     def infer_yuv420(self, y, u, v, prompt=["pixar, cg"], strength=0.4, steps=20, seed=42, prompt_embeds=None,
-                     controlnet_scale=1, **_ignored):
-        """Fast path: YUV420P planes (u8 numpy, already at the working size; (B,H,W) or (H,W)) -> planes."""
+                     controlnet_scale=1, height=None, width=None, **_ignored):
+        """Fast path: YUV420P planes (u8 numpy, (B,H,W) or (H,W)) -> planes at the working size. With height/width
+        different from the planes' size the frame is colour-converted, center-cropped and Lanczos-resized on the GPU
+        (same result as frame.to_image() + the reference's PIL crop/resize, videopipeline.py:92-107)."""
         y, u, v = (np.ascontiguousarray(a) for a in (y, u, v))
         if y.ndim == 2:
             y, u, v = y[None], u[None], v[None]
         b, h, w = y.shape
-        self._prepare(b, h, w, float(strength), int(steps), 7.5, int(seed), prompt, prompt_embeds, controlnet_scale)
-        oy, ou, ov = np.empty_like(y), np.empty_like(u), np.empty_like(v)
-        self.engine.infer_yuv420(y, u, v, oy, ou, ov)
+        oh, ow = (h if height is None else int(height)), (w if width is None else int(width))
+        self._prepare(b, oh, ow, float(strength), int(steps), 7.5, int(seed), prompt, prompt_embeds, controlnet_scale)
+        oy = np.empty((b, oh, ow), np.uint8)
+        ou, ov = np.empty((b, oh // 2, ow // 2), np.uint8), np.empty((b, oh // 2, ow // 2), np.uint8)
+        if (oh, ow) == (h, w):
+            self.engine.infer_yuv420(y, u, v, oy, ou, ov)
+        else:
+            key = (w, h, ow, oh, b)
+            if getattr(self.engine, "_resize_key", None) != key:
+                self.engine.set_resize(w, h)
+            self.engine.infer_yuv420_resized(y, u, v, oy, ou, ov)
         return oy, ou, ov
