@@ -27,9 +27,9 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 // Every loop is fully unrolled with compile-time indices so v[] stays in registers.
 //   sbias : optional shared-memory copy of (bias [+ rowvec]) for this tile's columns (index 0 = this chunk)
 //   rpre  : optional residual values for this chunk, already loaded (4 x uint4 = 32 bf16)
-__device__ __forceinline__ void epilogue_store32(const GemmParams& p, float (&v)[32], int n_img, long grow, int col,
-                                                 int ncols, const float* sbias, bool rowvec_in_sbias,
-                                                 const uint4* rpre) {
+__device__ __forceinline__ void epilogue_math32(const GemmParams& p, float (&v)[32], int n_img, long grow, int col,
+                                                int ncols, const float* sbias, bool rowvec_in_sbias,
+                                                const uint4* rpre) {
     if (ncols <= 0) return;
     const bool full = (ncols >= 32);
     if (sbias) {
@@ -94,6 +94,14 @@ __device__ __forceinline__ void epilogue_store32(const GemmParams& p, float (&v)
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
     }
+}
+
+__device__ __forceinline__ void epilogue_store32(const GemmParams& p, float (&v)[32], int n_img, long grow, int col,
+                                                 int ncols, const float* sbias, bool rowvec_in_sbias,
+                                                 const uint4* rpre) {
+    if (ncols <= 0) return;
+    const bool full = (ncols >= 32);
+    epilogue_math32(p, v, n_img, grow, col, ncols, sbias, rowvec_in_sbias, rpre);
     if (p.out_f32) {
         float* o = reinterpret_cast<float*>(p.out) + grow * p.ldo + col;
         if (full && ((p.ldo & 3) == 0) && ((col & 3) == 0)) {
@@ -121,9 +129,10 @@ __device__ __forceinline__ void epilogue_store32(const GemmParams& p, float (&v)
     }
 }
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int kEpi>   // 0: direct st.global epilogue, 1: bf16 tile through smem + TMA store, 2: fp32 split-K partials through TMA
+__global__ void __launch_bounds__(kGemmThreads, (kEpi == 1 ? 2 : 1))
 conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapR, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stages = p.stages;
@@ -133,10 +142,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const bool halo = p.halo != 0;
     const uint32_t a_stage = halo ? (uint32_t)kHaloABytes : (uint32_t)kbs * kABytes;
     const uint32_t stage_bytes = halo ? ((uint32_t)kHaloABytes + 3u * b_bytes) : (uint32_t)kbs * ((uint32_t)kABytes + b_bytes);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.bar_off);
     uint64_t* empty_bar = full_bar + stages;
     uint64_t* tmem_full_bar = empty_bar + stages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* res_bar = tmem_full_bar + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
+    uint8_t* stag = smem + p.stage_off;   // epilogue staging (and residual tile) region
     // [block_n] bias (+ time-embedding row) of this tile, 16-byte aligned for float4 reads
     float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
 
@@ -169,7 +180,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 mbar_init(&empty_bar[s], 1);
             }
             mbar_init(tmem_full_bar, 1);
+            mbar_init(res_bar, 1);
             fence_barrier_init();
+            if (kEpi != 0) tma_prefetch_desc(&mapC);
+            if (kEpi == 1 && p.tma_res) tma_prefetch_desc(&mapR);
             // The constant operand (weights) of the first ring pass is requested right away: before the TMEM
             // allocation / CTA barrier below and before waiting for the producer kernel of the activations (PDL).
             int kb = kb_begin;
@@ -214,6 +228,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             int s = 0, dbg_it = 0;
             uint32_t ph = 0;
             pdl_wait();
+            // The residual tile rides behind the first ring pass: [chunk of 32 columns][128 rows][64 B], 64-byte swizzle
+            const int res_at = min(stages, total_iters) - 1;
+            auto issue_residual = [&]() {
+                mbar_expect_tx(res_bar, (uint32_t)p.block_n * 256u);
+                for (int c = 0; c < p.block_n; c += 32)
+                    tma_load_4d(stag + (size_t)(c >> 5) * 8192, &mapR, res_bar, col0 + c, w0, h0, n0);
+            };
             if (halo) {
                 // iteration = (64-channel block cb, column shift dx): ONE 8 x 18-pixel halo tile serves the three
                 // row taps (dy = -1, 0, +1) as 1024-byte-aligned offsets; three weight tiles (one per dy) ride along.
@@ -230,6 +251,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     if (!pre)
                         for (int dyi = 0; dyi < 3; ++dyi)
                             tma_load_2d(sb + (size_t)dyi * b_bytes, &mapB, &full_bar[s], ((dyi * 3 + dxi) * kpt + cbh) * 64, col0);
+                    if (kEpi == 1 && p.tma_res && dbg_it == res_at) issue_residual();
                     ++dbg_it;
                     if (++s == stages) { s = 0; ph ^= 1u; }
                 }
@@ -258,6 +280,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     if (++cb == kpt) { cb = 0; ++tap; }
                 }
                 if (dbg_cta && dbg_it < 16) p.dbg[16 + 2 * dbg_it + 1] = clock64();
+                if (kEpi == 1 && p.tma_res && dbg_it == res_at) issue_residual();
                 ++dbg_it;
                 if (++s == stages) { s = 0; ph ^= 1u; }
             }
@@ -327,7 +350,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
         pdl_wait();   // bias / time-embedding rows above are constants; everything below depends on earlier kernels
         const bool res_vec = (p.residual != nullptr) && row_ok && ((p.ldr & 7) == 0) && ((col0 & 7) == 0) &&
-                             (p.splits == 1) && (p.act != ACT_GEGLU);
+                             (p.splits == 1) && (p.act != ACT_GEGLU) && !p.tma_res;
+        // this warp's 32 rows as a sub-box of the tile rectangle (all extents are powers of two)
+        const int sw0 = w0 + (q * 32) % p.BW, sh0 = h0 + ((q * 32) / p.BW) % p.BH, sn0 = n0 + (q * 32) / (p.BW * p.BH);
         uint4 rnext[4];
         if (res_vec && col0 + 32 <= p.N) {
             const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + grow * p.ldr + col0);
@@ -339,7 +364,113 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         tc_fence_after_sync();
         if (threadIdx.x == 64) VSD_STAMP(4);
         const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
-        if (p.splits > 1) {
+        if (kEpi == 2) {
+            // split-K partials: [32 rows][128 B] fp32 chunks, 128-byte swizzle, stored with one 5-D box per warp and chunk
+            for (int c = 0; c < p.block_n; c += 32) {
+                uint32_t u[32];
+                tmem_ld32(tbase + c, u);
+                uint8_t* buf = stag + (size_t)((c >> 5) * 4 + q) * 4096;
+                uint8_t* myrow = buf + lane * 128;
+                const int sx = lane & 7;
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<uint4*>(myrow + ((j ^ sx) << 4)) = make_uint4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (col0 + c < p.N && elect_one()) {
+                    tma_store_5d(&mapC, buf, col0 + c, sw0, sh0, sn0, split);
+                    tma_store_commit();
+                }
+            }
+            tma_store_wait_all();
+        } else if (kEpi == 1 && p.act == ACT_GEGLU) {
+            const int half = p.block_n >> 1;
+            const int ocol0 = col0 >> 1;
+            for (int c = 0; c < half; c += 32) {
+                uint32_t u[32], g[32];
+                tmem_ld32(tbase + c, u);
+                tmem_ld32(tbase + half + c, g);
+                uint8_t* buf = stag + (size_t)((c >> 5) * 4 + q) * 2048;
+                uint8_t* myrow = buf + lane * 64;
+                const int sx = (lane >> 1) & 3;
+                tmem_ld_wait();
+                const float4* bu = reinterpret_cast<const float4*>(sbias + c);
+                const float4* bg = reinterpret_cast<const float4*>(sbias + half + c);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float v[8];
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const float4 tu = bu[j * 2 + h2], tg = bg[j * 2 + h2];
+                        const int b0 = j * 8 + h2 * 4;
+                        v[h2 * 4 + 0] = (__uint_as_float(u[b0 + 0]) + tu.x) * gelu_erf(__uint_as_float(g[b0 + 0]) + tg.x);
+                        v[h2 * 4 + 1] = (__uint_as_float(u[b0 + 1]) + tu.y) * gelu_erf(__uint_as_float(g[b0 + 1]) + tg.y);
+                        v[h2 * 4 + 2] = (__uint_as_float(u[b0 + 2]) + tu.z) * gelu_erf(__uint_as_float(g[b0 + 2]) + tg.z);
+                        v[h2 * 4 + 3] = (__uint_as_float(u[b0 + 3]) + tu.w) * gelu_erf(__uint_as_float(g[b0 + 3]) + tg.w);
+                    }
+                    *reinterpret_cast<uint4*>(myrow + ((j ^ sx) << 4)) =
+                        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (elect_one()) {
+                    tma_store_4d(&mapC, buf, ocol0 + c, sw0, sh0, sn0);
+                    tma_store_commit();
+                }
+            }
+            tma_store_wait_all();
+        } else if (kEpi == 1) {
+            if (p.tma_res) mbar_wait(res_bar, 0, 4);
+            for (int c = 0; c < p.block_n; c += 32) {
+                uint32_t u[32];
+                tmem_ld32(tbase + c, u);
+                const int col = col0 + c;
+                const int ncols = min(32, p.N - col);
+                uint8_t* buf = stag + (size_t)((c >> 5) * 4 + q) * 2048;
+                uint8_t* myrow = buf + lane * 64;
+                const int sx = (lane >> 1) & 3;
+                uint4 rcur[4];
+                const bool have_pre = res_vec && ncols == 32;
+                if (have_pre) {
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) rcur[q4] = rnext[q4];
+                    if (c + 32 < p.block_n && col + 64 <= p.N) {
+                        const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + grow * p.ldr + col + 32);
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) rnext[q4] = r4[q4];
+                    }
+                }
+                tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]);
+                if (row_ok) {
+                    if (p.tma_res) {
+                        uint4 rs[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) rs[j] = *reinterpret_cast<const uint4*>(myrow + ((j ^ sx) << 4));
+                        epilogue_math32(p, v, n_img, grow, col, ncols, use_sbias ? sbias + c : nullptr, rowvec_in_sbias, rs);
+                    } else {
+                        epilogue_math32(p, v, n_img, grow, col, ncols, use_sbias ? sbias + c : nullptr, rowvec_in_sbias,
+                                        have_pre ? rcur : nullptr);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<uint4*>(myrow + ((j ^ sx) << 4)) =
+                        make_uint4(pack_bf16x2(v[j * 8], v[j * 8 + 1]), pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
+                                   pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (ncols > 0 && elect_one()) {
+                    tma_store_4d(&mapC, buf, col, sw0, sh0, sn0);
+                    tma_store_commit();
+                }
+            }
+            tma_store_wait_all();
+        } else if (kEpi != 0) {
+        } else if (p.splits > 1) {
             float* dst = p.partial + ((long)split * rows_total + grow) * p.N;
             for (int c = 0; c < p.block_n; c += 32) {
                 uint32_t u[32];
@@ -495,13 +626,14 @@ static void resolve_encode() {
 }
 
 static int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-                  const cuuint32_t* box) {
+                  const cuuint32_t* box, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                  CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     std::call_once(g_encode_once, resolve_encode);
     VSD_REQUIRE(g_encode != nullptr, "cuTensorMapEncodeTiled driver entry point not available (no CUDA driver?)");
     VSD_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map base must be 16-byte aligned");
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides,
-                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+    CUresult r = g_encode(m, dtype, (cuuint32_t)rank, const_cast<void*>(base), dims, strides,
+                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r) + " rank=" +
@@ -520,6 +652,21 @@ int make_tmap_act(CUtensorMap* m, const void* base, int C, int W, int H, int N, 
     return encode(m, base, 4, dims, strides, box);
 }
 
+// Epilogue maps: 32-column boxes over a [NB][H][W][ld] bf16 tensor (64-byte swizzle), or over the fp32 split-K workspace
+// [splits][NB][H][W][N] (128-byte swizzle).
+static int make_tmap_epi_bf16(CUtensorMap* m, const void* base, int C, int W, int H, int N, int ld, int boxW, int boxH, int boxN) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+    cuuint32_t box[4] = {32, (cuuint32_t)boxW, (cuuint32_t)boxH, (cuuint32_t)boxN};
+    return encode(m, base, 4, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B);
+}
+static int make_tmap_epi_partial(CUtensorMap* m, const void* base, int C, int W, int H, int N, int splits, int boxW, int boxH, int boxN) {
+    cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)splits};
+    cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4, (cuuint64_t)N * H * W * C * 4};
+    cuuint32_t box[5] = {32, (cuuint32_t)boxW, (cuuint32_t)boxH, (cuuint32_t)boxN, 1};
+    return encode(m, base, 5, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 int make_tmap_2d(CUtensorMap* m, const void* base, int K, int rows, int ld, int box_rows) {
     VSD_REQUIRE((ld % 8) == 0, "matrix row stride must be a multiple of 8 elements");
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
@@ -536,7 +683,9 @@ int gemm_init() {
     VSD_CHECK_CUDA(cudaGetDevice(&dev));
     VSD_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     VSD_CHECK_CUDA(cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
     return 0;
 }
 
@@ -643,6 +792,21 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
     }
     p.partial = partial_ws;
 
+    // Epilogue through shared memory + bulk tensor stores (see GemmParams::tma_out)
+    static const bool tma_epi = !(getenv("VSD_TMA_EPI") && atoi(getenv("VSD_TMA_EPI")) == 0);
+    const int n_out = (act == ACT_GEGLU) ? N / 2 : N;
+    const int bn_out = (act == ACT_GEGLU) ? bn / 2 : bn;
+    int tma_out = 0, tma_res = 0;
+    if (tma_epi) {
+        if (splits > 1) {
+            if ((N % 4) == 0 && (reinterpret_cast<uintptr_t>(partial_ws) & 15) == 0) tma_out = 2;
+        } else if (!out_f32 && (ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (bn_out % 32) == 0) {
+            tma_out = 1;
+            if (residual != nullptr && (ldr % 8) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0) tma_res = 1;
+        }
+    }
+    int stag_bytes = tma_out == 2 ? bn * 512 : (tma_out == 1 ? bn_out * 256 : 0);   // 128 rows x (4 | 2) bytes per column
+
     // Tiles up to 160 columns run two CTAs per SM (one CTA's epilogue overlaps the other's main loop);
     // wider tiles take the whole SM with a deeper ring.
     const int stage_bytes = kABytes + bn * 128;
@@ -654,9 +818,19 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
     // stage carries kb_per_stage 64-wide k-blocks; keep >= 3 stages in flight when the budget allows.
     int kbs = force_kb_per_stage > 0 ? force_kb_per_stage : 2;
     if (halo) kbs = 1;
-    while (kbs > 1 && ((smem_budget - 3072) / (kbs * stage_bytes) < (force_kb_per_stage > 0 ? 2 : 3) || kbs > p.kb_per_split)) --kbs;
-    const int stage_total = halo ? (kHaloABytes + 3 * bn * 128) : kbs * stage_bytes;
-    int stages = (smem_budget - 3072) / stage_total;
+    int stages = 0, stage_total = 0;
+    for (;;) {
+        // the residual tile needs its own region (it is in flight while the ring is busy); plain staging reuses the ring
+        const int ring_budget = smem_budget - 3072 - (tma_res ? stag_bytes : 0);
+        int k2 = kbs;
+        while (k2 > 1 && (ring_budget / (k2 * stage_bytes) < (force_kb_per_stage > 0 ? 2 : 3) || k2 > p.kb_per_split)) --k2;
+        stage_total = halo ? (kHaloABytes + 3 * bn * 128) : k2 * stage_bytes;
+        stages = ring_budget / stage_total;
+        if (tma_res && stages < 2) { tma_res = 0; continue; }   // no room: read the residual straight from global memory
+        if (tma_out && !tma_res && stag_bytes > smem_budget - 3072) { tma_out = 0; stag_bytes = 0; continue; }
+        kbs = k2;
+        break;
+    }
     if (halo) VSD_REQUIRE(stages >= 2, "halo tile does not leave room for two pipeline stages");
     if (stages > 8) stages = 8;
     const int stage_iters = (p.kb_per_split + kbs - 1) / kbs;
@@ -664,7 +838,17 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
     if (stages < 1) stages = 1;
     p.stages = stages;
     p.kb_per_stage = kbs;
-    op->smem_bytes = stages * stage_total + 1024 /*align slack*/ + (2 * stages + 1) * 8 + 64 + bn * 4;
+    const int ring_bytes = stages * stage_total;
+    int region = ring_bytes;
+    p.stage_off = 0;
+    if (tma_res) { p.stage_off = (unsigned)ring_bytes; region = ring_bytes + stag_bytes; }
+    else if (stag_bytes > region) region = stag_bytes;
+    p.bar_off = (unsigned)region;
+    p.tma_out = tma_out; p.tma_res = tma_res;
+    p.sbw = p.BW < 32 ? p.BW : 32;
+    p.sbh = (32 / p.sbw) < p.BH ? (32 / p.sbw) : p.BH;
+    p.sbn = 32 / (p.sbw * p.sbh);
+    op->smem_bytes = region + 1024 /*align slack*/ + (2 * stages + 2) * 8 + 64 + bn * 4;
     // With programmatic dependent launch CTAs of different kernels co-reside on an SM. TMEM is not part of the block
     // scheduler's accounting, so bound the CTAs per SM through shared memory: smem >= tmem_cols * 450 B guarantees that
     // the co-resident CTAs' TMEM columns sum to <= 512 (otherwise tcgen05.alloc of a CTA the others wait on could spin).
@@ -683,12 +867,20 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
     if (rc) return rc;
     rc = make_tmap_2d(&op->mapB, wt, taps * a.C, N, ldw, bn);
     if (rc) return rc;
+    op->mapC = op->mapA;   // placeholders when unused (a valid descriptor keeps the kernel parameter well-formed)
+    op->mapR = op->mapA;
+    if (tma_out == 1) rc = make_tmap_epi_bf16(&op->mapC, out, n_out, a.W, a.H, a.NB, ldo, p.sbw, p.sbh, p.sbn);
+    else if (tma_out == 2) rc = make_tmap_epi_partial(&op->mapC, partial_ws, N, a.W, a.H, a.NB, splits, p.sbw, p.sbh, p.sbn);
+    if (rc) return rc;
+    if (tma_res) rc = make_tmap_epi_bf16(&op->mapR, residual, N, a.W, a.H, a.NB, ldr, p.BW, p.BH, p.BN);
+    if (rc) return rc;
     op->grid = dim3(m_tiles, n_tiles, splits);
     return 0;
 }
 
 int launch_gemm_op(const GemmOp& op, cudaStream_t st) {
-    VSD_CHECK_CUDA(launch_k(conv_gemm_kernel, op.grid, dim3(kGemmThreads), (size_t)op.smem_bytes, st, op.mapA, op.mapB, op.p));
+    auto kern = op.p.tma_out == 2 ? conv_gemm_kernel<2> : (op.p.tma_out == 1 ? conv_gemm_kernel<1> : conv_gemm_kernel<0>);
+    VSD_CHECK_CUDA(launch_k(kern, op.grid, dim3(kGemmThreads), (size_t)op.smem_bytes, st, op.mapA, op.mapB, op.mapC, op.mapR, op.p));
     if (op.p.splits > 1) {
         const long rows = (long)op.p.NB * op.p.H * op.p.W;
         return launch_splitk_reduce(op.p, rows, st);

@@ -82,11 +82,18 @@ struct GemmParams {
     int act, relu;
     float* partial;       // [splits, rows, N] fp32 when splits > 1
     int a_static, b_static;  // operand is constant (weights): its first stages may be fetched before pdl_wait()
+    // Epilogue through shared memory + bulk tensor stores: each epilogue warp stages its 32 rows x 32 columns in the
+    // swizzled layout of mapC's box (sbw x sbh x sbn pixels) and one lane issues the store; TMA clips rows / columns
+    // outside the tensor. tma_out: 0 = direct st.global, 1 = bf16 output (4-D map), 2 = fp32 split-K partials (5-D map).
+    // tma_res: the residual tile is fetched by TMA (mapR) into the staging region while the main loop runs.
+    int tma_out, tma_res;
+    int sbw, sbh, sbn;
+    unsigned int stage_off, bar_off;   // byte offsets of the staging region / the mbarrier block in dynamic smem
     long long* dbg;       // optional: CTA (0,0,0) writes clock64() phase stamps here (bring-up only)
 };
 
 struct GemmOp {
-    CUtensorMap mapA, mapB;
+    CUtensorMap mapA, mapB, mapC, mapR;
     GemmParams p;
     dim3 grid;
     int smem_bytes;
