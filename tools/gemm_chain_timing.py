@@ -1,0 +1,79 @@
+"""Where does the time of a small dependent GEMM go inside a CUDA graph? A ping-pong chain x -> y -> x ... of identical
+GEMMs (PDL edges, warm L2) with phase stamps (SM clock + globaltimer) from CTA 0 of every kernel. Bring-up tool."""
+import ctypes
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from videosd_b200._lib import _p, check, cur_stream, lib  # noqa: E402
+
+c_int = ctypes.c_int
+N_CHAIN = 24
+# rows, K, N, taps(h,w), bn, splits, occ, kbs
+CASES = [
+    ("16x16 lin 1280->1280", (1, 1, 256, 1280), 1280, 1, 128, 1, 1, 2),
+    ("16x16 lin 1280->1280", (1, 1, 256, 1280), 1280, 1, 64, 1, 1, 2),
+    ("16x16 lin 1280->1280", (1, 1, 256, 1280), 1280, 1, 32, 1, 1, 2),
+    ("16x16 lin 1280->1280 sp2", (1, 1, 256, 1280), 1280, 1, 128, 2, 1, 2),
+    ("16x16 lin 1280->1280 sp4", (1, 1, 256, 1280), 1280, 1, 128, 4, 1, 2),
+    ("16x16 lin 1280->1280 sp6", (1, 1, 256, 1280), 1280, 1, 128, 6, 1, 2),
+    ("16x16 lin 1280->1280 sp8", (1, 1, 256, 1280), 1280, 1, 128, 8, 1, 1),
+    ("16x16 lin 1280->1280 sp4 bn64", (1, 1, 256, 1280), 1280, 1, 64, 4, 1, 2),
+    ("32x32 lin 640->640 sp2", (1, 1, 1024, 640), 640, 1, 64, 2, 1, 2),
+    ("32x32 conv3x3 640->640 sp3", (1, 32, 32, 640), 640, 9, 128, 3, 1, 2),
+    ("32x32 conv3x3 640->640 sp6", (1, 32, 32, 640), 640, 9, 128, 6, 1, 2),
+    ("16x16 conv3x3 1280->1280 sp8", (1, 16, 16, 1280), 1280, 9, 128, 8, 1, 2),
+    ("32x32 lin 640->640", (1, 1, 1024, 640), 640, 1, 64, 1, 1, 2),
+    ("64x64 lin 320->320", (1, 1, 4096, 320), 320, 1, 64, 1, 2, 1),
+    ("16x16 conv3x3 1280->1280 sp4", (1, 16, 16, 1280), 1280, 9, 96, 4, 1, 1),
+    ("64x64 conv3x3 320->320", (1, 64, 64, 320), 320, 9, 96, 1, 1, 1),
+]
+import os as _os
+if _os.environ.get('CHAIN_ONLY'):
+    CASES = [c_ for c_ in CASES if _os.environ['CHAIN_ONLY'] in c_[0]]
+for (name, (nb, h, w, c), n, taps, bn, sp, occ, kbs) in CASES:
+    if n != c:
+        continue
+    bufs = [torch.randn((nb, h, w, c), device="cuda").bfloat16() * 0.5 for _ in range(2)]
+    wt = (torch.randn((n, taps * c), device="cuda") * (taps * c) ** -0.5).bfloat16()
+    bias = torch.zeros((n,), device="cuda")
+    dbg = torch.zeros((N_CHAIN, 128), dtype=torch.int64, device="cuda")
+
+    def launch(i):
+        check(lib().vsd_op_conv_gemm_timed(_p(bufs[i & 1]), c_int(nb), c_int(h), c_int(w), c_int(c), c_int(c), c_int(taps), _p(wt),
+                                           c_int(n), _p(bufs[(i + 1) & 1]), c_int(n), _p(bias), c_int(bn), c_int(sp), c_int(occ),
+                                           c_int(kbs), _p(dbg[i]), cur_stream()), "timed")
+
+    launch(0)
+    torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(gr, stream=s):
+            for i in range(N_CHAIN):
+                launch(i)
+    for _ in range(3):
+        gr.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        gr.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    per = e0.elapsed_time(e1) * 1e3 / (10 * N_CHAIN)
+    d = dbg.cpu()
+    gt = d[:, 100:112].double()          # globaltimer ns at stamps 0..11
+    ck = d[:, 0:12].double()
+    sel = slice(8, N_CHAIN)
+    start2start = (gt[9:, 0] - gt[8:-1, 0]).mean().item() / 1e3
+    prev_end_to_start = (gt[9:, 0] - gt[8:-1, 6]).mean().item() / 1e3      # negative = overlapped prologue (PDL)
+    prev_end_to_wait = (gt[9:, 7] - gt[8:-1, 6]).mean().item() / 1e3       # previous CTA0 teardown -> our pdl_wait returned
+    ph = lambda a, b: ((ck[sel, b] - ck[sel, a]).mean().item())            # noqa: E731
+    print(f"{name:32s} bn={bn:3d} sp={sp} occ={occ} kbs={kbs}: {per:6.2f} us/kernel in graph | start->start {start2start:6.2f} us | "
+          f"prevEnd->start {prev_end_to_start:6.2f} us, prevEnd->pdlwait {prev_end_to_wait:6.2f} us | cycles: setup {ph(0,1):.0f}, "
+          f"start->pdlwait {ph(0,7):.0f}, pdlwait->firstMMA {ph(7,2):.0f}, mainloop {ph(2,3):.0f}, ->accum ready {ph(3,4):.0f}, "
+          f"epilogue {ph(4,5):.0f}, teardown {ph(5,6):.0f}, total {ph(0,6):.0f}"
+          + (f" | cluster: dump {ph(4,8):.0f}, sync {ph(8,9):.0f}, reduce {ph(9,10):.0f}" if sp > 1 else ""), flush=True)

@@ -129,8 +129,57 @@ __device__ __forceinline__ void epilogue_store32(const GemmParams& p, float (&v)
     }
 }
 
-template <int kEpi>   // 0: direct st.global epilogue, 1: bf16 tile through smem + TMA store, 2: fp32 split-K partials through TMA
-__global__ void __launch_bounds__(kGemmThreads, (kEpi == 1 ? 2 : 1))
+// Epilogue of 4 consecutive columns of one output row (bias, per-image row, scale, residual, ReLU, store).
+__device__ __forceinline__ void splitk_finish4(const GemmParams& p, float (&v)[4], long grow, int col) {
+    const int ncols = min(4, p.N - col);
+    const bool vec = (ncols == 4) && ((p.N & 3) == 0);
+    if (vec && !p.rowvec && !p.out_scale && (!p.residual || (p.ldr & 3) == 0)) {
+        if (p.bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+            v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+        }
+        if (p.residual) {
+            const uint2 r = *reinterpret_cast<const uint2*>(p.residual + grow * p.ldr + col);
+            const float2 a = unpack_bf16x2(r.x), c = unpack_bf16x2(r.y);
+            v[0] += a.x; v[1] += a.y; v[2] += c.x; v[3] += c.y;
+        }
+        if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+    } else
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (j < ncols) {
+            if (p.bias) v[j] += __ldg(p.bias + col + j);
+            if (p.rowvec) v[j] += __ldg(p.rowvec + (grow / ((long)p.H * p.W)) * p.N + col + j);
+            if (p.out_scale) v[j] *= __ldg(p.out_scale);
+            if (p.residual) v[j] += __bfloat162float(p.residual[grow * p.ldr + col + j]);
+            if (p.relu) v[j] = fmaxf(v[j], 0.f);
+        }
+    }
+    if (p.out_f32) {
+        float* o = reinterpret_cast<float*>(p.out) + grow * p.ldo + col;
+        if (vec && ((p.ldo & 3) == 0)) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j < ncols) o[j] = v[j];
+        }
+    } else {
+        bf16* o = reinterpret_cast<bf16*>(p.out) + grow * p.ldo + col;
+        if (vec && ((p.ldo & 3) == 0)) *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+        else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j < ncols) o[j] = __float2bfloat16(v[j]);
+        }
+    }
+}
+
+template <int kEpi>   // 0: direct st.global epilogue, 1: bf16 tile through smem + TMA store, 2: fp32 split-K partials through TMA,
+                      // 3: split-K across a thread-block cluster, reduced through distributed shared memory
+__global__ void __launch_bounds__(kGemmThreads, (kEpi == 1 || kEpi == 3 ? 2 : 1))
 conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapR, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -154,7 +203,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const bool dbg_cta = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
-#define VSD_STAMP(i) do { if (dbg_cta) p.dbg[i] = clock64(); } while (0)
+#define VSD_STAMP(i) do { if (dbg_cta) { p.dbg[i] = clock64(); p.dbg[100 + (i)] = (long long)globaltimer_ns(); } } while (0)
     if (threadIdx.x == 0) VSD_STAMP(0);
     pdl_launch_dependents();   // the next kernel may begin its own prologue / weight prefetch now
 
@@ -228,6 +277,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             int s = 0, dbg_it = 0;
             uint32_t ph = 0;
             pdl_wait();
+            VSD_STAMP(7);
             // The residual tile rides behind the first ring pass: [chunk of 32 columns][128 rows][64 B], 64-byte swizzle
             const int res_at = min(stages, total_iters) - 1;
             auto issue_residual = [&]() {
@@ -364,7 +414,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         tc_fence_after_sync();
         if (threadIdx.x == 64) VSD_STAMP(4);
         const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
-        if (kEpi == 2) {
+        if (kEpi == 2 || kEpi == 3) {
             // split-K partials: [32 rows][128 B] fp32 chunks, 128-byte swizzle, stored with one 5-D box per warp and chunk
             for (int c = 0; c < p.block_n; c += 32) {
                 uint32_t u[32];
@@ -383,7 +433,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     tma_store_commit();
                 }
             }
-            tma_store_wait_all();
+            if (kEpi == 3) {
+                // the cluster peers read these partials right after the cluster barrier: wait for the writes themselves
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                asm volatile("fence.proxy.async;" ::: "memory");
+                __threadfence();
+            } else {
+                tma_store_wait_all();
+            }
         } else if (kEpi == 1 && p.act == ACT_GEGLU) {
             const int half = p.block_n >> 1;
             const int ocol0 = col0 >> 1;
@@ -548,6 +605,61 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             }
         }
     }
+    if (kEpi == 3) {
+        // Split-K inside a thread-block cluster (1,1,splits): the CTAs are co-scheduled, so they can wait for each other.
+        // Every CTA reduces a band of the tile's rows from the L2-resident partials (split order => deterministic),
+        // applies the epilogue and stores coalesced rows. No second kernel.
+        if (threadIdx.x == 64) VSD_STAMP(8);
+        cluster_sync_all();
+        if (threadIdx.x == 64) VSD_STAMP(9);
+        if (warp >= 2) {
+            // Row band of this CTA; a warp walks rows, its lanes walk 4-column groups (coalesced 16-byte loads, 8-byte stores).
+            // No integer division: tile extents are powers of two (lbw / lbh), narrow tiles pack several rows per warp.
+            const int g4 = p.block_n >> 2;
+            const int rows_per = (kBlockM + p.splits - 1) / p.splits;
+            const int r_begin = split * rows_per;
+            const int r_end = min(kBlockM, r_begin + rows_per);
+            const int lg = (g4 <= 8) ? 3 : ((g4 <= 16) ? 4 : 5);          // lanes per row = 1 << lg (>= g4 when g4 <= 32)
+            const int lanes_row = 1 << lg;
+            const int rows_warp = 32 >> lg;                               // rows one warp covers per step
+            const int lane_r = lane >> lg, lane_g = lane & (lanes_row - 1);
+            const long rows_total = (long)p.NB * p.H * p.W;
+            const size_t split_stride4 = (size_t)(rows_total * p.N) >> 2;  // float4 units (N % 4 == 0)
+            const int wq = warp - 2;
+            for (int g0 = lane_g; g0 < g4; g0 += lanes_row) {
+                const int col = col0 + g0 * 4;
+                for (int rb = r_begin + wq * rows_warp + lane_r; rb < r_end; rb += 8 * rows_warp) {   // two rows in flight
+                    float v[2][4];
+                    long grow[2]; bool ok[2];
+                    const float4* src[2];
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const int r = rb + k * 4 * rows_warp;
+                        const int n_img = n0 + (r >> (p.lbw + p.lbh)), hh = h0 + ((r >> p.lbw) & (p.BH - 1)), ww = w0 + (r & (p.BW - 1));
+                        ok[k] = (r < r_end) && (n_img < p.NB) && (hh < p.H) && (ww < p.W) && (col < p.N);
+                        grow[k] = ((long)n_img * p.H + hh) * p.W + ww;
+                        src[k] = reinterpret_cast<const float4*>(ok[k] ? p.partial + grow[k] * p.N + col : p.partial);
+                        v[k][0] = v[k][1] = v[k][2] = v[k][3] = 0.f;
+                    }
+                    float4 x[2][8];   // all loads are issued before the first add (splits <= 8)
+#pragma unroll
+                    for (int z = 0; z < 8; ++z)
+#pragma unroll
+                        for (int k = 0; k < 2; ++k)
+                            if (z < p.splits) x[k][z] = __ldcg(src[k] + (size_t)z * split_stride4);
+#pragma unroll
+                    for (int z = 0; z < 8; ++z)
+#pragma unroll
+                        for (int k = 0; k < 2; ++k)
+                            if (z < p.splits) { v[k][0] += x[k][z].x; v[k][1] += x[k][z].y; v[k][2] += x[k][z].z; v[k][3] += x[k][z].w; }
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                        if (ok[k]) splitk_finish4(p, v[k], grow[k], col);
+                }
+            }
+        }
+        if (threadIdx.x == 64) VSD_STAMP(10);
+    }
     if (threadIdx.x == 64) VSD_STAMP(5);
     tc_fence_before_sync();
     __syncthreads();
@@ -583,34 +695,7 @@ __global__ void splitk_reduce_kernel(const GemmParams p, long rows) {
             for (int j = 0; j < 4; ++j)
                 if (j < ncols) v[j] += src[(long)s * split_stride + j];
     }
-    const int n_img = (int)(grow / ((long)p.H * p.W));
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        if (j < ncols) {
-            if (p.bias) v[j] += __ldg(p.bias + col + j);
-            if (p.rowvec) v[j] += __ldg(p.rowvec + (long)n_img * p.N + col + j);
-            if (p.out_scale) v[j] *= __ldg(p.out_scale);
-            if (p.residual) v[j] += __bfloat162float(p.residual[grow * p.ldr + col + j]);
-            if (p.relu) v[j] = fmaxf(v[j], 0.f);
-        }
-    }
-    if (p.out_f32) {
-        float* o = reinterpret_cast<float*>(p.out) + grow * p.ldo + col;
-        if (vec && ((p.ldo & 3) == 0)) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-        else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (j < ncols) o[j] = v[j];
-        }
-    } else {
-        bf16* o = reinterpret_cast<bf16*>(p.out) + grow * p.ldo + col;
-        if (vec && ((p.ldo & 3) == 0)) *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
-        else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (j < ncols) o[j] = __float2bfloat16(v[j]);
-        }
-    }
+    splitk_finish4(p, v, grow, col);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -686,6 +771,7 @@ int gemm_init() {
     VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
     VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
     VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
     return 0;
 }
 
@@ -787,7 +873,7 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
     p.splits = splits;
     if (splits > 1) {
         VSD_REQUIRE(partial_ws != nullptr && (size_t)splits * rows * N * 4 <= partial_ws_bytes,
-                    "split-K workspace too small");
+                    "split-K workspace too small");   // (the cluster variant does not touch it; kept as the common bound)
         VSD_REQUIRE(act == ACT_NONE, "split-K cannot be combined with GEGLU");
     }
     p.partial = partial_ws;
@@ -796,16 +882,23 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
     static const bool tma_epi = !(getenv("VSD_TMA_EPI") && atoi(getenv("VSD_TMA_EPI")) == 0);
     const int n_out = (act == ACT_GEGLU) ? N / 2 : N;
     const int bn_out = (act == ACT_GEGLU) ? bn / 2 : bn;
-    int tma_out = 0, tma_res = 0;
-    if (tma_epi) {
+    int tma_out = 0, tma_res = 0, cluster_k = 0;
+    // Measured on B200 (profiles/r01_cluster_splitk.md): the in-cluster reduce reads its 64 KB band at ~11 B/clk/SM and loses
+    // to the separate, fully parallel reduce kernel (9.9 vs 7.7 us for 256x1280x1280, 4 splits) => opt-in only.
+    static const bool cluster_ok = getenv("VSD_CLUSTER_SPLITK") && atoi(getenv("VSD_CLUSTER_SPLITK")) != 0;
+    const bool out_tma_ok = !out_f32 && (ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (bn_out % 32) == 0;
+    if (splits > 1 && splits <= 8 && cluster_ok && tma_epi && (N % 4) == 0 && (reinterpret_cast<uintptr_t>(partial_ws) & 15) == 0) {
+        cluster_k = 1;     // partials through TMA into the (L2-resident) workspace, reduced by the cluster itself
+        tma_out = 2;
+    } else if (tma_epi) {
         if (splits > 1) {
             if ((N % 4) == 0 && (reinterpret_cast<uintptr_t>(partial_ws) & 15) == 0) tma_out = 2;
-        } else if (!out_f32 && (ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (bn_out % 32) == 0) {
+        } else if (out_tma_ok) {
             tma_out = 1;
             if (residual != nullptr && (ldr % 8) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0) tma_res = 1;
         }
     }
-    int stag_bytes = tma_out == 2 ? bn * 512 : (tma_out == 1 ? bn_out * 256 : 0);   // 128 rows x (4 | 2) bytes per column
+    int stag_bytes = (tma_out == 2) ? bn * 512 : (tma_out == 1 ? bn_out * 256 : 0);   // 128 rows x (4 | 2) bytes per column
 
     // Tiles up to 160 columns run two CTAs per SM (one CTA's epilogue overlaps the other's main loop);
     // wider tiles take the whole SM with a deeper ring.
@@ -827,7 +920,7 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
         stage_total = halo ? (kHaloABytes + 3 * bn * 128) : k2 * stage_bytes;
         stages = ring_budget / stage_total;
         if (tma_res && stages < 2) { tma_res = 0; continue; }   // no room: read the residual straight from global memory
-        if (tma_out && !tma_res && stag_bytes > smem_budget - 3072) { tma_out = 0; stag_bytes = 0; continue; }
+        if (tma_out && !tma_res && stag_bytes > smem_budget - 3072) { tma_out = 0; stag_bytes = 0; cluster_k = 0; continue; }
         kbs = k2;
         break;
     }
@@ -844,7 +937,9 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
     if (tma_res) { p.stage_off = (unsigned)ring_bytes; region = ring_bytes + stag_bytes; }
     else if (stag_bytes > region) region = stag_bytes;
     p.bar_off = (unsigned)region;
-    p.tma_out = tma_out; p.tma_res = tma_res;
+    p.tma_out = tma_out; p.tma_res = tma_res; p.cluster_k = cluster_k;
+    p.lbw = 0; while ((1 << p.lbw) < p.BW) ++p.lbw;
+    p.lbh = 0; while ((1 << p.lbh) < p.BH) ++p.lbh;
     p.sbw = p.BW < 32 ? p.BW : 32;
     p.sbh = (32 / p.sbw) < p.BH ? (32 / p.sbw) : p.BH;
     p.sbn = 32 / (p.sbw * p.sbh);
@@ -879,6 +974,11 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
 }
 
 int launch_gemm_op(const GemmOp& op, cudaStream_t st) {
+    if (op.p.cluster_k) {
+        VSD_CHECK_CUDA(launch_k_cluster(conv_gemm_kernel<3>, op.grid, dim3(kGemmThreads), (size_t)op.smem_bytes, op.p.splits, st, op.mapA,
+                                        op.mapB, op.mapC, op.mapR, op.p));
+        return 0;
+    }
     auto kern = op.p.tma_out == 2 ? conv_gemm_kernel<2> : (op.p.tma_out == 1 ? conv_gemm_kernel<1> : conv_gemm_kernel<0>);
     VSD_CHECK_CUDA(launch_k(kern, op.grid, dim3(kGemmThreads), (size_t)op.smem_bytes, st, op.mapA, op.mapB, op.mapC, op.mapR, op.p));
     if (op.p.splits > 1) {

@@ -46,6 +46,26 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
+// same, as thread-block clusters of (1, 1, cluster_z) CTAs
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, int cluster_z, cudaStream_t st,
+                                    Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled();
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 1;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = (unsigned)cluster_z;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 // ---- tensor maps (driver entry point resolved at run time; the library does not link libcuda)
 int make_tmap_act(CUtensorMap* m, const void* base, int C, int W, int H, int N, int ld, int boxW, int boxH, int boxN);
@@ -87,6 +107,9 @@ struct GemmParams {
     // outside the tensor. tma_out: 0 = direct st.global, 1 = bf16 output (4-D map), 2 = fp32 split-K partials (5-D map).
     // tma_res: the residual tile is fetched by TMA (mapR) into the staging region while the main loop runs.
     int tma_out, tma_res;
+    int lbw, lbh;         // log2 of BW, BH
+    int cluster_k;        // split-K inside a thread-block cluster (1,1,splits): partial tiles are reduced through distributed
+                          // shared memory by the cluster itself (fixed order => deterministic); no workspace, no second kernel
     int sbw, sbh, sbn;
     unsigned int stage_off, bar_off;   // byte offsets of the staging region / the mbarrier block in dynamic smem
     long long* dbg;       // optional: CTA (0,0,0) writes clock64() phase stamps here (bring-up only)
