@@ -161,6 +161,12 @@ int vsd_infer_yuv420(vsd_ctx* ctx, const uint8_t* y, const uint8_t* u, const uin
 /* Packed RGB24 in / out ([batch][h][w][3]); the PIL-compatible path of VideoSDPipeline.infer. */
 int vsd_infer_rgb(vsd_ctx* ctx, const uint8_t* rgb_in, uint8_t* rgb_out);
 
+/* CLIP text encoder (diffusert/lcm/lcm_controlnet.py:175-179 `self.text_encoder(ids)[0]`): the SD1.5
+ * text tower (transformers CLIPTextModel keys under the "text_encoder." prefix, loaded with vsd_load_weight). token_ids: 77 ids
+ * (tokenizer output padded to max_length, host); context: fp32 [77][768] last_hidden_state (host), ready for vsd_set_context.
+ * Runs on the context's stream, once per prompt change. */
+int vsd_encode_prompt(vsd_ctx* ctx, const int* token_ids_77, float* context_77x768);
+
 /* GPU center-crop + Lanczos resize (videopipeline.py:92-107 does PIL crop + resize(LANCZOS) on
  * the CPU). The host passes Pillow-compatible windows / 22-bit coefficients (videosd_b200/resample.py); results are
  * bit-identical to Pillow. Geometry: input frames in_w x in_h, crop (x0, y0, cw, ch) -> working size. */

@@ -48,3 +48,7 @@ def test_sobel_and_controlnet_embedding_convs(chk):
 
 def test_crop_lanczos_resize_bit_exact_vs_pillow(chk):
     _run(chk, chk.check_resize)
+
+
+def test_clip_text_encoder_vs_oracle(chk):
+    _run(chk, chk.check_clip)

@@ -219,3 +219,29 @@ def test_controlnet_branch_frame_and_reference_golden(setup, golden):
     finally:
         eng.set_controlnet(False, 1.0)
         cn.cpu()
+
+
+def test_prompt_goes_through_gpu_text_encoder(setup):
+    """SURVEY.md 8(f) next-row #3: prompt -> tokenizer -> CLIP text tower on the GPU -> cross-attention K/V caches."""
+    from PIL import Image
+
+    from oracle.clip import ClipTextOracle
+    from videosd_b200 import weights
+    from videosd_b200.videopipeline import VideoSDPipeline
+
+    pipe = VideoSDPipeline(model="m", controlnet="c", random_init=True, text_encoder=True, device=0)
+    img = Image.fromarray((np.random.RandomState(1).rand(256, 256, 3) * 255).astype(np.uint8))
+    kw = dict(width=256, height=256, strength=0.5, steps=4, seed=42)
+    a = np.asarray(pipe.infer(img, prompt="pixar, cg", **kw))
+    b = np.asarray(pipe.infer(img, prompt="an oil painting of a harbour at dusk", **kw))
+    a2 = np.asarray(pipe.infer(img, prompt="pixar, cg", **kw))
+    assert np.array_equal(a, a2) and not np.array_equal(a, b)          # the prompt conditions the frame, deterministically
+    # the context the engine used equals the oracle text tower on the same token ids (bf16 tolerance)
+    ids = pipe.tokenizer("pixar, cg")
+    ref_model = ClipTextOracle()
+    ref_model.load_state_dict(weights.random_clip_state_dict(2468))
+    ref = ref_model(torch.tensor([ids]))[0]
+    got = pipe.engine.encode_prompt(ids)
+    assert ((got - ref).norm() / ref.norm()).item() < 1e-2
+    explicit = np.asarray(pipe.infer(img, prompt="ignored", prompt_embeds=got[None], **kw))
+    assert np.array_equal(explicit, a)

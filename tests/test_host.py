@@ -140,6 +140,48 @@ def test_lanczos_tables_reproduce_pillow_bit_exactly():
     assert ks == 7 and b.shape == (512, 2) and (k.sum(axis=1) - (1 << 22)).__abs__().max() <= 8   # rows sum to ~1.0
 
 
+def test_clip_tokenizer_matches_transformers_on_a_synthetic_vocabulary(tmp_path):
+    """The real vocab.json / merges.txt cannot be downloaded here; the BPE algorithm itself is checked against
+    transformers.CLIPTokenizer on a small vocabulary (byte alphabet + a few merges)."""
+    import json
+
+    transformers = pytest.importorskip("transformers")
+    from videosd_b200 import tokenizer as T
+
+    chars = sorted(set(T._bytes_to_unicode().values()))
+    vocab = {}
+    for c in chars:
+        vocab[c] = len(vocab)
+    for c in chars:
+        vocab[c + "</w>"] = len(vocab)
+    vocab["</w>"] = len(vocab)
+    merges = [("p", "i"), ("pi", "x"), ("a", "r</w>"), ("pix", "ar</w>"), ("c", "g</w>"), ("t", "h"), ("th", "e</w>"), ("c", "a"),
+              ("ca", "t</w>"), ("o", "n</w>"), ("'", "s</w>"), ("m", "a"), ("ma", "t</w>")]
+    for a, b in merges:
+        vocab[a + b] = len(vocab)
+    vocab["<|startoftext|>"] = len(vocab)
+    vocab["<|endoftext|>"] = len(vocab)
+    (tmp_path / "vocab.json").write_text(json.dumps(vocab))
+    (tmp_path / "merges.txt").write_text("#version: 0.2\n" + "\n".join(a + " " + b for a, b in merges) + "\n")
+    hf = transformers.CLIPTokenizer(str(tmp_path / "vocab.json"), str(tmp_path / "merges.txt"))
+    mine = T.load(str(tmp_path))
+    assert isinstance(mine, T.ClipTokenizer)
+    for text in ["pixar, cg", "The cat's on   the 12 mat!!", "a photo of a caf\u00e9 \u2014 na\u00efve", "x" * 200, "",
+                 "hello_world __ it's 3.14%"]:
+        assert mine(text) == hf(text, padding="max_length", max_length=77, truncation=True).input_ids, text
+    h = T.load(None)                       # stand-in without a vocabulary: framing and determinism
+    ids = h("pixar, cg")
+    assert len(ids) == 77 and ids[0] == 49406 and ids[4:] == [49407] * 73 and ids == h("Pixar,  CG")
+
+
+def test_clip_weight_table_matches_oracle_module():
+    from oracle.clip import ClipTextOracle
+    from videosd_b200 import weights
+
+    want = {k: tuple(v.shape) for k, v in ClipTextOracle().state_dict().items()}
+    assert weights.clip_param_shapes() == want
+
+
 def test_session_router_pins_and_batches():
     from videosd_b200.parallel import SessionRouter, shard_streams
 

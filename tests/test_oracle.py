@@ -1,5 +1,6 @@
 """CPU tests of the oracle (the checker): golden vectors produced by the reference's own code
 (tests/golden/make_reference_golden.py), structural identities and the colour spec."""
+import pytest
 import numpy as np
 import torch
 
@@ -181,3 +182,35 @@ def test_controlnet_structure_and_reference_golden(golden, oracle_models):
         np.testing.assert_allclose(out["latents_in"][i].numpy(), golden[f"cn_latents_in_{i}"], rtol=0, atol=2e-4)
         np.testing.assert_allclose(out["eps"][i].numpy(), golden[f"cn_eps_{i}"], rtol=0, atol=2e-4)
     assert np.abs(out["rgb"][0].astype(int) - golden["cn_rgb_out"].astype(int)).max() <= 1
+
+
+def test_clip_text_oracle_matches_transformers_clip_text_model():
+    """Pins oracle/clip.py against the real third-party implementation the reference calls (transformers CLIPTextModel,
+    lcm_controlnet.py:175-179), on the same seeded full-size weights: the text-encoder parity is NOT unpinned."""
+    transformers = pytest.importorskip("transformers")
+    from oracle.clip import ClipTextOracle
+    from videosd_b200 import weights
+
+    sd = weights.random_clip_state_dict(5)
+    assert sum(v.numel() for v in sd.values()) == 123_060_480          # SURVEY.md 8(a) row a13
+    cfg = transformers.CLIPTextConfig(vocab_size=49408, hidden_size=768, intermediate_size=3072, num_hidden_layers=12,
+                                      num_attention_heads=12, max_position_embeddings=77, hidden_act="quick_gelu",
+                                      layer_norm_eps=1e-5, projection_dim=768)
+    hf = transformers.CLIPTextModel(cfg).eval()
+    hf_keys = {k for k in hf.state_dict() if "position_ids" not in k}
+    assert hf_keys == set(sd)                                           # same state-dict keys as the checkpoint format
+    hf.load_state_dict(sd, strict=False)
+    mine = ClipTextOracle()
+    mine.load_state_dict(sd, strict=True)
+    ids = torch.randint(0, 49408, (2, 77), generator=torch.Generator().manual_seed(1))
+    ids[:, 0] = 49406
+    ids[1, 9:] = 49407                                                  # a short prompt padded with <|endoftext|>
+    with torch.no_grad():
+        ref = hf(ids)[0]
+    got = mine(ids)
+    assert (ref - got).abs().max().item() < 1e-4
+    # causal: positions before a changed token are unaffected
+    ids2 = ids.clone()
+    ids2[0, 40] = 123
+    got2 = mine(ids2)
+    assert torch.equal(got2[0, :40], got[0, :40]) and not torch.equal(got2[0, 40:], got[0, 40:])

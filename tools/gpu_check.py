@@ -404,6 +404,44 @@ def check_controlnet():
     run("direct_conv", direct)
 
 
+def check_clip():
+    """CLIP text encoder on the GPU vs the oracle restatement (itself pinned against transformers.CLIPTextModel)."""
+    from oracle.clip import ClipTextOracle
+    from videosd_b200 import weights
+    from videosd_b200.engine import Engine
+
+    def enc():
+        sd = weights.random_clip_state_dict(5)
+        ref_model = ClipTextOracle()
+        ref_model.load_state_dict(sd)
+        eng = Engine(0)
+        eng.load_state_dict("text_encoder", sd)
+        g = torch.Generator().manual_seed(1)
+        ids = torch.randint(0, 49406, (3, 77), generator=g)
+        ids[:, 0] = 49406
+        ids[1, 9:] = 49407
+        ids[2, 3:] = 49407
+        ref = ref_model(ids)
+        outs = []
+        for b in range(3):
+            got = eng.encode_prompt(ids[b].tolist())
+            outs.append(got)
+            record(f"clip_last_hidden_state_rel_{b}", ((got - ref[b]).norm() / ref[b].norm()).item(), 1e-2,
+                   {"max_abs": (got - ref[b]).abs().max().item()})
+        again = eng.encode_prompt(ids[0].tolist())
+        record("clip_deterministic", 0.0 if torch.equal(again, outs[0]) else 1.0, 0.0)
+        ids2 = ids[0].clone()
+        ids2[40] = 123
+        got2 = eng.encode_prompt(ids2.tolist())
+        record("clip_causal_prefix_unchanged", 0.0 if torch.equal(got2[:40], outs[0][:40]) else 1.0, 0.0)
+        record("clip_causal_suffix_changed", 0.0 if not torch.equal(got2[40:], outs[0][40:]) else 1.0, 0.0)
+        t0 = time.time()
+        for _ in range(20):
+            eng.encode_prompt(ids[0].tolist())
+        record("clip_encode_ms", (time.time() - t0) / 20 * 1e3, 1e9)
+    run("clip_encode", enc)
+
+
 def check_resize():
     """Center crop + Lanczos on the GPU vs Pillow itself (the reference's own CPU path, videopipeline.py:92-107)."""
     import numpy as np

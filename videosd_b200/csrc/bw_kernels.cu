@@ -417,6 +417,29 @@ __global__ void layernorm_kernel(const bf16* __restrict__ x, int ldx, bf16* __re
     }
 }
 
+// fp32 rows in, bf16 rows out (CLIP text tower: the residual stream stays fp32). One warp per row, two passes.
+__global__ void layernorm_f32in_kernel(const float* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, int rows, int C, float eps) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* xr = x + (long)row * C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += xr[c];
+    const float mean = warp_sum(s) / (float)C;
+    float v = 0.f;
+    for (int c = lane; c < C; c += 32) { const float d = xr[c] - mean; v += d * d; }
+    const float rstd = rsqrtf(warp_sum(v) / (float)C + eps);
+    for (int c = lane; c < C; c += 32) y[(long)row * C + c] = __float2bfloat16((xr[c] - mean) * rstd * gamma[c] + beta[c]);
+}
+
+int launch_layernorm_f32in(const float* x, bf16* y, const float* gamma, const float* beta, int rows, int C, float eps, cudaStream_t st) {
+    VSD_CHECK_CUDA(launch_k(layernorm_f32in_kernel, dim3((rows + 3) / 4), dim3(128), 0, st, x, y, gamma, beta, rows, C, eps));
+    return 0;
+}
+
 int launch_layernorm(const bf16* x, int ldx, bf16* y, int ldy, const float* gamma, const float* beta, int rows, int C,
                      float eps, cudaStream_t st) {
     VSD_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && C <= 2048, "LayerNorm needs C%8==0, C<=2048");
@@ -586,6 +609,88 @@ int launch_conv3x3_small_cin(const void* x, int x_kind, int NB, int H, int W, in
     else if (Cin == 1) VSD_CHECK_CUDA(launch_k(conv3x3_small_cin_kernel<1>, dim3(grid), dim3(128), 0, st, x, x_kind, NB, H, W, w, bias, y, ldy, Cout, relu, res, ldr));
     else VSD_CHECK_CUDA(launch_k(conv3x3_small_cin_kernel<2>, dim3(grid), dim3(128), 0, st, x, x_kind, NB, H, W, w, bias, y, ldy, Cout, relu, res, ldr));
     VSD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ CLIP text encoder pieces
+// x[t][:] = token_embedding[ids[t]][:] + position_embedding[t][:]   (transformers CLIPTextEmbeddings), bf16 tables
+__global__ void clip_embed_kernel(const int* __restrict__ ids, const bf16* __restrict__ tok, const bf16* __restrict__ pos,
+                                  float* __restrict__ x, int T, int C, int vocab) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int t = blockIdx.x;
+    int id = ids[t];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+        x[(long)t * C + c] = __bfloat162float(tok[(long)id * C + c]) + __bfloat162float(pos[(long)t * C + c]);
+}
+
+// Causal multi-head self-attention over T <= 96 tokens, head dim 64 (CLIP text tower: 12 heads, T = 77).
+// qkv: [T][3*heads*64] (q | k | v); out: [T][heads*64]. One warp per query row; K / V of the head live in shared memory.
+__global__ void clip_attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, int heads, float scale) {
+    pdl_launch_dependents();
+    pdl_wait();
+    constexpr int D = 64, KS = 66;   // padded K row stride (bank-conflict free column reads)
+    extern __shared__ uint8_t sm_raw[];
+    bf16* sk = reinterpret_cast<bf16*>(sm_raw);          // [T][KS]
+    bf16* sv = sk + (size_t)T * KS;                      // [T][D]
+    float* sq = reinterpret_cast<float*>(sv + (size_t)T * D);   // [warps][D]
+    const int h = blockIdx.x, ld = 3 * heads * D;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < T * D; i += blockDim.x) {
+        const int t = i / D, c = i % D;
+        sk[t * KS + c] = qkv[(long)t * ld + heads * D + h * D + c];
+        sv[t * D + c] = qkv[(long)t * ld + 2 * heads * D + h * D + c];
+    }
+    __syncthreads();
+    const int row = blockIdx.y * warps + warp;
+    if (row >= T) return;
+    float* q = sq + warp * D;
+    q[lane] = __bfloat162float(qkv[(long)row * ld + h * D + lane]) * scale;
+    q[lane + 32] = __bfloat162float(qkv[(long)row * ld + h * D + lane + 32]) * scale;
+    __syncwarp();
+    float sc[3], m = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int j = r * 32 + lane;
+        float a = -INFINITY;
+        if (j <= row) {                                   // causal mask: keys 0..row
+            a = 0.f;
+            for (int c = 0; c < D; ++c) a += q[c] * __bfloat162float(sk[j * KS + c]);
+        }
+        sc[r] = a;
+        m = fmaxf(m, a);
+    }
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        sc[r] = (r * 32 + lane <= row) ? __expf(sc[r] - m) : 0.f;
+        sum += sc[r];
+    }
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.f / sum;
+    float o0 = 0.f, o1 = 0.f;
+    for (int j = 0; j <= row; ++j) {
+        const float pj = __shfl_sync(0xffffffffu, sc[j >> 5], j & 31);
+        const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(sv + j * D + 2 * lane));
+        o0 += pj * v.x;
+        o1 += pj * v.y;
+    }
+    *reinterpret_cast<uint32_t*>(out + (long)row * heads * D + h * D + 2 * lane) = pack_bf16x2(o0 * inv, o1 * inv);
+}
+
+int launch_clip_embed(const int* ids, const bf16* tok, const bf16* pos, float* x, int T, int C, int vocab, cudaStream_t st) {
+    VSD_CHECK_CUDA(launch_k(clip_embed_kernel, dim3(T), dim3(256), 0, st, ids, tok, pos, x, T, C, vocab));
+    return 0;
+}
+
+int launch_clip_attention(const bf16* qkv, bf16* out, int T, int heads, cudaStream_t st) {
+    VSD_REQUIRE(T >= 1 && T <= 96, "CLIP attention handles up to 96 tokens");
+    const int warps = 4;
+    const size_t smem = (size_t)T * 66 * 2 + (size_t)T * 64 * 2 + warps * 64 * 4;
+    VSD_CHECK_CUDA(launch_k(clip_attention_kernel, dim3(heads, (T + warps - 1) / warps), dim3(warps * 32), smem, st, qkv, out, T, heads,
+                            0.125f));
     return 0;
 }
 

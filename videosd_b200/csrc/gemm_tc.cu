@@ -73,7 +73,20 @@ __device__ __forceinline__ void epilogue_math32(const GemmParams& p, float (&v)[
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= sc;
     }
-    if (p.residual) {
+    if (p.residual && p.res_f32) {
+        const float* r = reinterpret_cast<const float*>(p.residual) + grow * p.ldr + col;
+        if (full && ((p.ldr & 3) == 0) && ((col & 3) == 0)) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 t = *reinterpret_cast<const float4*>(r + q * 4);
+                v[q * 4] += t.x; v[q * 4 + 1] += t.y; v[q * 4 + 2] += t.z; v[q * 4 + 3] += t.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j < ncols) v[j] += r[j];
+        }
+    } else if (p.residual) {
         const bf16* r = p.residual + grow * p.ldr + col;
         if (rpre || (full && ((p.ldr & 7) == 0) && ((col & 7) == 0))) {
             const uint4* r4 = reinterpret_cast<const uint4*>(r);
@@ -93,6 +106,10 @@ __device__ __forceinline__ void epilogue_math32(const GemmParams& p, float (&v)[
     if (p.relu) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (p.act == ACT_QUICK_GELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.f + __expf(-1.702f * v[j]));
     }
 }
 
@@ -133,7 +150,7 @@ __device__ __forceinline__ void epilogue_store32(const GemmParams& p, float (&v)
 __device__ __forceinline__ void splitk_finish4(const GemmParams& p, float (&v)[4], long grow, int col) {
     const int ncols = min(4, p.N - col);
     const bool vec = (ncols == 4) && ((p.N & 3) == 0);
-    if (vec && !p.rowvec && !p.out_scale && (!p.residual || (p.ldr & 3) == 0)) {
+    if (vec && !p.rowvec && !p.out_scale && !p.res_f32 && (!p.residual || (p.ldr & 3) == 0)) {
         if (p.bias) {
             const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
             v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
@@ -154,7 +171,8 @@ __device__ __forceinline__ void splitk_finish4(const GemmParams& p, float (&v)[4
             if (p.bias) v[j] += __ldg(p.bias + col + j);
             if (p.rowvec) v[j] += __ldg(p.rowvec + (grow / ((long)p.H * p.W)) * p.N + col + j);
             if (p.out_scale) v[j] *= __ldg(p.out_scale);
-            if (p.residual) v[j] += __bfloat162float(p.residual[grow * p.ldr + col + j]);
+            if (p.residual) v[j] += p.res_f32 ? reinterpret_cast<const float*>(p.residual)[grow * p.ldr + col + j]
+                                              : __bfloat162float(p.residual[grow * p.ldr + col + j]);
             if (p.relu) v[j] = fmaxf(v[j], 0.f);
         }
     }
@@ -400,7 +418,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
         pdl_wait();   // bias / time-embedding rows above are constants; everything below depends on earlier kernels
         const bool res_vec = (p.residual != nullptr) && row_ok && ((p.ldr & 7) == 0) && ((col0 & 7) == 0) &&
-                             (p.splits == 1) && (p.act != ACT_GEGLU) && !p.tma_res;
+                             (p.splits == 1) && (p.act != ACT_GEGLU) && !p.tma_res && !p.res_f32;
         // this warp's 32 rows as a sub-box of the tile rectangle (all extents are powers of two)
         const int sw0 = w0 + (q * 32) % p.BW, sh0 = h0 + ((q * 32) / p.BW) % p.BH, sn0 = n0 + (q * 32) / (p.BW * p.BH);
         uint4 rnext[4];
@@ -895,7 +913,7 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
             if ((N % 4) == 0 && (reinterpret_cast<uintptr_t>(partial_ws) & 15) == 0) tma_out = 2;
         } else if (out_tma_ok) {
             tma_out = 1;
-            if (residual != nullptr && (ldr % 8) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0) tma_res = 1;
+            if (residual != nullptr && !(act_flags & ACT_RES_F32_FLAG) && (ldr % 8) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0) tma_res = 1;
         }
     }
     int stag_bytes = (tma_out == 2) ? bn * 512 : (tma_out == 1 ? bn_out * 256 : 0);   // 128 rows x (4 | 2) bytes per column
@@ -951,6 +969,7 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
 
     p.out = out; p.ldo = ldo; p.out_f32 = out_f32;
     p.bias = bias; p.rowvec = rowvec; p.residual = residual; p.ldr = ldr;
+    p.res_f32 = (act_flags & ACT_RES_F32_FLAG) ? 1 : 0;
     p.act = act;
     p.relu = (act_flags & ACT_RELU_FLAG) ? 1 : 0;
     p.a_static = (act_flags & ACT_A_STATIC_FLAG) ? 1 : 0;

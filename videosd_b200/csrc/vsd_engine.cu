@@ -136,6 +136,9 @@ struct Engine {
     // GPU center-crop + Lanczos resize of arbitrary-size input frames
     struct Resize { int in_w = 0, in_h = 0, x0 = 0, y0 = 0, cw = 0, ch = 0, hks = 0, vks = 0;
                     int *hb = nullptr, *hk = nullptr, *vb = nullptr, *vk = nullptr; uint8_t *src = nullptr, *tmp = nullptr, *yuv = nullptr; } rz;
+    // CLIP text encoder: built on first use, independent of configure()
+    struct Clip { bool built = false; int* ids = nullptr; float* x = nullptr; bf16 *xn = nullptr, *qkv = nullptr, *att = nullptr, *h = nullptr,
+                  *out = nullptr; std::vector<Launch> plan; } clip;
     bool cn_enabled = false;
     float* cn_scales = nullptr;        // device [13]: logspace(-1,0,13) * conditioning scale (guess mode)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -935,6 +938,98 @@ static std::vector<std::string> transformer_prefixes(bool with_controlnet) {
 }
 static bool has_controlnet_weights(const Engine* e) { return e->w.find("controlnet.conv_in.weight") != e->w.end(); }
 
+// ------------------------------------------------------------------------------------------------ CLIP text encoder
+// transformers CLIPTextModel, SD1.5 text tower (12 layers, 768 wide, 12 heads, quick-GELU MLP 3072, causal mask, final LN);
+// the reference runs it in _encode_prompt (lcm_controlnet.py:175-179). Weights: "text_encoder." + transformers keys.
+// 77 tokens = one 128-row tile: every linear is the tcgen05 GEMM (bias / quick-GELU / residual fused), attention is a small
+// CUDA-core kernel (12 heads x 77 x 77), 86 launches per prompt.
+static void free_clip(Engine* e) {
+    void* ptrs[7] = {e->clip.ids, e->clip.x, e->clip.xn, e->clip.qkv, e->clip.att, e->clip.h, e->clip.out};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    e->clip = Engine::Clip();
+}
+
+static int build_clip(Engine* e) {
+    constexpr int T = 77, C = 768, L = 12, HEADS = 12, FF = 3072, VOCAB = 49408;
+    Engine::Clip& c = e->clip;
+    if (c.built) return 0;
+    const std::string root = "text_encoder.text_model.";
+    ENG_REQUIRE(e->w.count(root + "embeddings.token_embedding.weight"), "text encoder weights are not loaded");
+    VSD_CHECK_CUDA(cudaMalloc(&c.ids, 128 * sizeof(int)));
+    auto ab = [&](bf16** p, size_t n) -> int { VSD_CHECK_CUDA(cudaMalloc(p, n * 2)); VSD_CHECK_CUDA(cudaMemset(*p, 0, n * 2)); return 0; };
+    VSD_CHECK_CUDA(cudaMalloc(&c.x, (size_t)128 * C * 4));
+    VSD_CHECK_CUDA(cudaMemset(c.x, 0, (size_t)128 * C * 4));
+    if (ab(&c.xn, (size_t)128 * C) || ab(&c.qkv, (size_t)128 * 3 * C) || ab(&c.att, (size_t)128 * C) ||
+        ab(&c.h, (size_t)128 * FF) || ab(&c.out, (size_t)128 * C))
+        return -2;
+    const int saved_autotune = e->autotune;
+    e->autotune = 0;                       // once per prompt change: the shape heuristics are plenty
+    Builder B{e, &c.plan};
+    Scope sc_("clip");
+    {
+        const bf16* tok = B.wb(root + "embeddings.token_embedding.weight");
+        const bf16* pos = B.wb(root + "embeddings.position_embedding.weight");
+        const int* ids = c.ids;
+        float* x = c.x;
+        if (!B.rc)
+            c.plan.push_back(mk([=](cudaStream_t st) { return launch_clip_embed(ids, tok, pos, x, T, C, VOCAB, st); }, "embed"));
+    }
+    const ActView axn{c.xn, 1, 1, T, C, C}, aatt{c.att, 1, 1, T, C, C}, ah{c.h, 1, 1, T, FF, FF};
+    auto ln = [&](const float* in, bf16* out, const std::string& name) {     // the residual stream x stays fp32
+        const float* g = B.wf(name + ".weight");
+        const float* b = B.wf(name + ".bias");
+        if (B.rc) return;
+        c.plan.push_back(mk([=](cudaStream_t st) { return launch_layernorm_f32in(in, out, g, b, T, C, 1e-5f, st); }, "ln"));
+    };
+    for (int l = 0; l < L && !B.rc; ++l) {
+        const std::string p = root + "encoder.layers." + std::to_string(l) + ".";
+        ln(c.x, c.xn, p + "layer_norm1");
+        const char* names[3] = {"q_proj", "k_proj", "v_proj"};
+        for (int j = 0; j < 3; ++j)      // q | k | v side by side in one [T][2304] buffer
+            B.gemm(axn, 1, B.wb(p + "self_attn." + names[j] + ".weight"), C, C, c.qkv + j * C, 3 * C, 0,
+                   B.wf(p + "self_attn." + names[j] + ".bias"), nullptr, nullptr, 0, ACT_NONE);
+        {
+            const bf16* qkv = c.qkv;
+            bf16* att = c.att;
+            c.plan.push_back(mk([=](cudaStream_t st) { return launch_clip_attention(qkv, att, T, HEADS, st); }, "attn"));
+        }
+        B.gemm(aatt, 1, B.wb(p + "self_attn.out_proj.weight"), C, C, c.x, C, 1, B.wf(p + "self_attn.out_proj.bias"), nullptr,
+               reinterpret_cast<const bf16*>(c.x), C, ACT_NONE | ACT_RES_F32_FLAG);                     // x += out_proj(att), fp32
+        ln(c.x, c.xn, p + "layer_norm2");
+        B.gemm(axn, 1, B.wb(p + "mlp.fc1.weight"), FF, C, c.h, FF, 0, B.wf(p + "mlp.fc1.bias"), nullptr, nullptr, 0, ACT_QUICK_GELU);
+        B.gemm(ah, 1, B.wb(p + "mlp.fc2.weight"), C, FF, c.x, C, 1, B.wf(p + "mlp.fc2.bias"), nullptr,
+               reinterpret_cast<const bf16*>(c.x), C, ACT_NONE | ACT_RES_F32_FLAG);                     // x += mlp(xn), fp32
+    }
+    ln(c.x, c.out, root + "final_layer_norm");
+    e->autotune = saved_autotune;
+    if (B.rc) {
+        set_error("text encoder plan failed: " + B.fail);
+        free_clip(e);
+        return B.rc;
+    }
+    c.built = true;
+    return 0;
+}
+
+// ids: 77 token ids (host). out: fp32 [77][768] last_hidden_state (host).
+static int encode_prompt(Engine* e, const int* ids_host, float* out_host) {
+    int rc = build_clip(e);
+    if (rc) return rc;
+    Engine::Clip& c = e->clip;
+    VSD_CHECK_CUDA(cudaMemcpyAsync(c.ids, ids_host, 77 * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    rc = run_plan(c.plan, e->stream);
+    if (rc) return rc;
+    std::vector<uint16_t> t((size_t)77 * 768);
+    VSD_CHECK_CUDA(cudaMemcpyAsync(t.data(), c.out, t.size() * 2, cudaMemcpyDeviceToHost, e->stream));
+    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    for (size_t i = 0; i < t.size(); ++i) {
+        const uint32_t u = (uint32_t)t[i] << 16;
+        memcpy(&out_host[i], &u, 4);
+    }
+    return vsd_check_pipeline_fault();
+}
+
 static void free_resize(Engine* e) {
     void* ptrs[7] = {e->rz.hb, e->rz.hk, e->rz.vb, e->rz.vk, e->rz.src, e->rz.tmp, e->rz.yuv};
     for (void* p : ptrs)
@@ -1326,6 +1421,7 @@ void vsd_destroy(vsd_ctx* c) {
     if (c->e.splitk_ws) cudaFree(c->e.splitk_ws);
     if (c->e.flush_buf) cudaFree(c->e.flush_buf);
     free_resize(&c->e);
+    free_clip(&c->e);
     if (c->e.gn_sync) cudaFree(c->e.gn_sync);
     if (c->e.cn_scales) cudaFree(c->e.cn_scales);
     if (c->e.ev0) cudaEventDestroy(c->e.ev0);
@@ -1429,6 +1525,11 @@ int vsd_set_controlnet(vsd_ctx* c, int enabled, const float* scales13) {
 int vsd_set_context(vsd_ctx* c, int slot, const float* context_77x768) {
     CTX_GUARD(c);
     return set_context(&c->e, slot, context_77x768);
+}
+
+int vsd_encode_prompt(vsd_ctx* c, const int* token_ids_77, float* context_77x768) {
+    CTX_GUARD(c);
+    return encode_prompt(&c->e, token_ids_77, context_77x768);
 }
 
 int vsd_set_noise(vsd_ctx* c, const float* init_noise_nhwc, const float* step_noise_nhwc) {

@@ -73,9 +73,11 @@ int make_tmap_2d(CUtensorMap* m, const void* base, int K, int rows, int ld, int 
 
 // ---- tcgen05 implicit-GEMM convolution / linear kernel -------------------------------------------
 // out[pixel, n] = epilogue( sum_{tap, c} A[pixel + tap offset, c] * Wt[n, tap*cin + c] )
-enum { ACT_NONE = 0, ACT_GEGLU = 1, ACT_RELU_FLAG = 16,
+enum { ACT_NONE = 0, ACT_GEGLU = 1, ACT_QUICK_GELU = 2,   // x * sigmoid(1.702 x) after the bias (CLIP MLP)
+       ACT_RELU_FLAG = 16,
        ACT_A_STATIC_FLAG = 32,   // the row operand is the constant one (swapped-operand V^T projection)
-       ACT_NO_STATIC_FLAG = 64 };  // neither operand is constant  // ReLU (after the residual add) may be OR-ed in
+       ACT_NO_STATIC_FLAG = 64,
+       ACT_RES_F32_FLAG = 128 };  // the residual operand is fp32 (with an fp32 output: an fp32 residual stream updated in place)  // neither operand is constant  // ReLU (after the residual add) may be OR-ed in
 
 struct GemmParams {
     // A operand traversal (NHWC activation, stride-1 taps; linear layers use H=NB=1, W=rows)
@@ -96,8 +98,8 @@ struct GemmParams {
     int ldo, out_f32;
     const float* bias;    // [N] or null
     const float* rowvec;  // [NB, N] or null (per-image broadcast, e.g. time embedding projection)
-    const bf16* residual; // [rows, ldr] or null
-    int ldr;
+    const bf16* residual; // [rows, ldr] or null (fp32 rows when res_f32)
+    int ldr, res_f32;
     const float* out_scale;  // optional device scalar: out = (acc + bias) * scale + residual (ControlNet conditioning scale)
     int act, relu;
     float* partial;       // [splits, rows, N] fp32 when splits > 1
@@ -166,6 +168,9 @@ int launch_splitk_reduce(const GemmParams& p, long rows, cudaStream_t st);
 int launch_conv3x3_small_cin(const void* x, int x_kind, int NB, int H, int W, int Cin, const float* w, const float* bias,
                              bf16* y, int ldy, int Cout, int relu /*0 none, 1 ReLU, 2 SiLU*/, cudaStream_t st,
                              const bf16* res = nullptr, int ldr = 0);
+int launch_clip_embed(const int* ids, const bf16* tok, const bf16* pos, float* x, int T, int C, int vocab, cudaStream_t st);
+int launch_layernorm_f32in(const float* x, bf16* y, const float* gamma, const float* beta, int rows, int C, float eps, cudaStream_t st);
+int launch_clip_attention(const bf16* qkv, bf16* out, int T, int heads, cudaStream_t st);
 int launch_crop_resize(const uint8_t* src, int in_w, int in_h, int x0, int y0, int cw, int ch, uint8_t* tmp, uint8_t* out,
                        int W, int H, const int* hb, const int* hk, int hks, const int* vb, const int* vk, int vks, int NB,
                        cudaStream_t st);

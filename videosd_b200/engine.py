@@ -104,6 +104,17 @@ class Engine:
             raise ValueError(f"context must be (77, 768), got {a.shape}")
         check(self._L.vsd_set_context(self._ctx, c_int(slot), _fptr(a)), "vsd_set_context")
 
+    def encode_prompt(self, token_ids):
+        """token_ids: 77 ints (CLIP tokenizer output padded to max_length) -> (77, 768) fp32 tensor, the text encoder's
+        last_hidden_state (lcm_controlnet.py:175-179). Needs the 'text_encoder' weights."""
+        ids = np.ascontiguousarray(np.asarray(token_ids, dtype=np.int32).reshape(-1))
+        if ids.shape != (77,):
+            raise ValueError(f"expected 77 token ids, got {ids.shape}")
+        out = np.empty((77, 768), dtype=np.float32)
+        check(self._L.vsd_encode_prompt(self._ctx, ids.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), _fptr(out)),
+              "vsd_encode_prompt")
+        return torch.from_numpy(out)
+
     def set_noise(self, init_noise_nchw, step_noise_nchw):
         """init: (B,4,h,w); steps: list of (B,4,h,w) (empty for single-step)."""
         init = np.ascontiguousarray(init_noise_nchw.permute(0, 2, 3, 1).contiguous().float().numpy())

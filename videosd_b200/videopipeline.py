@@ -7,10 +7,12 @@ the output RGB frame runs in the CUDA engine (videosd_b200/engine.py -> libvideo
 diffusers + PyTorch. `infer_yuv420` additionally moves the YUV420<->RGB conversions that the reference leaves to
 PyAV/libswscale in server.py:108,117 inside the boundary.
 
-Not on this path (SURVEY.md 8(f) "next" rows): the canny ControlNet branch (the reference runs it every step; here its
-residuals are zero), GPU crop/Lanczos (PIL on the host, like the reference), and the CLIP text encoder: pass
-`prompt_encoder=callable(list[str]) -> (77, 768)` in the config to plug one in; without it a deterministic
-pseudo-embedding derived from the prompt text is used (no tokenizer vocabulary exists offline).
+SURVEY.md 8(f) "next" rows inside the boundary: the canny ControlNet branch + Sobel (`use_controlnet=True`), the center
+crop + Lanczos resize of arbitrary-size frames (GPU kernels, bit-identical to the reference's PIL calls) and the CLIP text
+encoder (`text_encoder=True` / a checkpoint with text_encoder/ + tokenizer/): prompts are tokenized on the host
+(videosd_b200/tokenizer.py) and encoded on the GPU once per prompt change. Without text-encoder weights a
+`prompt_encoder=callable(list[str]) -> (77, 768)` can be plugged in; without either a deterministic pseudo-embedding
+derived from the prompt text is used.
 """
 import asyncio
 import concurrent.futures
@@ -95,6 +97,8 @@ class VideoSDPipeline:
         # The reference runs the canny ControlNet before every UNet pass; the north star's hot path excludes it, so it is
         # opt-in here: use_controlnet=True adds ~35 % FLOPs per step.
         self.use_controlnet = bool(kwargs.get("use_controlnet", False))
+        self.use_text_encoder = bool(kwargs.get("text_encoder", False))
+        self.tokenizer = None
         self.noise_mode = kwargs.get("noise_mode", "reference_cuda")
         self.engine = Engine(self.device)          # raises if the CUDA library / a B200 is missing: no fallback
         self.load_model(self.model_name, self.controlnet_name, kwargs.get("random_init", False))
@@ -116,12 +120,21 @@ class VideoSDPipeline:
             self.engine.load_state_dict("vae", _weights.load_safetensors_dir(os.path.join(model_name, "vae")))
             if self.use_controlnet:
                 self.engine.load_state_dict("controlnet", _weights.load_safetensors_dir(str(controlnet_model)))
+            if os.path.isdir(os.path.join(model_name, "text_encoder")):
+                from . import tokenizer as _tok
+                self.engine.load_state_dict("text_encoder", _weights.load_safetensors_dir(os.path.join(model_name, "text_encoder")))
+                self.tokenizer = _tok.load(os.path.join(model_name, "tokenizer"))
+                self.use_text_encoder = True
         elif random_init or os.environ.get("VIDEOSD_RANDOM_INIT") == "1":
             self.engine.load_state_dict("unet", _weights.random_state_dict(_weights.unet_param_shapes(), 1234))
             self.engine.load_state_dict("vae", _weights.random_state_dict(_weights.taesd_param_shapes(), 4321))
             if self.use_controlnet:
                 self.engine.load_state_dict("controlnet",
                                             _weights.random_state_dict(_weights.controlnet_param_shapes(), 9876))
+            if self.use_text_encoder:
+                from . import tokenizer as _tok
+                self.engine.load_state_dict("text_encoder", _weights.random_clip_state_dict(2468))
+                self.tokenizer = _tok.load(None)
         else:
             raise FileNotFoundError(
                 f"model '{model_name}' is not a local diffusers directory (unet/, vae/ with .safetensors). "
@@ -160,6 +173,11 @@ class VideoSDPipeline:
                 emb = torch.as_tensor(prompt_embeds).reshape(-1, 77, 768)[0]
             elif self.prompt_encoder is not None:
                 emb = torch.as_tensor(self.prompt_encoder(prompt)).reshape(-1, 77, 768)[0]
+            elif self.use_text_encoder:
+                # lcm_controlnet.py:144-179: tokenizer(prompt, padding="max_length", max_length=77) -> text_encoder(ids)[0];
+                # a list of prompts is a batch there, and server.py sends one prompt per stream: the first entry conditions it
+                text = prompt if isinstance(prompt, str) else prompt[0]
+                emb = self.engine.encode_prompt(self.tokenizer(text))
             else:
                 emb = _pseudo_prompt_embedding(prompt)
             for b in range(batch):

@@ -141,6 +141,44 @@ def taesd_param_shapes():
     return o
 
 
+def clip_param_shapes():
+    """transformers CLIPTextModel state-dict keys (SD1.5 text tower): 123 060 480 parameters."""
+    out = {"text_model.embeddings.token_embedding.weight": (49408, 768),
+           "text_model.embeddings.position_embedding.weight": (77, 768)}
+    for i in range(12):
+        p = f"text_model.encoder.layers.{i}."
+        for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            out[p + f"self_attn.{n}.weight"] = (768, 768)
+            out[p + f"self_attn.{n}.bias"] = (768,)
+        for n in ("layer_norm1", "layer_norm2"):
+            out[p + n + ".weight"] = (768,)
+            out[p + n + ".bias"] = (768,)
+        out[p + "mlp.fc1.weight"] = (3072, 768)
+        out[p + "mlp.fc1.bias"] = (3072,)
+        out[p + "mlp.fc2.weight"] = (768, 3072)
+        out[p + "mlp.fc2.bias"] = (768,)
+    out["text_model.final_layer_norm.weight"] = (768,)
+    out["text_model.final_layer_norm.bias"] = (768,)
+    return out
+
+
+def random_clip_state_dict(seed):
+    """Seeded random text tower: embeddings N(0, 0.02) (CLIP's own init), linears U(+-1/sqrt(fan_in)), LayerNorm affine
+    (1 + 0.1 N, 0.1 N) so that gamma / beta are exercised."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for name, shape in clip_param_shapes().items():
+        if "embedding" in name:
+            sd[name] = torch.randn(shape, generator=g) * 0.02
+        elif "layer_norm" in name:
+            sd[name] = (1.0 if name.endswith("weight") else 0.0) + 0.1 * torch.randn(shape, generator=g)
+        elif len(shape) == 2:
+            sd[name] = (torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(shape[1])
+        else:
+            sd[name] = (torch.rand(shape, generator=g) * 2 - 1) * 0.05
+    return sd
+
+
 def random_state_dict(shapes, seed):
     """torch.nn default-style init (U(+-1/sqrt(fan_in)); norm affine = (1, 0)) from a seeded generator."""
     g = torch.Generator().manual_seed(seed)
