@@ -11,8 +11,21 @@ from videosd_b200._lib import _p, check, cur_stream, lib  # noqa: E402
 
 c_int = ctypes.c_int
 N_CHAIN = 24
-# rows, K, N, taps(h,w), bn, splits, occ, kbs
+# rows, K, N, taps(h,w), bn, splits, occ (+ mode << 8: 1 halo, 2 CTA pairs), kbs
+PAIR = 2 << 8
 CASES = [
+    ("16x16 lin 1280->1280 pair", (1, 1, 256, 1280), 1280, 1, 128, 1, 1 | PAIR, 2),
+    ("16x16 lin 1280->1280 pair", (1, 1, 256, 1280), 1280, 1, 64, 1, 1 | PAIR, 2),
+    ("16x16 lin 1280->1280 pair sp4", (1, 1, 256, 1280), 1280, 1, 128, 4, 1 | PAIR, 2),
+    ("32x32 lin 640->640 pair", (1, 1, 1024, 640), 640, 1, 64, 1, 1 | PAIR, 2),
+    ("32x32 lin 640->640 pair", (1, 1, 1024, 640), 640, 1, 128, 1, 1 | PAIR, 2),
+    ("64x64 lin 320->320 pair", (1, 1, 4096, 320), 320, 1, 160, 1, 1 | PAIR, 1),
+    ("64x64 conv3x3 320->320 pair", (1, 64, 64, 320), 320, 9, 160, 1, 1 | PAIR, 1),
+    ("64x64 conv3x3 320->320 pair+halo", (1, 64, 64, 320), 320, 9, 160, 1, 1 | (3 << 8), 1),
+    ("64x64 conv3x3 320->320 halo", (1, 64, 64, 320), 320, 9, 160, 1, 1 | (1 << 8), 1),
+    ("64x64 conv3x3 320->320 halo", (1, 64, 64, 320), 320, 9, 96, 1, 1 | (1 << 8), 1),
+    ("64x64 conv3x3 320->320 pair+halo", (1, 64, 64, 320), 320, 9, 96, 1, 1 | (3 << 8), 1),
+    ("16x16 conv3x3 1280->1280 pair sp4", (1, 16, 16, 1280), 1280, 9, 128, 4, 1 | PAIR, 2),
     ("16x16 lin 1280->1280", (1, 1, 256, 1280), 1280, 1, 128, 1, 1, 2),
     ("16x16 lin 1280->1280", (1, 1, 256, 1280), 1280, 1, 64, 1, 1, 2),
     ("16x16 lin 1280->1280", (1, 1, 256, 1280), 1280, 1, 32, 1, 1, 2),
@@ -72,7 +85,7 @@ for (name, (nb, h, w, c), n, taps, bn, sp, occ, kbs) in CASES:
     prev_end_to_start = (gt[9:, 0] - gt[8:-1, 6]).mean().item() / 1e3      # negative = overlapped prologue (PDL)
     prev_end_to_wait = (gt[9:, 7] - gt[8:-1, 6]).mean().item() / 1e3       # previous CTA0 teardown -> our pdl_wait returned
     ph = lambda a, b: ((ck[sel, b] - ck[sel, a]).mean().item())            # noqa: E731
-    print(f"{name:32s} bn={bn:3d} sp={sp} occ={occ} kbs={kbs}: {per:6.2f} us/kernel in graph | start->start {start2start:6.2f} us | "
+    print(f"{name:34s} bn={bn:3d} sp={sp} occ={occ & 255} mode={occ >> 8} kbs={kbs}: {per:6.2f} us/kernel in graph | start->start {start2start:6.2f} us | "
           f"prevEnd->start {prev_end_to_start:6.2f} us, prevEnd->pdlwait {prev_end_to_wait:6.2f} us | cycles: setup {ph(0,1):.0f}, "
           f"start->pdlwait {ph(0,7):.0f}, pdlwait->firstMMA {ph(7,2):.0f}, mainloop {ph(2,3):.0f}, ->accum ready {ph(3,4):.0f}, "
           f"epilogue {ph(4,5):.0f}, teardown {ph(5,6):.0f}, total {ph(0,6):.0f}"

@@ -73,7 +73,7 @@ def ref_conv(x_nhwc, w_ohwi, taps, bias=None, rowvec=None, residual=None):
 
 
 def gemm_case(name, nb, h, w, c, n, taps, bias=False, rowvec=False, residual=False, out_f32=False, block_n=0, splits=0,
-              tol=1e-2, halo=False):
+              tol=1e-2, halo=False, pair=False):
     def fn():
         x = randn((nb, h, w, c), 1).bfloat16()
         wt = randn((n, taps * c), 2, scale=(taps * c) ** -0.5).bfloat16()
@@ -81,7 +81,7 @@ def gemm_case(name, nb, h, w, c, n, taps, bias=False, rowvec=False, residual=Fal
         rv = randn((nb, n), 4) if rowvec else None
         res = randn((nb, h, w, n), 5).bfloat16() if residual else None
         y = ops.conv_gemm(x, wt, taps, bias=b, rowvec=rv, residual=res, out_f32=out_f32, block_n=block_n, splits=splits,
-                          halo=halo)
+                          halo=halo, pair=pair)
         torch.cuda.synchronize()
         ref = ref_conv(x, wt, taps, b, rv, res)
         record(name, rel_err(y, ref), tol, {"shape": [nb, h, w, c, n, taps], "block_n": block_n, "splits": splits})
@@ -124,6 +124,16 @@ def check_gemm():
     gemm_case("halo_512x512_64_64", 1, 512, 512, 64, 64, 9, bias=True, halo=True)
     gemm_case("halo_96x96_b4_320", 4, 96, 96, 320, 320, 9, bias=True, halo=True)
     gemm_case("halo_b3_16x16_64", 3, 16, 16, 64, 64, 9, bias=True, halo=True)
+    # CTA pairs (cta_group::2): 256-row tiles across two SMs, each CTA streams half of the weight tile
+    gemm_case("pair_lin_256x1280_1280", 1, 1, 256, 1280, 1280, 1, bias=True, pair=True, block_n=128)
+    gemm_case("pair_lin_4096x320_320_res", 1, 1, 4096, 320, 320, 1, bias=True, residual=True, pair=True, block_n=160)
+    gemm_case("pair_lin_odd_tiles_77x768", 1, 1, 77, 768, 768, 1, bias=True, pair=True, block_n=64)
+    gemm_case("pair_lin_1024x640_split2", 1, 1, 1024, 640, 640, 1, bias=True, pair=True, block_n=128, splits=2)
+    gemm_case("pair_conv_64x64_320_320", 1, 64, 64, 320, 320, 9, bias=True, rowvec=True, residual=True, pair=True, block_n=96)
+    gemm_case("pair_conv_16x16_1280_split4", 1, 16, 16, 1280, 1280, 9, bias=True, pair=True, block_n=128, splits=4)
+    gemm_case("pair_halo_64x64_320_320", 1, 64, 64, 320, 320, 9, bias=True, residual=True, halo=True, pair=True, block_n=160)
+    gemm_case("pair_halo_odd_45x80_64", 1, 45, 80, 64, 64, 9, bias=True, halo=True, pair=True)
+    gemm_case("pair_b4_96x96_320", 4, 96, 96, 320, 320, 9, bias=True, pair=True, block_n=256)
 
     def geglu():
         m, c = 4096, 320

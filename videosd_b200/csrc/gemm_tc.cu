@@ -195,16 +195,21 @@ __device__ __forceinline__ void splitk_finish4(const GemmParams& p, float (&v)[4
     }
 }
 
-template <int kEpi>   // 0: direct st.global epilogue, 1: bf16 tile through smem + TMA store, 2: fp32 split-K partials through TMA,
+// kPair: the kernel runs as CTA pairs (cluster (2,1,1) over adjacent 128-row tiles): ONE tcgen05.mma.cta_group::2 of the
+// leader drives both SMs' tensor cores on a 256 x block_n tile, each CTA streams its own 128 activation rows but only
+// HALF of the weight tile (block_n / 2 rows) -- the weight bytes entering each SM are halved.
+template <int kEpi, bool kPair>   // 0: direct st.global epilogue, 1: bf16 tile through smem + TMA store, 2: fp32 split-K partials through TMA,
                       // 3: split-K across a thread-block cluster, reduced through distributed shared memory
-__global__ void __launch_bounds__(kGemmThreads, (kEpi == 1 || kEpi == 3 ? 2 : 1))
+__global__ void __launch_bounds__(kGemmThreads, ((kEpi == 1 || kEpi == 3) && !kPair ? 2 : 1))
 conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapR, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stages = p.stages;
     const int kbs = p.kb_per_stage;                       // 64-wide k-blocks carried by one pipeline stage
-    const uint32_t b_bytes = (uint32_t)p.block_n * 128u;  // one k-block of the B tile
+    const uint32_t rank = kPair ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs, owns the full barriers)
+    const uint32_t b_rows = kPair ? (uint32_t)p.block_n >> 1 : (uint32_t)p.block_n;   // weight rows this CTA streams
+    const uint32_t b_bytes = b_rows * 128u;               // one k-block of (this CTA's part of) the B tile
     // stage layout: [A k-block 0 .. kbs-1][B k-block 0 .. kbs-1]; halo mode: [A halo tile 8 x 18 px][B tap dy=-1,0,1]
     const bool halo = p.halo != 0;
     const uint32_t a_stage = halo ? (uint32_t)kHaloABytes : (uint32_t)kbs * kABytes;
@@ -231,6 +236,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const int tn = mt / (p.tiles_w * p.tiles_h);
     const int w0 = tw * p.BW, h0 = th * p.BH, n0 = tn * p.BN;
     const int col0 = blockIdx.y * p.block_n;
+    const int bcol0 = col0 + (int)(rank * b_rows);       // first weight row this CTA loads
     const int split = blockIdx.z;
     const int kb_begin = split * p.kb_per_split;
     const int kb_end = min(kb_begin + p.kb_per_split, p.kb_total);
@@ -238,6 +244,47 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     // Stage bookkeeping shared by the early prefetch and the producer loop
     const int total_iters = halo ? (kb_end - kb_begin) : (kb_end - kb_begin + kbs - 1) / kbs;
     const int npre = ((p.a_static && !halo) || p.b_static) ? min(stages, total_iters) : 0;
+    // Loads count their bytes on the LEADER's full barrier (pair mode: through its shared::cluster address); only the leader
+    // arms it, with the bytes of both CTAs.
+    const uint32_t fbar_addr = kPair ? dsmem_addr(smem_u32(full_bar), 0u) : smem_u32(full_bar);
+    auto load_a = [&](void* dst, int s, int c0, int c1, int c2, int c3) {
+        if (kPair) tma_load_4d_pair(dst, &mapA, fbar_addr + (uint32_t)s * 8u, c0, c1, c2, c3);
+        else tma_load_4d(dst, &mapA, &full_bar[s], c0, c1, c2, c3);
+    };
+    auto load_b = [&](void* dst, int s, int c0, int c1) {
+        if (kPair) tma_load_2d_pair(dst, &mapB, fbar_addr + (uint32_t)s * 8u, c0, c1);
+        else tma_load_2d(dst, &mapB, &full_bar[s], c0, c1);
+    };
+    auto expect = [&](int s, uint32_t bytes) {
+        if (!kPair) mbar_expect_tx(&full_bar[s], bytes);
+        else if (rank == 0) mbar_expect_tx(&full_bar[s], 2u * bytes);
+    };
+    // The constant operand (weights) of the first ring pass is requested right away: before waiting for the producer
+    // kernel of the activations (PDL) and, without pairs, even before the TMEM allocation / CTA barrier.
+    auto early_prefetch = [&]() {
+        int kb = kb_begin;
+        if (halo) {
+            const int kpt = p.cin >> 6;
+            for (int it = 0; it < npre; ++it, ++kb) {   // iteration = (channel block, column shift)
+                uint8_t* sb = smem + (size_t)it * stage_bytes + a_stage;
+                const int cb = kb / 3, dxi = kb - cb * 3;
+                expect(it, stage_bytes);
+                for (int dyi = 0; dyi < 3; ++dyi)
+                    load_b(sb + (size_t)dyi * b_bytes, it, ((dyi * 3 + dxi) * kpt + cb) * 64, bcol0);
+            }
+        } else {
+            for (int it = 0; it < npre; ++it) {
+                const int nkb = min(kbs, kb_end - kb);
+                uint8_t* sa = smem + (size_t)it * stage_bytes;
+                uint8_t* sb = sa + a_stage;
+                expect(it, (uint32_t)nkb * ((uint32_t)kABytes + b_bytes));
+                for (int j = 0; j < nkb; ++j, ++kb) {
+                    if (p.b_static) load_b(sb + (size_t)j * b_bytes, it, kb * 64, bcol0);
+                    else load_a(sa + (size_t)j * kABytes, it, kb * 64, w0, h0, n0);  // taps == 1
+                }
+            }
+        }
+    };
     if (warp == 0) {
         if (elect_one()) {
             tma_prefetch_desc(&mapA);
@@ -251,36 +298,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             fence_barrier_init();
             if (kEpi != 0) tma_prefetch_desc(&mapC);
             if (kEpi == 1 && p.tma_res) tma_prefetch_desc(&mapR);
-            // The constant operand (weights) of the first ring pass is requested right away: before the TMEM
-            // allocation / CTA barrier below and before waiting for the producer kernel of the activations (PDL).
-            int kb = kb_begin;
-            if (halo) {
-                const int kpt = p.cin >> 6;
-                for (int it = 0; it < npre; ++it, ++kb) {   // iteration = (channel block, column shift)
-                    uint8_t* sb = smem + (size_t)it * stage_bytes + a_stage;
-                    const int cb = kb / 3, dxi = kb - cb * 3;
-                    mbar_expect_tx(&full_bar[it], stage_bytes);
-                    for (int dyi = 0; dyi < 3; ++dyi)
-                        tma_load_2d(sb + (size_t)dyi * b_bytes, &mapB, &full_bar[it], ((dyi * 3 + dxi) * kpt + cb) * 64, col0);
-                }
-            } else {
-                for (int it = 0; it < npre; ++it) {
-                    const int nkb = min(kbs, kb_end - kb);
-                    uint8_t* sa = smem + (size_t)it * stage_bytes;
-                    uint8_t* sb = sa + a_stage;
-                    mbar_expect_tx(&full_bar[it], (uint32_t)nkb * ((uint32_t)kABytes + b_bytes));
-                    for (int j = 0; j < nkb; ++j, ++kb) {
-                        if (p.b_static) tma_load_2d(sb + (size_t)j * b_bytes, &mapB, &full_bar[it], kb * 64, col0);
-                        else tma_load_4d(sa + (size_t)j * kABytes, &mapA, &full_bar[it], kb * 64, w0, h0, n0);  // taps == 1
-                    }
-                }
-            }
+            if (!kPair) early_prefetch();   // pairs: after the cluster barrier (the peer's barriers must exist first)
         }
         __syncwarp();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    if (warp == 1) {
+        if (kPair) tmem_alloc_pair(tmem_slot, (uint32_t)p.tmem_cols);
+        else tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    }
     tc_fence_before_sync();
-    __syncthreads();
+    if (kPair) cluster_sync_all(); else __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) VSD_STAMP(1);
@@ -294,6 +321,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             int cb = kb_begin - tap * kpt;
             int s = 0, dbg_it = 0;
             uint32_t ph = 0;
+            if (kPair) early_prefetch();
             pdl_wait();
             VSD_STAMP(7);
             // The residual tile rides behind the first ring pass: [chunk of 32 columns][128 rows][64 B], 64-byte swizzle
@@ -310,15 +338,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     const bool pre = dbg_it < npre;
                     if (!pre) {
                         mbar_wait(&empty_bar[s], ph ^ 1u, 1);
-                        mbar_expect_tx(&full_bar[s], stage_bytes);
+                        expect(s, stage_bytes);
                     }
                     uint8_t* sa = smem + (size_t)s * stage_bytes;
                     uint8_t* sb = sa + a_stage;
                     const int cbh = kb / 3, dxi = kb - cbh * 3;
-                    tma_load_4d(sa, &mapA, &full_bar[s], cbh * 64, w0 + dxi - 1, h0 - 1, n0);
+                    load_a(sa, s, cbh * 64, w0 + dxi - 1, h0 - 1, n0);
                     if (!pre)
                         for (int dyi = 0; dyi < 3; ++dyi)
-                            tma_load_2d(sb + (size_t)dyi * b_bytes, &mapB, &full_bar[s], ((dyi * 3 + dxi) * kpt + cbh) * 64, col0);
+                            load_b(sb + (size_t)dyi * b_bytes, s, ((dyi * 3 + dxi) * kpt + cbh) * 64, bcol0);
                     if (kEpi == 1 && p.tma_res && dbg_it == res_at) issue_residual();
                     ++dbg_it;
                     if (++s == stages) { s = 0; ph ^= 1u; }
@@ -329,7 +357,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 const bool pre = dbg_it < npre;
                 if (!pre) {
                     mbar_wait(&empty_bar[s], ph ^ 1u, 1);
-                    mbar_expect_tx(&full_bar[s], (uint32_t)nkb * ((uint32_t)kABytes + b_bytes));
+                    expect(s, (uint32_t)nkb * ((uint32_t)kABytes + b_bytes));
                 }
                 if (dbg_cta && dbg_it < 16) p.dbg[16 + 2 * dbg_it] = clock64();
                 uint8_t* sa = smem + (size_t)s * stage_bytes;
@@ -342,9 +370,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         dx = tap - ty * 3 - 1;
                     }
                     if (!(pre && p.a_static))
-                        tma_load_4d(sa + (size_t)j * kABytes, &mapA, &full_bar[s], cb * 64, w0 + dx, h0 + dy, n0);
+                        load_a(sa + (size_t)j * kABytes, s, cb * 64, w0 + dx, h0 + dy, n0);
                     if (!(pre && p.b_static))
-                        tma_load_2d(sb + (size_t)j * b_bytes, &mapB, &full_bar[s], kb * 64, col0);
+                        load_b(sb + (size_t)j * b_bytes, s, kb * 64, bcol0);
                     if (++cb == kpt) { cb = 0; ++tap; }
                 }
                 if (dbg_cta && dbg_it < 16) p.dbg[16 + 2 * dbg_it + 1] = clock64();
@@ -354,8 +382,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
-        const uint32_t idesc = umma_idesc_bf16(kBlockM, (uint32_t)p.block_n);
+    } else if (warp == 1 && (!kPair || rank == 0)) {
+        const uint32_t idesc = umma_idesc_bf16(kPair ? 2 * kBlockM : kBlockM, (uint32_t)p.block_n);
         int s = 0, dbg_it = 0;
         uint32_t ph = 0;
         bool first = true;
@@ -373,12 +401,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     for (int j = 0; j < nkb; ++j) {
 #pragma unroll
                         for (int k = 0; k < kBlockK / 16; ++k) {
-                            umma_bf16(tmem_base, umma_desc_sw128(a_addr + j * a_step + k * 32),
-                                      umma_desc_sw128(b_addr + j * b_bytes + k * 32), idesc,
-                                      (first && j == 0 && k == 0) ? 0u : 1u);
+                            if (kPair)
+                                umma_bf16_pair(tmem_base, umma_desc_sw128(a_addr + j * a_step + k * 32),
+                                               umma_desc_sw128(b_addr + j * b_bytes + k * 32), idesc,
+                                               (first && j == 0 && k == 0) ? 0u : 1u);
+                            else
+                                umma_bf16(tmem_base, umma_desc_sw128(a_addr + j * a_step + k * 32),
+                                          umma_desc_sw128(b_addr + j * b_bytes + k * 32), idesc,
+                                          (first && j == 0 && k == 0) ? 0u : 1u);
                         }
                     }
-                    umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
+                    if (kPair) umma_commit_pair(&empty_bar[s]);   // frees the stage in both CTAs when these MMAs retire
+                    else umma_commit(&empty_bar[s]);
                 }
                 __syncwarp();
                 if (lane == 0 && dbg_cta && dbg_it < 16) p.dbg[64 + 2 * dbg_it + 1] = clock64();
@@ -388,10 +422,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             kb += halo ? 1 : nkb;
             if (++s == stages) { s = 0; ph ^= 1u; }
         }
-        if (elect_one()) umma_commit(tmem_full_bar);
+        if (elect_one()) {
+            if (kPair) umma_commit_pair(tmem_full_bar);
+            else umma_commit(tmem_full_bar);
+        }
         __syncwarp();
         if (lane == 0) VSD_STAMP(3);
-    } else {
+    } else if (warp >= 2) {
         const int q = warp & 3;
         const int r = q * 32 + lane;
         const int bw = r % p.BW;
@@ -680,8 +717,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
     if (threadIdx.x == 64) VSD_STAMP(5);
     tc_fence_before_sync();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (kPair) cluster_sync_all(); else __syncthreads();   // pairs: neither CTA frees TMEM / leaves while the other still uses the pair
+    if (warp == 1) {
+        if (kPair) tmem_dealloc_pair(tmem_base, (uint32_t)p.tmem_cols);
+        else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
     if (threadIdx.x == 32) VSD_STAMP(6);
 #undef VSD_STAMP
 }
@@ -786,10 +826,13 @@ int gemm_init() {
     VSD_CHECK_CUDA(cudaGetDevice(&dev));
     VSD_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     VSD_CHECK_CUDA(cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
-    VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
-    VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
-    VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
     return 0;
 }
 
@@ -829,7 +872,9 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
     p.taps = taps; p.cin = a.C; p.H = a.H; p.W = a.W; p.NB = a.NB;
     // Halo mode for 3x3 convolutions: 8 x 16 pixel tiles; per 64-channel block three column-shifted 8 x 18 halo
     // tiles replace nine 128-pixel tap tiles (2.7x less activation traffic into the SM).
-    const bool halo = (taps == 9) && (a.H >= 16) && (a.W >= 8) && (force_halo != 0) && (force_halo > 0);
+    // force_halo is a mode word: bit 0 = halo tiles, bit 1 = CTA pairs (cta_group::2)
+    const bool halo = (taps == 9) && (a.H >= 16) && (a.W >= 8) && (force_halo > 0) && (force_halo & 1);
+    const bool pair = (force_halo > 0) && (force_halo & 2);
     p.halo = halo ? 1 : 0;
     if (halo) { p.BW = 8; p.BH = 16; p.BN = 1; }
     else pick_tile_rect(a.NB, a.H, a.W, &p.BW, &p.BH, &p.BN);
@@ -838,6 +883,7 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
     p.tiles_n = (a.NB + p.BN - 1) / p.BN;
     p.N = N;
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    p.pair = pair ? 1 : 0;
     p.kb_total = halo ? 3 * (a.C / 64) : taps * (a.C / 64);   // halo: iterations of (channel block, column shift)
 
     // N tile: prefer a divisor of N that keeps the grid near a multiple of the SM count.
@@ -905,7 +951,7 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
     // to the separate, fully parallel reduce kernel (9.9 vs 7.7 us for 256x1280x1280, 4 splits) => opt-in only.
     static const bool cluster_ok = getenv("VSD_CLUSTER_SPLITK") && atoi(getenv("VSD_CLUSTER_SPLITK")) != 0;
     const bool out_tma_ok = !out_f32 && (ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (bn_out % 32) == 0;
-    if (splits > 1 && splits <= 8 && cluster_ok && tma_epi && (N % 4) == 0 && (reinterpret_cast<uintptr_t>(partial_ws) & 15) == 0) {
+    if (splits > 1 && splits <= 8 && cluster_ok && !pair && tma_epi && (N % 4) == 0 && (reinterpret_cast<uintptr_t>(partial_ws) & 15) == 0) {
         cluster_k = 1;     // partials through TMA into the (L2-resident) workspace, reduced by the cluster itself
         tma_out = 2;
     } else if (tma_epi) {
@@ -920,10 +966,12 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
 
     // Tiles up to 160 columns run two CTAs per SM (one CTA's epilogue overlaps the other's main loop);
     // wider tiles take the whole SM with a deeper ring.
-    const int stage_bytes = kABytes + bn * 128;
+    const int b_tile = pair ? bn * 64 : bn * 128;     // bytes of one k-block of the weight tile held by one CTA
+    const int stage_bytes = kABytes + b_tile;
     int occ = force_occupancy > 0 ? force_occupancy : ((bn > 160) ? 1 : 2);
-    if (occ == 2 && 2 * (kABytes + bn * 128) + 4096 > g_max_smem / 2) occ = 1;   // not even two stages fit twice
-    if (halo && occ == 2 && force_occupancy <= 0 && 2 * (kHaloABytes + 3 * bn * 128) + 4096 > g_max_smem / 2) occ = 1;
+    if (pair) occ = 1;
+    if (occ == 2 && 2 * (kABytes + b_tile) + 4096 > g_max_smem / 2) occ = 1;   // not even two stages fit twice
+    if (halo && occ == 2 && force_occupancy <= 0 && 2 * (kHaloABytes + 3 * b_tile) + 4096 > g_max_smem / 2) occ = 1;
     const int smem_budget = (occ == 1) ? g_max_smem : (g_max_smem / 2 - 1024);
     // Each barrier round trip (TMA -> full -> MMA -> commit -> empty -> TMA) costs several hundred cycles, so a
     // stage carries kb_per_stage 64-wide k-blocks; keep >= 3 stages in flight when the budget allows.
@@ -935,7 +983,7 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
         const int ring_budget = smem_budget - 3072 - (tma_res ? stag_bytes : 0);
         int k2 = kbs;
         while (k2 > 1 && (ring_budget / (k2 * stage_bytes) < (force_kb_per_stage > 0 ? 2 : 3) || k2 > p.kb_per_split)) --k2;
-        stage_total = halo ? (kHaloABytes + 3 * bn * 128) : k2 * stage_bytes;
+        stage_total = halo ? (kHaloABytes + 3 * b_tile) : k2 * stage_bytes;
         stages = ring_budget / stage_total;
         if (tma_res && stages < 2) { tma_res = 0; continue; }   // no room: read the residual straight from global memory
         if (tma_out && !tma_res && stag_bytes > smem_budget - 3072) { tma_out = 0; stag_bytes = 0; cluster_k = 0; continue; }
@@ -979,7 +1027,7 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
     int rc = halo ? make_tmap_act(&op->mapA, a.ptr, a.C, a.W, a.H, a.NB, a.ld, 8, 18, 1)
                   : make_tmap_act(&op->mapA, a.ptr, a.C, a.W, a.H, a.NB, a.ld, p.BW, p.BH, p.BN);
     if (rc) return rc;
-    rc = make_tmap_2d(&op->mapB, wt, taps * a.C, N, ldw, bn);
+    rc = make_tmap_2d(&op->mapB, wt, taps * a.C, N, ldw, pair ? bn / 2 : bn);
     if (rc) return rc;
     op->mapC = op->mapA;   // placeholders when unused (a valid descriptor keeps the kernel parameter well-formed)
     op->mapR = op->mapA;
@@ -988,18 +1036,26 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
     if (rc) return rc;
     if (tma_res) rc = make_tmap_epi_bf16(&op->mapR, residual, N, a.W, a.H, a.NB, ldr, p.BW, p.BH, p.BN);
     if (rc) return rc;
-    op->grid = dim3(m_tiles, n_tiles, splits);
+    // pairs: adjacent 128-row tiles share one cluster; an odd tile count is padded with a tile outside the tensor (TMA reads
+    // zeros / clips the stores, the direct epilogue masks the rows)
+    op->grid = dim3(pair ? (m_tiles + 1) & ~1 : m_tiles, n_tiles, splits);
     return 0;
 }
 
 int launch_gemm_op(const GemmOp& op, cudaStream_t st) {
     if (op.p.cluster_k) {
-        VSD_CHECK_CUDA(launch_k_cluster(conv_gemm_kernel<3>, op.grid, dim3(kGemmThreads), (size_t)op.smem_bytes, op.p.splits, st, op.mapA,
-                                        op.mapB, op.mapC, op.mapR, op.p));
+        VSD_CHECK_CUDA(launch_k_cluster(conv_gemm_kernel<3, false>, op.grid, dim3(kGemmThreads), (size_t)op.smem_bytes, 1, op.p.splits, st,
+                                        op.mapA, op.mapB, op.mapC, op.mapR, op.p));
         return 0;
     }
-    auto kern = op.p.tma_out == 2 ? conv_gemm_kernel<2> : (op.p.tma_out == 1 ? conv_gemm_kernel<1> : conv_gemm_kernel<0>);
-    VSD_CHECK_CUDA(launch_k(kern, op.grid, dim3(kGemmThreads), (size_t)op.smem_bytes, st, op.mapA, op.mapB, op.mapC, op.mapR, op.p));
+    if (op.p.pair) {
+        auto kern = op.p.tma_out == 2 ? conv_gemm_kernel<2, true> : (op.p.tma_out == 1 ? conv_gemm_kernel<1, true> : conv_gemm_kernel<0, true>);
+        VSD_CHECK_CUDA(launch_k_cluster(kern, op.grid, dim3(kGemmThreads), (size_t)op.smem_bytes, 2, 1, st, op.mapA, op.mapB, op.mapC,
+                                        op.mapR, op.p));
+    } else {
+        auto kern = op.p.tma_out == 2 ? conv_gemm_kernel<2, false> : (op.p.tma_out == 1 ? conv_gemm_kernel<1, false> : conv_gemm_kernel<0, false>);
+        VSD_CHECK_CUDA(launch_k(kern, op.grid, dim3(kGemmThreads), (size_t)op.smem_bytes, st, op.mapA, op.mapB, op.mapC, op.mapR, op.p));
+    }
     if (op.p.splits > 1) {
         const long rows = (long)op.p.NB * op.p.H * op.p.W;
         return launch_splitk_reduce(op.p, rows, st);

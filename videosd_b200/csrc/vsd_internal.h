@@ -46,10 +46,10 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
-// same, as thread-block clusters of (1, 1, cluster_z) CTAs
+// same, as thread-block clusters of (cluster_x, 1, cluster_z) CTAs
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_k_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, int cluster_z, cudaStream_t st,
-                                    Args... args) {
+inline cudaError_t launch_k_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, int cluster_x, int cluster_z,
+                                    cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -59,7 +59,7 @@ inline cudaError_t launch_k_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 bl
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled();
     attr[1].id = cudaLaunchAttributeClusterDimension;
-    attr[1].val.clusterDim.x = 1;
+    attr[1].val.clusterDim.x = (unsigned)cluster_x;
     attr[1].val.clusterDim.y = 1;
     attr[1].val.clusterDim.z = (unsigned)cluster_z;
     cfg.attrs = attr;
@@ -90,6 +90,7 @@ struct GemmParams {
     int block_n;          // multiple of 32, <= 256
     int tmem_cols;        // power of two >= block_n
     int stages, kb_per_stage;
+    int pair;             // CTA pairs (cta_group::2): see conv_gemm_kernel<.., kPair>
     int halo;             // 3x3 conv halo mode (8x16 tiles, column-shifted 8x18 activation tiles shared by 3 row taps)
     // K split
     int kb_total, kb_per_split, splits;

@@ -92,9 +92,9 @@ int vsd_op_conv_gemm(const void* x, int nb, int h, int w, int c, int ldx, int ta
     if (rc) return rc;
     GemmOp op;
     ActView a{x, nb, h, w, c, ldx};
-    // test knob: act bit 8 requests the 3x3 halo mode
-    const int want_halo = (act & 256) ? 1 : 0;
-    act &= ~256;
+    // test knobs: act bit 8 requests the 3x3 halo mode, bit 9 CTA pairs (cta_group::2)
+    const int want_halo = ((act & 256) ? 1 : 0) | ((act & 512) ? 2 : 0);
+    act &= ~(256 | 512);
     rc = build_gemm_op(&op, a, taps, reinterpret_cast<const bf16*>(wt), n, taps * c, out, ldo, out_f32, bias, rowvec,
                        reinterpret_cast<const bf16*>(residual), ldr, act, g_ws, g_ws_bytes, block_n, splits, 0, 0, want_halo);
     if (rc) return rc;
@@ -112,7 +112,7 @@ int vsd_op_conv_gemm_timed(const void* x, int nb, int h, int w, int c, int ldx, 
     GemmOp op;
     ActView a{x, nb, h, w, c, ldx};
     rc = build_gemm_op(&op, a, taps, reinterpret_cast<const bf16*>(wt), n, taps * c, out, ldo, 0, bias, nullptr, nullptr, 0,
-                       0, g_ws, g_ws_bytes, block_n, splits, occ, kb_per_stage);
+                       0, g_ws, g_ws_bytes, block_n, splits, occ & 0xFF, kb_per_stage, occ >> 8 /* mode: 1 halo, 2 pairs */);
     if (rc) return rc;
     op.p.dbg = dbg;
     return launch_gemm_op(op, reinterpret_cast<cudaStream_t>(stream));
