@@ -82,6 +82,9 @@ class Arena {
 struct Launch {
     std::function<int(cudaStream_t)> fn;
     std::string tag;   // dotted scope, e.g. "step0.unet.down0.attn1.ff1" (used by the section profiler)
+    // Independent work inside a frame runs on a side stream (a parallel branch of the captured graph): a `side` launch forks
+    // from the main stream right where it sits in the plan; the first later launch marked `join` waits for the side stream.
+    int side = 0, join = 0;
     int operator()(cudaStream_t st) const { return fn(st); }
 };
 static thread_local std::string g_scope;   // current tag while a plan is being built
@@ -111,6 +114,9 @@ struct Engine {
     Arena arena;
     size_t arena_static_mark = 0;
     float* splitk_ws = nullptr; size_t splitk_bytes = 0;
+    float* splitk_ws_side = nullptr;   // split-K workspace of the side-stream branch (runs concurrently with the main one)
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     uint8_t *d_y = nullptr, *d_u = nullptr, *d_v = nullptr, *d_rgb_in = nullptr;       // inputs
     uint8_t *d_oy = nullptr, *d_ou = nullptr, *d_ov = nullptr, *d_rgb_out = nullptr;   // outputs
     float *init_latents = nullptr, *noisy = nullptr, *init_noise = nullptr, *step_noise = nullptr, *image = nullptr;
@@ -376,6 +382,23 @@ struct Builder {
     std::vector<Launch>* out;
     int rc = 0;
     std::string fail;
+    int side_mode = 0;     // launches pushed while set run on the side stream
+    size_t side_from = 0;
+    static bool branches_enabled() {
+        static const bool on = !(getenv("VSD_BRANCHES") && atoi(getenv("VSD_BRANCHES")) == 0);
+        return on;
+    }
+    void begin_side() { if (branches_enabled()) { side_mode = 1; side_from = out->size(); } }
+    void end_side() {
+        if (!side_mode) return;
+        for (size_t i = side_from; i < out->size(); ++i) (*out)[i].side = 1;
+        side_mode = 0;
+    }
+    void join_next() { join_pending = branches_enabled(); }   // the next launch pushed on the main stream waits for the side stream
+    bool join_pending = false;
+    void mark_join(size_t first) {
+        if (join_pending && out->size() > first) { (*out)[first].join = 1; join_pending = false; }
+    }
 
     const bf16* wb(const std::string& n) {
         auto it = e->w.find(n);
@@ -426,11 +449,13 @@ struct Builder {
             }
             fbn = it->second.bn; fsp = it->second.splits; focc = it->second.occ; fkbs = it->second.kbs; fhalo = it->second.halo;
         }
-        int r = build_gemm_op(&op, a, taps, wt, N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act, e->splitk_ws,
-                              e->splitk_bytes, fbn, fsp, focc, fkbs, fhalo);
+        int r = build_gemm_op(&op, a, taps, wt, N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act,
+                              side_mode ? e->splitk_ws_side : e->splitk_ws, e->splitk_bytes, fbn, fsp, focc, fkbs, fhalo);
         if (r) { rc = r; fail = get_error(); return; }
         op.p.out_scale = out_scale;
+        const size_t first = out->size();
         out->push_back(mk([op](cudaStream_t st) { return launch_gemm_op(op, st); }, "gemm"));
+        if (!side_mode) mark_join(first);
     }
     void conv(const View& x, const std::string& name, int taps, const View& o, const float* rowvec, const View* res,
               int act, bool has_bias = true) {
@@ -467,13 +492,22 @@ struct Builder {
         int r = build_attn_op(&op, q, ldq, k, ldk, vt, ldvt, o.p, o.ld, o.nb, heads, d, nq, nk, q_rows, k_rows, vt_cols,
                               vt_rows);
         if (r) { rc = r; fail = get_error(); return; }
+        const size_t first = out->size();
         out->push_back(mk([op](cudaStream_t st) { return launch_attn_op(op, st); }, "attn"));
+        mark_join(first);
     }
 
     // ---- diffusers ResnetBlock2D (Appendix A.3)
     void resnet(const View& x, const std::string& p, const float* temb_rowvec, const View& o) {
         Scope sc_(short_name(p));
         const size_t m = e->arena.mark();
+        View sc;
+        if (x.c != o.c) {   // the 1x1 shortcut only needs x: it runs beside norm1 / conv1 / norm2 on the side stream
+            sc = alloc(x.nb, x.h, x.w, o.c);
+            begin_side();
+            conv(x, p + ".conv_shortcut", 1, sc, nullptr, nullptr, ACT_NONE);
+            end_side();
+        }
         View t1 = alloc(x.nb, x.h, x.w, x.c);
         groupnorm(x, p + ".norm1", 1e-5f, 1, t1);
         View h1 = alloc(x.nb, x.h, x.w, o.c);
@@ -481,8 +515,7 @@ struct Builder {
         View t2 = alloc(x.nb, x.h, x.w, o.c);
         groupnorm(h1, p + ".norm2", 1e-5f, 1, t2);
         if (x.c != o.c) {
-            View sc = alloc(x.nb, x.h, x.w, o.c);
-            conv(x, p + ".conv_shortcut", 1, sc, nullptr, nullptr, ACT_NONE);
+            join_next();
             conv(t2, p + ".conv2", 9, o, nullptr, &sc, ACT_NONE);
         } else {
             conv(t2, p + ".conv2", 9, o, nullptr, &x, ACT_NONE);
@@ -506,7 +539,6 @@ struct Builder {
         View n1 = alloc(NB, x.h, x.w, C);
         layernorm(h0, tb + ".norm1", n1);
         View qk = alloc(NB, x.h, x.w, 2 * heads * dkp);
-        gemm(n1.act_rows(), 1, wb(tb + ".attn1.qk.weight"), qk.c, C, qk.p, qk.ld, 0, nullptr, nullptr, nullptr, 0, ACT_NONE);
         // V^T[C][tokens] = Wv * n1^T : weight as the row operand, activations as the column operand
         const int cols_img = (HW + 7) / 8 * 8;
         const int ldvt = NB * cols_img;
@@ -514,6 +546,7 @@ struct Builder {
         if (!vt) bad("activation arena exhausted");
         const bf16* wv = wb(tb + ".attn1.to_v.weight");
         if (!rc) {
+            begin_side();   // the V^T projection only needs norm1's output: it overlaps the Q|K projection on the main stream
             ActView aw{wv, 1, 1, C, C, C};
             if (cols_img == HW) {
                 gemm(aw, 1, n1.p, (int)M, n1.ld, vt, ldvt, 0, nullptr, nullptr, nullptr, 0, ACT_NONE | ACT_A_STATIC_FLAG);
@@ -522,7 +555,10 @@ struct Builder {
                     gemm(aw, 1, n1.p + (long)b * HW * n1.ld, HW, n1.ld, vt + (long)b * cols_img, ldvt, 0, nullptr, nullptr,
                          nullptr, 0, ACT_NONE | ACT_A_STATIC_FLAG);
             }
+            end_side();
         }
+        gemm(n1.act_rows(), 1, wb(tb + ".attn1.qk.weight"), qk.c, C, qk.p, qk.ld, 0, nullptr, nullptr, nullptr, 0, ACT_NONE);
+        join_next();
         View a1 = alloc(NB, x.h, x.w, C);
         attention(qk.p, qk.ld, qk.p + heads * dkp, qk.ld, vt, ldvt, a1, heads, d, HW, HW, HW, HW, cols_img, C);
         View h1 = alloc(NB, x.h, x.w, C);
@@ -902,10 +938,28 @@ static void build_controlnet_residuals(Builder& B, CNStatic& C, const std::funct
            B.wf("controlnet.controlnet_mid_block.bias"), nullptr, mid_out.p, mid_out.ld, ACT_NONE, e->cn_scales + 12);
 }
 
-static int run_plan(const std::vector<Launch>& plan, cudaStream_t st) {
+static int run_plan(Engine* e, const std::vector<Launch>& plan, cudaStream_t st) {
+    bool side_busy = false;
     for (const auto& l : plan) {
+        if (l.side && e->side) {
+            VSD_CHECK_CUDA(cudaEventRecord(e->ev_fork, st));          // fork: everything issued so far on the main stream
+            VSD_CHECK_CUDA(cudaStreamWaitEvent(e->side, e->ev_fork, 0));
+            int rc = l(e->side);
+            if (rc) return rc;
+            side_busy = true;
+            continue;
+        }
+        if (l.join && side_busy) {
+            VSD_CHECK_CUDA(cudaEventRecord(e->ev_join, e->side));
+            VSD_CHECK_CUDA(cudaStreamWaitEvent(st, e->ev_join, 0));
+            side_busy = false;
+        }
         int rc = l(st);
         if (rc) return rc;
+    }
+    if (side_busy) {   // never leave the side stream dangling (stream capture requires the join)
+        VSD_CHECK_CUDA(cudaEventRecord(e->ev_join, e->side));
+        VSD_CHECK_CUDA(cudaStreamWaitEvent(st, e->ev_join, 0));
     }
     return 0;
 }
@@ -1023,7 +1077,7 @@ static int encode_prompt(Engine* e, const int* ids_host, float* out_host) {
     if (rc) return rc;
     Engine::Clip& c = e->clip;
     VSD_CHECK_CUDA(cudaMemcpyAsync(c.ids, ids_host, 77 * sizeof(int), cudaMemcpyHostToDevice, e->stream));
-    rc = run_plan(c.plan, e->stream);
+    rc = run_plan(e, c.plan, e->stream);
     if (rc) return rc;
     std::vector<uint16_t> t((size_t)77 * 768);
     VSD_CHECK_CUDA(cudaMemcpyAsync(t.data(), c.out, t.size() * 2, cudaMemcpyDeviceToHost, e->stream));
@@ -1051,7 +1105,8 @@ static int configure(Engine* e, int nb, int H, int W) {
     free_resize(e);
     e->arena.destroy();
     if (e->splitk_ws) cudaFree(e->splitk_ws);
-    e->splitk_ws = nullptr;
+    if (e->splitk_ws_side) cudaFree(e->splitk_ws_side);
+    e->splitk_ws = nullptr; e->splitk_ws_side = nullptr;
     e->NB = nb; e->H = H; e->W = W; e->h8 = H / 8; e->w8 = W / 8;
     e->configured = false; e->schedule_set = false; e->context_set = false;
     e->xattn.clear(); e->temb.clear(); e->eps.clear(); e->lat.clear(); e->den.clear();
@@ -1061,6 +1116,7 @@ static int configure(Engine* e, int nb, int H, int W) {
     if (rc) return rc;
     e->splitk_bytes = (size_t)(16.0 * 1048576.0 * (scale < 1 ? 1 : scale)) + (size_t)48 * 1048576;
     VSD_CHECK_CUDA(cudaMalloc(&e->splitk_ws, e->splitk_bytes));
+    VSD_CHECK_CUDA(cudaMalloc(&e->splitk_ws_side, e->splitk_bytes));
     Arena& A = e->arena;
     const size_t px = (size_t)nb * H * W, lpx = (size_t)nb * e->h8 * e->w8;
     e->d_y = (uint8_t*)A.alloc(px); e->d_u = (uint8_t*)A.alloc(px / 4); e->d_v = (uint8_t*)A.alloc(px / 4);
@@ -1349,9 +1405,9 @@ static int capture(Engine* e, bool yuv, cudaGraphExec_t* exec) {
     cudaGraph_t g = nullptr;
     VSD_CHECK_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
     int rc = 0;
-    if (yuv) rc = run_plan(e->plan_pre_yuv, e->stream);
-    if (!rc) rc = run_plan(e->plan_core, e->stream);
-    if (!rc) rc = run_plan(e->plan_post, e->stream);
+    if (yuv) rc = run_plan(e, e->plan_pre_yuv, e->stream);
+    if (!rc) rc = run_plan(e, e->plan_core, e->stream);
+    if (!rc) rc = run_plan(e, e->plan_post, e->stream);
     cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
     if (rc) { if (g) cudaGraphDestroy(g); return rc; }
     VSD_CHECK_CUDA(ce);
@@ -1393,7 +1449,10 @@ vsd_ctx* vsd_create(int device) {
         delete c;
         return nullptr;
     }
-    if (cudaStreamCreateWithFlags(&c->e.stream, cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&c->e.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->e.side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->e.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->e.ev_join, cudaEventDisableTiming) != cudaSuccess) {
         set_error("cudaStreamCreate failed");
         delete c;
         return nullptr;
@@ -1424,6 +1483,10 @@ void vsd_destroy(vsd_ctx* c) {
         for (auto& kv : c->e.w) cudaFree(kv.second.p);
     c->e.arena.destroy();
     if (c->e.splitk_ws) cudaFree(c->e.splitk_ws);
+    if (c->e.splitk_ws_side) cudaFree(c->e.splitk_ws_side);
+    if (c->e.ev_fork) cudaEventDestroy(c->e.ev_fork);
+    if (c->e.ev_join) cudaEventDestroy(c->e.ev_join);
+    if (c->e.side) cudaStreamDestroy(c->e.side);
     if (c->e.flush_buf) cudaFree(c->e.flush_buf);
     free_resize(&c->e);
     free_clip(&c->e);
@@ -1722,7 +1785,7 @@ int vsd_debug_unet(vsd_ctx* c, const float* latents_nhwc, int step, float* eps_n
     const size_t lpx = (size_t)e->NB * e->h8 * e->w8;
     float* dst = (step == 0) ? e->noisy : e->lat[step - 1];
     VSD_CHECK_CUDA(cudaMemcpyAsync(dst, latents_nhwc, lpx * 16, cudaMemcpyHostToDevice, e->stream));
-    int rc = run_plan(e->plan_unet[step], e->stream);
+    int rc = run_plan(e, e->plan_unet[step], e->stream);
     if (rc) return rc;
     VSD_CHECK_CUDA(cudaMemcpyAsync(eps_nhwc, e->eps[step], lpx * 16, cudaMemcpyDeviceToHost, e->stream));
     VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
@@ -1798,9 +1861,9 @@ int vsd_debug_run_eager(vsd_ctx* c, int yuv) {
     Engine* e = &c->e;
     ENG_REQUIRE(e->schedule_set && e->context_set, "schedule and context must be set");
     int rc = 0;
-    if (yuv) rc = run_plan(e->plan_pre_yuv, e->stream);
-    if (!rc) rc = run_plan(e->plan_core, e->stream);
-    if (!rc) rc = run_plan(e->plan_post, e->stream);
+    if (yuv) rc = run_plan(e, e->plan_pre_yuv, e->stream);
+    if (!rc) rc = run_plan(e, e->plan_core, e->stream);
+    if (!rc) rc = run_plan(e, e->plan_post, e->stream);
     if (rc) return rc;
     VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
     return vsd_check_pipeline_fault();
