@@ -127,11 +127,26 @@ def run_ours(args):
     pool.load_state_dict("unet", weights.random_state_dict(weights.unet_param_shapes(), 1234))
     pool.load_state_dict("vae", weights.random_state_dict(weights.taesd_param_shapes(), 4321))
     pool.configure(B, H, W)
+    # The pool's GEMM configurations are tuned for L frames in flight. The single-lane (latency mode) figure comes from one
+    # more lane on the same weights whose configurations are tuned for ONE frame in flight.
+    from videosd_b200.engine import Engine
+    solo = None
+    if L > 1:
+        solo = Engine(local_rank, parent=pool.lanes[0])
+        solo.set_autotune(1)
+        solo.configure(B, H, W)
     ts = pool.set_schedule(args.strength, args.lcm_steps)
     ctx = torch.randn((B, 77, 768), generator=torch.Generator().manual_seed(7))
     for b in range(B):
         pool.set_context(b, ctx[b])
     pool.set_reference_noise()
+    if solo is not None:
+        solo.set_schedule(args.strength, args.lcm_steps)
+        for b in range(B):
+            solo.set_context(b, ctx[b])
+        solo.set_reference_noise()
+    else:
+        solo = pool.lanes[0]
     eng = pool.lanes[0]
 
     nfr = 8
@@ -143,7 +158,9 @@ def run_ours(args):
     outs = [(torch.empty((B, H, W), dtype=torch.uint8).pin_memory(),
              torch.empty((B, H // 2, W // 2), dtype=torch.uint8).pin_memory(),
              torch.empty((B, H // 2, W // 2), dtype=torch.uint8).pin_memory()) for _ in range(L)]
-    streams = [torch.cuda.ExternalStream(e.stream, device=local_rank) for e in pool.lanes]
+    all_lanes = pool.lanes + ([solo] if solo is not pool.lanes[0] else [])
+    outs.append(tuple(torch.empty_like(t).pin_memory() for t in outs[0]))
+    stream_of = {id(e): torch.cuda.ExternalStream(e.stream, device=local_rank) for e in all_lanes}
 
     def barrier():
         torch.cuda.synchronize()
@@ -158,13 +175,13 @@ def run_ours(args):
         n = len(lanes)
         e0 = torch.cuda.Event(enable_timing=True)
         ends = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
-        e0.record(streams[0])
+        e0.record(stream_of[id(lanes[0])])
         for i in range(1, n):
-            streams[i].wait_event(e0)
+            stream_of[id(lanes[i])].wait_event(e0)
         for k in range(k_steps):
             lanes[k % n].run_yuv420()
         for i in range(n):
-            ends[i].record(streams[i])
+            ends[i].record(stream_of[id(lanes[i])])
         for e in lanes:
             e.sync()
         return max(e0.elapsed_time(ev) for ev in ends)
@@ -177,7 +194,7 @@ def run_ours(args):
         def worker(i):
             for k in range(i, k_steps, n):
                 t1 = time.perf_counter()
-                lanes[i].infer_yuv420(*pinned[k % nfr], *outs[i])
+                lanes[i].infer_yuv420(*pinned[k % nfr], *outs[all_lanes.index(lanes[i])])
                 lat[i].append((time.perf_counter() - t1) * 1e3)
 
         ths = [threading.Thread(target=worker, args=(i,)) for i in range(n)]
@@ -189,12 +206,13 @@ def run_ours(args):
         return (time.perf_counter() - t0) * 1e3, [v for l in lat for v in l]
 
     # ---- warm-up (>= 3 steps per lane), then the timed regions
-    for e in pool.lanes:
+    for e in all_lanes:
         e.upload_yuv420(*pinned[0])
         for _ in range(Wm):
             e.run_yuv420()
         e.sync()
     e2e_run(pool.lanes, Wm * L)
+    e2e_run([solo], Wm)
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
@@ -202,8 +220,8 @@ def run_ours(args):
     barrier()
     e2e_ms, lat = e2e_run(pool.lanes, K)               # e2e: all lanes
     barrier()
-    dev1_ms = device_run(pool.lanes[:1], K)            # single lane (one frame in flight): latency-optimal mode
-    e2e1_ms, lat1 = e2e_run(pool.lanes[:1], K)
+    dev1_ms = device_run([solo], K)                    # single lane (one frame in flight): latency-optimal mode
+    e2e1_ms, lat1 = e2e_run([solo], K)
     clocks = sampler.stop()
     barrier()
     oy = outs[0][0]

@@ -126,8 +126,10 @@ vsd_ctx* vsd_create_lane(vsd_ctx* parent);
 int vsd_load_weight(vsd_ctx* ctx, const char* name, const float* host_f32, const int64_t* shape, int ndim);
 int vsd_num_weights(vsd_ctx* ctx);
 /* GEMM autotuner (on by default): at plan-build time each distinct GEMM shape is timed over (block_n, split-K,
- * CTAs/SM) candidates with the L2 flushed. vsd_tuning_report dumps the choices as text. */
-int vsd_set_autotune(vsd_ctx* ctx, int enabled);
+ * CTAs/SM, k-blocks per stage, halo tiles, CTA pairs) candidates with the L2 flushed. frames_in_flight: 0 = off (shape
+ * heuristics), 1 = lowest latency of a single frame, n > 1 = n frames in flight on this GPU (lanes): a candidate's cost is
+ * its duration x max(share of the SMs it occupies, 1/n). vsd_tuning_report dumps the choices as text. */
+int vsd_set_autotune(vsd_ctx* ctx, int frames_in_flight);
 int vsd_tuning_report(vsd_ctx* ctx, char* buf, long cap);
 int vsd_tuning_load(vsd_ctx* ctx, const char* text);   /* returns the number of entries loaded */
 

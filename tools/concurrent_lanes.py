@@ -12,11 +12,12 @@ from videosd_b200 import weights  # noqa: E402
 from videosd_b200.engine import LanePool  # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+TUNE_FOR = int(sys.argv[2]) if len(sys.argv) > 2 else None   # frames in flight the GEMM autotuner optimises for (default N)
 H = W = 512
 usd = weights.random_state_dict(weights.unet_param_shapes(), 1234)
 vsd = weights.random_state_dict(weights.taesd_param_shapes(), 4321)
 ctx = torch.randn((77, 768), generator=torch.Generator().manual_seed(7))
-pool = LanePool(0, N)
+pool = LanePool(0, N, tune_for=TUNE_FOR)
 pool.load_state_dict("unet", usd); pool.load_state_dict("vae", vsd)
 pool.configure(1, H, W); pool.set_schedule(0.5, 4); pool.set_context(0, ctx); pool.set_reference_noise()
 engs = pool.lanes

@@ -132,7 +132,10 @@ struct Engine {
     std::vector<Launch> plan_pre_yuv, plan_pre_rgb, plan_core, plan_post;
     std::vector<std::vector<Launch>> plan_unet;  // per step (debug entry)
     cudaGraphExec_t graph_yuv = nullptr, graph_rgb = nullptr;
-    // GEMM autotuner: (block_n, splits, occupancy) per distinct shape, timed with L2 flushed
+    // GEMM autotuner: (block_n, splits, occupancy, mode) per distinct shape, timed with L2 flushed. 0 = off (heuristics);
+    // n >= 1 = tune for n frames in flight on this GPU: a launch costs its duration times max(share of the SMs it holds, 1/n),
+    // so with one frame in flight the fastest configuration wins and with several, configurations that leave SMs to the
+    // other frames are preferred over split-K / many small CTAs.
     int autotune = 1;
     struct Tuned { int bn, splits, occ, kbs, halo; float us; };
     std::unordered_map<std::string, Tuned> tuned;
@@ -328,6 +331,7 @@ static int tune_gemm(Engine* e, const ActView& a, int taps, const bf16* wt, int 
     const int sps[8] = {1, 2, 3, 4, 6, 8, 12, 16};
     const int kb_total = taps * (a.C / 64);
     Engine::Tuned best{0, 1, 0, 1, 0, 1e30f};
+    float best_cost = 1e30f;
     for (int bi = 0; bi < 8; ++bi) {
         const int bn = bns[bi];
         if (geglu && bn != 128) continue;
@@ -357,7 +361,9 @@ static int tune_gemm(Engine* e, const ActView& a, int taps, const bf16* wt, int 
                         float us = 0.f;
                         int rc = time_gemm(e, op, &us);
                         if (rc) return rc;
-                        if (us < best.us) best = Engine::Tuned{bn, sp, occ, kbs, mode, us};
+                        const float util = std::min(1.0f, (float)ctas / (148.0f * (float)occ));
+                        const float cost = us * std::max(util, 1.0f / (float)std::max(e->autotune, 1));
+                        if (cost < best_cost) { best_cost = cost; best = Engine::Tuned{bn, sp, occ, kbs, mode, us}; }
                     }
                 }
             }
@@ -1512,7 +1518,7 @@ int vsd_num_weights(vsd_ctx* c) { return c ? (int)c->e.w.size() : -1; }
 
 int vsd_set_autotune(vsd_ctx* c, int enabled) {
     if (!c) return -1;
-    c->e.autotune = enabled ? 1 : 0;
+    c->e.autotune = enabled < 0 ? 0 : enabled;   // 0 off, n = tune for n frames in flight
     return 0;
 }
 

@@ -182,8 +182,10 @@ class Engine:
     def launches_per_frame(self, yuv=True):
         return int(self._L.vsd_launches_per_frame(self._ctx, c_int(1 if yuv else 0)))
 
-    def set_autotune(self, enabled):
-        check(self._L.vsd_set_autotune(self._ctx, c_int(1 if enabled else 0)), "vsd_set_autotune")
+    def set_autotune(self, frames_in_flight):
+        """0 / False: shape heuristics only. n >= 1: time candidate GEMM configurations on the device and pick for n frames in
+        flight on this GPU (1 = lowest latency; more = configurations that leave SMs to the other frames)."""
+        check(self._L.vsd_set_autotune(self._ctx, c_int(int(frames_in_flight))), "vsd_set_autotune")
 
     def tuning_report(self):
         buf = ctypes.create_string_buffer(1 << 18)
@@ -225,10 +227,12 @@ class LanePool:
     are in flight (CUDA kernels of independent frames overlap and fill the SMs that a single batch-1 frame leaves
     idle). Configuration calls are broadcast to every lane."""
 
-    def __init__(self, device=0, lanes=2):
+    def __init__(self, device=0, lanes=2, tune_for=None):
         self.lanes = [Engine(device)]
         self._n = lanes
         self._next = 0
+        # the GEMM autotuner picks configurations for `tune_for` frames in flight (default: the number of lanes)
+        self.lanes[0].set_autotune(lanes if tune_for is None else tune_for)
 
     def load_state_dict(self, prefix, sd):
         self.lanes[0].load_state_dict(prefix, sd)
