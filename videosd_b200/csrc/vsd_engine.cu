@@ -82,8 +82,9 @@ class Arena {
 struct Launch {
     std::function<int(cudaStream_t)> fn;
     std::string tag;   // dotted scope, e.g. "step0.unet.down0.attn1.ff1" (used by the section profiler)
-    // Independent work inside a frame runs on a side stream (a parallel branch of the captured graph): a `side` launch forks
-    // from the main stream right where it sits in the plan; the first later launch marked `join` waits for the side stream.
+    // Independent work inside a frame runs on side streams (parallel branches of the captured graph): a launch with side = k
+    // (1, 2) forks from the main stream right where it sits in the plan; a later launch whose `join` has bit k-1 set waits
+    // for side stream k. Stream 1 carries short branches (V^T projection, resnet shortcut), stream 2 the ControlNet.
     int side = 0, join = 0;
     int operator()(cudaStream_t st) const { return fn(st); }
 };
@@ -114,9 +115,10 @@ struct Engine {
     Arena arena;
     size_t arena_static_mark = 0;
     float* splitk_ws = nullptr; size_t splitk_bytes = 0;
-    float* splitk_ws_side = nullptr;   // split-K workspace of the side-stream branch (runs concurrently with the main one)
-    cudaStream_t side = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    float* splitk_ws_side[2] = {nullptr, nullptr};   // split-K workspaces of the side-stream branches (they run concurrently)
+    cudaStream_t side[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
+    unsigned int* gn_sync2 = nullptr;   // grid-barrier state of fused GroupNorms running on side stream 2
     uint8_t *d_y = nullptr, *d_u = nullptr, *d_v = nullptr, *d_rgb_in = nullptr;       // inputs
     uint8_t *d_oy = nullptr, *d_ou = nullptr, *d_ov = nullptr, *d_rgb_out = nullptr;   // outputs
     float *init_latents = nullptr, *noisy = nullptr, *init_noise = nullptr, *step_noise = nullptr, *image = nullptr;
@@ -388,23 +390,33 @@ struct Builder {
     std::vector<Launch>* out;
     int rc = 0;
     std::string fail;
-    int side_mode = 0;     // launches pushed while set run on the side stream
+    int cur_stream = 0;    // launches pushed now run on: 0 main stream, 1 / 2 side streams
+    int nested = 0;        // begin_side() inside a branch: the inner work simply stays serial on that branch's stream
     size_t side_from = 0;
+    int join_pending = 0;  // bitmask: the next launch pushed on the main stream waits for these side streams
     static bool branches_enabled() {
         static const bool on = !(getenv("VSD_BRANCHES") && atoi(getenv("VSD_BRANCHES")) == 0);
         return on;
     }
-    void begin_side() { if (branches_enabled()) { side_mode = 1; side_from = out->size(); } }
+    void begin_side(int k = 1) {
+        if (!branches_enabled()) return;
+        if (cur_stream != 0) { ++nested; return; }
+        cur_stream = k;
+        side_from = out->size();
+    }
     void end_side() {
-        if (!side_mode) return;
-        for (size_t i = side_from; i < out->size(); ++i) (*out)[i].side = 1;
-        side_mode = 0;
+        if (!branches_enabled()) return;
+        if (nested > 0) { --nested; return; }
+        for (size_t i = side_from; i < out->size(); ++i) (*out)[i].side = cur_stream;
+        cur_stream = 0;
     }
-    void join_next() { join_pending = branches_enabled(); }   // the next launch pushed on the main stream waits for the side stream
-    bool join_pending = false;
+    void join_next(int k = 1) {
+        if (branches_enabled() && cur_stream == 0) join_pending |= 1 << (k - 1);
+    }
     void mark_join(size_t first) {
-        if (join_pending && out->size() > first) { (*out)[first].join = 1; join_pending = false; }
+        if (join_pending && cur_stream == 0 && out->size() > first) { (*out)[first].join |= join_pending; join_pending = 0; }
     }
+    float* splitk_workspace() { return cur_stream == 0 ? e->splitk_ws : e->splitk_ws_side[cur_stream - 1]; }
 
     const bf16* wb(const std::string& n) {
         auto it = e->w.find(n);
@@ -456,12 +468,12 @@ struct Builder {
             fbn = it->second.bn; fsp = it->second.splits; focc = it->second.occ; fkbs = it->second.kbs; fhalo = it->second.halo;
         }
         int r = build_gemm_op(&op, a, taps, wt, N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act,
-                              side_mode ? e->splitk_ws_side : e->splitk_ws, e->splitk_bytes, fbn, fsp, focc, fkbs, fhalo);
+                              splitk_workspace(), e->splitk_bytes, fbn, fsp, focc, fkbs, fhalo);
         if (r) { rc = r; fail = get_error(); return; }
         op.p.out_scale = out_scale;
         const size_t first = out->size();
         out->push_back(mk([op](cudaStream_t st) { return launch_gemm_op(op, st); }, "gemm"));
-        if (!side_mode) mark_join(first);
+        mark_join(first);
     }
     void conv(const View& x, const std::string& name, int taps, const View& o, const float* rowvec, const View* res,
               int act, bool has_bias = true) {
@@ -477,7 +489,7 @@ struct Builder {
         float* ws = alloc_f32((size_t)groupnorm_ws_floats(x.nb, x.h * x.w, x.c, 32));
         if (rc) return;
         const View xi = x, oo = o;
-        unsigned int* sync = e->gn_sync;
+        unsigned int* sync = cur_stream == 2 ? e->gn_sync2 : e->gn_sync;
         out->push_back(mk([=](cudaStream_t st) {
             return launch_groupnorm(xi.p, xi.ld, oo.p, oo.ld, g, b, xi.nb, xi.h * xi.w, xi.c, 32, eps, silu, ws, sync, st);
         }, "gn"));
@@ -945,28 +957,36 @@ static void build_controlnet_residuals(Builder& B, CNStatic& C, const std::funct
 }
 
 static int run_plan(Engine* e, const std::vector<Launch>& plan, cudaStream_t st) {
-    bool side_busy = false;
+    bool busy[2] = {false, false};
+    auto join = [&](int k) -> int {
+        VSD_CHECK_CUDA(cudaEventRecord(e->ev_join[k], e->side[k]));
+        VSD_CHECK_CUDA(cudaStreamWaitEvent(st, e->ev_join[k], 0));
+        busy[k] = false;
+        return 0;
+    };
     for (const auto& l : plan) {
-        if (l.side && e->side) {
-            VSD_CHECK_CUDA(cudaEventRecord(e->ev_fork, st));          // fork: everything issued so far on the main stream
-            VSD_CHECK_CUDA(cudaStreamWaitEvent(e->side, e->ev_fork, 0));
-            int rc = l(e->side);
+        if (l.side && e->side[l.side - 1]) {
+            const int k = l.side - 1;
+            VSD_CHECK_CUDA(cudaEventRecord(e->ev_fork[k], st));          // fork: everything issued so far on the main stream
+            VSD_CHECK_CUDA(cudaStreamWaitEvent(e->side[k], e->ev_fork[k], 0));
+            int rc = l(e->side[k]);
             if (rc) return rc;
-            side_busy = true;
+            busy[k] = true;
             continue;
         }
-        if (l.join && side_busy) {
-            VSD_CHECK_CUDA(cudaEventRecord(e->ev_join, e->side));
-            VSD_CHECK_CUDA(cudaStreamWaitEvent(st, e->ev_join, 0));
-            side_busy = false;
-        }
+        for (int k = 0; k < 2; ++k)
+            if ((l.join >> k & 1) && busy[k]) {
+                int rc = join(k);
+                if (rc) return rc;
+            }
         int rc = l(st);
         if (rc) return rc;
     }
-    if (side_busy) {   // never leave the side stream dangling (stream capture requires the join)
-        VSD_CHECK_CUDA(cudaEventRecord(e->ev_join, e->side));
-        VSD_CHECK_CUDA(cudaStreamWaitEvent(st, e->ev_join, 0));
-    }
+    for (int k = 0; k < 2; ++k)   // never leave a side stream dangling (stream capture requires the join)
+        if (busy[k]) {
+            int rc = join(k);
+            if (rc) return rc;
+        }
     return 0;
 }
 
@@ -1111,8 +1131,11 @@ static int configure(Engine* e, int nb, int H, int W) {
     free_resize(e);
     e->arena.destroy();
     if (e->splitk_ws) cudaFree(e->splitk_ws);
-    if (e->splitk_ws_side) cudaFree(e->splitk_ws_side);
-    e->splitk_ws = nullptr; e->splitk_ws_side = nullptr;
+    for (int k = 0; k < 2; ++k) {
+        if (e->splitk_ws_side[k]) cudaFree(e->splitk_ws_side[k]);
+        e->splitk_ws_side[k] = nullptr;
+    }
+    e->splitk_ws = nullptr;
     e->NB = nb; e->H = H; e->W = W; e->h8 = H / 8; e->w8 = W / 8;
     e->configured = false; e->schedule_set = false; e->context_set = false;
     e->xattn.clear(); e->temb.clear(); e->eps.clear(); e->lat.clear(); e->den.clear();
@@ -1122,7 +1145,7 @@ static int configure(Engine* e, int nb, int H, int W) {
     if (rc) return rc;
     e->splitk_bytes = (size_t)(16.0 * 1048576.0 * (scale < 1 ? 1 : scale)) + (size_t)48 * 1048576;
     VSD_CHECK_CUDA(cudaMalloc(&e->splitk_ws, e->splitk_bytes));
-    VSD_CHECK_CUDA(cudaMalloc(&e->splitk_ws_side, e->splitk_bytes));
+    for (int k = 0; k < 2; ++k) VSD_CHECK_CUDA(cudaMalloc(&e->splitk_ws_side[k], e->splitk_bytes));
     Arena& A = e->arena;
     const size_t px = (size_t)nb * H * W, lpx = (size_t)nb * e->h8 * e->w8;
     e->d_y = (uint8_t*)A.alloc(px); e->d_u = (uint8_t*)A.alloc(px / 4); e->d_v = (uint8_t*)A.alloc(px / 4);
@@ -1327,11 +1350,21 @@ static int set_schedule(Engine* e, int steps, const int* timesteps, const float*
         {
             Scope sc_("step" + std::to_string(i));
             if (use_cn) {
+                // The ControlNet reads only the step's input latents: it runs as a parallel graph branch (side stream 2)
+                // beside the UNet encoder + mid block and joins before its residuals are added. Its temporaries keep their
+                // own arena region (the UNet's are allocated above the ControlNet's high-water mark).
+                const size_t saved_peak = A.peak;
+                A.peak = A.off;
                 {
                     Scope sc2_("cn");
+                    B.begin_side(2);
                     build_controlnet(B, lat_in, i, CN);
+                    B.end_side();
                 }
+                if (Builder::branches_enabled()) A.off = A.peak;
+                if (saved_peak > A.peak) A.peak = saved_peak;
                 build_unet(B, lat_in, e->eps[i], i, S, [&](const std::function<View(int)>& skip_view, const View& mid_out) {
+                    B.join_next(2);
                     build_controlnet_residuals(B, CN, skip_view, mid_out);
                 });
             } else {
@@ -1450,15 +1483,18 @@ vsd_ctx* vsd_create(int device) {
     if (ensure_init()) return nullptr;
     vsd_ctx* c = new vsd_ctx();
     c->e.device = device;
-    if (cudaMalloc(&c->e.gn_sync, 64) != cudaSuccess || cudaMemset(c->e.gn_sync, 0, 64) != cudaSuccess) {
+    if (cudaMalloc(&c->e.gn_sync, 64) != cudaSuccess || cudaMemset(c->e.gn_sync, 0, 64) != cudaSuccess ||
+        cudaMalloc(&c->e.gn_sync2, 64) != cudaSuccess || cudaMemset(c->e.gn_sync2, 0, 64) != cudaSuccess) {
         set_error("cudaMalloc failed");
         delete c;
         return nullptr;
     }
-    if (cudaStreamCreateWithFlags(&c->e.stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&c->e.side, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->e.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->e.ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    bool ok = cudaStreamCreateWithFlags(&c->e.stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int k = 0; k < 2 && ok; ++k)
+        ok = cudaStreamCreateWithFlags(&c->e.side[k], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->e.ev_fork[k], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->e.ev_join[k], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
         set_error("cudaStreamCreate failed");
         delete c;
         return nullptr;
@@ -1489,10 +1525,13 @@ void vsd_destroy(vsd_ctx* c) {
         for (auto& kv : c->e.w) cudaFree(kv.second.p);
     c->e.arena.destroy();
     if (c->e.splitk_ws) cudaFree(c->e.splitk_ws);
-    if (c->e.splitk_ws_side) cudaFree(c->e.splitk_ws_side);
-    if (c->e.ev_fork) cudaEventDestroy(c->e.ev_fork);
-    if (c->e.ev_join) cudaEventDestroy(c->e.ev_join);
-    if (c->e.side) cudaStreamDestroy(c->e.side);
+    for (int k = 0; k < 2; ++k) {
+        if (c->e.splitk_ws_side[k]) cudaFree(c->e.splitk_ws_side[k]);
+        if (c->e.ev_fork[k]) cudaEventDestroy(c->e.ev_fork[k]);
+        if (c->e.ev_join[k]) cudaEventDestroy(c->e.ev_join[k]);
+        if (c->e.side[k]) cudaStreamDestroy(c->e.side[k]);
+    }
+    if (c->e.gn_sync2) cudaFree(c->e.gn_sync2);
     if (c->e.flush_buf) cudaFree(c->e.flush_buf);
     free_resize(&c->e);
     free_clip(&c->e);
