@@ -163,6 +163,13 @@ int vsd_infer_yuv420(vsd_ctx* ctx, const uint8_t* y, const uint8_t* u, const uin
 /* Packed RGB24 in / out ([batch][h][w][3]); the PIL-compatible path of VideoSDPipeline.infer. */
 int vsd_infer_rgb(vsd_ctx* ctx, const uint8_t* rgb_in, uint8_t* rgb_out);
 
+/* AutoencoderKL option (the pipeline's declared VAE, lcm_controlnet.py:69; encode = `latent_dist
+ * .sample() * scaling_factor` :298-313, decode = `vae.decode(denoised / scaling_factor)` :594-596). kind 0 = AutoencoderTiny
+ * (default, what the reference loads), 1 = AutoencoderKL (diffusers keys under "vae_kl."); switching invalidates the schedule.
+ * vsd_set_vae_noise: the sample() noise, fp32 [batch][h/8][w/8][4] host (zeros => the distribution's mean). */
+int vsd_set_vae(vsd_ctx* ctx, int kind);
+int vsd_set_vae_noise(vsd_ctx* ctx, const float* noise_nhwc);
+
 /* CLIP text encoder (diffusert/lcm/lcm_controlnet.py:175-179 `self.text_encoder(ids)[0]`): the SD1.5
  * text tower (transformers CLIPTextModel keys under the "text_encoder." prefix, loaded with vsd_load_weight). token_ids: 77 ids
  * (tokenizer output padded to max_length, host); context: fp32 [77][768] last_hidden_state (host), ready for vsd_set_context.

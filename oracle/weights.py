@@ -79,3 +79,48 @@ def build_controlnet(seed=9876):
     for p in net.parameters():
         p.requires_grad_(False)
     return net
+
+
+def build_vae_kl(seed=2222, probe_hw=64):
+    """Seeded random AutoencoderKL, calibrated like the TAESD stand-in so the parity tests are not vacuous: latent means of
+    O(1 / 0.18215) (so `sample * scaling_factor` has unit scale like real SD latents), posterior std ~ e^-3, and a decoder
+    whose output spans roughly [-1, 1]."""
+    from .autoencoder_kl import SCALING, AutoencoderKLOracle
+
+    prev = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    net = AutoencoderKLOracle().eval()
+    g = torch.Generator().manual_seed(seed + 1)
+    _perturb_norms(net, g)
+    with torch.no_grad():
+        x = torch.rand((1, 3, probe_hw, probe_hw), generator=g) * 2 - 1
+        m = net.encode_moments(x)
+        mean_std = m[:, :4].std().item()
+        net.quant_conv.weight[:4] *= (1.0 / SCALING) / max(mean_std, 1e-6)
+        net.quant_conv.bias[:4] *= (1.0 / SCALING) / max(mean_std, 1e-6)
+        net.quant_conv.weight[4:] *= 0.5 / max(m[:, 4:].std().item(), 1e-6)
+        net.quant_conv.bias[4:] = -6.0
+        z = net.encode(x, torch.randn((1, 4, probe_hw // 8, probe_hw // 8), generator=g))
+        y = net.decode(z)
+        s = 0.5 / max(y.std().item(), 1e-6)
+        net.decoder.conv_out.weight *= s
+        net.decoder.conv_out.bias.copy_((net.decoder.conv_out.bias - y.mean()) * s)
+    torch.random.set_rng_state(prev)
+    for p in net.parameters():
+        p.requires_grad_(False)
+    return net
+
+
+class KLAdapter:
+    """Gives AutoencoderKLOracle the (encode, decode, scaling_factor) surface oracle/pipeline.py uses: encode() is
+    `latent_dist.sample()` with the supplied noise (lcm_controlnet.py:298-313)."""
+
+    def __init__(self, net, vae_noise):
+        from .autoencoder_kl import SCALING
+        self.net, self.noise, self.scaling_factor = net, vae_noise, SCALING
+
+    def encode(self, x):
+        return self.net.encode(x, self.noise.to(x.device)) / self.scaling_factor
+
+    def decode(self, z):
+        return self.net.decoder(self.net.post_quant_conv(z))

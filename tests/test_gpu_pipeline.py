@@ -245,3 +245,45 @@ def test_prompt_goes_through_gpu_text_encoder(setup):
     assert ((got - ref).norm() / ref.norm()).item() < 1e-2
     explicit = np.asarray(pipe.infer(img, prompt="ignored", prompt_embeds=got[None], **kw))
     assert np.array_equal(explicit, a)
+
+
+def test_autoencoder_kl_option(setup):
+    """AutoencoderKL encode (`latent_dist.sample() * scaling_factor`) and decode around the same
+    UNet loop. 22 resnets + two 1024-token single-head attentions per direction in bf16: the sampled latents are within 3e-2
+    of the fp32 oracle (tolerance of this option, wider than the TAESD path's 1e-2), the frame within the 40 dB bar."""
+    from oracle import imageproc, pipeline
+    from oracle.weights import KLAdapter, build_vae_kl, random_context
+
+    eng, ug, _ = setup
+    H = W = 256
+    net = build_vae_kl()
+    vae_noise = torch.randn((1, 4, H // 8, W // 8), generator=torch.Generator().manual_seed(99))
+    eng.load_state_dict("vae_kl", net.state_dict())
+    ctx = random_context(1, seed=8)
+    eng.configure(1, H, W)
+    eng.set_vae("kl")
+    try:
+        eng.set_vae_noise(vae_noise)
+        eng.set_schedule(0.5, 4)
+        eng.set_context(0, ctx[0])
+        eng.set_reference_noise()
+        y, u, v = (a[None] for a in imageproc.synthetic_frame(H, W, seed=3, shift=5))
+        rgb = imageproc.yuv420_to_rgb(y[0], u[0], v[0])[None]
+        net.cuda()
+        ref = pipeline.lcm_img2img(ug, KLAdapter(net, vae_noise), rgb, ctx, steps=4, strength=0.5, device="cuda")
+        oy, ou, ov = np.empty_like(y), np.empty_like(u), np.empty_like(v)
+        eng.infer_yuv420(y, u, v, oy, ou, ov)
+        eng.sync()
+        assert rel(eng.debug_read("init_latents"), ref["init_latents"]) < 3e-2
+        ry, ru, rv = imageproc.rgb_to_yuv420(ref["rgb"][0])
+        assert psnr(oy[0], ry) >= 40.0 and psnr(ou[0], ru) >= 40.0 and psnr(ov[0], rv) >= 40.0
+        oy2, ou2, ov2 = np.empty_like(y), np.empty_like(u), np.empty_like(v)
+        eng.infer_yuv420(y, u, v, oy2, ou2, ov2)
+        assert np.array_equal(oy, oy2) and np.array_equal(ou, ou2) and np.array_equal(ov, ov2)
+        # zero sample noise => the posterior mean: a different, still valid frame
+        eng.set_vae_noise(torch.zeros_like(vae_noise))
+        eng.infer_yuv420(y, u, v, oy2, ou2, ov2)
+        assert not np.array_equal(oy, oy2)
+    finally:
+        eng.set_vae("taesd")
+        net.cpu()

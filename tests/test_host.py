@@ -174,6 +174,16 @@ def test_clip_tokenizer_matches_transformers_on_a_synthetic_vocabulary(tmp_path)
     assert len(ids) == 77 and ids[0] == 49406 and ids[4:] == [49407] * 73 and ids == h("Pixar,  CG")
 
 
+def test_autoencoder_kl_weight_table_matches_oracle_module():
+    from oracle.autoencoder_kl import AutoencoderKLOracle
+    from videosd_b200 import weights
+
+    net = AutoencoderKLOracle()
+    want = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    assert weights.autoencoder_kl_param_shapes() == want
+    assert sum(p.numel() for p in net.parameters()) == 83_653_863
+
+
 def test_clip_weight_table_matches_oracle_module():
     from oracle.clip import ClipTextOracle
     from videosd_b200 import weights

@@ -214,3 +214,27 @@ def test_clip_text_oracle_matches_transformers_clip_text_model():
     ids2[0, 40] = 123
     got2 = mine(ids2)
     assert torch.equal(got2[0, :40], got[0, :40]) and not torch.equal(got2[0, 40:], got[0, 40:])
+
+
+def test_autoencoder_kl_oracle_structure_and_sampling():
+    """AutoencoderKL restatement (parity unpinned: diffusers is not installable): shapes, the asymmetric stride-2 padding,
+    `sample = mean + exp(0.5 * clamp(logvar)) * noise`, scaling factor, and the calibrated random init."""
+    from oracle.autoencoder_kl import SCALING, AutoencoderKLOracle
+    from oracle.weights import KLAdapter, build_vae_kl
+
+    net = build_vae_kl()
+    x = torch.rand((1, 3, 64, 48), generator=torch.Generator().manual_seed(0)) * 2 - 1
+    m = net.encode_moments(x)
+    assert m.shape == (1, 8, 8, 6)
+    noise = torch.randn((1, 4, 8, 6), generator=torch.Generator().manual_seed(1))
+    z = net.encode(x, noise)
+    want = (m[:, :4] + torch.exp(0.5 * m[:, 4:].clamp(-30, 20)) * noise) * SCALING
+    assert torch.allclose(z, want) and 0.3 < z.std().item() < 3.0
+    assert torch.allclose(net.encode(x, torch.zeros_like(noise)), m[:, :4] * SCALING)
+    img = net.decode(z)
+    assert img.shape == (1, 3, 64, 48) and img.abs().max().item() < 4.0
+    ad = KLAdapter(net, noise)
+    assert torch.allclose(ad.encode(x) * ad.scaling_factor, z) and torch.allclose(ad.decode(z / ad.scaling_factor), img)
+    d = AutoencoderKLOracle().encoder.down_blocks[0].downsamplers[0]
+    y = d(torch.ones(1, 128, 8, 8))
+    assert y.shape == (1, 128, 4, 4)          # pad right / bottom only, stride 2

@@ -41,10 +41,17 @@ def main():
     B = parts[2] if len(parts) > 2 else 1
     do_time = "--no-time" not in sys.argv
     use_cn = "--controlnet" in sys.argv
+    use_kl = "--kl" in sys.argv
     cn_scale = 0.7
     rep = {"H": H, "W": W, "B": B}
     t0 = time.time()
     unet, vae = build_unet(), build_taesd()
+    kl_net = vae_noise = None
+    if use_kl:
+        from oracle.weights import KLAdapter, build_vae_kl
+        kl_net = build_vae_kl()
+        vae_noise = torch.randn((B, 4, H // 8, W // 8), generator=torch.Generator().manual_seed(99))
+        vae = KLAdapter(kl_net, vae_noise)
     cn = None
     if use_cn:
         from oracle.weights import build_controlnet
@@ -54,11 +61,17 @@ def main():
     eng = Engine(0)
     t0 = time.time()
     eng.load_state_dict("unet", unet.state_dict())
-    eng.load_state_dict("vae", vae.state_dict())
+    if use_kl:
+        eng.load_state_dict("vae_kl", kl_net.state_dict())
+    else:
+        eng.load_state_dict("vae", vae.state_dict())
     if use_cn:
         eng.load_state_dict("controlnet", cn.state_dict())
     print(f"weights loaded in {time.time()-t0:.1f}s", flush=True)
     eng.configure(B, H, W)
+    if use_kl:
+        eng.set_vae("kl")
+        eng.set_vae_noise(vae_noise)
     if use_cn:
         eng.set_controlnet(True, cn_scale)
     ts = eng.set_schedule(0.5, 4)
@@ -71,7 +84,11 @@ def main():
     with open(f"gpurun_out/tuning_{H}x{W}x{B}.txt", "w") as f:
         f.write(eng.tuning_report())
 
-    unet_g, vae_g = unet.cuda(), vae.cuda()
+    if use_kl:
+        kl_net.cuda()
+        unet_g, vae_g = unet.cuda(), vae
+    else:
+        unet_g, vae_g = unet.cuda(), vae.cuda()
     cn_g = cn.cuda() if use_cn else None
     frames = [imageproc.synthetic_frame(H, W, seed=b, shift=17 * b) for b in range(B)]
     y = np.stack([f[0] for f in frames]); u = np.stack([f[1] for f in frames]); v = np.stack([f[2] for f in frames])
@@ -114,7 +131,7 @@ def main():
         rep["free_running"].append(r)
         print("free-running", r, flush=True)
     img = eng.debug_read("image", channels=4, spatial="image")[:, :3]
-    rep["image_rel"] = rel(img * 2 - 1, ref["image"])
+    rep["image_rel"] = rel(img if use_kl else img * 2 - 1, ref["image"])   # TAESD's buffer holds the image before its x*2-1 tail
     ref_rgb = ref["rgb"]
     ref_yuv = [imageproc.rgb_to_yuv420(ref_rgb[b]) for b in range(B)]
     p_y = psnr(oy, np.stack([r[0] for r in ref_yuv]))

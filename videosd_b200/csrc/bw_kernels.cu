@@ -334,7 +334,9 @@ int groupnorm_ws_floats(int NB, int HW, int C, int groups) {
 int launch_groupnorm(const bf16* x, int ldx, bf16* y, int ldy, const float* gamma, const float* beta, int NB, int HW,
                      int C, int groups, float eps, int silu, float* partial_ws, unsigned int* sync, cudaStream_t st) {
     VSD_REQUIRE(C % 8 == 0 && C % groups == 0 && ldx % 8 == 0 && ldy % 8 == 0, "GroupNorm needs C%8==0 and 16-byte rows");
-    VSD_REQUIRE(C / 8 <= 1024 && C / groups >= 8 && groups <= 32, "GroupNorm needs 8 <= C/groups, C <= 8192, groups <= 32");
+    // a thread's 8-channel vector may touch at most two groups: channels per group >= 8, or exactly 4 (AutoencoderKL, C = 128)
+    VSD_REQUIRE(C / 8 <= 1024 && (C / groups >= 8 || C / groups == 4) && groups <= 32,
+                "GroupNorm needs C/groups >= 8 (or == 4), C <= 8192, groups <= 32");
     int ppc, chunks;
     gn_geometry(NB, HW, C, &ppc, &chunks);
     const int vpp = C / 8;
@@ -487,7 +489,7 @@ int launch_upsample_nearest(const bf16* x, int ldx, bf16* y, int ldy, int NB, in
 
 // 3x3 stride-2 pad-1 patches -> rows of a [NB*Ho*Wo][9*C] matrix (tap-major), feeding the tcgen05 GEMM.
 __global__ void im2col_s2_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int NB, int Hi, int Wi,
-                                 int C, int Ho, int Wo) {
+                                 int C, int Ho, int Wo, int pad) {
     pdl_launch_dependents();
     pdl_wait();
     const int vpp = C >> 3;
@@ -499,7 +501,7 @@ __global__ void im2col_s2_kernel(const bf16* __restrict__ x, int ldx, bf16* __re
         const int wo = (int)(q % Wo); q /= Wo;
         const int ho = (int)(q % Ho);
         const int n = (int)(q / Ho);
-        const int hi = 2 * ho + tap / 3 - 1, wi = 2 * wo + tap % 3 - 1;
+        const int hi = 2 * ho + tap / 3 - pad, wi = 2 * wo + tap % 3 - pad;   // pad 0: zeros only right / below (AutoencoderKL)
         uint4 t = make_uint4(0, 0, 0, 0);
         if (hi >= 0 && hi < Hi && wi >= 0 && wi < Wi)
             t = *reinterpret_cast<const uint4*>(x + (((long)n * Hi + hi) * Wi + wi) * ldx + vi * 8);
@@ -507,12 +509,12 @@ __global__ void im2col_s2_kernel(const bf16* __restrict__ x, int ldx, bf16* __re
     }
 }
 
-int launch_im2col_s2(const bf16* x, int ldx, bf16* y, int NB, int Hi, int Wi, int C, int Ho, int Wo, cudaStream_t st) {
+int launch_im2col_s2(const bf16* x, int ldx, bf16* y, int NB, int Hi, int Wi, int C, int Ho, int Wo, cudaStream_t st, int pad) {
     VSD_REQUIRE(C % 8 == 0 && ldx % 8 == 0, "im2col needs C%8==0");
     const long total = (long)NB * Ho * Wo * 9 * (C / 8);
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    VSD_CHECK_CUDA(launch_k(im2col_s2_kernel, dim3(blocks), dim3(256), 0, st, x, ldx, y, NB, Hi, Wi, C, Ho, Wo));
+    VSD_CHECK_CUDA(launch_k(im2col_s2_kernel, dim3(blocks), dim3(256), 0, st, x, ldx, y, NB, Hi, Wi, C, Ho, Wo, pad));
     VSD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -520,6 +522,7 @@ int launch_im2col_s2(const bf16* x, int ldx, bf16* y, int NB, int Hi, int Wi, in
 // ------------------------------------------------------------------------------------------ edge convolutions
 // 3x3 pad-1 stride-1 convolution with Cin <= 4 (UNet conv_in, TAESD encoder/decoder first layers) on CUDA cores.
 // x_kind 0: fp32 NHWC (Cin channels)          1: u8 RGB NHWC with the TAESD-encode prologue ((2*(u/255)-1)+1)/2
+//        3: u8 RGB NHWC, VaeImageProcessor only (2*(u/255)-1, AutoencoderKL)
 //        2: fp32 NHWC with the TAESD-decode prologue tanh(z/3)*3
 // One thread = one pixel x 64 output channels (blockIdx.y selects the 64-channel slab); weights [Cout][3][3][Cin].
 template <int CIN>
@@ -558,10 +561,10 @@ conv3x3_small_cin_kernel(const void* __restrict__ xin, int x_kind, int NB, int H
         for (int c = 0; c < CIN; ++c) {
             float v = 0.f;
             if (ok) {
-                if (x_kind == 1) {
+                if (x_kind == 1 || x_kind == 3) {
                     const float u8 = (float)reinterpret_cast<const uint8_t*>(xin)[src * 3 + c];
                     const float img = __fsub_rn(__fmul_rn(2.0f, __fdiv_rn(u8, 255.0f)), 1.0f);  // VaeImageProcessor
-                    v = __fmul_rn(__fadd_rn(img, 1.0f), 0.5f);                                   // TAESD encode
+                    v = (x_kind == 1) ? __fmul_rn(__fadd_rn(img, 1.0f), 0.5f) : img;             // TAESD encode | AutoencoderKL
                 } else {
                     v = reinterpret_cast<const float*>(xin)[src * CIN + c];
                     if (x_kind == 2) v = tanhf(v / 3.0f) * 3.0f;
@@ -601,13 +604,131 @@ conv3x3_small_cin_kernel(const void* __restrict__ xin, int x_kind, int NB, int H
 int launch_conv3x3_small_cin(const void* x, int x_kind, int NB, int H, int W, int Cin, const float* w, const float* bias,
                              bf16* y, int ldy, int Cout, int relu, cudaStream_t st, const bf16* res, int ldr) {
     VSD_REQUIRE(Cin >= 1 && Cin <= 4 && ldy % 8 == 0 && Cout % 8 == 0, "small-Cin conv: Cin<=4, Cout%8==0");
-    VSD_REQUIRE(x_kind != 1 || Cin == 3, "u8 input implies 3 channels");
+    VSD_REQUIRE((x_kind != 1 && x_kind != 3) || Cin == 3, "u8 input implies 3 channels");
     const long pixels = (long)NB * H * W;
     dim3 grid((unsigned)((pixels + 127) / 128), (Cout + 63) / 64);
     if (Cin == 3) VSD_CHECK_CUDA(launch_k(conv3x3_small_cin_kernel<3>, dim3(grid), dim3(128), 0, st, x, x_kind, NB, H, W, w, bias, y, ldy, Cout, relu, res, ldr));
     else if (Cin == 4) VSD_CHECK_CUDA(launch_k(conv3x3_small_cin_kernel<4>, dim3(grid), dim3(128), 0, st, x, x_kind, NB, H, W, w, bias, y, ldy, Cout, relu, res, ldr));
     else if (Cin == 1) VSD_CHECK_CUDA(launch_k(conv3x3_small_cin_kernel<1>, dim3(grid), dim3(128), 0, st, x, x_kind, NB, H, W, w, bias, y, ldy, Cout, relu, res, ldr));
     else VSD_CHECK_CUDA(launch_k(conv3x3_small_cin_kernel<2>, dim3(grid), dim3(128), 0, st, x, x_kind, NB, H, W, w, bias, y, ldy, Cout, relu, res, ldr));
+    VSD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ AutoencoderKL pieces
+// Row softmax of the mid-block attention scores: P[r][c] = softmax_c(scale * S[r][c]); fp32 in, bf16 out, columns >= cols
+// (up to ldp) are written as zeros so the following P*V GEMM can run over a padded K extent. One block per row.
+__global__ void softmax_rows_kernel(const float* __restrict__ S, int lds, bf16* __restrict__ P, int ldp, int cols, float scale) {
+    pdl_launch_dependents();
+    pdl_wait();
+    extern __shared__ float srow[];
+    __shared__ float red[32];
+    const float* s = S + (long)blockIdx.x * lds;
+    bf16* p = P + (long)blockIdx.x * ldp;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    float m = -INFINITY;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+        const float v = s[c] * scale;
+        srow[c] = v;
+        m = fmaxf(m, v);
+    }
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    m = red[0];
+    for (int i = 1; i < nw; ++i) m = fmaxf(m, red[i]);
+    __syncthreads();
+    float sum = 0.f;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+        const float e = __expf(srow[c] - m);
+        srow[c] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    float tot = 0.f;
+    for (int i = 0; i < nw; ++i) tot += red[i];     // fixed order: deterministic
+    const float inv = 1.f / tot;
+    for (int c = threadIdx.x; c < ldp; c += blockDim.x) p[c] = __float2bfloat16(c < cols ? srow[c] * inv : 0.f);
+}
+
+int launch_softmax_rows(const float* S, int lds, bf16* P, int ldp, int rows, int cols, float scale, cudaStream_t st) {
+    VSD_REQUIRE(cols > 0 && cols <= 12288 && ldp >= cols, "softmax row length must be <= 12288");
+    VSD_CHECK_CUDA(launch_k(softmax_rows_kernel, dim3(rows), dim3(256), (size_t)cols * 4, st, S, lds, P, ldp, cols, scale));
+    return 0;
+}
+
+// quant_conv (1x1, 8 -> 8) + DiagonalGaussianDistribution.sample() + scaling_factor:
+// z = (mean + exp(0.5 * clamp(logvar, -30, 20)) * noise) * scaling, moments = Wq * enc_out + bq   (fp32, [px][8] -> [px][4])
+__global__ void kl_sample_kernel(const float* __restrict__ enc8, const float* __restrict__ wq, const float* __restrict__ bq,
+                                 const float* __restrict__ noise, float* __restrict__ z, long px, float scaling) {
+    pdl_launch_dependents();
+    pdl_wait();
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < px; i += (long)gridDim.x * blockDim.x) {
+        float x[8], mo[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) x[c] = enc8[i * 8 + c];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+            float a = bq[o];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) a += wq[o * 8 + c] * x[c];
+            mo[o] = a;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float lv = fminf(fmaxf(mo[4 + c], -30.f), 20.f);
+            z[i * 4 + c] = (mo[c] + expf(0.5f * lv) * noise[i * 4 + c]) * scaling;
+        }
+    }
+}
+
+// post_quant_conv (1x1, 4 -> 4) on latents / scaling_factor   (fp32 [px][4] -> [px][4])
+__global__ void kl_post_quant_kernel(const float* __restrict__ lat, const float* __restrict__ wp, const float* __restrict__ bp,
+                                     float* __restrict__ out, long px, float inv_scaling) {
+    pdl_launch_dependents();
+    pdl_wait();
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < px; i += (long)gridDim.x * blockDim.x) {
+        float x[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) x[c] = lat[i * 4 + c] * inv_scaling;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            float a = bp[o];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) a += wp[o * 4 + c] * x[c];
+            out[i * 4 + o] = a;
+        }
+    }
+}
+
+// b_out'[o] = b_out[o] + sum_c Wo[o][c] * bv[c]: the V-projection bias folded through the attention (softmax rows sum to 1)
+__global__ void fold_v_bias_kernel(const bf16* __restrict__ wo, const float* __restrict__ bv, const float* __restrict__ bo,
+                                   float* __restrict__ out, int C) {
+    const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (o >= C) return;
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a += __bfloat162float(wo[(long)o * C + c]) * bv[c];
+    a = warp_sum(a);
+    if (lane == 0) out[o] = bo[o] + a;
+}
+
+int launch_kl_sample(const float* enc8, const float* wq, const float* bq, const float* noise, float* z, long px, float scaling,
+                     cudaStream_t st) {
+    int blocks = (int)((px + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    VSD_CHECK_CUDA(launch_k(kl_sample_kernel, dim3(blocks), dim3(256), 0, st, enc8, wq, bq, noise, z, px, scaling));
+    return 0;
+}
+int launch_kl_post_quant(const float* lat, const float* wp, const float* bp, float* out, long px, float inv_scaling, cudaStream_t st) {
+    int blocks = (int)((px + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    VSD_CHECK_CUDA(launch_k(kl_post_quant_kernel, dim3(blocks), dim3(256), 0, st, lat, wp, bp, out, px, inv_scaling));
+    return 0;
+}
+int launch_fold_v_bias(const bf16* wo, const float* bv, const float* bo, float* out, int C, cudaStream_t st) {
+    fold_v_bias_kernel<<<(C + 7) / 8, 256, 0, st>>>(wo, bv, bo, out, C);
     VSD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -150,6 +150,11 @@ struct Engine {
     // CLIP text encoder: built on first use, independent of configure()
     struct Clip { bool built = false; int* ids = nullptr; float* x = nullptr; bf16 *xn = nullptr, *qkv = nullptr, *att = nullptr, *h = nullptr,
                   *out = nullptr; std::vector<Launch> plan; } clip;
+    // VAE: 0 = AutoencoderTiny / TAESD (what the reference loads, videopipeline.py:67-69), 1 = AutoencoderKL (the pipeline's
+    // declared VAE type; weights under "vae_kl.")
+    int vae_kind = 0;
+    float* vae_noise = nullptr;   // [NB][h8][w8][4] noise of latent_dist.sample()
+    std::unordered_map<std::string, float*> derived;   // small tensors computed from weights at plan-build time (persistent)
     bool cn_enabled = false;
     float* cn_scales = nullptr;        // device [13]: logspace(-1,0,13) * conditioning scale (guess mode)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -197,7 +202,10 @@ static int load_weight(Engine* e, const std::string& name, const float* host, co
     DevW dw;
     dw.shape.assign(shape, shape + ndim);
     std::string key = name;
-    if (ndim == 4) {
+    if (ndim == 4 && name.find("quant_conv") != std::string::npos) {   // AutoencoderKL 1x1 (post_)quant_conv: fp32 [out][in]
+        int rc = upload(&dw, host, (size_t)numel * 4);
+        if (rc) return rc;
+    } else if (ndim == 4) {
         const long co = shape[0], ci = shape[1], kh = shape[2], kw = shape[3];
         if (ci <= 4) {  // edge convolutions stay fp32, OHWI
             std::vector<float> t((size_t)numel);
@@ -516,7 +524,7 @@ struct Builder {
     }
 
     // ---- diffusers ResnetBlock2D (Appendix A.3)
-    void resnet(const View& x, const std::string& p, const float* temb_rowvec, const View& o) {
+    void resnet(const View& x, const std::string& p, const float* temb_rowvec, const View& o, float eps = 1e-5f) {
         Scope sc_(short_name(p));
         const size_t m = e->arena.mark();
         View sc;
@@ -527,11 +535,11 @@ struct Builder {
             end_side();
         }
         View t1 = alloc(x.nb, x.h, x.w, x.c);
-        groupnorm(x, p + ".norm1", 1e-5f, 1, t1);
+        groupnorm(x, p + ".norm1", eps, 1, t1);
         View h1 = alloc(x.nb, x.h, x.w, o.c);
         conv(t1, p + ".conv1", 9, h1, temb_rowvec, nullptr, ACT_NONE);
         View t2 = alloc(x.nb, x.h, x.w, o.c);
-        groupnorm(h1, p + ".norm2", 1e-5f, 1, t2);
+        groupnorm(h1, p + ".norm2", eps, 1, t2);
         if (x.c != o.c) {
             join_next();
             conv(t2, p + ".conv2", 9, o, nullptr, &sc, ACT_NONE);
@@ -609,13 +617,13 @@ struct Builder {
         e->arena.release(m);
     }
 
-    void conv_s2(const View& x, const std::string& name, const View& o, bool has_bias) {
+    void conv_s2(const View& x, const std::string& name, const View& o, bool has_bias, int pad = 1) {
         const size_t m = e->arena.mark();
         View cols = alloc(o.nb, o.h, o.w, 9 * x.c);
         if (rc) return;
         const View xi = x, ci = cols, oo = o;
         out->push_back(mk([=](cudaStream_t st) {
-            return launch_im2col_s2(xi.p, xi.ld, ci.p, xi.nb, xi.h, xi.w, xi.c, oo.h, oo.w, st);
+            return launch_im2col_s2(xi.p, xi.ld, ci.p, xi.nb, xi.h, xi.w, xi.c, oo.h, oo.w, st, pad);
         }, "im2col"));
         const bf16* wt = wb(name + ".weight");
         const float* b = has_bias ? wf(name + ".bias") : nullptr;
@@ -829,6 +837,173 @@ static void build_taesd_decoder(Builder& B, const float* z, float* image_out /*[
     taesd_block(B, x, p + std::to_string(layer++), o);
     B.gemm(o.act(), 9, B.wb(p + std::to_string(layer) + ".weight"), 3, 9 * 64, image_out, 4, 1,
            B.wf(p + std::to_string(layer) + ".bias"), nullptr, nullptr, 0, ACT_NONE);
+}
+
+// ------------------------------------------------------------------------------------------------ AutoencoderKL
+// diffusers AutoencoderKL of SD1.5: widths (128, 256, 512, 512), GroupNorm eps 1e-6, mid-block
+// self-attention with ONE head of 512 channels. All 3x3 / 1x1 convolutions and the attention projections run on the tcgen05
+// GEMM kernel; the 4096 x 4096 attention is two GEMMs around a row softmax (S = Q K^T in fp32, P = softmax(S / sqrt(512)) in
+// bf16, O = P V); the V bias is folded into the out-projection bias (softmax rows sum to one).
+static void kl_attention(Builder& B, const View& x, const std::string& p, const View& o) {
+    Engine* e = B.e;
+    const size_t m = e->arena.mark();
+    const int C = x.c, HW = x.h * x.w, NB = x.nb;
+    if (HW % 64 != 0) { B.bad("AutoencoderKL attention needs (H/8)*(W/8) to be a multiple of 64"); return; }
+    View t = B.alloc(NB, x.h, x.w, C);
+    B.groupnorm(x, p + ".group_norm", 1e-6f, 0, t);
+    View qk = B.alloc(NB, x.h, x.w, 2 * C);            // q | k side by side
+    B.gemm(t.act_rows(), 1, B.wb(p + ".to_q.weight"), C, C, qk.p, qk.ld, 0, B.wf(p + ".to_q.bias"), nullptr, nullptr, 0, ACT_NONE);
+    B.gemm(t.act_rows(), 1, B.wb(p + ".to_k.weight"), C, C, qk.p + C, qk.ld, 0, B.wf(p + ".to_k.bias"), nullptr, nullptr, 0, ACT_NONE);
+    // folded out-projection bias (computed once, at plan-build time)
+    float* bfold = nullptr;
+    {
+        auto it = e->derived.find(p + ".folded_out_bias");
+        if (it == e->derived.end()) {
+            const bf16* wo = B.wb(p + ".to_out.0.weight");
+            const float* bv = B.wf(p + ".to_v.bias");
+            const float* bo = B.wf(p + ".to_out.0.bias");
+            if (B.rc) return;
+            if (cudaMalloc(&bfold, (size_t)C * 4) != cudaSuccess || launch_fold_v_bias(wo, bv, bo, bfold, C, e->stream) ||
+                cudaStreamSynchronize(e->stream) != cudaSuccess) {
+                B.bad("fold_v_bias failed");
+                return;
+            }
+            e->derived.emplace(p + ".folded_out_bias", bfold);
+        } else {
+            bfold = it->second;
+        }
+    }
+    bf16* vt = reinterpret_cast<bf16*>(e->arena.alloc((size_t)C * HW * 2));                     // V^T [C][HW], one image
+    float* S = reinterpret_cast<float*>(e->arena.alloc((size_t)HW * HW * 4));
+    bf16* P = reinterpret_cast<bf16*>(e->arena.alloc((size_t)HW * HW * 2));
+    View a = B.alloc(NB, x.h, x.w, C);
+    if (!vt || !S || !P) { B.bad("activation arena exhausted"); return; }
+    const bf16* wv = B.wb(p + ".to_v.weight");
+    if (B.rc) return;
+    for (int b = 0; b < NB; ++b) {
+        const bf16* tb = t.p + (long)b * HW * t.ld;
+        const bf16* qb = qk.p + (long)b * HW * qk.ld;
+        ActView aw{wv, 1, 1, C, C, C};
+        B.gemm(aw, 1, tb, HW, t.ld, vt, HW, 0, nullptr, nullptr, nullptr, 0, ACT_NONE | ACT_A_STATIC_FLAG);      // V^T = Wv t^T
+        ActView aq{qb, 1, 1, HW, C, qk.ld};
+        B.gemm(aq, 1, qb + C, HW, qk.ld, S, HW, 1, nullptr, nullptr, nullptr, 0, ACT_NONE | ACT_NO_STATIC_FLAG);    // S = Q K^T
+        {
+            const float scale = 1.0f / sqrtf((float)C);
+            B.out->push_back(mk([=](cudaStream_t st) { return launch_softmax_rows(S, HW, P, HW, HW, HW, scale, st); }, "softmax"));
+        }
+        ActView ap{P, 1, 1, HW, HW, HW};
+        B.gemm(ap, 1, vt, C, HW, a.p + (long)b * HW * a.ld, a.ld, 0, nullptr, nullptr, nullptr, 0, ACT_NONE | ACT_NO_STATIC_FLAG);   // O = P V
+    }
+    B.gemm(a.act_rows(), 1, B.wb(p + ".to_out.0.weight"), C, C, o.p, o.ld, 0, bfold, nullptr, x.p, x.ld, ACT_NONE);   // + residual
+    e->arena.release(m);
+}
+
+static void kl_mid(Builder& B, const View& x, const std::string& p, const View& o) {
+    const size_t m = B.e->arena.mark();
+    View a = B.alloc(x.nb, x.h, x.w, x.c), b = B.alloc(x.nb, x.h, x.w, x.c);
+    B.resnet(x, p + ".resnets.0", nullptr, a, 1e-6f);
+    kl_attention(B, a, p + ".attentions.0", b);
+    B.resnet(b, p + ".resnets.1", nullptr, o, 1e-6f);
+    B.e->arena.release(m);
+}
+
+// rgb u8 -> latents (fp32 [NB][h8][w8][4]) = latent_dist.sample(noise) * scaling_factor   (lcm_controlnet.py:298-313)
+static void build_kl_encoder(Builder& B, const uint8_t* rgb, float* latents_out) {
+    Engine* e = B.e;
+    const int NB = e->NB;
+    int h = e->H, w = e->W;
+    const std::string p = "vae_kl.encoder.";
+    const int widths[4] = {128, 256, 512, 512};
+    View x = B.alloc(NB, h, w, 128);
+    {
+        const float* wt = B.wf(p + "conv_in.weight");
+        const float* b = B.wf(p + "conv_in.bias");
+        if (!B.rc) {
+            const View o = x;
+            B.out->push_back(mk([=](cudaStream_t st) {
+                return launch_conv3x3_small_cin(rgb, 3, o.nb, o.h, o.w, 3, wt, b, o.p, o.ld, 128, 0, st);
+            }, "conv_rgb"));
+        }
+    }
+    for (int i = 0; i < 4; ++i) {
+        const std::string bp = p + "down_blocks." + std::to_string(i);
+        for (int j = 0; j < 2; ++j) {
+            View o = B.alloc(NB, h, w, widths[i]);
+            B.resnet(x, bp + ".resnets." + std::to_string(j), nullptr, o, 1e-6f);
+            x = o;
+        }
+        if (i < 3) {
+            h /= 2; w /= 2;
+            View d = B.alloc(NB, h, w, widths[i]);
+            B.conv_s2(x, bp + ".downsamplers.0.conv", d, true, 0);   // F.pad(0,1,0,1) + conv stride 2 pad 0
+            x = d;
+        }
+    }
+    View mo = B.alloc(NB, h, w, 512);
+    kl_mid(B, x, p + "mid_block", mo);
+    View n = B.alloc(NB, h, w, 512);
+    B.groupnorm(mo, p + "conv_norm_out", 1e-6f, 1, n);
+    const long lpx = (long)NB * h * w;
+    float* enc8 = B.alloc_f32((size_t)lpx * 8);
+    B.gemm(n.act(), 9, B.wb(p + "conv_out.weight"), 8, 9 * 512, enc8, 8, 1, B.wf(p + "conv_out.bias"), nullptr, nullptr, 0, ACT_NONE);
+    const float* wq = B.wf("vae_kl.quant_conv.weight");
+    const float* bq = B.wf("vae_kl.quant_conv.bias");
+    if (B.rc) return;
+    const float* noise = e->vae_noise;
+    B.out->push_back(mk([=](cudaStream_t st) { return launch_kl_sample(enc8, wq, bq, noise, latents_out, lpx, 0.18215f, st); },
+                        "kl_sample"));
+}
+
+// latents (as the scheduler leaves them) -> image fp32 [NB][H][W][4] (3 used), already in [-1, 1]   (lcm_controlnet.py:594-596)
+static void build_kl_decoder(Builder& B, const float* z, float* image_out) {
+    Engine* e = B.e;
+    const int NB = e->NB;
+    int h = e->h8, w = e->w8;
+    const std::string p = "vae_kl.decoder.";
+    const long lpx = (long)NB * h * w;
+    float* zq = B.alloc_f32((size_t)lpx * 4);
+    {
+        const float* wp = B.wf("vae_kl.post_quant_conv.weight");
+        const float* bp = B.wf("vae_kl.post_quant_conv.bias");
+        if (B.rc) return;
+        B.out->push_back(mk([=](cudaStream_t st) { return launch_kl_post_quant(z, wp, bp, zq, lpx, 1.0f / 0.18215f, st); },
+                            "post_quant"));
+    }
+    View x = B.alloc(NB, h, w, 512);
+    {
+        const float* wt = B.wf(p + "conv_in.weight");
+        const float* b = B.wf(p + "conv_in.bias");
+        if (!B.rc) {
+            const View o = x;
+            B.out->push_back(mk([=](cudaStream_t st) {
+                return launch_conv3x3_small_cin(zq, 0, o.nb, o.h, o.w, 4, wt, b, o.p, o.ld, 512, 0, st);
+            }, "conv_z"));
+        }
+    }
+    View mo = B.alloc(NB, h, w, 512);
+    kl_mid(B, x, p + "mid_block", mo);
+    x = mo;
+    const int rev[4] = {512, 512, 256, 128};
+    for (int i = 0; i < 4; ++i) {
+        const std::string bp = p + "up_blocks." + std::to_string(i);
+        for (int j = 0; j < 3; ++j) {
+            View o = B.alloc(NB, h, w, rev[i]);
+            B.resnet(x, bp + ".resnets." + std::to_string(j), nullptr, o, 1e-6f);
+            x = o;
+        }
+        if (i < 3) {
+            h *= 2; w *= 2;
+            View up = B.alloc(NB, h, w, rev[i]);
+            B.upsample(x, up);
+            View c = B.alloc(NB, h, w, rev[i]);
+            B.conv(up, bp + ".upsamplers.0.conv", 9, c, nullptr, nullptr, ACT_NONE);
+            x = c;
+        }
+    }
+    View n = B.alloc(NB, h, w, 128);
+    B.groupnorm(x, p + "conv_norm_out", 1e-6f, 1, n);
+    B.gemm(n.act(), 9, B.wb(p + "conv_out.weight"), 3, 9 * 128, image_out, 4, 1, B.wf(p + "conv_out.bias"), nullptr, nullptr, 0,
+           ACT_NONE);
 }
 
 // ------------------------------------------------------------------------------------------------ ControlNet
@@ -1154,6 +1329,7 @@ static int configure(Engine* e, int nb, int H, int W) {
     e->d_rgb_out = (uint8_t*)A.alloc(px * 3);
     e->init_latents = (float*)A.alloc(lpx * 16); e->noisy = (float*)A.alloc(lpx * 16);
     e->init_noise = (float*)A.alloc(lpx * 16);
+    e->vae_noise = (float*)A.alloc(lpx * 16);   // zero-initialised arena: sample() = mean until vsd_set_vae_noise
     e->step_noise = (float*)A.alloc(lpx * 16 * 16);  // up to 16 steps
     e->image = (float*)A.alloc(px * 16);
     e->ctx_bf16 = (bf16*)A.alloc((size_t)nb * 128 * 768 * 2);
@@ -1300,7 +1476,8 @@ static int set_schedule(Engine* e, int steps, const int* timesteps, const float*
     const size_t enc_mark = A.mark();
     {
         Scope sc_("taesd_enc");
-        build_taesd_encoder(B, e->d_rgb_in, e->init_latents);
+        if (e->vae_kind == 1) build_kl_encoder(B, e->d_rgb_in, e->init_latents);
+        else build_taesd_encoder(B, e->d_rgb_in, e->init_latents);
     }
     A.release(enc_mark);
     {
@@ -1389,13 +1566,15 @@ static int set_schedule(Engine* e, int steps, const int* timesteps, const float*
     B.out = &e->plan_core;
     {
         Scope sc_("taesd_dec");
-        build_taesd_decoder(B, e->den[steps - 1], e->image);
+        if (e->vae_kind == 1) build_kl_decoder(B, e->den[steps - 1], e->image);
+        else build_taesd_decoder(B, e->den[steps - 1], e->image);
     }
     A.release(unet_mark);
     {
         Engine* ee = e;
         e->plan_post.push_back(mk([ee](cudaStream_t st) {
-            return launch_pack_rgb_yuv420(ee->image, 4, ee->d_rgb_out, ee->d_oy, ee->d_ou, ee->d_ov, ee->NB, ee->H, ee->W, 1, st);
+            return launch_pack_rgb_yuv420(ee->image, 4, ee->d_rgb_out, ee->d_oy, ee->d_ou, ee->d_ov, ee->NB, ee->H, ee->W,
+                                          ee->vae_kind == 1 ? 0 : 1 /* TAESD's decoder ends with x*2-1 */, st);
         }, "pack"));
     }
     if (B.rc) {
@@ -1535,6 +1714,7 @@ void vsd_destroy(vsd_ctx* c) {
     if (c->e.flush_buf) cudaFree(c->e.flush_buf);
     free_resize(&c->e);
     free_clip(&c->e);
+    for (auto& kv : c->e.derived) cudaFree(kv.second);
     if (c->e.gn_sync) cudaFree(c->e.gn_sync);
     if (c->e.cn_scales) cudaFree(c->e.cn_scales);
     if (c->e.ev0) cudaEventDestroy(c->e.ev0);
@@ -1638,6 +1818,31 @@ int vsd_set_controlnet(vsd_ctx* c, int enabled, const float* scales13) {
 int vsd_set_context(vsd_ctx* c, int slot, const float* context_77x768) {
     CTX_GUARD(c);
     return set_context(&c->e, slot, context_77x768);
+}
+
+/* 0 = AutoencoderTiny (default, weights "vae."), 1 = AutoencoderKL (weights "vae_kl."). Invalidates the schedule. */
+int vsd_set_vae(vsd_ctx* c, int kind) {
+    CTX_GUARD(c);
+    ENG_REQUIRE(kind == 0 || kind == 1, "vae kind must be 0 (AutoencoderTiny) or 1 (AutoencoderKL)");
+    Engine* e = &c->e;
+    if (e->vae_kind != kind) {
+        VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+        free_graphs(e);
+        e->vae_kind = kind;
+        e->schedule_set = false;
+    }
+    return 0;
+}
+
+/* Noise of `latent_dist.sample()` (AutoencoderKL only): fp32 [batch][h/8][w/8][4] (NHWC), host. */
+int vsd_set_vae_noise(vsd_ctx* c, const float* noise_nhwc) {
+    CTX_GUARD(c);
+    Engine* e = &c->e;
+    ENG_REQUIRE(e->configured, "configure() first");
+    const size_t lpx = (size_t)e->NB * e->h8 * e->w8;
+    VSD_CHECK_CUDA(cudaMemcpyAsync(e->vae_noise, noise_nhwc, lpx * 16, cudaMemcpyHostToDevice, e->stream));
+    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
 }
 
 int vsd_encode_prompt(vsd_ctx* c, const int* token_ids_77, float* context_77x768) {

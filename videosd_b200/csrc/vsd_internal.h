@@ -164,7 +164,12 @@ int launch_layernorm(const bf16* x, int ldx, bf16* y, int ldy, const float* gamm
                      float eps, cudaStream_t st);
 int launch_upsample_nearest(const bf16* x, int ldx, bf16* y, int ldy, int NB, int Hi, int Wi, int Ho, int Wo, int C,
                             cudaStream_t st);
-int launch_im2col_s2(const bf16* x, int ldx, bf16* y, int NB, int Hi, int Wi, int C, int Ho, int Wo, cudaStream_t st);
+int launch_im2col_s2(const bf16* x, int ldx, bf16* y, int NB, int Hi, int Wi, int C, int Ho, int Wo, cudaStream_t st, int pad = 1);
+int launch_softmax_rows(const float* S, int lds, bf16* P, int ldp, int rows, int cols, float scale, cudaStream_t st);
+int launch_kl_sample(const float* enc8, const float* wq, const float* bq, const float* noise, float* z, long px, float scaling,
+                     cudaStream_t st);
+int launch_kl_post_quant(const float* lat, const float* wp, const float* bp, float* out, long px, float inv_scaling, cudaStream_t st);
+int launch_fold_v_bias(const bf16* wo, const float* bv, const float* bo, float* out, int C, cudaStream_t st);
 int launch_splitk_reduce(const GemmParams& p, long rows, cudaStream_t st);
 int launch_conv3x3_small_cin(const void* x, int x_kind, int NB, int H, int W, int Cin, const float* w, const float* bias,
                              bf16* y, int ldy, int Cout, int relu /*0 none, 1 ReLU, 2 SiLU*/, cudaStream_t st,

@@ -104,6 +104,19 @@ class Engine:
             raise ValueError(f"context must be (77, 768), got {a.shape}")
         check(self._L.vsd_set_context(self._ctx, c_int(slot), _fptr(a)), "vsd_set_context")
 
+    def set_vae(self, kind):
+        """'taesd' (AutoencoderTiny, the default: what the reference loads) or 'kl' (AutoencoderKL, weights under 'vae_kl')."""
+        k = {"taesd": 0, "tiny": 0, 0: 0, "kl": 1, 1: 1}[kind]
+        check(self._L.vsd_set_vae(self._ctx, c_int(k)), "vsd_set_vae")
+        self._sched_key = None
+
+    def set_vae_noise(self, noise_nchw):
+        """Noise of AutoencoderKL's `latent_dist.sample()`: (B, 4, h/8, w/8)."""
+        a = np.ascontiguousarray(torch.as_tensor(noise_nchw).detach().to(torch.float32).permute(0, 2, 3, 1).contiguous().numpy())
+        if a.shape != (self.batch, self.height // 8, self.width // 8, 4):
+            raise ValueError(f"vae noise must be (B, 4, h/8, w/8), got NHWC {a.shape}")
+        check(self._L.vsd_set_vae_noise(self._ctx, _fptr(a)), "vsd_set_vae_noise")
+
     def encode_prompt(self, token_ids):
         """token_ids: 77 ints (CLIP tokenizer output padded to max_length) -> (77, 768) fp32 tensor, the text encoder's
         last_hidden_state (lcm_controlnet.py:175-179). Needs the 'text_encoder' weights."""

@@ -98,6 +98,9 @@ class VideoSDPipeline:
         # opt-in here: use_controlnet=True adds ~35 % FLOPs per step.
         self.use_controlnet = bool(kwargs.get("use_controlnet", False))
         self.use_text_encoder = bool(kwargs.get("text_encoder", False))
+        # vae="kl": the pipeline's declared AutoencoderKL instead of the AutoencoderTiny the reference loads
+        # (videopipeline.py:67-69); SURVEY.md 8(f) next-row #4
+        self.vae_kind = str(kwargs.get("vae", "taesd"))
         self.tokenizer = None
         self.noise_mode = kwargs.get("noise_mode", "reference_cuda")
         self.engine = Engine(self.device)          # raises if the CUDA library / a B200 is missing: no fallback
@@ -120,6 +123,8 @@ class VideoSDPipeline:
             self.engine.load_state_dict("vae", _weights.load_safetensors_dir(os.path.join(model_name, "vae")))
             if self.use_controlnet:
                 self.engine.load_state_dict("controlnet", _weights.load_safetensors_dir(str(controlnet_model)))
+            if self.vae_kind == "kl":
+                self.engine.load_state_dict("vae_kl", _weights.load_safetensors_dir(os.path.join(model_name, "vae_kl")))
             if os.path.isdir(os.path.join(model_name, "text_encoder")):
                 from . import tokenizer as _tok
                 self.engine.load_state_dict("text_encoder", _weights.load_safetensors_dir(os.path.join(model_name, "text_encoder")))
@@ -131,6 +136,8 @@ class VideoSDPipeline:
             if self.use_controlnet:
                 self.engine.load_state_dict("controlnet",
                                             _weights.random_state_dict(_weights.controlnet_param_shapes(), 9876))
+            if self.vae_kind == "kl":
+                self.engine.load_state_dict("vae_kl", _weights.random_state_dict(_weights.autoencoder_kl_param_shapes(), 2222))
             if self.use_text_encoder:
                 from . import tokenizer as _tok
                 self.engine.load_state_dict("text_encoder", _weights.random_clip_state_dict(2468))
@@ -146,6 +153,8 @@ class VideoSDPipeline:
                  controlnet_scale=1.0):
         if self._shape != (batch, height, width):
             self.engine.configure(batch, height, width)
+            if self.vae_kind == "kl":
+                self.engine.set_vae("kl")
             self._shape = (batch, height, width)
             self._noise_key = self._prompt_key = None
         if self.use_controlnet and self._cn_scale != float(controlnet_scale):
@@ -165,6 +174,12 @@ class VideoSDPipeline:
                 init = torch.randn((batch, 4, h8, w8), generator=g, device=f"cuda:{self.device}", dtype=torch.float16)
                 _, st = reference_cpu_noise(batch, h8, w8, len(ts))
                 # the CPU stream also yields the init draw first; step noises follow it, as in the reference
+                if self.vae_kind == "kl":
+                    # latent_dist.sample() draws from the same device generator BEFORE the init noise (lcm_controlnet.py:298-331)
+                    g = torch.Generator(device=f"cuda:{self.device}").manual_seed(int(seed))
+                    vn = torch.randn((batch, 4, h8, w8), generator=g, device=f"cuda:{self.device}", dtype=torch.float16)
+                    init = torch.randn((batch, 4, h8, w8), generator=g, device=f"cuda:{self.device}", dtype=torch.float16)
+                    self.engine.set_vae_noise(vn.float().cpu())
                 self.engine.set_noise(init.float().cpu(), st)
             self._noise_key = nkey
         pkey = prompt if isinstance(prompt, str) else tuple(prompt)

@@ -141,6 +141,63 @@ def taesd_param_shapes():
     return o
 
 
+def autoencoder_kl_param_shapes():
+    """diffusers AutoencoderKL (SD1.5 VAE) state-dict keys: 83 653 863 parameters."""
+    out = {}
+
+    def conv(p, cin, cout, k=3):
+        out[p + ".weight"] = (cout, cin, k, k)
+        out[p + ".bias"] = (cout,)
+
+    def norm(p, c):
+        out[p + ".weight"] = (c,)
+        out[p + ".bias"] = (c,)
+
+    def resnet(p, cin, cout):
+        norm(p + ".norm1", cin)
+        conv(p + ".conv1", cin, cout)
+        norm(p + ".norm2", cout)
+        conv(p + ".conv2", cout, cout)
+        if cin != cout:
+            conv(p + ".conv_shortcut", cin, cout, 1)
+
+    def mid(p, c):
+        a = p + ".attentions.0"
+        norm(a + ".group_norm", c)
+        for n in ("to_q", "to_k", "to_v", "to_out.0"):
+            out[f"{a}.{n}.weight"] = (c, c)
+            out[f"{a}.{n}.bias"] = (c,)
+        resnet(p + ".resnets.0", c, c)
+        resnet(p + ".resnets.1", c, c)
+
+    w = (128, 256, 512, 512)
+    conv("encoder.conv_in", 3, w[0])
+    for i in range(4):
+        cin = w[max(i - 1, 0)]
+        resnet(f"encoder.down_blocks.{i}.resnets.0", cin, w[i])
+        resnet(f"encoder.down_blocks.{i}.resnets.1", w[i], w[i])
+        if i < 3:
+            conv(f"encoder.down_blocks.{i}.downsamplers.0.conv", w[i], w[i])
+    mid("encoder.mid_block", 512)
+    norm("encoder.conv_norm_out", 512)
+    conv("encoder.conv_out", 512, 8)
+    conv("decoder.conv_in", 4, 512)
+    mid("decoder.mid_block", 512)
+    rev = (512, 512, 256, 128)
+    for i in range(4):
+        cin = rev[max(i - 1, 0)]
+        resnet(f"decoder.up_blocks.{i}.resnets.0", cin, rev[i])
+        resnet(f"decoder.up_blocks.{i}.resnets.1", rev[i], rev[i])
+        resnet(f"decoder.up_blocks.{i}.resnets.2", rev[i], rev[i])
+        if i < 3:
+            conv(f"decoder.up_blocks.{i}.upsamplers.0.conv", rev[i], rev[i])
+    norm("decoder.conv_norm_out", 128)
+    conv("decoder.conv_out", 128, 3)
+    conv("quant_conv", 8, 8, 1)
+    conv("post_quant_conv", 4, 4, 1)
+    return out
+
+
 def clip_param_shapes():
     """transformers CLIPTextModel state-dict keys (SD1.5 text tower): 123 060 480 parameters."""
     out = {"text_model.embeddings.token_embedding.weight": (49408, 768),
