@@ -848,7 +848,7 @@ static void kl_attention(Builder& B, const View& x, const std::string& p, const 
     Engine* e = B.e;
     const size_t m = e->arena.mark();
     const int C = x.c, HW = x.h * x.w, NB = x.nb;
-    if (HW % 64 != 0) { B.bad("AutoencoderKL attention needs (H/8)*(W/8) to be a multiple of 64"); return; }
+    const int HWp = (HW + 63) / 64 * 64;   // key count padded to the GEMM's 64-wide k-blocks: P gets zero columns there
     View t = B.alloc(NB, x.h, x.w, C);
     B.groupnorm(x, p + ".group_norm", 1e-6f, 0, t);
     View qk = B.alloc(NB, x.h, x.w, 2 * C);            // q | k side by side
@@ -873,9 +873,9 @@ static void kl_attention(Builder& B, const View& x, const std::string& p, const 
             bfold = it->second;
         }
     }
-    bf16* vt = reinterpret_cast<bf16*>(e->arena.alloc((size_t)C * HW * 2));                     // V^T [C][HW], one image
+    bf16* vt = reinterpret_cast<bf16*>(e->arena.alloc((size_t)C * HWp * 2));                    // V^T [C][HWp], one image
     float* S = reinterpret_cast<float*>(e->arena.alloc((size_t)HW * HW * 4));
-    bf16* P = reinterpret_cast<bf16*>(e->arena.alloc((size_t)HW * HW * 2));
+    bf16* P = reinterpret_cast<bf16*>(e->arena.alloc((size_t)HW * HWp * 2));
     View a = B.alloc(NB, x.h, x.w, C);
     if (!vt || !S || !P) { B.bad("activation arena exhausted"); return; }
     const bf16* wv = B.wb(p + ".to_v.weight");
@@ -883,16 +883,21 @@ static void kl_attention(Builder& B, const View& x, const std::string& p, const 
     for (int b = 0; b < NB; ++b) {
         const bf16* tb = t.p + (long)b * HW * t.ld;
         const bf16* qb = qk.p + (long)b * HW * qk.ld;
+        if (HWp != HW)   // the padded key columns of V^T meet zero probabilities, but must be finite: clear them every frame
+            B.out->push_back(mk([=](cudaStream_t st) {
+                VSD_CHECK_CUDA(cudaMemset2DAsync(vt + HW, (size_t)HWp * 2, 0, (size_t)(HWp - HW) * 2, (size_t)C, st));
+                return 0;
+            }, "memset"));
         ActView aw{wv, 1, 1, C, C, C};
-        B.gemm(aw, 1, tb, HW, t.ld, vt, HW, 0, nullptr, nullptr, nullptr, 0, ACT_NONE | ACT_A_STATIC_FLAG);      // V^T = Wv t^T
+        B.gemm(aw, 1, tb, HW, t.ld, vt, HWp, 0, nullptr, nullptr, nullptr, 0, ACT_NONE | ACT_A_STATIC_FLAG);     // V^T = Wv t^T
         ActView aq{qb, 1, 1, HW, C, qk.ld};
         B.gemm(aq, 1, qb + C, HW, qk.ld, S, HW, 1, nullptr, nullptr, nullptr, 0, ACT_NONE | ACT_NO_STATIC_FLAG);    // S = Q K^T
         {
             const float scale = 1.0f / sqrtf((float)C);
-            B.out->push_back(mk([=](cudaStream_t st) { return launch_softmax_rows(S, HW, P, HW, HW, HW, scale, st); }, "softmax"));
+            B.out->push_back(mk([=](cudaStream_t st) { return launch_softmax_rows(S, HW, P, HWp, HW, HW, scale, st); }, "softmax"));
         }
-        ActView ap{P, 1, 1, HW, HW, HW};
-        B.gemm(ap, 1, vt, C, HW, a.p + (long)b * HW * a.ld, a.ld, 0, nullptr, nullptr, nullptr, 0, ACT_NONE | ACT_NO_STATIC_FLAG);   // O = P V
+        ActView ap{P, 1, 1, HW, HWp, HWp};
+        B.gemm(ap, 1, vt, C, HWp, a.p + (long)b * HW * a.ld, a.ld, 0, nullptr, nullptr, nullptr, 0, ACT_NONE | ACT_NO_STATIC_FLAG);  // O = P V
     }
     B.gemm(a.act_rows(), 1, B.wb(p + ".to_out.0.weight"), C, C, o.p, o.ld, 0, bfold, nullptr, x.p, x.ld, ACT_NONE);   // + residual
     e->arena.release(m);
