@@ -115,6 +115,14 @@ def test_non_multiple_of_64_size_and_other_schedules(setup):
     ts, ref, _, out, ref_yuv, _ = _frame(eng, ug, vg, 128, 128, 1, strength=0.5, steps=1)   # single step: no noise
     assert ts == [499]
     _check_frame(eng, ref, out, ref_yuv, 1)
+    # the UI's extremes (home/index.tsx: steps 1-12, strength 0.05-1): twelve steps, and a strength so low that the
+    # timestep table is shorter than the requested step count
+    ts, ref, _, out, ref_yuv, _ = _frame(eng, ug, vg, 128, 128, 1, strength=0.9, steps=12)
+    assert len(ts) == 12 and ts[0] == 899
+    _check_frame(eng, ref, out, ref_yuv, 12, lat_tol=4e-2)
+    ts, ref, _, out, ref_yuv, _ = _frame(eng, ug, vg, 128, 128, 1, strength=0.05, steps=4)
+    assert ts == [39, 19]
+    _check_frame(eng, ref, out, ref_yuv, 2)
 
 
 def test_golden_from_reference_call(setup, golden):
