@@ -259,7 +259,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["tflops"],
-                         "traffic": 11.6e9 if (H, W, B) == (512, 512, 1) else None,   # DRAM bytes per frame, ncu (profiles/r01_summary.md)
+                         "traffic": 12.5e9 if (H, W, B) == (512, 512, 1) else None,   # DRAM bytes per frame, ncu (profiles/r01_summary.md)
                          "note": f"whole-frame algorithmic FLOPs ({flop_per_frame/1e9:.1f} GFLOP/frame) / device time, "
                                  f"of {peaks['source']} sustained bf16 peak; dominant kernel conv_gemm_kernel (tcgen05)"},
         }
