@@ -120,6 +120,7 @@ def run_ours(args):
 
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep NCCL's banner out of stdout (one JSON line there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     H, W, B = args.height, args.width, args.batch
     L = max(1, args.lanes)
