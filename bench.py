@@ -321,15 +321,15 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=80)
+    ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--height", type=int, default=512)
     ap.add_argument("--width", type=int, default=512)
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--strength", type=float, default=0.5)
     ap.add_argument("--lcm-steps", type=int, default=4)
-    ap.add_argument("--lanes", type=int, default=3, help="frames in flight per GPU (lanes sharing one weight copy)")
+    ap.add_argument("--lanes", type=int, default=4, help="frames in flight per GPU (lanes sharing one weight copy)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
