@@ -128,12 +128,15 @@ def run_ours(args):
     pool.load_state_dict("unet", weights.random_state_dict(weights.unet_param_shapes(), 1234))
     pool.load_state_dict("vae", weights.random_state_dict(weights.taesd_param_shapes(), 4321))
     pool.configure(B, H, W)
-    # The pool's GEMM configurations are tuned for L frames in flight. The single-lane (latency mode) figure comes from one
-    # more lane on the same weights whose configurations are tuned for ONE frame in flight.
+    # The pool's GEMM configurations are tuned for L frames in flight. The single-lane (latency mode) figure comes from a
+    # second engine whose configurations are tuned for ONE frame in flight.
     from videosd_b200.engine import Engine
     solo = None
     if L > 1:
-        solo = Engine(local_rank, parent=pool.lanes[0])
+        # its own engine (own weight copy): it is timed alone, after the pool's lanes have drained
+        solo = Engine(local_rank)
+        solo.load_state_dict("unet", weights.random_state_dict(weights.unet_param_shapes(), 1234))
+        solo.load_state_dict("vae", weights.random_state_dict(weights.taesd_param_shapes(), 4321))
         solo.set_autotune(1)
         solo.configure(B, H, W)
     ts = pool.set_schedule(args.strength, args.lcm_steps)

@@ -148,7 +148,10 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, int ldx, bf16* __res
 // then normalises its chunk from shared memory: one launch and one read of x instead of two launches and two reads.
 static __device__ unsigned int g_bw_fault = 0;
 
-__global__ void gn_fused_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy,
+// kShared: several engines (lanes) may run this kernel at the same time on one GPU => 4 blocks per SM must fit (<= 51
+// registers per thread). Alone on the GPU the kernel may use 2 blocks per SM and all the registers it likes (faster).
+template <bool kShared>
+__global__ void __launch_bounds__(320, (kShared ? 4 : 2)) gn_fused_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C, int groups,
                                 float eps, int silu, int px_per_chunk, float* __restrict__ partial, unsigned int* sync,
                                 long long* dbg) {
@@ -332,7 +335,7 @@ int groupnorm_ws_floats(int NB, int HW, int C, int groups) {
 }
 
 int launch_groupnorm(const bf16* x, int ldx, bf16* y, int ldy, const float* gamma, const float* beta, int NB, int HW,
-                     int C, int groups, float eps, int silu, float* partial_ws, unsigned int* sync, cudaStream_t st) {
+                     int C, int groups, float eps, int silu, float* partial_ws, unsigned int* sync, cudaStream_t st, int shared_gpu) {
     VSD_REQUIRE(C % 8 == 0 && C % groups == 0 && ldx % 8 == 0 && ldy % 8 == 0, "GroupNorm needs C%8==0 and 16-byte rows");
     // a thread's 8-channel vector may touch at most two groups: channels per group >= 8, or exactly 4 (AutoencoderKL, C = 128)
     VSD_REQUIRE(C / 8 <= 1024 && (C / groups >= 8 || C / groups == 4) && groups <= 32,
@@ -347,15 +350,22 @@ int launch_groupnorm(const bf16* x, int ldx, bf16* y, int ldy, const float* gamm
         const size_t fsmem = (size_t)64 * 4 + (size_t)vpp * R * 16 + (size_t)ppc * vpp * 16;
         static bool attr_set = false;
         if (!attr_set) {
-            VSD_CHECK_CUDA(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            VSD_CHECK_CUDA(cudaFuncSetAttribute(gn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            VSD_CHECK_CUDA(cudaFuncSetAttribute(gn_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
             attr_set = true;
         }
-        // Co-residency bound for the grid barrier: <= 128 blocks of <= 48 KiB and <= 320 threads each. An SM holds at
-        // least 4 such blocks, so 148 SMs hold >= 592: even 4 lanes running this kernel at the same time (4 x 128
-        // blocks) are all resident and no lane can starve another's late blocks. Larger tensors use two kernels.
+        // Co-residency bound for the grid barrier: <= 128 blocks of <= 48 KiB and <= 320 threads each. shared_gpu: <= 51
+        // registers per thread, an SM holds at least 4 such blocks, 148 SMs hold >= 592: even 4 lanes running this kernel at
+        // the same time (4 x 128 blocks) are all resident and no lane can starve another's late blocks; the engine keeps it
+        // to four concurrent users per GPU (lanes 0-3, main stream only). Otherwise (one engine on the GPU): 2 blocks per
+        // SM, 296 >= 128. Larger tensors use two kernels.
         if (sync != nullptr && fsmem <= 48 * 1024 && (long)chunks * NB <= 128 && groups <= 32 && vpp * R <= 320) {
-            VSD_CHECK_CUDA(launch_k(gn_fused_kernel, dim3(chunks, NB), dim3(vpp * R), fsmem, st, x, ldx, y, ldy, gamma, beta, HW,
-                                    C, groups, eps, silu, ppc, partial_ws, sync, g_gn_dbg));
+            if (shared_gpu)
+                VSD_CHECK_CUDA(launch_k(gn_fused_kernel<true>, dim3(chunks, NB), dim3(vpp * R), fsmem, st, x, ldx, y, ldy, gamma, beta, HW,
+                                        C, groups, eps, silu, ppc, partial_ws, sync, g_gn_dbg));
+            else
+                VSD_CHECK_CUDA(launch_k(gn_fused_kernel<false>, dim3(chunks, NB), dim3(vpp * R), fsmem, st, x, ldx, y, ldy, gamma, beta, HW,
+                                        C, groups, eps, silu, ppc, partial_ws, sync, g_gn_dbg));
             return 0;
         }
     }

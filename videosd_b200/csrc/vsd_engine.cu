@@ -118,7 +118,11 @@ struct Engine {
     float* splitk_ws_side[2] = {nullptr, nullptr};   // split-K workspaces of the side-stream branches (they run concurrently)
     cudaStream_t side[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
-    unsigned int* gn_sync2 = nullptr;   // grid-barrier state of fused GroupNorms running on side stream 2
+    // The fused GroupNorm's grid barrier needs every block of the kernel resident at once. 148 SMs hold >= 592 such blocks, so at
+    // most FOUR fused GroupNorms (<= 128 blocks each) may run concurrently on a GPU: the main streams of the first four lanes.
+    // Further lanes and the ControlNet branch (side stream 2) use the two-kernel GroupNorm.
+    int lane_index = 0, lanes_created = 1;
+    Engine* root = nullptr;   // the engine owning the weights (null for that engine itself)
     uint8_t *d_y = nullptr, *d_u = nullptr, *d_v = nullptr, *d_rgb_in = nullptr;       // inputs
     uint8_t *d_oy = nullptr, *d_ou = nullptr, *d_ov = nullptr, *d_rgb_out = nullptr;   // outputs
     float *init_latents = nullptr, *noisy = nullptr, *init_noise = nullptr, *step_noise = nullptr, *image = nullptr;
@@ -497,9 +501,10 @@ struct Builder {
         float* ws = alloc_f32((size_t)groupnorm_ws_floats(x.nb, x.h * x.w, x.c, 32));
         if (rc) return;
         const View xi = x, oo = o;
-        unsigned int* sync = cur_stream == 2 ? e->gn_sync2 : e->gn_sync;
+        unsigned int* sync = (cur_stream == 2 || e->lane_index >= 4) ? nullptr : e->gn_sync;
+        const int shared_gpu = ((e->root ? e->root : e)->lanes_created > 1) ? 1 : 0;   // other lanes may run GroupNorms too
         out->push_back(mk([=](cudaStream_t st) {
-            return launch_groupnorm(xi.p, xi.ld, oo.p, oo.ld, g, b, xi.nb, xi.h * xi.w, xi.c, 32, eps, silu, ws, sync, st);
+            return launch_groupnorm(xi.p, xi.ld, oo.p, oo.ld, g, b, xi.nb, xi.h * xi.w, xi.c, 32, eps, silu, ws, sync, st, shared_gpu);
         }, "gn"));
     }
     void layernorm(const View& x, const std::string& name, const View& o) {
@@ -1667,8 +1672,7 @@ vsd_ctx* vsd_create(int device) {
     if (ensure_init()) return nullptr;
     vsd_ctx* c = new vsd_ctx();
     c->e.device = device;
-    if (cudaMalloc(&c->e.gn_sync, 64) != cudaSuccess || cudaMemset(c->e.gn_sync, 0, 64) != cudaSuccess ||
-        cudaMalloc(&c->e.gn_sync2, 64) != cudaSuccess || cudaMemset(c->e.gn_sync2, 0, 64) != cudaSuccess) {
+    if (cudaMalloc(&c->e.gn_sync, 64) != cudaSuccess || cudaMemset(c->e.gn_sync, 0, 64) != cudaSuccess) {
         set_error("cudaMalloc failed");
         delete c;
         return nullptr;
@@ -1695,6 +1699,13 @@ vsd_ctx* vsd_create_lane(vsd_ctx* parent) {
     if (!c) return nullptr;
     c->e.w = parent->e.w;
     c->e.owns_weights = false;
+    c->e.lane_index = parent->e.lanes_created++;
+    c->e.root = &parent->e;
+    if (parent->e.schedule_set) {   // the parent's plan was built for an engine alone on the GPU (GroupNorm variant): rebuild it
+        cudaStreamSynchronize(parent->e.stream);
+        free_graphs(&parent->e);
+        parent->e.schedule_set = false;
+    }
     c->e.tuned = parent->e.tuned;
     c->e.autotune = parent->e.autotune;
     return c;
@@ -1715,7 +1726,6 @@ void vsd_destroy(vsd_ctx* c) {
         if (c->e.ev_join[k]) cudaEventDestroy(c->e.ev_join[k]);
         if (c->e.side[k]) cudaStreamDestroy(c->e.side[k]);
     }
-    if (c->e.gn_sync2) cudaFree(c->e.gn_sync2);
     if (c->e.flush_buf) cudaFree(c->e.flush_buf);
     free_resize(&c->e);
     free_clip(&c->e);

@@ -158,7 +158,7 @@ int attn_init();
 // ---- bandwidth kernels ---------------------------------------------------------------------------
 int launch_groupnorm(const bf16* x, int ldx, bf16* y, int ldy, const float* gamma, const float* beta, int NB, int HW,
                      int C, int groups, float eps, int silu, float* partial_ws, unsigned int* sync /*2 zeroed words or null*/,
-                     cudaStream_t st);
+                     cudaStream_t st, int shared_gpu = 1);
 int groupnorm_ws_floats(int NB, int HW, int C, int groups);
 int launch_layernorm(const bf16* x, int ldx, bf16* y, int ldy, const float* gamma, const float* beta, int rows, int C,
                      float eps, cudaStream_t st);

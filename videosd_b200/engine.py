@@ -40,6 +40,8 @@ class Engine:
         if not self._ctx:
             raise VsdError("vsd_create failed: " + (L.vsd_last_error() or b"?").decode())
         self._ctx = ctypes.c_void_p(self._ctx)
+        if parent is not None:
+            parent._sched_key = None   # vsd_create_lane drops a plan the parent built while it was alone on the GPU
         self._schedule = _sched.LCMSchedule()
         self.batch = self.height = self.width = None
         self.timesteps = None
