@@ -315,7 +315,8 @@ static int load_weight(Engine* e, const std::string& name, const float* host, co
 // ------------------------------------------------------------------------------------------------ GEMM autotuner
 static int time_gemm(Engine* e, const GemmOp& op, float* us) {
     float best = 1e30f;
-    for (int rep = 0; rep < 2; ++rep) {
+    static const int reps = getenv("VSD_TUNE_REPS") ? atoi(getenv("VSD_TUNE_REPS")) : 2;
+    for (int rep = 0; rep < reps; ++rep) {
         VSD_CHECK_CUDA(cudaMemsetAsync(e->flush_buf, rep, e->flush_bytes, e->stream));   // evict L2: weights come from HBM
         VSD_CHECK_CUDA(cudaEventRecord(e->ev0, e->stream));
         int rc = launch_gemm_op(op, e->stream);
