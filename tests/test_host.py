@@ -192,6 +192,31 @@ def test_clip_weight_table_matches_oracle_module():
     assert weights.clip_param_shapes() == want
 
 
+def test_lanczos_tables_vs_pillow_random_geometries():
+    """Property test: for random source / working sizes the host tables + fixed-point arithmetic the CUDA kernels apply
+    reproduce Pillow's crop + LANCZOS resize bit for bit (the reference's own CPU path, videopipeline.py:92-107)."""
+    from PIL import Image
+
+    from videosd_b200 import resample
+    from videosd_b200.videopipeline import VideoSDPipeline
+
+    rs = np.random.RandomState(1234)
+    for _ in range(40):
+        iw, ih = int(rs.randint(9, 400)), int(rs.randint(9, 400))
+        w, h = 8 * int(rs.randint(2, 33)), 8 * int(rs.randint(2, 33))
+        src = rs.randint(0, 256, (ih, iw, 3)).astype(np.uint8)
+        if rs.rand() < 0.5:
+            src[:: int(rs.randint(2, 9))] = 255 * int(rs.randint(0, 2))      # hard edges: ringing must clamp like Pillow
+        ref = np.asarray(VideoSDPipeline._fit(Image.fromarray(src), w, h))
+        got = resample.resize_reference_numpy(src, w, h)
+        assert got.shape == ref.shape and np.array_equal(got, ref), (iw, ih, w, h)
+        plan = resample.resize_plan(iw, ih, w, h)
+        x0, y0, cw, ch = plan["crop"]
+        assert 0 <= x0 and 0 <= y0 and x0 + cw <= iw and y0 + ch <= ih
+        hb, hk, hks = plan["h"]
+        assert hb.shape == (w, 2) and hk.shape == (w, hks) and (hb[:, 0] + hb[:, 1] <= cw).all()
+
+
 def test_session_router_pins_and_batches():
     from videosd_b200.parallel import SessionRouter, shard_streams
 

@@ -59,6 +59,8 @@ def main():
     ctx = random_context(B)
     print(f"oracle built in {time.time()-t0:.1f}s", flush=True)
     eng = Engine(0)
+    if os.environ.get("TUNE_FOR"):
+        eng.set_autotune(int(os.environ["TUNE_FOR"]))
     t0 = time.time()
     eng.load_state_dict("unet", unet.state_dict())
     if use_kl:
