@@ -73,7 +73,7 @@ def ref_conv(x_nhwc, w_ohwi, taps, bias=None, rowvec=None, residual=None):
 
 
 def gemm_case(name, nb, h, w, c, n, taps, bias=False, rowvec=False, residual=False, out_f32=False, block_n=0, splits=0,
-              tol=1e-2, halo=False, pair=False):
+              tol=1e-2, halo=False, pair=False, persist=False, relu=False):
     def fn():
         x = randn((nb, h, w, c), 1).bfloat16()
         wt = randn((n, taps * c), 2, scale=(taps * c) ** -0.5).bfloat16()
@@ -81,9 +81,11 @@ def gemm_case(name, nb, h, w, c, n, taps, bias=False, rowvec=False, residual=Fal
         rv = randn((nb, n), 4) if rowvec else None
         res = randn((nb, h, w, n), 5).bfloat16() if residual else None
         y = ops.conv_gemm(x, wt, taps, bias=b, rowvec=rv, residual=res, out_f32=out_f32, block_n=block_n, splits=splits,
-                          halo=halo, pair=pair)
+                          halo=halo, pair=pair, persist=persist, act=16 if relu else 0)
         torch.cuda.synchronize()
         ref = ref_conv(x, wt, taps, b, rv, res)
+        if relu:
+            ref = torch.relu(ref)
         record(name, rel_err(y, ref), tol, {"shape": [nb, h, w, c, n, taps], "block_n": block_n, "splits": splits})
 
     run(name, fn)
@@ -134,6 +136,13 @@ def check_gemm():
     gemm_case("pair_halo_64x64_320_320", 1, 64, 64, 320, 320, 9, bias=True, residual=True, halo=True, pair=True, block_n=160)
     gemm_case("pair_halo_odd_45x80_64", 1, 45, 80, 64, 64, 9, bias=True, halo=True, pair=True)
     gemm_case("pair_b4_96x96_320", 4, 96, 96, 320, 320, 9, bias=True, pair=True, block_n=256)
+    # persistent weight-stationary 3x3 convolution (TAESD shapes): one CTA per SM walks the 8x16 tiles
+    gemm_case("persist_64x64_64_64", 1, 64, 64, 64, 64, 9, bias=True, persist=True)
+    gemm_case("persist_512x512_64_64_res_relu", 1, 512, 512, 64, 64, 9, bias=True, residual=True, relu=True, persist=True)
+    gemm_case("persist_odd_45x80_64_64", 1, 45, 80, 64, 64, 9, bias=True, persist=True)
+    gemm_case("persist_b3_32x24_64_64_nobias", 3, 32, 24, 64, 64, 9, persist=True)
+    gemm_case("persist_128x128_64_32", 1, 128, 128, 64, 32, 9, bias=True, relu=True, persist=True)
+    gemm_case("persist_16x8_64_64_one_tile", 1, 16, 8, 64, 64, 9, bias=True, persist=True)
 
     def geglu():
         m, c = 4096, 320

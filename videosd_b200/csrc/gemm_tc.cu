@@ -726,6 +726,168 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #undef VSD_STAMP
 }
 
+// ------------------------------------------------------------------------------------------ persistent 3x3 convolution
+// For the TAESD layers (64 -> <= 64 channels on up to 512 x 512 pixels) the whole weight tensor is 9 x N x 64 x 2 B <= 72 KiB, yet
+// conv_gemm_kernel re-fetches it for every 128-pixel tile (57 % of the bytes entering the SM). Here one CTA per SM keeps the
+// weights in shared memory and walks over the 8 x 16-pixel tiles: per tile only the three column-shifted 8 x 18 halo tiles of
+// activations are loaded; two TMEM accumulators alternate so the epilogue of tile i overlaps the MMAs of tile i + 1.
+// warp 0: TMA producer | warp 1: MMA issue (+ TMEM alloc) | warps 2..5: epilogue (bias / residual / ReLU -> smem -> TMA store)
+__global__ void __launch_bounds__(kGemmThreads, 1)
+conv_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                    const __grid_constant__ CUtensorMap mapC, const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int S = p.stages;                                   // activation ring depth
+    const uint32_t b_bytes = (uint32_t)p.block_n * 128u;      // one tap of the weights: [block_n][64] bf16
+    uint8_t* sB = smem;                                       // [9 taps][b_bytes]
+    uint8_t* sA = sB + 9u * b_bytes;                          // [S][18 KiB] halo tiles
+    uint8_t* stag = sA + (size_t)S * kHaloABytes;             // [block_n / 32][4 warps][2 KiB] output staging
+    uint64_t* b_full = reinterpret_cast<uint64_t*>(smem + p.bar_off);
+    uint64_t* a_full = b_full + 1;
+    uint64_t* a_empty = a_full + S;
+    uint64_t* acc_full = a_empty + S;                         // [2]
+    uint64_t* acc_empty = acc_full + 2;                       // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    pdl_launch_dependents();
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapB);
+        tma_prefetch_desc(&mapC);
+        mbar_init(b_full, 1);
+        for (int s = 0; s < S; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int k = 0; k < 2; ++k) { mbar_init(&acc_full[k], 1); mbar_init(&acc_empty[k], 128); }
+        fence_barrier_init();
+        mbar_expect_tx(b_full, 9u * b_bytes);                 // the weights are constants: fetch them before the PDL wait
+        for (int tap = 0; tap < 9; ++tap) tma_load_2d(sB + (size_t)tap * b_bytes, &mapB, b_full, tap * 64, 0);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    for (int i = threadIdx.x; i < p.block_n; i += blockDim.x) sbias[i] = (p.bias && i < p.N) ? __ldg(p.bias + i) : 0.f;
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t acc_cols = (uint32_t)p.tmem_cols >> 1;     // columns of one accumulator buffer
+
+    if (warp == 0) {
+        if (elect_one()) {
+            pdl_wait();
+            int it = 0;
+            for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+                const int w0 = (t % p.tiles_w) * 8, h0 = ((t / p.tiles_w) % p.tiles_h) * 16, n0 = t / (p.tiles_w * p.tiles_h);
+                for (int dxi = 0; dxi < 3; ++dxi, ++it) {
+                    const int s = it % S;
+                    if (it >= S) mbar_wait(&a_empty[s], (uint32_t)((it / S) - 1) & 1u, 1);
+                    mbar_expect_tx(&a_full[s], (uint32_t)kHaloABytes);
+                    tma_load_4d(sA + (size_t)s * kHaloABytes, &mapA, &a_full[s], 0, w0 + dxi - 1, h0 - 1, n0);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        const uint32_t idesc = umma_idesc_bf16(kBlockM, (uint32_t)p.block_n);
+        mbar_wait(b_full, 0, 2);
+        int it = 0, i = 0;
+        for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
+            const int ab = i & 1, use = i >> 1;
+            if (use > 0) mbar_wait(&acc_empty[ab], (uint32_t)(use - 1) & 1u, 3);   // the epilogue has drained this buffer
+            tc_fence_after_sync();
+            const uint32_t tacc = tmem_base + (uint32_t)ab * acc_cols;
+            for (int dxi = 0; dxi < 3; ++dxi, ++it) {
+                const int s = it % S;
+                mbar_wait(&a_full[s], (uint32_t)(it / S) & 1u, 4);
+                tc_fence_after_sync();
+                const uint32_t a_addr = smem_u32(sA + (size_t)s * kHaloABytes);
+                if (elect_one()) {
+                    for (int dyi = 0; dyi < 3; ++dyi) {
+                        const uint32_t b_addr = smem_u32(sB + (size_t)(dyi * 3 + dxi) * b_bytes);
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k)
+                            umma_bf16(tacc, umma_desc_sw128(a_addr + dyi * 1024 + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                                      (dxi == 0 && dyi == 0 && k == 0) ? 0u : 1u);
+                    }
+                    umma_commit(&a_empty[s]);
+                }
+                __syncwarp();
+            }
+            if (elect_one()) umma_commit(&acc_full[ab]);
+            __syncwarp();
+        }
+    } else {
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int bw = r & 7, bh = r >> 3;                      // 8 x 16 tile
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        pdl_wait();
+        int i = 0;
+        for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
+            const int ab = i & 1, use = i >> 1;
+            const int w0 = (t % p.tiles_w) * 8, h0 = ((t / p.tiles_w) % p.tiles_h) * 16, n0 = t / (p.tiles_w * p.tiles_h);
+            const int hh = h0 + bh, ww = w0 + bw;
+            const bool row_ok = (hh < p.H) && (ww < p.W);
+            const long grow = ((long)n0 * p.H + hh) * p.W + ww;
+            // the residual row of this thread is requested before the accumulator is waited for
+            uint4 rres[8];
+            const bool res_pre = (p.residual != nullptr) && row_ok && ((p.ldr & 7) == 0) && (p.block_n <= 64);
+            if (res_pre) {
+                const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + grow * p.ldr);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (j * 8 < p.N) rres[j] = r4[j];
+            }
+            mbar_wait(&acc_full[ab], (uint32_t)use & 1u, 5);
+            tc_fence_after_sync();
+            const uint32_t tacc = tmem_base + lane_off + (uint32_t)ab * acc_cols;
+            // the previous tile's bulk stores must have read the staging buffers before they are overwritten
+            tma_store_wait_all();
+            __syncwarp();
+            for (int c = 0; c < p.block_n; c += 32) {
+                uint32_t u[32];
+                tmem_ld32(tacc + c, u);
+                tmem_ld_wait();
+                if (c + 32 >= p.block_n) {                      // last read of this accumulator: hand it back to the MMA warp
+                    tc_fence_before_sync();
+                    mbar_arrive(&acc_empty[ab]);
+                }
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]);
+                const int ncols = min(32, p.N - c);
+                if (row_ok) {
+                    if (res_pre && ncols == 32) {
+                        uint4 rc[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) rc[j] = (c == 0) ? rres[j] : rres[4 + j];
+                        epilogue_math32(p, v, n0, grow, c, ncols, sbias + c, false, rc);
+                    } else {
+                        epilogue_math32(p, v, n0, grow, c, ncols, sbias + c, false, nullptr);
+                    }
+                }
+                uint8_t* buf = stag + (size_t)((c >> 5) * 4 + q) * 2048;
+                uint8_t* myrow = buf + lane * 64;
+                const int sx = (lane >> 1) & 3;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<uint4*>(myrow + ((j ^ sx) << 4)) =
+                        make_uint4(pack_bf16x2(v[j * 8], v[j * 8 + 1]), pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
+                                   pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (ncols > 0 && elect_one()) {
+                    tma_store_4d(&mapC, buf, c, w0, h0 + q * 4, n0);   // warp q: rows 32q .. 32q+31 = image rows h0+4q .. +3
+                    tma_store_commit();
+                }
+            }
+        }
+        tma_store_wait_all();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
 // Sums split-K partials (fixed order => deterministic) and applies the epilogue. One thread per (row, 4 columns):
 // many threads with one float4 per split each keep plenty of loads in flight for this latency-bound pass.
 __global__ void splitk_reduce_kernel(const GemmParams p, long rows) {
@@ -833,6 +995,7 @@ int gemm_init() {
     VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
     VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
     VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
     return 0;
 }
 
@@ -859,6 +1022,44 @@ static void pick_tile_rect(int NB, int H, int W, int* BW, int* BH, int* BN) {
     *BW = bbw; *BH = bbh; *BN = bbn;
 }
 
+// Persistent weight-stationary 3x3 convolution (conv_persist_kernel): 64 input channels, <= 64 output channels, bf16 output.
+static int build_persist_op(GemmOp* op, const ActView& a, const bf16* wt, int N, int ldw, void* out, int ldo, int out_f32,
+                            const float* bias, const float* rowvec, const bf16* residual, int ldr, int act_flags) {
+    GemmParams& p = op->p;
+    VSD_REQUIRE(p.taps == 9 && a.C == 64 && N >= 8 && N <= 64 && a.H >= 16 && a.W >= 8, "persistent conv: 3x3, 64 -> <= 64 channels");
+    VSD_REQUIRE(!out_f32 && rowvec == nullptr && (ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (N % 8) == 0 &&
+                (act_flags & 0xF) == ACT_NONE && !(act_flags & ACT_RES_F32_FLAG), "persistent conv: bf16 output, no row vector");
+    p.persist = 1; p.halo = 1; p.pair = 0;
+    p.BW = 8; p.BH = 16; p.BN = 1;
+    p.tiles_w = (a.W + 7) / 8; p.tiles_h = (a.H + 15) / 16; p.tiles_n = a.NB;
+    p.N = N;
+    p.block_n = N <= 32 ? 32 : 64;
+    p.tmem_cols = 2 * p.block_n;                      // two accumulator buffers (64 or 128 columns, powers of two)
+    p.splits = 1; p.kb_total = 3; p.kb_per_split = 3; p.kb_per_stage = 1;
+    p.stages = 4;
+    p.out = out; p.ldo = ldo; p.out_f32 = 0;
+    p.bias = bias; p.rowvec = nullptr; p.residual = residual; p.ldr = ldr; p.res_f32 = 0;
+    p.act = ACT_NONE; p.relu = (act_flags & ACT_RELU_FLAG) ? 1 : 0;
+    p.tma_out = 1; p.tma_res = 0; p.cluster_k = 0;
+    p.sbw = 8; p.sbh = 4; p.sbn = 1;                  // a warp's 32 rows = 8 x 4 pixels
+    p.lbw = 3; p.lbh = 4;
+    const int region = 9 * p.block_n * 128 + p.stages * kHaloABytes + p.block_n * 256;
+    p.stage_off = 0;
+    p.bar_off = (unsigned)region;
+    op->smem_bytes = region + 1024 + (1 + 2 * p.stages + 4) * 8 + 64 + p.block_n * 4 + 64;
+    VSD_REQUIRE(op->smem_bytes <= g_max_smem, "persistent conv does not fit shared memory");
+    int rc = make_tmap_act(&op->mapA, a.ptr, a.C, a.W, a.H, a.NB, a.ld, 8, 18, 1);
+    if (rc) return rc;
+    rc = make_tmap_2d(&op->mapB, wt, 9 * a.C, N, ldw, p.block_n);
+    if (rc) return rc;
+    rc = make_tmap_epi_bf16(&op->mapC, out, N, a.W, a.H, a.NB, ldo, 8, 4, 1);
+    if (rc) return rc;
+    op->mapR = op->mapA;
+    const int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    op->grid = dim3(tiles < g_num_sms ? tiles : g_num_sms, 1, 1);
+    return 0;
+}
+
 int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N, int ldw, void* out, int ldo,
                   int out_f32, const float* bias, const float* rowvec, const bf16* residual, int ldr, int act_flags,
                   float* partial_ws, size_t partial_ws_bytes, int force_block_n, int force_splits, int force_occupancy,
@@ -875,6 +1076,7 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
     // force_halo is a mode word: bit 0 = halo tiles, bit 1 = CTA pairs (cta_group::2)
     const bool halo = (taps == 9) && (a.H >= 16) && (a.W >= 8) && (force_halo > 0) && (force_halo & 1);
     const bool pair = (force_halo > 0) && (force_halo & 2);
+    const bool persist = (force_halo > 0) && (force_halo & 4);
     p.halo = halo ? 1 : 0;
     if (halo) { p.BW = 8; p.BH = 16; p.BN = 1; }
     else pick_tile_rect(a.NB, a.H, a.W, &p.BW, &p.BH, &p.BN);
@@ -884,6 +1086,8 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
     p.N = N;
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     p.pair = pair ? 1 : 0;
+    p.persist = 0;
+    if (persist) return build_persist_op(op, a, wt, N, ldw, out, ldo, out_f32, bias, rowvec, residual, ldr, act_flags);
     p.kb_total = halo ? 3 * (a.C / 64) : taps * (a.C / 64);   // halo: iterations of (channel block, column shift)
 
     // N tile: prefer a divisor of N that keeps the grid near a multiple of the SM count.
@@ -1043,6 +1247,10 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
 }
 
 int launch_gemm_op(const GemmOp& op, cudaStream_t st) {
+    if (op.p.persist) {
+        VSD_CHECK_CUDA(launch_k(conv_persist_kernel, op.grid, dim3(kGemmThreads), (size_t)op.smem_bytes, st, op.mapA, op.mapB, op.mapC, op.p));
+        return 0;
+    }
     if (op.p.cluster_k) {
         VSD_CHECK_CUDA(launch_k_cluster(conv_gemm_kernel<3, false>, op.grid, dim3(kGemmThreads), (size_t)op.smem_bytes, 1, op.p.splits, st,
                                         op.mapA, op.mapB, op.mapC, op.mapR, op.p));

@@ -347,6 +347,22 @@ static int tune_gemm(Engine* e, const ActView& a, int taps, const bf16* wt, int 
     const int kb_total = taps * (a.C / 64);
     Engine::Tuned best{0, 1, 0, 1, 0, 1e30f};
     float best_cost = 1e30f;
+    {   // persistent weight-stationary variant for the TAESD-shaped 3x3 convolutions (mode 4)
+        static const int persist_ok = !(getenv("VSD_TUNE_PERSIST") && atoi(getenv("VSD_TUNE_PERSIST")) == 0);
+        if (persist_ok && taps == 9 && a.C == 64 && N <= 64 && N % 8 == 0 && !out_f32 && rowvec == nullptr && a.H >= 16 && a.W >= 8 &&
+            (act & 0xF) == ACT_NONE) {
+            GemmOp op;
+            if (!build_gemm_op(&op, a, taps, wt, N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act, e->splitk_ws, e->splitk_bytes,
+                               0, 1, 1, 1, 4)) {
+                float us = 0.f;
+                int rc = time_gemm(e, op, &us);
+                if (rc) return rc;
+                const float util = std::min(1.0f, (float)op.grid.x / 148.0f);
+                best_cost = us * std::max(util, 1.0f / (float)std::max(e->autotune, 1));
+                best = Engine::Tuned{op.p.block_n, 1, 1, 1, 4, us};
+            }
+        }
+    }
     for (int bi = 0; bi < 8; ++bi) {
         const int bn = bns[bi];
         if (geglu && bn != 128) continue;

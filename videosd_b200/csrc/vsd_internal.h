@@ -91,6 +91,7 @@ struct GemmParams {
     int tmem_cols;        // power of two >= block_n
     int stages, kb_per_stage;
     int pair;             // CTA pairs (cta_group::2): see conv_gemm_kernel<.., kPair>
+    int persist;          // persistent weight-stationary 3x3 convolution (conv_persist_kernel)
     int halo;             // 3x3 conv halo mode (8x16 tiles, column-shifted 8x18 activation tiles shared by 3 row taps)
     // K split
     int kb_total, kb_per_split, splits;
