@@ -5,7 +5,13 @@
 // every 3x3 tap is ONE 4-D TMA box load at a shifted (w, h) coordinate; TMA's out-of-bounds zero fill is the
 // convolution padding. Operands land in shared memory in the 128-byte swizzled K-major layout that
 // tcgen05.mma reads directly; accumulators live in TMEM and are read back with tcgen05.ld by 4 epilogue warps
-// that fuse bias, time-embedding broadcast, residual add and GEGLU before the bf16 (or fp32) store.
+// that fuse bias, time-embedding broadcast, residual add, ReLU / GEGLU / quick-GELU, stage the tile in swizzled shared
+// memory and store it with cp.async.bulk.tensor (direct st.global for fp32 / unaligned outputs).
+//
+// Variants chosen per shape by the engine's autotuner: halo tiles for 3x3 (three column-shifted 8x18 halo tiles per channel
+// block serve all nine taps), CTA pairs (tcgen05.mma.cta_group::2 on 256-row tiles, each SM streams half of the weight tile),
+// 1-4 k-blocks per pipeline stage, 1-2 CTAs per SM, split-K (+ splitk_reduce_kernel), and conv_persist_kernel (weights
+// stationary in shared memory, one CTA per SM) for the TAESD-shaped layers.
 //
 // warp 0: TMA producer | warp 1: TMEM alloc + MMA issue | warps 2..5: epilogue (TMEM lane quarter = warp % 4)
 #include "tc_common.cuh"

@@ -1,10 +1,12 @@
 // Frame-level engine behind the C ABI (include/videosd.h, "engine" section): owns the weights (bf16, repacked
 // for the tcgen05 kernels), builds a static launch plan for one (batch, height, width, steps) configuration
 //   YUV420/RGB in -> TAESD encode -> add noise -> steps x (UNet, LCM step) -> TAESD decode -> pack RGB/YUV420
-// and replays it as one CUDA graph per frame batch. Mirrors the sequencing of
-// diffusert/lcm/lcm_controlnet.py:380-618 (ControlNet residuals = 0) with the UNet2DConditionModel /
-// AutoencoderTiny topology of SURVEY.md Appendix A. Activations are NHWC bf16; latents, scheduler math and
-// normalisation statistics are fp32.
+// and replays it as one CUDA graph per frame batch (PDL edges; the V^T projections, resnet shortcuts and the ControlNet run
+// as parallel branches on side streams). Mirrors the sequencing of diffusert/lcm/lcm_controlnet.py:380-618 with the
+// UNet2DConditionModel / AutoencoderTiny topology of SURVEY.md Appendix A; optional: the canny ControlNet + Sobel front end,
+// center crop + Lanczos resize of the input, the CLIP text tower (once per prompt), AutoencoderKL instead of AutoencoderTiny.
+// Activations are NHWC bf16; latents, scheduler math and normalisation statistics are fp32. Lanes (vsd_create_lane) keep
+// several frames in flight on one copy of the weights.
 #include "vsd_internal.h"
 #include "../../include/videosd.h"
 #include <cmath>
