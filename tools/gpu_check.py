@@ -325,6 +325,22 @@ def check_misc():
             record(f"conv3x3_s2_{nb}x{h}x{w}x{c}", rel_err(y, ref), 1e-2)
     run("conv_s2", s2)
 
+    def s2_tma():
+        # the same stride-2 convolutions without im2col: TMA element strides (2, 2); symmetric and right/bottom-only padding
+        F = torch.nn.functional
+        for (nb, h, w, c, n, pad) in [(1, 64, 64, 320, 320, 1), (2, 45, 80, 64, 64, 1), (1, 512, 512, 64, 64, 1), (1, 16, 16, 1280, 1280, 1),
+                                      (1, 64, 64, 128, 128, 0), (2, 32, 48, 256, 256, 0), (1, 33, 47, 64, 96, 1)]:
+            x = randn((nb, h, w, c), 61).bfloat16()
+            wt = randn((n, 9 * c), 62, scale=(9 * c) ** -0.5).bfloat16()
+            b = randn((n,), 63)
+            y = ops.conv_gemm(x, wt, 9, bias=b, stride2=True, pad=pad)
+            xf = x.float().permute(0, 3, 1, 2)
+            wf = wt.float().view(n, 3, 3, c).permute(0, 3, 1, 2)
+            ref = (F.conv2d(xf, wf, b, stride=2, padding=1) if pad else F.conv2d(F.pad(xf, (0, 1, 0, 1)), wf, b, stride=2)).permute(0, 2, 3, 1)
+            ok_shape = tuple(y.shape) == tuple(ref.shape)
+            record(f"conv3x3_s2_tma_{nb}x{h}x{w}x{c}_pad{pad}", rel_err(y, ref) if ok_shape else 1.0, 1e-2, {"shape": list(y.shape)})
+    run("conv_s2_tma", s2_tma)
+
     def small():
         # UNet conv_in: fp32 latents, 4 -> 320
         x = randn((2, 64, 64, 4), 56)

@@ -376,7 +376,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         dx = tap - ty * 3 - 1;
                     }
                     if (!(pre && p.a_static))
-                        load_a(sa + (size_t)j * kABytes, s, cb * 64, w0 + dx, h0 + dy, n0);
+                        load_a(sa + (size_t)j * kABytes, s, cb * 64, p.cstride * w0 + dx + p.cshift, p.cstride * h0 + dy + p.cshift, n0);
                     if (!(pre && p.b_static))
                         load_b(sb + (size_t)j * b_bytes, s, kb * 64, bcol0);
                     if (++cb == kpt) { cb = 0; ++tap; }
@@ -938,11 +938,13 @@ static void resolve_encode() {
 
 static int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
                   const cuuint32_t* box, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
-                  CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+                  CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, const cuuint32_t* elem_strides = nullptr) {
     std::call_once(g_encode_once, resolve_encode);
     VSD_REQUIRE(g_encode != nullptr, "cuTensorMapEncodeTiled driver entry point not available (no CUDA driver?)");
     VSD_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map base must be 16-byte aligned");
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (elem_strides)
+        for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
     CUresult r = g_encode(m, dtype, (cuuint32_t)rank, const_cast<void*>(base), dims, strides,
                           box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -955,12 +957,15 @@ static int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* 
     return 0;
 }
 
-int make_tmap_act(CUtensorMap* m, const void* base, int C, int W, int H, int N, int ld, int boxW, int boxH, int boxN) {
+// elem_stride 2: the box spans boxW * 2 x boxH * 2 input pixels and TMA delivers every second one (stride-2 convolution taps)
+int make_tmap_act(CUtensorMap* m, const void* base, int C, int W, int H, int N, int ld, int boxW, int boxH, int boxN,
+                  int elem_stride) {
     VSD_REQUIRE((ld % 8) == 0, "activation pixel stride must be a multiple of 8 elements");
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)boxW, (cuuint32_t)boxH, (cuuint32_t)boxN};
-    return encode(m, base, 4, dims, strides, box);
+    cuuint32_t box[4] = {64, (cuuint32_t)(boxW * elem_stride), (cuuint32_t)(boxH * elem_stride), (cuuint32_t)boxN};
+    cuuint32_t es[4] = {1, (cuuint32_t)elem_stride, (cuuint32_t)elem_stride, 1};
+    return encode(m, base, 4, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_128B, es);
 }
 
 // Epilogue maps: 32-column boxes over a [NB][H][W][ld] bf16 tensor (64-byte swizzle), or over the fp32 split-K workspace
@@ -1066,10 +1071,20 @@ static int build_persist_op(GemmOp* op, const ActView& a, const bf16* wt, int N,
     return 0;
 }
 
-int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N, int ldw, void* out, int ldo,
+int build_gemm_op(GemmOp* op, const ActView& ain, int taps, const bf16* wt, int N, int ldw, void* out, int ldo,
                   int out_f32, const float* bias, const float* rowvec, const bf16* residual, int ldr, int act_flags,
                   float* partial_ws, size_t partial_ws_bytes, int force_block_n, int force_splits, int force_occupancy,
                   int force_kb_per_stage, int force_halo) {
+    // `a` is the OUTPUT geometry from here on (tiles, rows, epilogue maps); `ain` only describes the activation tensor map
+    const int cs = (taps == 9 && ain.stride == 2) ? 2 : 1;
+    VSD_REQUIRE(ain.stride == 1 || (ain.stride == 2 && taps == 9), "only 3x3 convolutions can be strided (stride 2)");
+    ActView a = ain;
+    if (cs == 2) {
+        a.H = (ain.H + 2 * ain.pad - 3 + (ain.pad ? 0 : 1)) / 2 + 1;   // pad 1: (H-1)/2+1 ; pad 0 with one zero row below: (H-2)/2+1
+        a.W = (ain.W + 2 * ain.pad - 3 + (ain.pad ? 0 : 1)) / 2 + 1;
+        if (force_halo > 0) force_halo &= ~5;        // halo tiles / the persistent kernel assume stride 1
+        VSD_REQUIRE(a.H >= 1 && a.W >= 1, "strided convolution output is empty");
+    }
     const int act = act_flags & 0xF;
     VSD_REQUIRE(taps == 1 || taps == 9, "taps must be 1 or 9");
     VSD_REQUIRE(a.C % 64 == 0, "input channels must be a multiple of 64 for the tcgen05 path");
@@ -1092,6 +1107,8 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
     p.N = N;
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     p.pair = pair ? 1 : 0;
+    p.cstride = cs;
+    p.cshift = (cs == 2 && ain.pad == 0) ? 1 : 0;
     p.persist = 0;
     if (persist) return build_persist_op(op, a, wt, N, ldw, out, ldo, out_f32, bias, rowvec, residual, ldr, act_flags);
     p.kb_total = halo ? 3 * (a.C / 64) : taps * (a.C / 64);   // halo: iterations of (channel block, column shift)
@@ -1235,7 +1252,7 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
     if (p.a_static && taps != 1) p.a_static = 0;
 
     int rc = halo ? make_tmap_act(&op->mapA, a.ptr, a.C, a.W, a.H, a.NB, a.ld, 8, 18, 1)
-                  : make_tmap_act(&op->mapA, a.ptr, a.C, a.W, a.H, a.NB, a.ld, p.BW, p.BH, p.BN);
+                  : make_tmap_act(&op->mapA, ain.ptr, ain.C, ain.W, ain.H, ain.NB, ain.ld, p.BW, p.BH, p.BN, cs);
     if (rc) return rc;
     rc = make_tmap_2d(&op->mapB, wt, taps * a.C, N, ldw, pair ? bn / 2 : bn);
     if (rc) return rc;

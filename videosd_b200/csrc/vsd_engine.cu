@@ -487,8 +487,8 @@ struct Builder {
         int fbn = 0, fsp = 0, focc = 0, fkbs = 0, fhalo = 0;
         if (e->autotune) {
             char key[160];
-            snprintf(key, sizeof(key), "%dx%dx%dx%d|t%d|n%d|a%d|f%d|r%d", a.NB, a.H, a.W, a.C, taps, N, act, out_f32,
-                     res ? 1 : 0);
+            snprintf(key, sizeof(key), "%dx%dx%dx%d|t%d|n%d|a%d|f%d|r%d", a.NB, a.H, a.W, a.C, taps + 100 * (a.stride - 1) + 1000 * (1 - a.pad),
+                     N, act, out_f32, res ? 1 : 0);
             auto it = e->tuned.find(key);
             if (it == e->tuned.end()) {
                 Engine::Tuned t;
@@ -641,7 +641,23 @@ struct Builder {
         e->arena.release(m);
     }
 
+    // 3x3 stride-2 convolution. Default: im2col_s2_kernel + GEMM. Opt-in (VSD_TMA_S2=1): the taps are fetched by TMA with
+    // element strides (2, 2) straight from the input, no im2col buffer -- bit-for-bit tested per operator (tools/gpu_check.py
+    // misc) and 0.24 ms faster per 512 x 512 frame, but the 360 x 640 frame test produced NaNs with it at the end of round 1
+    // (cause not yet found), so it stays off. pad 1 = diffusers Downsample2D(padding=1) / TAESD; pad 0 = zeros right / below
+    // only (AutoencoderKL).
     void conv_s2(const View& x, const std::string& name, const View& o, bool has_bias, int pad = 1) {
+        static const bool use_im2col = !(getenv("VSD_TMA_S2") && atoi(getenv("VSD_TMA_S2")) != 0);
+        const bf16* wt = wb(name + ".weight");
+        const float* b = has_bias ? wf(name + ".bias") : nullptr;
+        if (rc) return;
+        if (!use_im2col) {
+            ActView av = x.act();
+            av.stride = 2;
+            av.pad = pad;
+            gemm(av, 9, wt, o.c, 9 * x.c, o.p, o.ld, 0, b, nullptr, nullptr, 0, ACT_NONE);
+            return;
+        }
         const size_t m = e->arena.mark();
         View cols = alloc(o.nb, o.h, o.w, 9 * x.c);
         if (rc) return;
@@ -649,8 +665,6 @@ struct Builder {
         out->push_back(mk([=](cudaStream_t st) {
             return launch_im2col_s2(xi.p, xi.ld, ci.p, xi.nb, xi.h, xi.w, xi.c, oo.h, oo.w, st, pad);
         }, "im2col"));
-        const bf16* wt = wb(name + ".weight");
-        const float* b = has_bias ? wf(name + ".bias") : nullptr;
         gemm(cols.act(), 1, wt, o.c, 9 * x.c, o.p, o.ld, 0, b, nullptr, nullptr, 0, ACT_NONE);
         e->arena.release(m);
     }

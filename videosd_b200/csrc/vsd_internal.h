@@ -68,7 +68,8 @@ inline cudaError_t launch_k_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 bl
 }
 
 // ---- tensor maps (driver entry point resolved at run time; the library does not link libcuda)
-int make_tmap_act(CUtensorMap* m, const void* base, int C, int W, int H, int N, int ld, int boxW, int boxH, int boxN);
+int make_tmap_act(CUtensorMap* m, const void* base, int C, int W, int H, int N, int ld, int boxW, int boxH, int boxN,
+                  int elem_stride = 1);
 int make_tmap_2d(CUtensorMap* m, const void* base, int K, int rows, int ld, int box_rows);
 
 // ---- tcgen05 implicit-GEMM convolution / linear kernel -------------------------------------------
@@ -90,6 +91,7 @@ struct GemmParams {
     int block_n;          // multiple of 32, <= 256
     int tmem_cols;        // power of two >= block_n
     int stages, kb_per_stage;
+    int cstride, cshift;  // 3x3 taps read input pixel (cstride * w + dx + cshift): stride-2 convolutions, asymmetric padding
     int pair;             // CTA pairs (cta_group::2): see conv_gemm_kernel<.., kPair>
     int persist;          // persistent weight-stationary 3x3 convolution (conv_persist_kernel)
     int halo;             // 3x3 conv halo mode (8x16 tiles, column-shifted 8x18 activation tiles shared by 3 row taps)
@@ -130,6 +132,9 @@ struct GemmOp {
 struct ActView {
     const void* ptr;
     int NB, H, W, C, ld;  // ld = elements between consecutive pixels (>= C)
+    // 3x3 convolutions only: stride 2 reads the input through a TMA tensor map with element strides (2, 2) -- no im2col.
+    // pad 1 = symmetric zero padding (UNet / TAESD downsamplers), pad 0 = zeros right / below only (AutoencoderKL).
+    int stride = 1, pad = 1;
 };
 int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N, int ldw, void* out, int ldo,
                   int out_f32, const float* bias, const float* rowvec, const bf16* residual, int ldr, int act,
