@@ -66,7 +66,6 @@ int vsd_op_attention(const void* q, int ldq, const void* k, int ldk, const void*
  * Transformer2DModel). x, y: dev bf16 [nb*hw][ld]. */
 int vsd_op_groupnorm(const void* x, int ldx, void* y, int ldy, const float* gamma, const float* beta, int nb, int hw,
                      int c, int groups, float eps, int silu, void* stream);
-int vsd_debug_set_gn_stamps(long long* dev_buf);   /* bring-up: clock64 phase stamps of the fused GroupNorm kernel */
 /* LayerNorm over the last dimension (BasicTransformerBlock.norm1/2/3). */
 int vsd_op_layernorm(const void* x, int ldx, void* y, int ldy, const float* gamma, const float* beta, int rows, int c,
                      float eps, void* stream);
@@ -132,6 +131,7 @@ int vsd_num_weights(vsd_ctx* ctx);
 int vsd_set_autotune(vsd_ctx* ctx, int frames_in_flight);
 int vsd_tuning_report(vsd_ctx* ctx, char* buf, long cap);
 int vsd_tuning_load(vsd_ctx* ctx, const char* text);   /* returns the number of entries loaded */
+long vsd_tuning_misses(vsd_ctx* ctx);                   /* shapes timed on the device because no loaded table entry covered them */
 
 /* Working size: `batch` frames of height x width (multiples of 8; infer(height=, width=) at videopipeline.py:75-88).
  * Must be called after the weights are loaded; invalidates schedule, contexts and noise. */

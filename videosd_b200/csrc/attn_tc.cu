@@ -330,6 +330,11 @@ int launch_attn_op(const AttnOp& op, cudaStream_t st) {
     return 0;
 }
 
+const unsigned int* trap_code_addr_attn() {
+    void* p = nullptr;
+    return cudaGetSymbolAddress(&p, g_trap_code) == cudaSuccess ? static_cast<const unsigned int*>(p) : nullptr;
+}
+
 unsigned int read_trap_code_attn() {
     unsigned int v = 0, z = 0;
     if (cudaMemcpyFromSymbol(&v, g_trap_code, sizeof(v)) != cudaSuccess) return 0xFFFFFFFFu;

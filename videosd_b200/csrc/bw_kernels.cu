@@ -7,6 +7,8 @@
 
 namespace vsd {
 
+static int bw_init_convs();
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -140,181 +142,129 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, int ldx, bf16* __res
     }
 }
 
-// Blocks of ~1024 channel-vectors (small tensors are latency-bound: spread them over many SMs), at most 128 chunks
-// per image so the per-block partial reduction stays short.
-// ---- single-kernel GroupNorm: statistics + grid barrier + normalisation from shared memory ------------------------
-// Each block keeps its pixel chunk in shared memory, publishes its partial sums, meets the other blocks at a
-// sense-reversal grid barrier (all blocks are co-resident: the host only selects this kernel when the grid fits),
-// then normalises its chunk from shared memory: one launch and one read of x instead of two launches and two reads.
-static __device__ unsigned int g_bw_fault = 0;
-
-// kShared: several engines (lanes) may run this kernel at the same time on one GPU => 4 blocks per SM must fit (<= 51
-// registers per thread). Alone on the GPU the kernel may use 2 blocks per SM and all the registers it likes (faster).
-template <bool kShared>
-__global__ void __launch_bounds__(320, (kShared ? 4 : 2)) gn_fused_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C, int groups,
-                                float eps, int silu, int px_per_chunk, float* __restrict__ partial, unsigned int* sync,
-                                long long* dbg) {
+// ---- cluster GroupNorm: statistics exchanged through distributed shared memory, no grid barrier ---------------------
+// GroupNorm statistics are independent per (image, group), so nothing has to synchronise grid-wide: a thread-block CLUSTER
+// owns `gpc` consecutive groups of one image (gpc * C/groups channels, a multiple of 8 => whole 16-byte vectors), its CS
+// CTAs split the pixels. Each CTA keeps its slice in shared memory, reduces it to (sum, sum of squares) per group in a fixed
+// order, the CTAs read each other's partials through DSMEM after ONE hardware cluster barrier (rank order => bit-identical in
+// every CTA and run to run), then each CTA normalises its slice from shared memory. One launch, x read once, no
+// co-residency assumption beyond what the hardware guarantees for a cluster (lanes / other processes cannot starve it).
+//   grid (CS * groups / gpc, NB), cluster (CS, 1, 1), block vpc * R threads (vpc = gpc * cpg / 8 vectors per pixel)
+__global__ void __launch_bounds__(256) gn_cluster_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta, int HW,
+                                                         int cpg, int gpc, int CS, float eps, int silu, int ppc, int cache) {
     extern __shared__ __align__(16) uint8_t gsm[];
-    const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
-    if (dbg_on) dbg[0] = clock64();
-    const int vpp = C >> 3;
-    const int cpg = C / groups;
-    float* gstat = reinterpret_cast<float*>(gsm);            // [groups*2] mean, rstd
-    float4* spart = reinterpret_cast<float4*>(gstat + 64);   // [blockDim.x]
-    uint4* chunk = reinterpret_cast<uint4*>(spart + blockDim.x);   // [px_per_chunk * vpp]
-    const int vi = threadIdx.x % vpp;
-    const int r0 = threadIdx.x / vpp;
-    const int R = blockDim.x / vpp;
-    const int n = blockIdx.y, ck = blockIdx.x, chunks = gridDim.x;
-    const int p_begin = ck * px_per_chunk;
-    const int p_end = min(HW, p_begin + px_per_chunk);
-    // this thread's 8 channels' affine parameters are constants: fetch them before waiting for the producer of x
-    float ga[8], be[8];
+    float* cpart = reinterpret_cast<float*>(gsm);            // [gpc][2] this CTA's partial sums (read by the cluster peers)
+    float* gstat = cpart + 16;                               // [gpc][2] mean, rstd
+    float4* spart = reinterpret_cast<float4*>(gsm + 128);    // [blockDim.x]
+    uint4* chunk = reinterpret_cast<uint4*>(spart + blockDim.x);   // [ppc * vpc] (when `cache`)
+    pdl_launch_dependents();
+    const int vpc = (gpc * cpg) >> 3;
+    const int v = threadIdx.x % vpc, r0 = threadIdx.x / vpc, R = blockDim.x / vpc;
+    const int rank = (int)cluster_ctarank();
+    const int set = blockIdx.x / CS, n = blockIdx.y;
+    const int c0 = set * gpc * cpg + v * 8;                  // first of this thread's 8 channels
+    const int p_begin = rank * ppc, p_end = min(HW, p_begin + ppc);
+    float ga[8], be[8];                                      // constants: fetched before waiting for the producer of x
     {
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
         ga[0] = g0.x; ga[1] = g0.y; ga[2] = g0.z; ga[3] = g0.w; ga[4] = g1.x; ga[5] = g1.y; ga[6] = g1.z; ga[7] = g1.w;
         be[0] = b0.x; be[1] = b0.y; be[2] = b0.z; be[3] = b0.w; be[4] = b1.x; be[5] = b1.y; be[6] = b1.z; be[7] = b1.w;
     }
     pdl_wait();
-    if (dbg_on) dbg[1] = clock64();
     float s[8], ss[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s[j] = 0.f; ss[j] = 0.f; }
-    const bf16* base = x + ((long)n * HW) * ldx + vi * 8;
+    const bf16* base = x + ((long)n * HW) * ldx + c0;
 #pragma unroll 4
     for (int p = p_begin + r0; p < p_end; p += R) {
         const uint4 t = *reinterpret_cast<const uint4*>(base + (long)p * ldx);
-        chunk[(p - p_begin) * vpp + vi] = t;
+        if (cache) chunk[(p - p_begin) * vpc + v] = t;
         float f[8];
         unpack8(t, f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] += f[j] * f[j]; }
     }
-    const int g0 = (vi * 8) / cpg;
-    float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;
+    const int g0 = (v * 8) / cpg;                            // local group of this vector's first channel
+    {
+        float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        if ((vi * 8 + j) / cpg == g0) { a0 += s[j]; b0 += ss[j]; }
-        else { a1 += s[j]; b1 += ss[j]; }
+        for (int j = 0; j < 8; ++j) {
+            if ((v * 8 + j) / cpg == g0) { a0 += s[j]; b0 += ss[j]; }
+            else { a1 += s[j]; b1 += ss[j]; }
+        }
+        spart[threadIdx.x] = make_float4(a0, b0, a1, b1);
     }
-    spart[threadIdx.x] = make_float4(a0, b0, a1, b1);
     __syncthreads();
-    if (threadIdx.x < groups) {
-        const int g = threadIdx.x;
-        const int v_lo = (g * cpg) >> 3, v_hi = ((g + 1) * cpg - 1) >> 3;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < gpc) {                                        // one (full) warp per local group: fixed order + fixed shuffle tree
+        const int g = warp;
+        const int v_lo = (g * cpg) >> 3, v_hi = ((g + 1) * cpg - 1) >> 3, nv = v_hi - v_lo + 1;
         float a = 0.f, b = 0.f;
-        for (int r = 0; r < R; ++r)
-            for (int v = v_lo; v <= v_hi; ++v) {
-                const float4 t = spart[r * vpp + v];
-                if ((v * 8) / cpg == g) { a += t.x; b += t.y; }
-                else { a += t.z; b += t.w; }
-            }
-        float* dst = partial + (((long)n * chunks + ck) * groups + g) * 2;
-        dst[0] = a;
-        dst[1] = b;
+        for (int e = lane; e < R * nv; e += 32) {
+            const int r = e / nv, vv = v_lo + (e - r * nv);
+            const float4 t = spart[r * vpc + vv];
+            if ((vv * 8) / cpg == g) { a += t.x; b += t.y; }
+            else { a += t.z; b += t.w; }
+        }
+        a = warp_sum(a);
+        b = warp_sum(b);
+        if (lane == 0) { cpart[g * 2] = a; cpart[g * 2 + 1] = b; }
     }
-    if (dbg_on) dbg[2] = clock64();
-    // ---- grid barrier (sense reversal; every block is co-resident, see launch_groupnorm). The LAST block to arrive
-    // reduces all partials in a fixed order and publishes (mean, rstd) per (image, group) before releasing the others,
-    // so the statistics are computed once instead of by every block (which also hammered the same L2 lines).
-    __shared__ unsigned int s_last, s_gen;
-    float* stats_out = partial + (long)gridDim.y * chunks * groups * 2;   // [NB][groups][2]
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        volatile unsigned int* gen_p = sync + 1;
-        s_gen = *gen_p;                      // read the generation before arriving
-        __threadfence();                     // this block's partials are visible before the arrival
-        const unsigned int old = atomicAdd(sync, 1u);
-        s_last = (old == gridDim.x * gridDim.y - 1) ? 1u : 0u;
-    }
-    __syncthreads();
-    if (s_last) {
-        __threadfence();
-        const int gpr = blockDim.x >> 3;     // (image, group) items per round, 8 threads each
-        const int j = threadIdx.x & 7;
-        const int items = (int)gridDim.y * groups;
-        for (int i0 = 0; i0 < items; i0 += gpr) {
-            const int item = i0 + (threadIdx.x >> 3);
-            const bool ok = (item < items) && ((threadIdx.x >> 3) < gpr);
-            const int in = ok ? item / groups : 0, ig = ok ? item % groups : 0;
-            const float2* src = reinterpret_cast<const float2*>(partial + (long)in * chunks * groups * 2) + ig;
-            float2 v[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const int c = j + 8 * k;
-                v[k] = (ok && c < chunks) ? __ldcg(src + (long)c * groups) : make_float2(0.f, 0.f);
-            }
-            float a = 0.f, b = 0.f;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) { a += v[k].x; b += v[k].y; }
-#pragma unroll
-            for (int o = 4; o > 0; o >>= 1) {
-                a += __shfl_xor_sync(0xffffffffu, a, o);
-                b += __shfl_xor_sync(0xffffffffu, b, o);
-            }
-            if (ok && j == 0) {
-                const float cnt = (float)HW * (float)cpg;
-                const float mean = a / cnt;
-                const float var = fmaxf(b / cnt - mean * mean, 0.f);
-                stats_out[item * 2] = mean;
-                stats_out[item * 2 + 1] = rsqrtf(var + eps);
-            }
+    cluster_sync_all();                                      // every CTA's cpart is complete and visible cluster-wide
+    if (threadIdx.x < gpc) {
+        const int g = threadIdx.x;
+        float a = 0.f, b = 0.f;
+        const uint32_t local = smem_u32(cpart + g * 2);
+        for (int rk = 0; rk < CS; ++rk) {
+            const uint32_t ra = dsmem_addr(local, (uint32_t)rk);
+            float pa, pb;
+            asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(pa), "=f"(pb) : "r"(ra) : "memory");
+            a += pa; b += pb;
         }
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            sync[0] = 0;
-            __threadfence();
-            atomicAdd(sync + 1, 1u);         // release
-        }
-    } else if (threadIdx.x == 0) {
-        volatile unsigned int* gen_p = sync + 1;
-        const long long t0 = clock64();
-        while (*gen_p == s_gen) {
-            if (clock64() - t0 > 2000000000LL) { atomicExch(&g_bw_fault, 0x90000001u); break; }
-        }
-        __threadfence();
+        const float cnt = (float)HW * (float)cpg;
+        const float mean = a / cnt;
+        const float var = fmaxf(b / cnt - mean * mean, 0.f);
+        gstat[g * 2] = mean;
+        gstat[g * 2 + 1] = rsqrtf(var + eps);
     }
     __syncthreads();
-    if (dbg_on) dbg[3] = clock64();
-    pdl_launch_dependents();   // only now: every block of this grid is resident, successors cannot starve it
-    if (threadIdx.x < groups * 2) gstat[threadIdx.x] = __ldcg(stats_out + (long)n * groups * 2 + threadIdx.x);
-    __syncthreads();
-    if (dbg_on) dbg[4] = clock64();
-    // fold statistics and affine parameters of this thread's 8 channels into one multiply-add each
+    // peers may still be reading this CTA's cpart: arrive now, wait right before exiting
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     float sc[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const int g = (vi * 8 + j) / cpg;
+        const int g = (v * 8 + j) / cpg;
         sc[j] = gstat[g * 2 + 1] * ga[j];
         sh[j] = be[j] - gstat[g * 2] * sc[j];
     }
-    bf16* yb = y + ((long)n * HW) * ldy + vi * 8;
+    bf16* yb = y + ((long)n * HW) * ldy + c0;
+#pragma unroll 2
     for (int p = p_begin + r0; p < p_end; p += R) {
         float f[8];
-        unpack8(chunk[(p - p_begin) * vpp + vi], f);
+        if (cache) unpack8(chunk[(p - p_begin) * vpc + v], f);
+        else unpack8(*reinterpret_cast<const uint4*>(base + (long)p * ldx), f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            float v = fmaf(f[j], sc[j], sh[j]);
-            if (silu) v = __fdividef(v, 1.0f + __expf(-v));
-            f[j] = v;
+            float o = fmaf(f[j], sc[j], sh[j]);
+            if (silu) o = __fdividef(o, 1.0f + __expf(-o));
+            f[j] = o;
         }
         *reinterpret_cast<uint4*>(yb + (long)p * ldy) = pack8(f);
     }
-    if (dbg_on) dbg[5] = clock64();
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-unsigned int read_trap_code_bw() {
-    unsigned int v = 0, z = 0;
-    if (cudaMemcpyFromSymbol(&v, g_bw_fault, sizeof(v)) != cudaSuccess) return 0xFFFFFFFFu;
-    if (v) cudaMemcpyToSymbol(g_bw_fault, &z, sizeof(z));
-    return v;
+// Function attributes are per DEVICE: called from ensure_init() once for every device this process uses (one worker thread
+// per GPU in one process is the deployment when Ray is absent).
+int bw_init() {
+    VSD_CHECK_CUDA(cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    return bw_init_convs();
 }
 
-long long* g_gn_dbg = nullptr;   // bring-up: phase stamps of block (0,0) of the fused kernel
-
+// Two-kernel fallback geometry: blocks of ~1024 channel-vectors, at most 128 chunks per image so the per-block partial
+// reduction stays short.
 static void gn_geometry(int NB, int HW, int C, int* px_per_chunk, int* chunks) {
     const long vecs = (long)HW * (C / 8);
     long want = (vecs + 1023) / 1024;
@@ -335,40 +285,41 @@ int groupnorm_ws_floats(int NB, int HW, int C, int groups) {
 }
 
 int launch_groupnorm(const bf16* x, int ldx, bf16* y, int ldy, const float* gamma, const float* beta, int NB, int HW,
-                     int C, int groups, float eps, int silu, float* partial_ws, unsigned int* sync, cudaStream_t st, int shared_gpu) {
+                     int C, int groups, float eps, int silu, float* partial_ws, cudaStream_t st) {
     VSD_REQUIRE(C % 8 == 0 && C % groups == 0 && ldx % 8 == 0 && ldy % 8 == 0, "GroupNorm needs C%8==0 and 16-byte rows");
     // a thread's 8-channel vector may touch at most two groups: channels per group >= 8, or exactly 4 (AutoencoderKL, C = 128)
     VSD_REQUIRE(C / 8 <= 1024 && (C / groups >= 8 || C / groups == 4) && groups <= 32,
                 "GroupNorm needs C/groups >= 8 (or == 4), C <= 8192, groups <= 32");
+    {
+        // cluster path (gn_cluster_kernel): the smallest group count per cluster whose channels form whole 16-byte vectors
+        const int cpg = C / groups;
+        int gpc = 1;
+        while (gpc <= 8 && ((gpc * cpg) % 8 != 0 || groups % gpc != 0)) gpc <<= 1;
+        const int vpc = gpc <= 8 ? gpc * cpg / 8 : 0;
+        static const int gn_mode = getenv("VSD_GN_MODE") ? atoi(getenv("VSD_GN_MODE")) : 0;   // 2: force the two-kernel path (A/B timing)
+        if (gn_mode == 0 && vpc >= 1 && vpc <= 240) {
+            const int sets = groups / gpc;
+            const int R = 240 / vpc;
+            // CTAs per cluster: enough CTAs to spread the tensor over the machine (~128), >= 16 pixels each, <= 8 (portable)
+            int CS = 1;
+            while (CS < 8 && (long)sets * NB * CS < 128 && HW / (CS * 2) >= 16) CS <<= 1;
+            int ppc = (HW + CS - 1) / CS;
+            while (CS < 8 && (size_t)ppc * vpc * 16 > 160 * 1024) { CS <<= 1; ppc = (HW + CS - 1) / CS; }
+            const long vecs_per_cta = (long)ppc * vpc;
+            if (vecs_per_cta <= 24 * 1024) {    // larger slices (AutoencoderKL at full resolution): the two-kernel path below
+                const int cache = (size_t)ppc * vpc * 16 <= 160 * 1024 ? 1 : 0;
+                const size_t smem = 128 + (size_t)vpc * R * 16 + (cache ? (size_t)ppc * vpc * 16 : 0);
+                VSD_CHECK_CUDA(launch_k_cluster(gn_cluster_kernel, dim3(CS * sets, NB), dim3(vpc * R), smem, CS, 1, st, x, ldx, y, ldy,
+                                                gamma, beta, HW, cpg, gpc, CS, eps, silu, ppc, cache));
+                return 0;
+            }
+        }
+    }
     int ppc, chunks;
     gn_geometry(NB, HW, C, &ppc, &chunks);
     const int vpp = C / 8;
     int R = 256 / vpp;
     if (R < 1) R = 1;
-    {
-        // fused single-kernel path when the chunk fits shared memory and the whole grid is co-resident
-        const size_t fsmem = (size_t)64 * 4 + (size_t)vpp * R * 16 + (size_t)ppc * vpp * 16;
-        static bool attr_set = false;
-        if (!attr_set) {
-            VSD_CHECK_CUDA(cudaFuncSetAttribute(gn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            VSD_CHECK_CUDA(cudaFuncSetAttribute(gn_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            attr_set = true;
-        }
-        // Co-residency bound for the grid barrier: <= 128 blocks of <= 48 KiB and <= 320 threads each. shared_gpu: <= 51
-        // registers per thread, an SM holds at least 4 such blocks, 148 SMs hold >= 592: even 4 lanes running this kernel at
-        // the same time (4 x 128 blocks) are all resident and no lane can starve another's late blocks; the engine keeps it
-        // to four concurrent users per GPU (lanes 0-3, main stream only). Otherwise (one engine on the GPU): 2 blocks per
-        // SM, 296 >= 128. Larger tensors use two kernels.
-        if (sync != nullptr && fsmem <= 48 * 1024 && (long)chunks * NB <= 128 && groups <= 32 && vpp * R <= 320) {
-            if (shared_gpu)
-                VSD_CHECK_CUDA(launch_k(gn_fused_kernel<true>, dim3(chunks, NB), dim3(vpp * R), fsmem, st, x, ldx, y, ldy, gamma, beta, HW,
-                                        C, groups, eps, silu, ppc, partial_ws, sync, g_gn_dbg));
-            else
-                VSD_CHECK_CUDA(launch_k(gn_fused_kernel<false>, dim3(chunks, NB), dim3(vpp * R), fsmem, st, x, ldx, y, ldy, gamma, beta, HW,
-                                        C, groups, eps, silu, ppc, partial_ws, sync, g_gn_dbg));
-            return 0;
-        }
-    }
     VSD_CHECK_CUDA(launch_k(gn_stats_kernel, dim3(chunks, NB), dim3(vpp * R), (size_t)vpp * R * sizeof(float4), st, x, ldx, HW, C, groups, ppc, partial_ws));
     VSD_CHECK_CUDA(cudaGetLastError());
     const size_t smem = (size_t)(groups * 2 + 2 * C) * sizeof(float);
@@ -1034,15 +985,15 @@ int launch_conv3x3_direct(const bf16* x, int ldx, int NB, int Hi, int Wi, int Ci
     const int Ho = (Hi - 1) / stride + 1, Wo = (Wi - 1) / stride + 1;
     const size_t smem = (size_t)16 * 9 * Cin * sizeof(float);
     VSD_REQUIRE(smem <= 96 * 1024, "direct conv: too many input channels");
-    static bool attr_set = false;
-    if (!attr_set) {
-        VSD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr_set = true;
-    }
     const long pixels = (long)NB * Ho * Wo;
     dim3 grid((unsigned)((pixels + 127) / 128), (Cout + 15) / 16);
     VSD_CHECK_CUDA(launch_k(conv3x3_direct_kernel, grid, dim3(128), smem, st, x, ldx, NB, Hi, Wi, Cin, w, bias, y, ldy, Ho, Wo,
                             Cout, stride, silu));
+    return 0;
+}
+
+static int bw_init_convs() {
+    VSD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     return 0;
 }
 

@@ -1301,6 +1301,11 @@ int launch_splitk_reduce(const GemmParams& p, long rows, cudaStream_t st) {
     return 0;
 }
 
+const unsigned int* trap_code_addr_gemm() {
+    void* p = nullptr;
+    return cudaGetSymbolAddress(&p, g_trap_code) == cudaSuccess ? static_cast<const unsigned int*>(p) : nullptr;
+}
+
 unsigned int read_trap_code_gemm() {
     unsigned int v = 0, z = 0;
     if (cudaMemcpyFromSymbol(&v, g_trap_code, sizeof(v)) != cudaSuccess) return 0xFFFFFFFFu;

@@ -99,6 +99,7 @@ struct Scope {
 template <typename F>
 static Launch mk(F f, const char* op) { return Launch{std::function<int(cudaStream_t)>(f), g_scope + "." + op}; }
 
+static constexpr int kMaxSteps = 50;
 struct StepScalars { float sqrt_a, sqrt_1ma, c_skip, c_out, sqrt_ap, sqrt_1map; int t; };
 
 struct Engine {
@@ -120,9 +121,6 @@ struct Engine {
     float* splitk_ws_side[2] = {nullptr, nullptr};   // split-K workspaces of the side-stream branches (they run concurrently)
     cudaStream_t side[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
-    // The fused GroupNorm's grid barrier needs every block of the kernel resident at once. 148 SMs hold >= 592 such blocks, so at
-    // most FOUR fused GroupNorms (<= 128 blocks each) may run concurrently on a GPU: the main streams of the first four lanes.
-    // Further lanes and the ControlNet branch (side stream 2) use the two-kernel GroupNorm.
     int lane_index = 0, lanes_created = 1;
     Engine* root = nullptr;   // the engine owning the weights (null for that engine itself)
     uint8_t *d_y = nullptr, *d_u = nullptr, *d_v = nullptr, *d_rgb_in = nullptr;       // inputs
@@ -147,8 +145,8 @@ struct Engine {
     int autotune = 1;
     struct Tuned { int bn, splits, occ, kbs, halo; float us; };
     std::unordered_map<std::string, Tuned> tuned;
+    long tune_misses = 0;   // shapes that had to be timed on the device (not found in a loaded tuning table)
     void* flush_buf = nullptr; size_t flush_bytes = 0;
-    unsigned int* gn_sync = nullptr;   // grid-barrier state for the fused GroupNorm kernel (never reused memory)
     // ControlNet: canny/Sobel-conditioned residuals added to the UNet skips every step
     // GPU center-crop + Lanczos resize of arbitrary-size input frames
     struct Resize { int in_w = 0, in_h = 0, x0 = 0, y0 = 0, cw = 0, ch = 0, hks = 0, vks = 0;
@@ -164,6 +162,10 @@ struct Engine {
     bool cn_enabled = false;
     float* cn_scales = nullptr;        // device [13]: logspace(-1,0,13) * conditioning scale (guess mode)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // device-side wait-timeout words of the two tensor-core translation units, copied behind every frame into pinned host
+    // memory so the production entry points can report a fault without an extra synchronisation
+    const unsigned int* fault_dev[2] = {nullptr, nullptr};
+    unsigned int* fault_host = nullptr;
     long launches_per_frame_yuv = 0;
     std::string err;
 };
@@ -317,7 +319,7 @@ static int load_weight(Engine* e, const std::string& name, const float* host, co
 // ------------------------------------------------------------------------------------------------ GEMM autotuner
 static int time_gemm(Engine* e, const GemmOp& op, float* us) {
     float best = 1e30f;
-    static const int reps = getenv("VSD_TUNE_REPS") ? atoi(getenv("VSD_TUNE_REPS")) : 2;
+    static const int reps = getenv("VSD_TUNE_REPS") ? atoi(getenv("VSD_TUNE_REPS")) : 3;
     for (int rep = 0; rep < reps; ++rep) {
         VSD_CHECK_CUDA(cudaMemsetAsync(e->flush_buf, rep, e->flush_bytes, e->stream));   // evict L2: weights come from HBM
         VSD_CHECK_CUDA(cudaEventRecord(e->ev0, e->stream));
@@ -485,8 +487,8 @@ struct Builder {
         if (rc) return;
         GemmOp op;
         int fbn = 0, fsp = 0, focc = 0, fkbs = 0, fhalo = 0;
+        char key[160];
         if (e->autotune) {
-            char key[160];
             snprintf(key, sizeof(key), "%dx%dx%dx%d|t%d|n%d|a%d|f%d|r%d", a.NB, a.H, a.W, a.C, taps + 100 * (a.stride - 1) + 1000 * (1 - a.pad),
                      N, act, out_f32, res ? 1 : 0);
             auto it = e->tuned.find(key);
@@ -495,11 +497,25 @@ struct Builder {
                 int r = tune_gemm(e, a, taps, wt, N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act, &t);
                 if (r) { rc = r; fail = get_error(); return; }
                 it = e->tuned.emplace(key, t).first;
+                ++e->tune_misses;
             }
             fbn = it->second.bn; fsp = it->second.splits; focc = it->second.occ; fkbs = it->second.kbs; fhalo = it->second.halo;
         }
         int r = build_gemm_op(&op, a, taps, wt, N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act,
                               splitk_workspace(), e->splitk_bytes, fbn, fsp, focc, fkbs, fhalo);
+        if (r && e->autotune) {
+            // a table entry written by another build of the kernels may no longer be a valid configuration: tune this shape now
+            snprintf(key, sizeof(key), "%dx%dx%dx%d|t%d|n%d|a%d|f%d|r%d", a.NB, a.H, a.W, a.C, taps + 100 * (a.stride - 1) + 1000 * (1 - a.pad),
+                     N, act, out_f32, res ? 1 : 0);
+            Engine::Tuned t;
+            r = tune_gemm(e, a, taps, wt, N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act, &t);
+            if (!r) {
+                e->tuned[key] = t;
+                ++e->tune_misses;
+                r = build_gemm_op(&op, a, taps, wt, N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act, splitk_workspace(),
+                                  e->splitk_bytes, t.bn, t.splits, t.occ, t.kbs, t.halo);
+            }
+        }
         if (r) { rc = r; fail = get_error(); return; }
         op.p.out_scale = out_scale;
         const size_t first = out->size();
@@ -520,10 +536,8 @@ struct Builder {
         float* ws = alloc_f32((size_t)groupnorm_ws_floats(x.nb, x.h * x.w, x.c, 32));
         if (rc) return;
         const View xi = x, oo = o;
-        unsigned int* sync = (cur_stream == 2 || e->lane_index >= 4) ? nullptr : e->gn_sync;
-        const int shared_gpu = ((e->root ? e->root : e)->lanes_created > 1) ? 1 : 0;   // other lanes may run GroupNorms too
         out->push_back(mk([=](cudaStream_t st) {
-            return launch_groupnorm(xi.p, xi.ld, oo.p, oo.ld, g, b, xi.nb, xi.h * xi.w, xi.c, 32, eps, silu, ws, sync, st, shared_gpu);
+            return launch_groupnorm(xi.p, xi.ld, oo.p, oo.ld, g, b, xi.nb, xi.h * xi.w, xi.c, 32, eps, silu, ws, st);
         }, "gn"));
     }
     void layernorm(const View& x, const std::string& name, const View& o) {
@@ -1373,7 +1387,7 @@ static int configure(Engine* e, int nb, int H, int W) {
     e->init_latents = (float*)A.alloc(lpx * 16); e->noisy = (float*)A.alloc(lpx * 16);
     e->init_noise = (float*)A.alloc(lpx * 16);
     e->vae_noise = (float*)A.alloc(lpx * 16);   // zero-initialised arena: sample() = mean until vsd_set_vae_noise
-    e->step_noise = (float*)A.alloc(lpx * 16 * 16);  // up to 16 steps
+    e->step_noise = (float*)A.alloc(lpx * 16 * kMaxSteps);  // LCM_ORIGIN_STEPS = 50 bounds the timestep table (lcm_controlnet.py:905-938)
     e->image = (float*)A.alloc(px * 16);
     e->ctx_bf16 = (bf16*)A.alloc((size_t)nb * 128 * 768 * 2);
     e->t_emb_in = (float*)A.alloc(320 * 4); e->t_h = (float*)A.alloc(1280 * 4); e->t_emb = (float*)A.alloc(1280 * 4);
@@ -1401,7 +1415,7 @@ static int configure(Engine* e, int nb, int H, int W) {
 static int set_schedule(Engine* e, int steps, const int* timesteps, const float* scalars /*steps x 6*/, float an_a,
                         float an_b, const float* w_emb256, int has_step_noise) {
     ENG_REQUIRE(e->configured, "configure() first");
-    ENG_REQUIRE(steps >= 1 && steps <= 16, "1..16 steps");
+    ENG_REQUIRE(steps >= 1 && steps <= kMaxSteps, "1..50 steps");
     VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
     free_graphs(e);
     e->arena.release(e->arena_static_mark);
@@ -1680,6 +1694,16 @@ static int capture(Engine* e, bool yuv, cudaGraphExec_t* exec) {
     return 0;
 }
 
+// Production entry points: queue the device-side fault words behind the frame (pinned host destination), synchronise,
+// and fail loudly when a bounded wait timed out somewhere in the frame (the frame's pixels are garbage then).
+static int finish_frame(Engine* e) {
+    for (int i = 0; i < 2; ++i)
+        VSD_CHECK_CUDA(cudaMemcpyAsync(e->fault_host + i, e->fault_dev[i], sizeof(unsigned int), cudaMemcpyDeviceToHost, e->stream));
+    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    if (e->fault_host[0] | e->fault_host[1]) return vsd_check_pipeline_fault();   // reads, reports and clears
+    return 0;
+}
+
 static int run_frame(Engine* e, bool yuv) {
     ENG_REQUIRE(e->schedule_set, "set_schedule() first");
     ENG_REQUIRE(e->context_set, "set_context() first");
@@ -1705,11 +1729,6 @@ vsd_ctx* vsd_create(int device) {
     if (ensure_init()) return nullptr;
     vsd_ctx* c = new vsd_ctx();
     c->e.device = device;
-    if (cudaMalloc(&c->e.gn_sync, 64) != cudaSuccess || cudaMemset(c->e.gn_sync, 0, 64) != cudaSuccess) {
-        set_error("cudaMalloc failed");
-        delete c;
-        return nullptr;
-    }
     bool ok = cudaStreamCreateWithFlags(&c->e.stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int k = 0; k < 2 && ok; ++k)
         ok = cudaStreamCreateWithFlags(&c->e.side[k], cudaStreamNonBlocking) == cudaSuccess &&
@@ -1720,6 +1739,15 @@ vsd_ctx* vsd_create(int device) {
         delete c;
         return nullptr;
     }
+    c->e.fault_dev[0] = trap_code_addr_gemm();
+    c->e.fault_dev[1] = trap_code_addr_attn();
+    if (!c->e.fault_dev[0] || !c->e.fault_dev[1] ||
+        cudaHostAlloc(reinterpret_cast<void**>(&c->e.fault_host), 4 * sizeof(unsigned int), cudaHostAllocDefault) != cudaSuccess) {
+        set_error("fault-word setup failed");
+        vsd_destroy(c);
+        return nullptr;
+    }
+    memset(c->e.fault_host, 0, 4 * sizeof(unsigned int));
     return c;
 }
 
@@ -1734,11 +1762,6 @@ vsd_ctx* vsd_create_lane(vsd_ctx* parent) {
     c->e.owns_weights = false;
     c->e.lane_index = parent->e.lanes_created++;
     c->e.root = &parent->e;
-    if (parent->e.schedule_set) {   // the parent's plan was built for an engine alone on the GPU (GroupNorm variant): rebuild it
-        cudaStreamSynchronize(parent->e.stream);
-        free_graphs(&parent->e);
-        parent->e.schedule_set = false;
-    }
     c->e.tuned = parent->e.tuned;
     c->e.autotune = parent->e.autotune;
     return c;
@@ -1763,10 +1786,10 @@ void vsd_destroy(vsd_ctx* c) {
     free_resize(&c->e);
     free_clip(&c->e);
     for (auto& kv : c->e.derived) cudaFree(kv.second);
-    if (c->e.gn_sync) cudaFree(c->e.gn_sync);
     if (c->e.cn_scales) cudaFree(c->e.cn_scales);
     if (c->e.ev0) cudaEventDestroy(c->e.ev0);
     if (c->e.ev1) cudaEventDestroy(c->e.ev1);
+    if (c->e.fault_host) cudaFreeHost(c->e.fault_host);
     cudaStreamDestroy(c->e.stream);
     delete c;
 }
@@ -1950,8 +1973,7 @@ int vsd_infer_yuv420(vsd_ctx* c, const uint8_t* y, const uint8_t* u, const uint8
     if (rc) return rc;
     rc = vsd_download_yuv420(c, out_y, out_u, out_v);
     if (rc) return rc;
-    VSD_CHECK_CUDA(cudaStreamSynchronize(c->e.stream));
-    return 0;
+    return finish_frame(&c->e);
 }
 
 int vsd_infer_rgb(vsd_ctx* c, const uint8_t* rgb_in, uint8_t* rgb_out) {
@@ -1963,8 +1985,7 @@ int vsd_infer_rgb(vsd_ctx* c, const uint8_t* rgb_in, uint8_t* rgb_out) {
     int rc = run_frame(e, false);
     if (rc) return rc;
     VSD_CHECK_CUDA(cudaMemcpyAsync(rgb_out, e->d_rgb_out, px * 3, cudaMemcpyDeviceToHost, e->stream));
-    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
-    return 0;
+    return finish_frame(e);
 }
 
 int vsd_set_resize(vsd_ctx* c, int in_w, int in_h, int x0, int y0, int cw, int ch, const int* h_bounds, const int* h_coeffs,
@@ -2006,8 +2027,7 @@ int vsd_infer_rgb_resized(vsd_ctx* c, const uint8_t* rgb_src, uint8_t* rgb_out) 
     if (rc) return rc;
     const size_t px = (size_t)e->NB * e->H * e->W;
     VSD_CHECK_CUDA(cudaMemcpyAsync(rgb_out, e->d_rgb_out, px * 3, cudaMemcpyDeviceToHost, e->stream));
-    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
-    return 0;
+    return finish_frame(e);
 }
 
 /* Same with YUV420P planes at the source geometry ([batch][in_h][in_w], [batch][in_h/2][in_w/2] x2): colour conversion at the
@@ -2031,8 +2051,7 @@ int vsd_infer_yuv420_resized(vsd_ctx* c, const uint8_t* y, const uint8_t* u, con
     if (rc) return rc;
     rc = vsd_download_yuv420(c, out_y, out_u, out_v);
     if (rc) return rc;
-    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
-    return 0;
+    return finish_frame(e);
 }
 
 /* bring-up / tests: the resized working-size input frame(s) of the last vsd_infer_rgb_resized call */
@@ -2053,6 +2072,9 @@ long vsd_launches_per_frame(vsd_ctx* c, int yuv) {
     // before capture: plan entries (a lower bound: GroupNorm and split-K entries launch two kernels each)
     return (long)e.plan_core.size() + (long)e.plan_post.size() + (yuv ? (long)e.plan_pre_yuv.size() : 0);
 }
+
+/* Number of GEMM shapes the autotuner had to time on the device since vsd_create (0 when a loaded table covered the plan). */
+long vsd_tuning_misses(vsd_ctx* c) { return c ? c->e.tune_misses : -1; }
 
 long vsd_arena_peak_bytes(vsd_ctx* c) { return c ? (long)c->e.arena.peak : -1; }
 

@@ -160,11 +160,11 @@ int build_attn_op(AttnOp* op, const bf16* q, int ldq, const bf16* k, int ldk, co
                   int vt_cols_per_img, int vt_rows);
 int launch_attn_op(const AttnOp& op, cudaStream_t st);
 int attn_init();
+int bw_init();   // per-device function attributes of the bandwidth kernels
 
 // ---- bandwidth kernels ---------------------------------------------------------------------------
 int launch_groupnorm(const bf16* x, int ldx, bf16* y, int ldy, const float* gamma, const float* beta, int NB, int HW,
-                     int C, int groups, float eps, int silu, float* partial_ws, unsigned int* sync /*2 zeroed words or null*/,
-                     cudaStream_t st, int shared_gpu = 1);
+                     int C, int groups, float eps, int silu, float* partial_ws /* two-kernel fallback only */, cudaStream_t st);
 int groupnorm_ws_floats(int NB, int HW, int C, int groups);
 int launch_layernorm(const bf16* x, int ldx, bf16* y, int ldy, const float* gamma, const float* beta, int rows, int C,
                      float eps, cudaStream_t st);
@@ -207,7 +207,8 @@ int ensure_init();
 
 unsigned int read_trap_code_gemm();
 unsigned int read_trap_code_attn();
-unsigned int read_trap_code_bw();
-extern long long* g_gn_dbg;   // bring-up: phase stamps of the fused GroupNorm kernel
+// device addresses of the same words on the current device (for asynchronous copies behind a frame)
+const unsigned int* trap_code_addr_gemm();
+const unsigned int* trap_code_addr_attn();
 
 }  // namespace vsd

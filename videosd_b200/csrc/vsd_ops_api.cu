@@ -43,6 +43,8 @@ int ensure_init() {
     if (rc) return rc;
     rc = attn_init();
     if (rc) return rc;
+    rc = bw_init();
+    if (rc) return rc;
     g_inited_devices.push_back(dev);
     return 0;
 }
@@ -72,10 +74,9 @@ int vsd_abi_version(void) { return VSD_ABI_VERSION; }
 int vsd_check_pipeline_fault(void) {
     unsigned int a = read_trap_code_gemm();
     unsigned int b = read_trap_code_attn();
-    unsigned int c = read_trap_code_bw();
-    if (a || b || c) {
+    if (a || b) {
         char buf[200];
-        snprintf(buf, sizeof(buf), "device-side wait timed out: gemm=0x%08x attn=0x%08x groupnorm-barrier=0x%08x", a, b, c);
+        snprintf(buf, sizeof(buf), "device-side wait timed out: gemm=0x%08x attn=0x%08x", a, b);
         set_error(buf);
         return -5;
     }
@@ -139,17 +140,9 @@ int vsd_op_groupnorm(const void* x, int ldx, void* y, int ldy, const float* gamm
     if (rc) return rc;
     rc = ensure_ws((size_t)groupnorm_ws_floats(nb, hw, c, groups) * 4 + 1024);
     if (rc) return rc;
-    static unsigned int* sync = nullptr;   // grid-barrier state of the fused kernel (zeroed once, self-resetting)
-    if (!sync) {
-        VSD_CHECK_CUDA(cudaMalloc(&sync, 64));
-        VSD_CHECK_CUDA(cudaMemset(sync, 0, 64));
-    }
     return launch_groupnorm(reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<bf16*>(y), ldy, gamma, beta, nb, hw,
-                            c, groups, eps, silu, g_ws, sync, reinterpret_cast<cudaStream_t>(stream));
+                            c, groups, eps, silu, g_ws, reinterpret_cast<cudaStream_t>(stream));
 }
-
-/* bring-up: route the fused GroupNorm's phase stamps (clock64 x6) to a device buffer (NULL disables) */
-int vsd_debug_set_gn_stamps(long long* dev_buf) { vsd::g_gn_dbg = dev_buf; return 0; }
 
 int vsd_op_layernorm(const void* x, int ldx, void* y, int ldy, const float* gamma, const float* beta, int rows, int c,
                      float eps, void* stream) {

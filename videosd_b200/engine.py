@@ -92,12 +92,16 @@ class Engine:
         return ts
 
     def set_controlnet(self, enabled, scale=1.0):
-        """Enable the canny ControlNet branch with conditioning scale `scale` (guess mode, as the reference calls it)."""
-        sc = np.ascontiguousarray((torch.logspace(-1, 0, 13) * float(scale)).numpy().astype(np.float32))
-        check(self._L.vsd_set_controlnet(self._ctx, c_int(1 if enabled else 0), _fptr(sc)), "vsd_set_controlnet")
-        if bool(enabled) != getattr(self, "_cn_enabled", False):
-            self._cn_enabled = bool(enabled)
-            self._sched_key = None      # the launch plan must be rebuilt
+        for e in self.lanes:
+            e.set_controlnet(enabled, scale)
+
+    def set_vae(self, kind):
+        for e in self.lanes:
+            e.set_vae(kind)
+
+    def set_vae_noise(self, noise_nchw):
+        for e in self.lanes:
+            e.set_vae_noise(noise_nchw)
 
     def set_context(self, slot, context):
         """context: (77, 768) float tensor/array (CLIP last_hidden_state for the prompt)."""
@@ -271,12 +275,16 @@ class LanePool:
         return ts
 
     def set_controlnet(self, enabled, scale=1.0):
-        """Enable the canny ControlNet branch with conditioning scale `scale` (guess mode, as the reference calls it)."""
-        sc = np.ascontiguousarray((torch.logspace(-1, 0, 13) * float(scale)).numpy().astype(np.float32))
-        check(self._L.vsd_set_controlnet(self._ctx, c_int(1 if enabled else 0), _fptr(sc)), "vsd_set_controlnet")
-        if bool(enabled) != getattr(self, "_cn_enabled", False):
-            self._cn_enabled = bool(enabled)
-            self._sched_key = None      # the launch plan must be rebuilt
+        for e in self.lanes:
+            e.set_controlnet(enabled, scale)
+
+    def set_vae(self, kind):
+        for e in self.lanes:
+            e.set_vae(kind)
+
+    def set_vae_noise(self, noise_nchw):
+        for e in self.lanes:
+            e.set_vae_noise(noise_nchw)
 
     def set_context(self, slot, context):
         for e in self.lanes:

@@ -169,11 +169,13 @@ class VideoSDPipeline:
             else:
                 # reference on a CUDA device: torch.manual_seed(seed) seeds the device Philox that draws the init
                 # noise in the model dtype (lcm_controlnet.py:331); step noise always comes from the re-armed CPU RNG
-                from .scheduler import reference_cpu_noise
                 g = torch.Generator(device=f"cuda:{self.device}").manual_seed(int(seed))
                 init = torch.randn((batch, 4, h8, w8), generator=g, device=f"cuda:{self.device}", dtype=torch.float16)
-                _, st = reference_cpu_noise(batch, h8, w8, len(ts))
-                # the CPU stream also yields the init draw first; step noises follow it, as in the reference
+                # On a CUDA device the init noise never touches the CPU RNG (randn_tensor(generator=None, device=cuda),
+                # lcm_controlnet.py:503-513, :331), so step noise i is draw i of the re-armed CPU global generator
+                # (videopipeline.py:126; scheduler.step :1033) -- no draw is skipped.
+                gc = torch.Generator()
+                st = [torch.randn((batch, 4, h8, w8), generator=gc) for _ in range(len(ts))] if len(ts) > 1 else []
                 if self.vae_kind == "kl":
                     # latent_dist.sample() draws from the same device generator BEFORE the init noise (lcm_controlnet.py:298-331)
                     g = torch.Generator(device=f"cuda:{self.device}").manual_seed(int(seed))
