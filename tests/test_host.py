@@ -169,7 +169,7 @@ def test_clip_tokenizer_matches_transformers_on_a_synthetic_vocabulary(tmp_path)
     for text in ["pixar, cg", "The cat's on   the 12 mat!!", "a photo of a caf\u00e9 \u2014 na\u00efve", "x" * 200, "",
                  "hello_world __ it's 3.14%"]:
         assert mine(text) == hf(text, padding="max_length", max_length=77, truncation=True).input_ids, text
-    h = T.load(None)                       # stand-in without a vocabulary: framing and determinism
+    h = T.load(None, allow_hash=True)                       # stand-in without a vocabulary: framing and determinism
     ids = h("pixar, cg")
     assert len(ids) == 77 and ids[0] == 49406 and ids[4:] == [49407] * 73 and ids == h("Pixar,  CG")
 
@@ -230,3 +230,22 @@ def test_session_router_pins_and_batches():
     assert r.assign("new") == 0
     all_streams = sorted(s for k in range(4) for s in shard_streams(32, 4, k))
     assert all_streams == list(range(32))
+
+
+def test_safetensors_directory_loader(tmp_path):
+    """weights.load_safetensors_dir: every *.safetensors file of a diffusers component directory, as fp32 tensors."""
+    from safetensors.torch import save_file
+
+    from videosd_b200 import weights
+
+    d = tmp_path / "vae"
+    d.mkdir()
+    sd = weights.random_state_dict(weights.taesd_param_shapes(), 3)
+    keys = sorted(sd)
+    save_file({k: sd[k].to(torch.float16) for k in keys[:40]}, str(d / "a.safetensors"))
+    save_file({k: sd[k] for k in keys[40:]}, str(d / "b.safetensors"))
+    got = weights.load_safetensors_dir(str(d))
+    assert sorted(got) == keys and all(v.dtype == torch.float32 for v in got.values())
+    assert torch.equal(got[keys[-1]], sd[keys[-1]]) and torch.equal(got[keys[0]], sd[keys[0]].to(torch.float16).float())
+    with pytest.raises(FileNotFoundError):
+        weights.load_safetensors_dir(str(tmp_path))

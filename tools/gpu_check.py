@@ -73,7 +73,7 @@ def ref_conv(x_nhwc, w_ohwi, taps, bias=None, rowvec=None, residual=None):
 
 
 def gemm_case(name, nb, h, w, c, n, taps, bias=False, rowvec=False, residual=False, out_f32=False, block_n=0, splits=0,
-              tol=1e-2, halo=False, pair=False, persist=False, relu=False):
+              tol=1e-2, halo=False, pair=False, persist=False, relu=False, cluster=None):
     def fn():
         x = randn((nb, h, w, c), 1).bfloat16()
         wt = randn((n, taps * c), 2, scale=(taps * c) ** -0.5).bfloat16()
@@ -81,7 +81,7 @@ def gemm_case(name, nb, h, w, c, n, taps, bias=False, rowvec=False, residual=Fal
         rv = randn((nb, n), 4) if rowvec else None
         res = randn((nb, h, w, n), 5).bfloat16() if residual else None
         y = ops.conv_gemm(x, wt, taps, bias=b, rowvec=rv, residual=res, out_f32=out_f32, block_n=block_n, splits=splits,
-                          halo=halo, pair=pair, persist=persist, act=16 if relu else 0)
+                          halo=halo, pair=pair, persist=persist, act=16 if relu else 0, cluster=cluster)
         torch.cuda.synchronize()
         ref = ref_conv(x, wt, taps, b, rv, res)
         if relu:
@@ -136,6 +136,21 @@ def check_gemm():
     gemm_case("pair_halo_64x64_320_320", 1, 64, 64, 320, 320, 9, bias=True, residual=True, halo=True, pair=True, block_n=160)
     gemm_case("pair_halo_odd_45x80_64", 1, 45, 80, 64, 64, 9, bias=True, halo=True, pair=True)
     gemm_case("pair_b4_96x96_320", 4, 96, 96, 320, 320, 9, bias=True, pair=True, block_n=256)
+    # split-K reduced inside a thread-block cluster (accumulators exchanged through distributed shared memory), and the same
+    # shapes through the separate reduce kernel
+    for ck in (True, False):
+        t = "cluster" if ck else "sepreduce"
+        gemm_case(f"{t}_conv_16x16_1280_split4", 1, 16, 16, 1280, 1280, 9, bias=True, rowvec=True, block_n=96, splits=4, cluster=ck)
+        gemm_case(f"{t}_conv_16x16_1280_split6_res", 1, 16, 16, 1280, 1280, 9, bias=True, residual=True, block_n=128, splits=6, cluster=ck)
+        gemm_case(f"{t}_conv_8x8_1280_split8", 1, 8, 8, 1280, 1280, 9, bias=True, residual=True, block_n=96, splits=8, cluster=ck)
+        gemm_case(f"{t}_conv_8x8_2560_split7_bn160", 1, 8, 8, 2560, 1280, 9, bias=True, block_n=160, splits=7, cluster=ck)
+        gemm_case(f"{t}_lin_256x1280_split3", 1, 1, 256, 1280, 1280, 1, bias=True, residual=True, block_n=64, splits=3, cluster=ck)
+        gemm_case(f"{t}_lin_64x5120_split8_bn32", 1, 1, 64, 5120, 1280, 1, bias=True, residual=True, block_n=32, splits=8, cluster=ck)
+        gemm_case(f"{t}_lin_1024x2560_split2_bn256", 1, 1, 1024, 2560, 640, 1, bias=True, block_n=256, splits=2, cluster=ck)
+        gemm_case(f"{t}_halo_32x32_640_split3", 1, 32, 32, 640, 640, 9, bias=True, halo=True, block_n=128, splits=3, cluster=ck)
+        gemm_case(f"{t}_odd_23x40_640_split5_relu", 1, 23, 40, 640, 640, 9, bias=True, relu=True, block_n=96, splits=5, cluster=ck)
+        gemm_case(f"{t}_b2_12x20_1280_split4_f32", 2, 12, 20, 1280, 320, 9, bias=True, out_f32=True, block_n=64, splits=4, cluster=ck)
+        gemm_case(f"{t}_n4_fp32out_split4", 1, 64, 64, 320, 4, 9, bias=True, out_f32=True, block_n=32, splits=4, cluster=ck)
     # persistent weight-stationary 3x3 convolution (TAESD shapes): one CTA per SM walks the 8x16 tiles
     gemm_case("persist_64x64_64_64", 1, 64, 64, 64, 64, 9, bias=True, persist=True)
     gemm_case("persist_512x512_64_64_res_relu", 1, 512, 512, 64, 64, 9, bias=True, residual=True, relu=True, persist=True)

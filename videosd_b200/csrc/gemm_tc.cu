@@ -475,7 +475,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         tc_fence_after_sync();
         if (threadIdx.x == 64) VSD_STAMP(4);
         const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
-        if (kEpi == 2 || kEpi == 3) {
+        if (kEpi == 3) {
+            // split-K inside a cluster: nothing to do here, the accumulator is sent to its reducer after the cluster barrier
+        } else if (kEpi == 2) {
             // split-K partials: [32 rows][128 B] fp32 chunks, 128-byte swizzle, stored with one 5-D box per warp and chunk
             for (int c = 0; c < p.block_n; c += 32) {
                 uint32_t u[32];
@@ -494,14 +496,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     tma_store_commit();
                 }
             }
-            if (kEpi == 3) {
-                // the cluster peers read these partials right after the cluster barrier: wait for the writes themselves
-                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-                asm volatile("fence.proxy.async;" ::: "memory");
-                __threadfence();
-            } else {
-                tma_store_wait_all();
-            }
+            tma_store_wait_all();
         } else if (kEpi == 1 && p.act == ACT_GEGLU) {
             const int half = p.block_n >> 1;
             const int ocol0 = col0 >> 1;
@@ -667,55 +662,66 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
     }
     if (kEpi == 3) {
-        // Split-K inside a thread-block cluster (1,1,splits): the CTAs are co-scheduled, so they can wait for each other.
-        // Every CTA reduces a band of the tile's rows from the L2-resident partials (split order => deterministic),
-        // applies the epilogue and stores coalesced rows. No second kernel.
+        // Split-K inside a thread-block cluster (1,1,splits): the CTAs are co-scheduled, so they can exchange their fp32
+        // accumulators through DISTRIBUTED SHARED MEMORY instead of a workspace in L2 + a second kernel. CTA z reduces the row
+        // band [z * rows_per, (z + 1) * rows_per) of the tile: every CTA pushes that band of its accumulator into CTA z's
+        // (idle) operand ring with st.shared::cluster, one cluster barrier later CTA z sums the `splits` copies in split order
+        // (=> deterministic), applies the epilogue and stores coalesced rows.
+        const int rows_per = (kBlockM + p.splits - 1) / p.splits;
+        float* recv = reinterpret_cast<float*>(smem);          // [splits][rows_per][block_n] fp32, aliases the operand ring
+        // The ring of EVERY CTA must be idle before anyone writes into it: this CTA's last MMAs have retired (tmem_full_bar;
+        // its TMA loads completed before those MMAs could be issued).
+        if (warp == 1) { mbar_wait(tmem_full_bar, 0, 8); tc_fence_after_sync(); }
         if (threadIdx.x == 64) VSD_STAMP(8);
         cluster_sync_all();
+        if (warp >= 2) {
+            const int q = warp & 3;
+            const int r = q * 32 + lane;                       // tile row held by this thread (TMEM lane)
+            const int dst = r / rows_per, lr = r - dst * rows_per;
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
+            const uint32_t remote = dsmem_addr(smem_u32(recv + ((size_t)split * rows_per + lr) * p.block_n), (uint32_t)dst);
+            for (int c = 0; c < p.block_n; c += 32) {
+                uint32_t u[32];
+                tmem_ld32(tbase + c, u);
+                tmem_ld_wait();
+                // rows are block_n * 4 bytes apart (a multiple of 128): XOR the 16-byte chunk index with the row so that the
+                // eight lanes of a store phase hit different banks of the receiver's shared memory
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};"
+                                 ::"r"(remote + ((uint32_t)(((c >> 2) + j) ^ (lr & 7)) << 4)),
+                                 "r"(u[4 * j]), "r"(u[4 * j + 1]), "r"(u[4 * j + 2]), "r"(u[4 * j + 3]) : "memory");
+            }
+        }
+        cluster_sync_all();                                    // release / acquire: every band has arrived
         if (threadIdx.x == 64) VSD_STAMP(9);
         if (warp >= 2) {
-            // Row band of this CTA; a warp walks rows, its lanes walk 4-column groups (coalesced 16-byte loads, 8-byte stores).
-            // No integer division: tile extents are powers of two (lbw / lbh), narrow tiles pack several rows per warp.
+            // A warp walks rows of this CTA's band, its lanes walk 4-column groups (conflict-free 16-byte smem reads, coalesced
+            // global stores). No integer division: tile extents are powers of two (lbw / lbh).
             const int g4 = p.block_n >> 2;
-            const int rows_per = (kBlockM + p.splits - 1) / p.splits;
             const int r_begin = split * rows_per;
             const int r_end = min(kBlockM, r_begin + rows_per);
             const int lg = (g4 <= 8) ? 3 : ((g4 <= 16) ? 4 : 5);          // lanes per row = 1 << lg (>= g4 when g4 <= 32)
             const int lanes_row = 1 << lg;
             const int rows_warp = 32 >> lg;                               // rows one warp covers per step
             const int lane_r = lane >> lg, lane_g = lane & (lanes_row - 1);
-            const long rows_total = (long)p.NB * p.H * p.W;
-            const size_t split_stride4 = (size_t)(rows_total * p.N) >> 2;  // float4 units (N % 4 == 0)
             const int wq = warp - 2;
+            const size_t src_stride4 = ((size_t)rows_per * p.block_n) >> 2;   // float4 units between two splits' copies
             for (int g0 = lane_g; g0 < g4; g0 += lanes_row) {
                 const int col = col0 + g0 * 4;
-                for (int rb = r_begin + wq * rows_warp + lane_r; rb < r_end; rb += 8 * rows_warp) {   // two rows in flight
-                    float v[2][4];
-                    long grow[2]; bool ok[2];
-                    const float4* src[2];
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const int r = rb + k * 4 * rows_warp;
-                        const int n_img = n0 + (r >> (p.lbw + p.lbh)), hh = h0 + ((r >> p.lbw) & (p.BH - 1)), ww = w0 + (r & (p.BW - 1));
-                        ok[k] = (r < r_end) && (n_img < p.NB) && (hh < p.H) && (ww < p.W) && (col < p.N);
-                        grow[k] = ((long)n_img * p.H + hh) * p.W + ww;
-                        src[k] = reinterpret_cast<const float4*>(ok[k] ? p.partial + grow[k] * p.N + col : p.partial);
-                        v[k][0] = v[k][1] = v[k][2] = v[k][3] = 0.f;
+                for (int r = r_begin + wq * rows_warp + lane_r; r < r_end; r += 4 * rows_warp) {
+                    const int n_img = n0 + (r >> (p.lbw + p.lbh)), hh = h0 + ((r >> p.lbw) & (p.BH - 1)), ww = w0 + (r & (p.BW - 1));
+                    if (!((n_img < p.NB) && (hh < p.H) && (ww < p.W) && (col < p.N))) continue;
+                    const long grow = ((long)n_img * p.H + hh) * p.W + ww;
+                    const int lr = r - r_begin;
+                    const float4* src = reinterpret_cast<const float4*>(recv + (size_t)lr * p.block_n) + (g0 ^ (lr & 7));
+                    float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+                    for (int z = 0; z < p.splits; ++z) {
+                        const float4 t = src[(size_t)z * src_stride4];
+                        v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
                     }
-                    float4 x[2][8];   // all loads are issued before the first add (splits <= 8)
-#pragma unroll
-                    for (int z = 0; z < 8; ++z)
-#pragma unroll
-                        for (int k = 0; k < 2; ++k)
-                            if (z < p.splits) x[k][z] = __ldcg(src[k] + (size_t)z * split_stride4);
-#pragma unroll
-                    for (int z = 0; z < 8; ++z)
-#pragma unroll
-                        for (int k = 0; k < 2; ++k)
-                            if (z < p.splits) { v[k][0] += x[k][z].x; v[k][1] += x[k][z].y; v[k][2] += x[k][z].z; v[k][3] += x[k][z].w; }
-#pragma unroll
-                    for (int k = 0; k < 2; ++k)
-                        if (ok[k]) splitk_finish4(p, v[k], grow[k], col);
+                    splitk_finish4(p, v, grow, col);
                 }
             }
         }
@@ -1174,13 +1180,14 @@ int build_gemm_op(GemmOp* op, const ActView& ain, int taps, const bf16* wt, int 
     const int n_out = (act == ACT_GEGLU) ? N / 2 : N;
     const int bn_out = (act == ACT_GEGLU) ? bn / 2 : bn;
     int tma_out = 0, tma_res = 0, cluster_k = 0;
-    // Measured on B200 (profiles/r01_cluster_splitk.md): the in-cluster reduce reads its 64 KB band at ~11 B/clk/SM and loses
-    // to the separate, fully parallel reduce kernel (9.9 vs 7.7 us for 256x1280x1280, 4 splits) => opt-in only.
-    static const bool cluster_ok = getenv("VSD_CLUSTER_SPLITK") && atoi(getenv("VSD_CLUSTER_SPLITK")) != 0;
+    // Split-K inside a thread-block cluster (1,1,splits): accumulators are exchanged through distributed shared memory and
+    // reduced by the cluster itself -- no fp32 partials through L2, no second kernel (conv_gemm_kernel<3>). Mode word bit 3
+    // requests it, bit 4 forbids it (the autotuner times both); without either it is used whenever it applies.
+    static const bool cluster_default = !(getenv("VSD_CLUSTER_SPLITK") && atoi(getenv("VSD_CLUSTER_SPLITK")) == 0);
+    const bool want_cluster = (force_halo > 0 && (force_halo & 24)) ? ((force_halo & 8) != 0) : cluster_default;
     const bool out_tma_ok = !out_f32 && (ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (bn_out % 32) == 0;
-    if (splits > 1 && splits <= 8 && cluster_ok && !pair && tma_epi && (N % 4) == 0 && (reinterpret_cast<uintptr_t>(partial_ws) & 15) == 0) {
-        cluster_k = 1;     // partials through TMA into the (L2-resident) workspace, reduced by the cluster itself
-        tma_out = 2;
+    if (splits > 1 && splits <= 8 && want_cluster && !pair && (N % 4) == 0) {
+        cluster_k = 1;
     } else if (tma_epi) {
         if (splits > 1) {
             if ((N % 4) == 0 && (reinterpret_cast<uintptr_t>(partial_ws) & 15) == 0) tma_out = 2;
@@ -1190,6 +1197,7 @@ int build_gemm_op(GemmOp* op, const ActView& ain, int taps, const bf16* wt, int 
         }
     }
     int stag_bytes = (tma_out == 2) ? bn * 512 : (tma_out == 1 ? bn_out * 256 : 0);   // 128 rows x (4 | 2) bytes per column
+    if (cluster_k) stag_bytes = splits * ((kBlockM + splits - 1) / splits) * bn * 4;   // receive buffer: `splits` copies of this CTA's row band
 
     // Tiles up to 160 columns run two CTAs per SM (one CTA's epilogue overlaps the other's main loop);
     // wider tiles take the whole SM with a deeper ring.
@@ -1213,7 +1221,8 @@ int build_gemm_op(GemmOp* op, const ActView& ain, int taps, const bf16* wt, int 
         stage_total = halo ? (kHaloABytes + 3 * b_tile) : k2 * stage_bytes;
         stages = ring_budget / stage_total;
         if (tma_res && stages < 2) { tma_res = 0; continue; }   // no room: read the residual straight from global memory
-        if (tma_out && !tma_res && stag_bytes > smem_budget - 3072) { tma_out = 0; stag_bytes = 0; cluster_k = 0; continue; }
+        if (cluster_k && stag_bytes > smem_budget - 3072) { cluster_k = 0; stag_bytes = 0; if (tma_epi && (reinterpret_cast<uintptr_t>(partial_ws) & 15) == 0) { tma_out = 2; stag_bytes = bn * 512; } continue; }
+        if (tma_out && !tma_res && stag_bytes > smem_budget - 3072) { tma_out = 0; stag_bytes = 0; continue; }
         kbs = k2;
         break;
     }

@@ -381,15 +381,17 @@ static int tune_gemm(Engine* e, const ActView& a, int taps, const bf16* wt, int 
                     const int use_halo = (ki == 3) ? 1 : 0;             // 4th variant: 3x3 halo mode
                     if (use_halo && (taps != 9 || a.H < 16 || a.W < 8)) continue;
                     const int kbs = use_halo ? 1 : kbss[ki];
-                    for (int pair = 0; pair < 2; ++pair) {              // CTA pairs (cta_group::2): whole-SM CTAs only
+                    for (int pc = 0; pc < 3; ++pc) {                    // plain | CTA pairs (cta_group::2, whole-SM CTAs only) | in-cluster split-K
                         static const int pairs_ok = !(getenv("VSD_TUNE_PAIRS") && atoi(getenv("VSD_TUNE_PAIRS")) == 0);
+                        const int pair = pc == 1 ? 1 : 0, ck = pc == 2 ? 1 : 0;
                         if (pair && (occ == 2 || !pairs_ok)) continue;
-                        const int mode = use_halo | (pair << 1);
+                        if (ck && (sp < 2 || sp > 8)) continue;
+                        const int mode = use_halo | (pair << 1) | (ck ? 8 : 16);   // bit 3: reduce inside the cluster, bit 4: separate reduce kernel
                         GemmOp op;
                         if (build_gemm_op(&op, a, taps, wt, N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act,
                                           e->splitk_ws, e->splitk_bytes, bn, sp, occ, kbs, mode))
                             continue;   // does not fit (workspace / smem): skip
-                        if (op.p.splits != sp || op.p.kb_per_stage != kbs || op.p.halo != use_halo || op.p.pair != pair) continue;
+                        if (op.p.splits != sp || op.p.kb_per_stage != kbs || op.p.halo != use_halo || op.p.pair != pair || op.p.cluster_k != ck) continue;
                         const long ctas = (long)op.grid.x * op.grid.y * op.grid.z;
                         if (sp > 1 && ctas > 4 * 148) continue;
                         if (occ == 2 && op.smem_bytes > 114 * 1024) continue;   // would not actually co-reside

@@ -94,10 +94,11 @@ int vsd_op_conv_gemm(const void* x, int nb, int h, int w, int c, int ldx, int ta
     GemmOp op;
     ActView a{x, nb, h, w, c, ldx};
     // test knobs: act bit 8 requests the 3x3 halo mode, bit 9 CTA pairs (cta_group::2)
-    const int want_halo = ((act & 256) ? 1 : 0) | ((act & 512) ? 2 : 0) | ((act & 1024) ? 4 : 0);   // bit 10: persistent conv
+    // bit 10: persistent conv; bits 13 / 14: force / forbid the in-cluster split-K reduction
+    const int want_halo = ((act & 256) ? 1 : 0) | ((act & 512) ? 2 : 0) | ((act & 1024) ? 4 : 0) | ((act & 8192) ? 8 : 0) | ((act & 16384) ? 16 : 0);
     // bit 11: 3x3 stride 2 (pad 1); bit 12 with it: zeros right / below only
     if (act & 2048) { a.stride = 2; a.pad = (act & 4096) ? 0 : 1; }
-    act &= ~(256 | 512 | 1024 | 2048 | 4096);
+    act &= ~(256 | 512 | 1024 | 2048 | 4096 | 8192 | 16384);
     rc = build_gemm_op(&op, a, taps, reinterpret_cast<const bf16*>(wt), n, taps * c, out, ldo, out_f32, bias, rowvec,
                        reinterpret_cast<const bf16*>(residual), ldr, act, g_ws, g_ws_bytes, block_n, splits, 0, 0, want_halo);
     if (rc) return rc;

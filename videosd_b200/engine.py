@@ -4,6 +4,7 @@ PyTorch/numpy only own host buffers here; every per-frame computation happens in
 GPU, calls serialised by the caller (like one Ray actor per GPU in the reference, diffusert/videopipeline.py:11).
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -12,6 +13,16 @@ from . import scheduler as _sched
 from ._lib import VsdError, check, lib
 
 c_int = ctypes.c_int
+
+# Committed GEMM tuning tables (videosd_b200/tuning/<H>x<W>x<B>_n<frames in flight>.txt, written by
+# tools/make_tuning_tables.py on a B200): loaded by default so every process runs the same kernel configurations
+# (same (frame, options) -> same output across processes and ranks) and configure() does not stall on device timing.
+# VSD_TUNING_DIR overrides the directory; VSD_TUNING_TABLES=0 disables loading (used when the tables are regenerated).
+TUNING_DIR = os.environ.get("VSD_TUNING_DIR") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "tuning")
+
+
+def tuning_table_path(batch, height, width, frames_in_flight):
+    return os.path.join(TUNING_DIR, f"{height}x{width}x{batch}_n{max(1, int(frames_in_flight))}.txt")
 
 
 def _fptr(a):
@@ -46,6 +57,8 @@ class Engine:
         self.batch = self.height = self.width = None
         self.timesteps = None
         self._sched_key = None
+        self._tune_for = parent._tune_for if parent is not None else 1
+        self._tables_loaded = set()
 
     def close(self):
         if getattr(self, "_ctx", None):
@@ -73,6 +86,23 @@ class Engine:
         self.batch, self.height, self.width = batch, height, width
         self._sched_key = None
         self._resize_key = None      # vsd_configure drops the resize tables / staging buffers
+        self.load_tuning_table()
+
+    def load_tuning_table(self):
+        """Loads the committed table for the current (size, batch, frames in flight); shapes it does not cover are
+        timed on the device when the plan is built (tuning_misses() counts them). Returns the entries loaded."""
+        if self._tune_for <= 0 or os.environ.get("VSD_TUNING_TABLES") == "0" or self.batch is None:
+            return 0
+        path = tuning_table_path(self.batch, self.height, self.width, self._tune_for)
+        if path in self._tables_loaded or not os.path.exists(path):
+            return 0
+        self._tables_loaded.add(path)
+        with open(path) as f:
+            return self.tuning_load(f.read())
+
+    def tuning_misses(self):
+        self._L.vsd_tuning_misses.restype = ctypes.c_long
+        return int(self._L.vsd_tuning_misses(self._ctx))
 
     def set_schedule(self, strength, steps, guidance_scale=7.5):
         ts = self._schedule.timesteps(strength, steps)
@@ -92,16 +122,12 @@ class Engine:
         return ts
 
     def set_controlnet(self, enabled, scale=1.0):
-        for e in self.lanes:
-            e.set_controlnet(enabled, scale)
-
-    def set_vae(self, kind):
-        for e in self.lanes:
-            e.set_vae(kind)
-
-    def set_vae_noise(self, noise_nchw):
-        for e in self.lanes:
-            e.set_vae_noise(noise_nchw)
+        """Enable the canny ControlNet branch with conditioning scale `scale` (guess mode, as the reference calls it)."""
+        sc = np.ascontiguousarray((torch.logspace(-1, 0, 13) * float(scale)).numpy().astype(np.float32))
+        check(self._L.vsd_set_controlnet(self._ctx, c_int(1 if enabled else 0), _fptr(sc)), "vsd_set_controlnet")
+        if bool(enabled) != getattr(self, "_cn_enabled", False):
+            self._cn_enabled = bool(enabled)
+            self._sched_key = None      # the launch plan must be rebuilt
 
     def set_context(self, slot, context):
         """context: (77, 768) float tensor/array (CLIP last_hidden_state for the prompt)."""
@@ -205,6 +231,8 @@ class Engine:
         """0 / False: shape heuristics only. n >= 1: time candidate GEMM configurations on the device and pick for n frames in
         flight on this GPU (1 = lowest latency; more = configurations that leave SMs to the other frames)."""
         check(self._L.vsd_set_autotune(self._ctx, c_int(int(frames_in_flight))), "vsd_set_autotune")
+        self._tune_for = int(frames_in_flight)
+        self.load_tuning_table()
 
     def tuning_report(self):
         buf = ctypes.create_string_buffer(1 << 18)

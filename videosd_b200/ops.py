@@ -14,9 +14,10 @@ c_float = ctypes.c_float
 
 
 def conv_gemm(x, weight_ohwi, taps, bias=None, rowvec=None, residual=None, act=0, out_f32=False, block_n=0, splits=0,
-              out=None, halo=False, pair=False, persist=False, stride2=False, pad=1):
+              out=None, halo=False, pair=False, persist=False, stride2=False, pad=1, cluster=None):
     """x: bf16 NHWC tensor (nb,h,w,c) (last-dim contiguous; pixel stride taken from x.stride(2)).
-    weight_ohwi: bf16 (n, taps*c). Returns (nb,h,w,n_out)."""
+    weight_ohwi: bf16 (n, taps*c). Returns (nb,h,w,n_out). cluster: True / False forces / forbids the in-cluster split-K
+    reduction (DSMEM exchange) when splits > 1; None = the library's default."""
     assert x.dtype == torch.bfloat16 and x.dim() == 4 and x.stride(3) == 1
     nb, h, w, c = x.shape
     ldx = x.stride(2)
@@ -30,7 +31,7 @@ def conv_gemm(x, weight_ohwi, taps, bias=None, rowvec=None, residual=None, act=0
     ldr = residual.stride(2) if residual is not None else 0
     check(lib().vsd_op_conv_gemm(_p(x), c_int(nb), c_int(h), c_int(w), c_int(c), c_int(ldx), c_int(taps),
                                  _p(weight_ohwi), c_int(n), _p(out), c_int(ldo), c_int(1 if out_f32 else 0), _p(bias),
-                                 _p(rowvec), _p(residual), c_int(ldr), c_int(act | (256 if halo else 0) | (512 if pair else 0) | (1024 if persist else 0) | ((2048 | (0 if pad else 4096)) if stride2 else 0)), c_int(block_n), c_int(splits),
+                                 _p(rowvec), _p(residual), c_int(ldr), c_int(act | (256 if halo else 0) | (512 if pair else 0) | (1024 if persist else 0) | ((2048 | (0 if pad else 4096)) if stride2 else 0) | (0 if cluster is None else (8192 if cluster else 16384))), c_int(block_n), c_int(splits),
                                  cur_stream()), "vsd_op_conv_gemm")
     return out
 

@@ -92,7 +92,12 @@ class HashTokenizer:
         return _frame([int.from_bytes(hashlib.sha256(w.encode()).digest()[:4], "little") % BOS for w in words])
 
 
-def load(path=None):
+def load(path=None, allow_hash=False):
+    """The checkpoint's CLIP BPE tokenizer. Without vocab.json + merges.txt this raises: a real text encoder fed with ids
+    of another vocabulary conditions on garbage. allow_hash=True (random-init text towers in tests / benchmarks, where ids
+    carry no meaning) returns the vocabulary-free HashTokenizer instead."""
     if path and os.path.exists(os.path.join(path, "vocab.json")) and os.path.exists(os.path.join(path, "merges.txt")):
         return ClipTokenizer(path)
-    return HashTokenizer()
+    if allow_hash:
+        return HashTokenizer()
+    raise FileNotFoundError(f"CLIP tokenizer files (vocab.json, merges.txt) not found under {path!r}")
