@@ -62,6 +62,18 @@ int vsd_op_attention(const void* q, int ldq, const void* k, int ldk, const void*
                      int batch, int heads, int d, int nq, int nk, int q_rows_per_img, int k_rows_per_img,
                      int vt_cols_per_img, int vt_rows, void* stream);
 
+/* Linear(LayerNorm(x)) with the LayerNorm folded into the tcgen05 GEMM (BasicTransformerBlock.norm1/2/3 followed by
+ * to_q|to_k / to_v / ff.net.0.proj): w_raw bf16 [n][c] is the original weight; swapped = 1 computes out^T (tokens along the
+ * columns, the V^T projection); act = 1: GEGLU with value / gate rows interleaved per 128-row tile. stats [rows][nst][2]:
+ * partial row sums of x and x^2 left by the GEMM that produced x (vsd_op_linear_stats), NULL = computed here. */
+int vsd_op_linear_ln(const void* x, int rows, int c, int ldx, const void* w_raw, int n, const float* gamma, const float* beta,
+                     const float* bias, float eps, void* out, int ldo, int swapped, int act, int block_n, const float* stats,
+                     int nst, void* stream);
+/* Linear (+ bias, + residual) that also leaves those row statistics of its output: stats_out [rows][n_tiles][2]; returns
+ * n_tiles. mode 0 plain, 1 CTA pairs; splits > 1 = split-K reduced inside the cluster. */
+int vsd_op_linear_stats(const void* x, int rows, int c, int ldx, const void* w, int n, const float* bias, const void* residual,
+                        int ldr, void* out, int ldo, float* stats_out, int block_n, int splits, int mode, void* stream);
+
 /* GroupNorm (+ optional SiLU) over NHWC bf16; statistics in fp32 (torch.nn.GroupNorm in ResnetBlock2D /
  * Transformer2DModel). x, y: dev bf16 [nb*hw][ld]. */
 int vsd_op_groupnorm(const void* x, int ldx, void* y, int ldy, const float* gamma, const float* beta, int nb, int hw,

@@ -180,6 +180,71 @@ def check_gemm():
 
     run("geglu_4096x320", geglu)
 
+    # LayerNorm folded into the consuming GEMM: row statistics gathered from the operand tiles in shared memory
+    F = torch.nn.functional
+    for (rows, c, n, bn) in [(4096, 320, 1024, 0), (4096, 320, 1024, 64), (1024, 640, 2048, 128), (256, 1280, 3072, 96), (64, 1280, 1536, 0),
+                             (77, 320, 320, 32), (920, 640, 640, 256), (3600, 320, 512, 160)]:
+        def ln_a(rows=rows, c=c, n=n, bn=bn):
+            x = (randn((rows, c), 71) * 2 + 0.7).bfloat16()
+            w = randn((n, c), 72, scale=c ** -0.5).bfloat16()
+            gam, bet, b = randn((c,), 73) * 0.3 + 1, randn((c,), 74) * 0.3, randn((n,), 75)
+            y = ops.linear_ln(x, w, gam, bet, bias=b, block_n=bn)
+            ref = F.layer_norm(x.float(), (c,), gam, bet, 1e-5) @ w.float().t() + b
+            record(f"ln_fold_rows_{rows}x{c}x{n}_bn{bn}", rel_err(y, ref), 1e-2)
+            y2 = ops.linear_ln(x, w, gam, bet, bias=b, block_n=bn)
+            record(f"ln_fold_rows_{rows}x{c}x{n}_bn{bn}_deterministic", float((y.float() - y2.float()).abs().max()), 0.0)
+        run("ln_fold_rows", ln_a)
+    for (rows, c, bn) in [(4096, 320, 0), (4096, 320, 256), (1024, 640, 160), (256, 1280, 64), (64, 1280, 32), (920, 640, 96), (3600, 320, 128)]:
+        def ln_b(rows=rows, c=c, bn=bn):
+            x = (randn((rows, c), 76) * 1.5 - 0.4).bfloat16()
+            w = randn((c, c), 77, scale=c ** -0.5).bfloat16()
+            gam, bet = randn((c,), 78) * 0.3 + 1, randn((c,), 79) * 0.3
+            y = ops.linear_ln(x, w, gam, bet, swapped=True, block_n=bn)
+            ref = (F.layer_norm(x.float(), (c,), gam, bet, 1e-5) @ w.float().t()).t()
+            record(f"ln_fold_cols_{rows}x{c}_bn{bn}", rel_err(y[:, :rows], ref), 1e-2)
+        run("ln_fold_cols", ln_b)
+
+    # producer side: a GEMM leaves the row statistics of what it stores; chained into a LayerNorm-folded consumer
+    for (rows, c, bn, splits, pair) in [(4096, 320, 160, 1, False), (4096, 320, 64, 1, True), (1024, 640, 128, 1, False),
+                                        (256, 1280, 96, 3, False), (256, 1280, 128, 1, False), (64, 1280, 64, 4, False),
+                                        (64, 1280, 32, 8, False), (920, 640, 96, 2, False), (77, 320, 32, 1, False)]:
+        def chain(rows=rows, c=c, bn=bn, splits=splits, pair=pair):
+            x = randn((rows, c), 91).bfloat16()
+            w1 = randn((c, c), 92, scale=c ** -0.5).bfloat16()
+            b1 = randn((c,), 93)
+            res = (randn((rows, c), 94) + 0.5).bfloat16()
+            h, st = ops.linear_stats(x, w1, bias=b1, residual=res, block_n=bn, splits=splits, pair=pair)
+            href = x.float() @ w1.float().t() + b1 + res.float()
+            record(f"rowstats_out_{rows}x{c}_bn{bn}_s{splits}_p{int(pair)}", rel_err(h, href), 1e-2)
+            tot = st.sum(dim=1)
+            record(f"rowstats_sum_{rows}x{c}_bn{bn}_s{splits}", rel_err(tot[:, 0], href.sum(-1)), 2e-3)
+            record(f"rowstats_sumsq_{rows}x{c}_bn{bn}_s{splits}", rel_err(tot[:, 1], (href * href).sum(-1)), 2e-3)
+            w2 = randn((2 * c, c), 95, scale=c ** -0.5).bfloat16()
+            gam, bet = randn((c,), 96) * 0.3 + 1, randn((c,), 97) * 0.3
+            y = ops.linear_ln(h, w2, gam, bet, stats=st)
+            ref = F.layer_norm(h.float(), (c,), gam, bet, 1e-5) @ w2.float().t()
+            record(f"ln_fold_chain_{rows}x{c}_bn{bn}_s{splits}", rel_err(y, ref), 1e-2)
+            yt = ops.linear_ln(h, w2[:c].contiguous(), gam, bet, swapped=True, stats=st)
+            record(f"ln_fold_chain_cols_{rows}x{c}_bn{bn}_s{splits}", rel_err(yt[:, :rows], ref[:, :c].t()), 1e-2)
+        run("ln_fold_chain", chain)
+
+    def ln_geglu():
+        for (m, c) in [(4096, 320), (256, 1280), (64, 1280)]:
+            x = (randn((m, c), 81) * 2 + 0.3).bfloat16()
+            w_full = randn((8 * c, c), 82, scale=c ** -0.5)
+            b_full = randn((8 * c,), 83)
+            gam, bet = randn((c,), 84) * 0.3 + 1, randn((c,), 85) * 0.3
+            half = 4 * c
+            idx = []
+            for t in range(half // 64):
+                idx += list(range(t * 64, t * 64 + 64)) + list(range(half + t * 64, half + t * 64 + 64))
+            idx = torch.tensor(idx, device=DEV)
+            y = ops.linear_ln(x, w_full[idx].bfloat16().contiguous(), gam, bet, bias=b_full[idx].contiguous(), act=1, block_n=128)
+            hfull = F.layer_norm(x.float(), (c,), gam, bet, 1e-5) @ w_full.bfloat16().float().t() + b_full
+            ref = hfull[:, :half] * F.gelu(hfull[:, half:])
+            record(f"ln_fold_geglu_{m}x{c}", rel_err(y, ref), 1e-2)
+    run("ln_fold_geglu", ln_geglu)
+
 
 def bench_gemm():
     """Rough timings (CUDA events) of representative layers; not a benchmark of record."""

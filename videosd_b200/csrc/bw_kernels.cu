@@ -415,6 +415,57 @@ int launch_layernorm(const bf16* x, int ldx, bf16* y, int ldy, const float* gamm
     return 0;
 }
 
+// LayerNorm folded into the consuming GEMM (conv_gemm_kernel, GemmParams::ln_mode): once per weight, at plan-build time,
+//   W'[n][k] = bf16(W[n][k] * gamma[k])   (in place),   wsum[n] = sum_k W'[n][k],   wb[n] = sum_k W[n][k] * beta[k] (+ bias[n])
+// so that W LN(x) + b = rstd * (W' x - mean * wsum) + wb. One warp per weight row, fixed summation order.
+__global__ void ln_fold_weight_kernel(bf16* __restrict__ W, int N, int K, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, const float* __restrict__ bias, float* __restrict__ wsum,
+                                      float* __restrict__ wb) {
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    bf16* row = W + (long)n * K;
+    float a = 0.f, b = 0.f;
+    for (int k = lane; k < K; k += 32) {
+        const float w = __bfloat162float(row[k]);
+        b += w * beta[k];
+        const bf16 wf = __float2bfloat16(w * gamma[k]);
+        row[k] = wf;
+        a += __bfloat162float(wf);
+    }
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (lane == 0) {
+        wsum[n] = a;
+        wb[n] = b + (bias ? bias[n] : 0.f);
+    }
+}
+
+// Row sums of x and x^2 ([rows][1][2]) in the layout the LayerNorm-folded GEMM consumes; in the engine these come for free
+// from the epilogue of the GEMM producing x, this kernel serves the operator tests and inputs no GEMM produced.
+__global__ void rowstats_kernel(const bf16* __restrict__ x, int ldx, int rows, int C, float* __restrict__ out) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float a = 0.f, b = 0.f;
+    for (int c = lane; c < C; c += 32) { const float v = __bfloat162float(x[(long)row * ldx + c]); a += v; b += v * v; }
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (lane == 0) { out[row * 2] = a; out[row * 2 + 1] = b; }
+}
+int launch_rowstats(const bf16* x, int ldx, int rows, int C, float* out, cudaStream_t st) {
+    rowstats_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, ldx, rows, C, out);
+    VSD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_ln_fold_weight(bf16* W, int N, int K, const float* gamma, const float* beta, const float* bias, float* wsum, float* wb,
+                          cudaStream_t st) {
+    ln_fold_weight_kernel<<<(N + 7) / 8, 256, 0, st>>>(W, N, K, gamma, beta, bias, wsum, wb);
+    VSD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------ data movement
 // torch F.interpolate(mode="nearest"): src = min(floor(dst * in/out), in-1)
 __global__ void upsample_nearest_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy, int NB,

@@ -228,6 +228,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     uint8_t* stag = smem + p.stage_off;   // epilogue staging (and residual tile) region
     // [block_n] bias (+ time-embedding row) of this tile, 16-byte aligned for float4 reads
     float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
+    float* swsum = sbias + p.block_n;          // LayerNorm fold: [block_n] column sums of W' (mode 1) | [block_n] column means (mode 2)
+    float* scol = swsum + p.block_n;           // mode 2: [block_n] column rstd
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -459,7 +461,36 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 sbias[i] = bv;
             }
         }
+        if (p.ln_mode == 1)
+            for (int i = threadIdx.x - 64; i < p.block_n; i += 128) swsum[i] = (col0 + i < p.N) ? __ldg(p.ln_wsum + col0 + i) : 0.f;
         pdl_wait();   // bias / time-embedding rows above are constants; everything below depends on earlier kernels
+        // LayerNorm folded into this GEMM (GemmParams::ln_mode): the GEMM that PRODUCED the normalised operand left, per row
+        // and per N tile of its own grid, the partial sums of x and x^2 of the values it stored (rowstats_out below). Reduce
+        // them here (fixed order) to mean / rstd: per output row (mode 1) or per output column (mode 2, swapped operands).
+        float ln_mean = 0.f, ln_rstd = 1.f;
+        if (p.ln_mode) {
+            const float inv_k = 1.0f / (float)(p.cin * p.taps);
+            if (p.ln_mode == 1) {
+                if (row_ok) {
+                    const float2* st = reinterpret_cast<const float2*>(p.ln_stats) + grow * p.ln_nst;
+                    float a = 0.f, b = 0.f;
+                    for (int t = 0; t < p.ln_nst; ++t) { const float2 v = st[t]; a += v.x; b += v.y; }
+                    ln_mean = a * inv_k;
+                    ln_rstd = rsqrtf(fmaxf(b * inv_k - ln_mean * ln_mean, 0.f) + p.ln_eps);
+                }
+            } else {
+                for (int i = threadIdx.x - 64; i < p.block_n; i += 128) {
+                    float a = 0.f, b = 0.f;
+                    if (col0 + i < p.N) {
+                        const float2* st = reinterpret_cast<const float2*>(p.ln_stats) + (long)(col0 + i) * p.ln_nst;
+                        for (int t = 0; t < p.ln_nst; ++t) { const float2 v = st[t]; a += v.x; b += v.y; }
+                    }
+                    const float m = a * inv_k;
+                    swsum[i] = m;
+                    scol[i] = rsqrtf(fmaxf(b * inv_k - m * m, 0.f) + p.ln_eps);
+                }
+            }
+        }
         const bool res_vec = (p.residual != nullptr) && row_ok && ((p.ldr & 7) == 0) && ((col0 & 7) == 0) &&
                              (p.splits == 1) && (p.act != ACT_GEGLU) && !p.tma_res && !p.res_f32;
         // this warp's 32 rows as a sub-box of the tile rectangle (all extents are powers of two)
@@ -510,6 +541,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 tmem_ld_wait();
                 const float4* bu = reinterpret_cast<const float4*>(sbias + c);
                 const float4* bg = reinterpret_cast<const float4*>(sbias + half + c);
+                if (p.ln_mode == 1) {          // folded LayerNorm (norm3 -> GEGLU projection)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        u[j] = __float_as_uint(ln_rstd * (__uint_as_float(u[j]) - ln_mean * swsum[c + j]));
+                        g[j] = __float_as_uint(ln_rstd * (__uint_as_float(g[j]) - ln_mean * swsum[half + c + j]));
+                    }
+                }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float v[8];
@@ -534,6 +572,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             }
             tma_store_wait_all();
         } else if (kEpi == 1) {
+            const float ln_ws_row = (p.ln_mode == 2 && row_ok) ? __ldg(p.ln_wsum + grow) : 0.f;
+            const float ln_rb_row = (p.ln_mode == 2 && row_ok && p.ln_rowbias) ? __ldg(p.ln_rowbias + grow) : 0.f;
+            float rst_s = 0.f, rst_q = 0.f;
             if (p.tma_res) mbar_wait(res_bar, 0, 4);
             for (int c = 0; c < p.block_n; c += 32) {
                 uint32_t u[32];
@@ -558,6 +599,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]);
+                if (p.ln_mode == 1) {          // folded LayerNorm over the rows of A: out = rstd * (acc - mean * colsum(W')) + bias'
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = ln_rstd * (v[j] - ln_mean * swsum[c + j]);
+                } else if (p.ln_mode == 2) {   // ... over the rows of B (output columns); per-row constants of the weight operand
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = scol[c + j] * (v[j] - swsum[c + j] * ln_ws_row) + ln_rb_row;
+                }
                 if (row_ok) {
                     if (p.tma_res) {
                         uint4 rs[4];
@@ -567,6 +615,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     } else {
                         epilogue_math32(p, v, n_img, grow, col, ncols, use_sbias ? sbias + c : nullptr, rowvec_in_sbias,
                                         have_pre ? rcur : nullptr);
+                    }
+                    if (p.rowstats_out) {      // a LayerNorm consumes this tensor: partial row sums of what is being stored
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < ncols) { rst_s += v[j]; rst_q += v[j] * v[j]; }
                     }
                 }
 #pragma unroll
@@ -581,6 +634,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     tma_store_commit();
                 }
             }
+            if (p.rowstats_out && row_ok)
+                reinterpret_cast<float2*>(p.rowstats_out)[grow * gridDim.y + blockIdx.y] = make_float2(rst_s, rst_q);
             tma_store_wait_all();
         } else if (kEpi != 0) {
         } else if (p.splits > 1) {
@@ -707,13 +762,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             const int lane_r = lane >> lg, lane_g = lane & (lanes_row - 1);
             const int wq = warp - 2;
             const size_t src_stride4 = ((size_t)rows_per * p.block_n) >> 2;   // float4 units between two splits' copies
-            for (int g0 = lane_g; g0 < g4; g0 += lanes_row) {
-                const int col = col0 + g0 * 4;
-                for (int r = r_begin + wq * rows_warp + lane_r; r < r_end; r += 4 * rows_warp) {
-                    const int n_img = n0 + (r >> (p.lbw + p.lbh)), hh = h0 + ((r >> p.lbw) & (p.BH - 1)), ww = w0 + (r & (p.BW - 1));
-                    if (!((n_img < p.NB) && (hh < p.H) && (ww < p.W) && (col < p.N))) continue;
-                    const long grow = ((long)n_img * p.H + hh) * p.W + ww;
-                    const int lr = r - r_begin;
+            for (int rb = r_begin + wq * rows_warp; rb < r_end; rb += 4 * rows_warp) {   // warp-uniform trip count (shuffles below)
+                const int r = rb + lane_r;
+                const int n_img = n0 + (r >> (p.lbw + p.lbh)), hh = h0 + ((r >> p.lbw) & (p.BH - 1)), ww = w0 + (r & (p.BW - 1));
+                const bool rok = (r < r_end) && (n_img < p.NB) && (hh < p.H) && (ww < p.W);
+                const long grow = ((long)n_img * p.H + hh) * p.W + ww;
+                const int lr = r - r_begin;
+                float rst_s = 0.f, rst_q = 0.f;
+                for (int g0 = lane_g; g0 < g4; g0 += lanes_row) {
+                    const int col = col0 + g0 * 4;
+                    if (!rok || col >= p.N) continue;
                     const float4* src = reinterpret_cast<const float4*>(recv + (size_t)lr * p.block_n) + (g0 ^ (lr & 7));
                     float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
@@ -721,7 +779,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         const float4 t = src[(size_t)z * src_stride4];
                         v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
                     }
-                    splitk_finish4(p, v, grow, col);
+                    splitk_finish4(p, v, grow, col);     // leaves the stored values in v
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (col + j < p.N) { rst_s += v[j]; rst_q += v[j] * v[j]; }
+                }
+                if (p.rowstats_out) {                    // LayerNorm consumer downstream: the lanes sharing a row fold their sums
+                    for (int o = lanes_row >> 1; o > 0; o >>= 1) {
+                        rst_s += __shfl_xor_sync(0xffffffffu, rst_s, o);
+                        rst_q += __shfl_xor_sync(0xffffffffu, rst_q, o);
+                    }
+                    if (rok && lane_g == 0)
+                        reinterpret_cast<float2*>(p.rowstats_out)[grow * gridDim.y + blockIdx.y] = make_float2(rst_s, rst_q);
                 }
             }
         }
@@ -1080,7 +1149,7 @@ static int build_persist_op(GemmOp* op, const ActView& a, const bf16* wt, int N,
 int build_gemm_op(GemmOp* op, const ActView& ain, int taps, const bf16* wt, int N, int ldw, void* out, int ldo,
                   int out_f32, const float* bias, const float* rowvec, const bf16* residual, int ldr, int act_flags,
                   float* partial_ws, size_t partial_ws_bytes, int force_block_n, int force_splits, int force_occupancy,
-                  int force_kb_per_stage, int force_halo) {
+                  int force_kb_per_stage, int force_halo, const LnFuse* ln) {
     // `a` is the OUTPUT geometry from here on (tiles, rows, epilogue maps); `ain` only describes the activation tensor map
     const int cs = (taps == 9 && ain.stride == 2) ? 2 : 1;
     VSD_REQUIRE(ain.stride == 1 || (ain.stride == 2 && taps == 9), "only 3x3 convolutions can be strided (stride 2)");
@@ -1116,6 +1185,14 @@ int build_gemm_op(GemmOp* op, const ActView& ain, int taps, const bf16* wt, int 
     p.cstride = cs;
     p.cshift = (cs == 2 && ain.pad == 0) ? 1 : 0;
     p.persist = 0;
+    if (ln && ln->mode) {
+        VSD_REQUIRE(taps == 1 && !persist && cs == 1, "LayerNorm fold: linear layers only");
+        VSD_REQUIRE(force_splits <= 1, "LayerNorm fold: split-K not supported (the epilogue is not linear in the partial sums)");
+        VSD_REQUIRE(ln->wsum != nullptr && ln->stats != nullptr && ln->nst >= 1 && (ln->mode == 1 || ln->mode == 2),
+                    "LayerNorm fold: missing column sums / row statistics");
+        force_splits = 1;
+    }
+    if (ln && ln->stats_out) VSD_REQUIRE(!persist && (act_flags & 0xF) == ACT_NONE, "row statistics: plain epilogue only");
     if (persist) return build_persist_op(op, a, wt, N, ldw, out, ldo, out_f32, bias, rowvec, residual, ldr, act_flags);
     p.kb_total = halo ? 3 * (a.C / 64) : taps * (a.C / 64);   // halo: iterations of (channel block, column shift)
 
@@ -1246,6 +1323,20 @@ int build_gemm_op(GemmOp* op, const ActView& ain, int taps, const bf16* wt, int 
     p.sbh = (32 / p.sbw) < p.BH ? (32 / p.sbw) : p.BH;
     p.sbn = 32 / (p.sbw * p.sbh);
     op->smem_bytes = region + 1024 /*align slack*/ + (2 * stages + 2) * 8 + 64 + bn * 4;
+    p.ln_mode = 0; p.ln_wsum = nullptr; p.ln_rowbias = nullptr; p.ln_eps = 0.f; p.ln_stats = nullptr; p.ln_nst = 0;
+    p.rowstats_out = nullptr;
+    if (ln && ln->mode) {
+        VSD_REQUIRE(tma_out == 1 && splits == 1, "LayerNorm fold needs the bf16 tensor-store epilogue");
+        p.ln_mode = ln->mode; p.ln_wsum = ln->wsum; p.ln_rowbias = ln->rowbias; p.ln_eps = ln->eps;
+        p.ln_stats = ln->stats; p.ln_nst = ln->nst;
+        op->smem_bytes += 2 * bn * 4;   // column sums / column statistics next to the staged bias
+    }
+    if (ln && ln->stats_out) {
+        // [rows][n_tiles][2] partial sums written by the epilogue that stores the rows: the bf16 tensor-store epilogue or the
+        // in-cluster split-K reduction (the separate split-K reduce kernel has no thread that sees a whole row)
+        VSD_REQUIRE((tma_out == 1 && splits == 1) || cluster_k, "row statistics need the tensor-store epilogue or the in-cluster split-K reduction");
+        p.rowstats_out = ln->stats_out;
+    }
     // With programmatic dependent launch CTAs of different kernels co-reside on an SM. TMEM is not part of the block
     // scheduler's accounting, so bound the CTAs per SM through shared memory: smem >= tmem_cols * 450 B guarantees that
     // the co-resident CTAs' TMEM columns sum to <= 512 (otherwise tcgen05.alloc of a CTA the others wait on could spin).

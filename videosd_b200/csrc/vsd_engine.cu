@@ -14,6 +14,7 @@
 #include <cstring>
 #include <functional>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -147,6 +148,7 @@ struct Engine {
     std::unordered_map<std::string, Tuned> tuned;
     long tune_misses = 0;   // shapes that had to be timed on the device (not found in a loaded tuning table)
     void* flush_buf = nullptr; size_t flush_bytes = 0;
+    void* tune_w = nullptr; size_t tune_w_bytes = 0;   // autotuner: cold copies of the weight operand being timed
     // ControlNet: canny/Sobel-conditioned residuals added to the UNet skips every step
     // GPU center-crop + Lanczos resize of arbitrary-size input frames
     struct Resize { int in_w = 0, in_h = 0, x0 = 0, y0 = 0, cw = 0, ch = 0, hks = 0, vks = 0;
@@ -177,6 +179,25 @@ struct Engine {
             return -1;                                                      \
         }                                                                   \
     } while (0)
+
+// LayerNorm folded into the consuming GEMM (GemmParams::ln_mode): the weight is scaled by gamma IN PLACE, once per device
+// pointer for the whole process (lanes and other engines sharing the weights find the derived vectors here).
+struct LnFold { float* wsum; float* wb; };
+static std::mutex g_ln_mu;
+static std::unordered_map<const void*, LnFold> g_ln_folded;
+static bool ln_fuse_enabled() {
+    static const bool on = !(getenv("VSD_LN_FUSE") && atoi(getenv("VSD_LN_FUSE")) == 0);
+    return on;
+}
+static void ln_unfold_forget(const void* w) {   // the weight buffer is being freed / replaced
+    std::lock_guard<std::mutex> lk(g_ln_mu);
+    auto it = g_ln_folded.find(w);
+    if (it != g_ln_folded.end()) {
+        cudaFree(it->second.wsum);
+        cudaFree(it->second.wb);
+        g_ln_folded.erase(it);
+    }
+}
 
 // ------------------------------------------------------------------------------------------------ weights
 static bool ends_with(const std::string& s, const char* suf) {
@@ -309,6 +330,7 @@ static int load_weight(Engine* e, const std::string& name, const float* host, co
     }
     auto old = e->w.find(key);
     if (old != e->w.end()) {
+        ln_unfold_forget(old->second.p);
         cudaFree(old->second.p);
         e->w.erase(old);
     }
@@ -317,19 +339,27 @@ static int load_weight(Engine* e, const std::string& name, const float* host, co
 }
 
 // ------------------------------------------------------------------------------------------------ GEMM autotuner
-static int time_gemm(Engine* e, const GemmOp& op, float* us) {
+// One candidate = kTuneCopies launches back to back (PDL edges between them, like the frame's chain), each reading its own COLD
+// copy of the constant operand (in a frame every weight is read once per pass out of 1.7 GB: never L2-resident), the
+// activations warm as in the frame; L2 is flushed before the burst. Averaging over the burst resolves differences far below
+// the ~2 us granularity of a single event pair, so the choice is stable from run to run.
+static constexpr int kTuneCopies = 8;
+static int time_gemm(Engine* e, const GemmOp* ops, int nops, float* us) {
     float best = 1e30f;
     static const int reps = getenv("VSD_TUNE_REPS") ? atoi(getenv("VSD_TUNE_REPS")) : 3;
     for (int rep = 0; rep < reps; ++rep) {
         VSD_CHECK_CUDA(cudaMemsetAsync(e->flush_buf, rep, e->flush_bytes, e->stream));   // evict L2: weights come from HBM
         VSD_CHECK_CUDA(cudaEventRecord(e->ev0, e->stream));
-        int rc = launch_gemm_op(op, e->stream);
-        if (rc) return rc;
+        for (int i = 0; i < nops; ++i) {
+            int rc = launch_gemm_op(ops[i], e->stream);
+            if (rc) return rc;
+        }
         VSD_CHECK_CUDA(cudaEventRecord(e->ev1, e->stream));
         VSD_CHECK_CUDA(cudaEventSynchronize(e->ev1));
         float ms = 0.f;
         VSD_CHECK_CUDA(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
-        if (ms * 1e3f < best) best = ms * 1e3f;
+        const float t = ms * 1e3f / (float)nops;
+        if (t < best) best = t;
     }
     *us = best;
     return 0;
@@ -337,14 +367,31 @@ static int time_gemm(Engine* e, const GemmOp& op, float* us) {
 
 static int tune_gemm(Engine* e, const ActView& a, int taps, const bf16* wt, int N, int ldw, void* outp, int ldo,
                      int out_f32, const float* bias, const float* rowvec, const bf16* res, int ldr, int act,
-                     Engine::Tuned* result) {
+                     Engine::Tuned* result, const LnFuse* ln = nullptr) {
     if (!e->flush_buf) {
         e->flush_bytes = (size_t)192 << 20;
         VSD_CHECK_CUDA(cudaMalloc(&e->flush_buf, e->flush_bytes));
         VSD_CHECK_CUDA(cudaEventCreate(&e->ev0));
         VSD_CHECK_CUDA(cudaEventCreate(&e->ev1));
     }
+    // cold copies of the constant operand (the weight matrix `wt`; for swapped-operand / two-activation GEMMs the same data)
+    const bf16* wcopy[kTuneCopies];
+    for (int i = 0; i < kTuneCopies; ++i) wcopy[i] = wt;
+    if (!(act & (ACT_A_STATIC_FLAG | ACT_NO_STATIC_FLAG))) {
+        const size_t wbytes = ((size_t)N * ldw * 2 + 255) & ~size_t(255);
+        if (wbytes * kTuneCopies > e->tune_w_bytes) {
+            if (e->tune_w) cudaFree(e->tune_w);
+            e->tune_w = nullptr; e->tune_w_bytes = 0;
+            VSD_CHECK_CUDA(cudaMalloc(&e->tune_w, wbytes * kTuneCopies));
+            e->tune_w_bytes = wbytes * kTuneCopies;
+        }
+        for (int i = 0; i < kTuneCopies; ++i) {
+            VSD_CHECK_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(e->tune_w) + i * wbytes, wt, (size_t)N * ldw * 2, cudaMemcpyDeviceToDevice, e->stream));
+            wcopy[i] = reinterpret_cast<const bf16*>(reinterpret_cast<char*>(e->tune_w) + i * wbytes);
+        }
+    }
     const bool geglu = (act & 0xF) == ACT_GEGLU;
+    const bool ln_consumer = ln != nullptr && ln->mode != 0;   // no split-K (the epilogue is not linear in the partial sums)
     const int bns[8] = {32, 64, 96, 128, 160, 192, 224, 256};
     const int kbss[3] = {1, 2, 4};
     const int sps[8] = {1, 2, 3, 4, 6, 8, 12, 16};
@@ -355,15 +402,18 @@ static int tune_gemm(Engine* e, const ActView& a, int taps, const bf16* wt, int 
         static const int persist_ok = !(getenv("VSD_TUNE_PERSIST") && atoi(getenv("VSD_TUNE_PERSIST")) == 0);
         if (persist_ok && taps == 9 && a.C == 64 && N <= 64 && N % 8 == 0 && !out_f32 && rowvec == nullptr && a.H >= 16 && a.W >= 8 &&
             (act & 0xF) == ACT_NONE) {
-            GemmOp op;
-            if (!build_gemm_op(&op, a, taps, wt, N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act, e->splitk_ws, e->splitk_bytes,
-                               0, 1, 1, 1, 4)) {
+            GemmOp ops[kTuneCopies];
+            bool ok = true;
+            for (int i = 0; i < kTuneCopies && ok; ++i)
+                ok = !build_gemm_op(&ops[i], a, taps, wcopy[i], N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act, e->splitk_ws,
+                                    e->splitk_bytes, 0, 1, 1, 1, 4);
+            if (ok) {
                 float us = 0.f;
-                int rc = time_gemm(e, op, &us);
+                int rc = time_gemm(e, ops, kTuneCopies, &us);
                 if (rc) return rc;
-                const float util = std::min(1.0f, (float)op.grid.x / 148.0f);
+                const float util = std::min(1.0f, (float)ops[0].grid.x / 148.0f);
                 best_cost = us * std::max(util, 1.0f / (float)std::max(e->autotune, 1));
-                best = Engine::Tuned{op.p.block_n, 1, 1, 1, 4, us};
+                best = Engine::Tuned{ops[0].p.block_n, 1, 1, 1, 4, us};
             }
         }
     }
@@ -373,7 +423,7 @@ static int tune_gemm(Engine* e, const ActView& a, int taps, const bf16* wt, int 
         if (bn != 32 && bn > ((N + 31) / 32) * 32) continue;
         for (int si = 0; si < 8; ++si) {
             const int sp = sps[si];
-            if (sp > 1 && (geglu || kb_total / sp < 2)) continue;
+            if (sp > 1 && (geglu || ln_consumer || kb_total / sp < 2)) continue;
             for (int occ = 1; occ <= 2; ++occ) {
                 static const int only_occ = getenv("VSD_TUNE_OCC") ? atoi(getenv("VSD_TUNE_OCC")) : 0;   // experiment knob
                 if (only_occ && occ != only_occ) continue;
@@ -384,19 +434,25 @@ static int tune_gemm(Engine* e, const ActView& a, int taps, const bf16* wt, int 
                     for (int pc = 0; pc < 3; ++pc) {                    // plain | CTA pairs (cta_group::2, whole-SM CTAs only) | in-cluster split-K
                         static const int pairs_ok = !(getenv("VSD_TUNE_PAIRS") && atoi(getenv("VSD_TUNE_PAIRS")) == 0);
                         const int pair = pc == 1 ? 1 : 0, ck = pc == 2 ? 1 : 0;
-                        if (pair && (occ == 2 || !pairs_ok)) continue;
+                        if (pair && (occ == 2 || !pairs_ok || ln_consumer)) continue;
                         if (ck && (sp < 2 || sp > 8)) continue;
                         const int mode = use_halo | (pair << 1) | (ck ? 8 : 16);   // bit 3: reduce inside the cluster, bit 4: separate reduce kernel
-                        GemmOp op;
-                        if (build_gemm_op(&op, a, taps, wt, N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act,
-                                          e->splitk_ws, e->splitk_bytes, bn, sp, occ, kbs, mode))
+                        GemmOp ops[kTuneCopies];
+                        GemmOp& op = ops[0];
+                        if (build_gemm_op(&op, a, taps, wcopy[0], N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act,
+                                          e->splitk_ws, e->splitk_bytes, bn, sp, occ, kbs, mode, ln))
                             continue;   // does not fit (workspace / smem): skip
                         if (op.p.splits != sp || op.p.kb_per_stage != kbs || op.p.halo != use_halo || op.p.pair != pair || op.p.cluster_k != ck) continue;
                         const long ctas = (long)op.grid.x * op.grid.y * op.grid.z;
                         if (sp > 1 && ctas > 4 * 148) continue;
                         if (occ == 2 && op.smem_bytes > 114 * 1024) continue;   // would not actually co-reside
+                        bool ok = true;
+                        for (int i = 1; i < kTuneCopies && ok; ++i)
+                            ok = !build_gemm_op(&ops[i], a, taps, wcopy[i], N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act,
+                                                e->splitk_ws, e->splitk_bytes, bn, sp, occ, kbs, mode, ln);
+                        if (!ok) continue;
                         float us = 0.f;
-                        int rc = time_gemm(e, op, &us);
+                        int rc = time_gemm(e, ops, kTuneCopies, &us);
                         if (rc) return rc;
                         const float util = std::min(1.0f, (float)ctas / (148.0f * (float)occ));
                         const float cost = us * std::max(util, 1.0f / (float)std::max(e->autotune, 1));
@@ -484,9 +540,14 @@ struct Builder {
     }
 
     // out = epilogue(conv/linear(a)); `a` may be any NHWC view, `o` any view with o.c == N (or N/2 for GEGLU)
-    void gemm(const ActView& a, int taps, const bf16* wt, int N, int ldw, void* outp, int ldo, int out_f32,
-              const float* bias, const float* rowvec, const bf16* res, int ldr, int act, const float* out_scale = nullptr) {
-        if (rc) return;
+    // returns the N tile count of the launch (the row-statistics layout a LayerNorm-folded consumer needs), 0 on failure
+    int gemm(const ActView& a, int taps, const bf16* wt, int N, int ldw, void* outp, int ldo, int out_f32,
+             const float* bias, const float* rowvec, const bf16* res, int ldr, int act, const float* out_scale = nullptr,
+             const LnFuse* ln = nullptr) {
+        if (rc) return 0;
+        // part of the tuning key: other kernel paths / a restricted set of configurations
+        if (ln && ln->mode) act |= (ln->mode == 1 ? ACT_LN_A_FLAG : ACT_LN_B_FLAG);
+        if (ln && ln->stats_out) act |= ACT_ROWSTATS_FLAG;
         GemmOp op;
         int fbn = 0, fsp = 0, focc = 0, fkbs = 0, fhalo = 0;
         char key[160];
@@ -496,33 +557,34 @@ struct Builder {
             auto it = e->tuned.find(key);
             if (it == e->tuned.end()) {
                 Engine::Tuned t;
-                int r = tune_gemm(e, a, taps, wt, N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act, &t);
-                if (r) { rc = r; fail = get_error(); return; }
+                int r = tune_gemm(e, a, taps, wt, N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act, &t, ln);
+                if (r) { rc = r; fail = get_error(); return 0; }
                 it = e->tuned.emplace(key, t).first;
                 ++e->tune_misses;
             }
             fbn = it->second.bn; fsp = it->second.splits; focc = it->second.occ; fkbs = it->second.kbs; fhalo = it->second.halo;
         }
         int r = build_gemm_op(&op, a, taps, wt, N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act,
-                              splitk_workspace(), e->splitk_bytes, fbn, fsp, focc, fkbs, fhalo);
+                              splitk_workspace(), e->splitk_bytes, fbn, fsp, focc, fkbs, fhalo, ln);
         if (r && e->autotune) {
             // a table entry written by another build of the kernels may no longer be a valid configuration: tune this shape now
             snprintf(key, sizeof(key), "%dx%dx%dx%d|t%d|n%d|a%d|f%d|r%d", a.NB, a.H, a.W, a.C, taps + 100 * (a.stride - 1) + 1000 * (1 - a.pad),
                      N, act, out_f32, res ? 1 : 0);
             Engine::Tuned t;
-            r = tune_gemm(e, a, taps, wt, N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act, &t);
+            r = tune_gemm(e, a, taps, wt, N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act, &t, ln);
             if (!r) {
                 e->tuned[key] = t;
                 ++e->tune_misses;
                 r = build_gemm_op(&op, a, taps, wt, N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act, splitk_workspace(),
-                                  e->splitk_bytes, t.bn, t.splits, t.occ, t.kbs, t.halo);
+                                  e->splitk_bytes, t.bn, t.splits, t.occ, t.kbs, t.halo, ln);
             }
         }
-        if (r) { rc = r; fail = get_error(); return; }
+        if (r) { rc = r; fail = get_error(); return 0; }
         op.p.out_scale = out_scale;
         const size_t first = out->size();
         out->push_back(mk([op](cudaStream_t st) { return launch_gemm_op(op, st); }, "gemm"));
         mark_join(first);
+        return (int)op.grid.y;
     }
     void conv(const View& x, const std::string& name, int taps, const View& o, const float* rowvec, const View* res,
               int act, bool has_bias = true) {
@@ -563,6 +625,28 @@ struct Builder {
         mark_join(first);
     }
 
+    // W' = W * gamma in place (once), wsum / wb derived vectors: see ln_fold_weight_kernel
+    LnFold ln_fold(const std::string& wname, const std::string& norm, const float* bias) {
+        LnFold f{nullptr, nullptr};
+        auto it = e->w.find(wname);
+        const float* g = wf(norm + ".weight");
+        const float* b = wf(norm + ".bias");
+        if (it == e->w.end() || !it->second.is_bf16) { miss(wname); return f; }
+        if (rc) return f;
+        std::lock_guard<std::mutex> lk(g_ln_mu);
+        auto fi = g_ln_folded.find(it->second.p);
+        if (fi != g_ln_folded.end()) return fi->second;
+        const int N = (int)it->second.shape[0], K = (int)it->second.shape[1];
+        if (cudaMalloc(&f.wsum, (size_t)N * 4) != cudaSuccess || cudaMalloc(&f.wb, (size_t)N * 4) != cudaSuccess ||
+            launch_ln_fold_weight(reinterpret_cast<bf16*>(it->second.p), N, K, g, b, bias, f.wsum, f.wb, e->stream) ||
+            cudaStreamSynchronize(e->stream) != cudaSuccess) {
+            bad("LayerNorm fold failed for " + wname);
+            return LnFold{nullptr, nullptr};
+        }
+        g_ln_folded.emplace(it->second.p, f);
+        return f;
+    }
+
     // ---- diffusers ResnetBlock2D (Appendix A.3)
     void resnet(const View& x, const std::string& p, const float* temb_rowvec, const View& o, float eps = 1e-5f) {
         Scope sc_(short_name(p));
@@ -600,10 +684,33 @@ struct Builder {
         View g = alloc(NB, x.h, x.w, C);
         groupnorm(x, p + ".norm", 1e-6f, 0, g);
         View h0 = alloc(NB, x.h, x.w, C);
-        conv(g, p + ".proj_in", 1, h0, nullptr, nullptr, ACT_NONE);
+        // The three LayerNorms are folded into the GEMMs that consume them (no kernel, no normalised copy of the stream). The
+        // GEMM that PRODUCES the residual stream (proj_in, attn1.to_out, attn2.to_out) leaves per row and per N tile the sums
+        // of x and x^2 of the values it stores (ACT_ROWSTATS_FLAG); the consumers read the raw stream and apply
+        //   W LN(x) + b = rstd * (W' x - mean * wsum) + (W beta + b),   W' = W * gamma folded into the weights at plan build.
+        // VSD_LN_FUSE=0 keeps the separate layernorm_kernel (decided once per process: the fold rewrites the weights in place).
+        const bool fuse = ln_fuse_enabled();
+        auto stats_buf = [&]() { return fuse ? alloc_f32((size_t)M * (C / 32) * 2) : nullptr; };   // [rows][<= C/32 tiles][2]
+        float* st0 = stats_buf();
+        float* st1 = stats_buf();
+        float* st2 = stats_buf();
+        const LnFuse p0{0, nullptr, nullptr, 0.f, nullptr, 0, st0}, p1{0, nullptr, nullptr, 0.f, nullptr, 0, st1},
+            p2{0, nullptr, nullptr, 0.f, nullptr, 0, st2};
+        const int nst0 = gemm(g.act(), 1, wb(p + ".proj_in.weight"), C, C, h0.p, h0.ld, 0, wf(p + ".proj_in.bias"), nullptr, nullptr, 0,
+                              ACT_NONE, nullptr, fuse ? &p0 : nullptr);
         // self attention
-        View n1 = alloc(NB, x.h, x.w, C);
-        layernorm(h0, tb + ".norm1", n1);
+        View n1 = h0;
+        LnFold f_qk{nullptr, nullptr}, f_v{nullptr, nullptr}, f_q2{nullptr, nullptr}, f_ff{nullptr, nullptr};
+        if (fuse) {
+            f_qk = ln_fold(tb + ".attn1.qk.weight", tb + ".norm1", nullptr);
+            f_v = ln_fold(tb + ".attn1.to_v.weight", tb + ".norm1", nullptr);
+            f_q2 = ln_fold(tb + ".attn2.to_q.weight", tb + ".norm2", nullptr);
+            f_ff = ln_fold(tb + ".ff.net.0.proj.weight", tb + ".norm3", wf(tb + ".ff.net.0.proj.bias"));
+        } else {
+            n1 = alloc(NB, x.h, x.w, C);
+            layernorm(h0, tb + ".norm1", n1);
+        }
+        const LnFuse l_qk{1, f_qk.wsum, nullptr, 1e-5f, st0, nst0, nullptr};
         View qk = alloc(NB, x.h, x.w, 2 * heads * dkp);
         // V^T[C][tokens] = Wv * n1^T : weight as the row operand, activations as the column operand
         const int cols_img = (HW + 7) / 8 * 8;
@@ -612,29 +719,39 @@ struct Builder {
         if (!vt) bad("activation arena exhausted");
         const bf16* wv = wb(tb + ".attn1.to_v.weight");
         if (!rc) {
-            begin_side();   // the V^T projection only needs norm1's output: it overlaps the Q|K projection on the main stream
+            begin_side();   // the V^T projection only needs norm1's input: it overlaps the Q|K projection on the main stream
             ActView aw{wv, 1, 1, C, C, C};
             if (cols_img == HW) {
-                gemm(aw, 1, n1.p, (int)M, n1.ld, vt, ldvt, 0, nullptr, nullptr, nullptr, 0, ACT_NONE | ACT_A_STATIC_FLAG);
+                const LnFuse l_v{2, f_v.wsum, f_v.wb, 1e-5f, st0, nst0, nullptr};
+                gemm(aw, 1, n1.p, (int)M, n1.ld, vt, ldvt, 0, nullptr, nullptr, nullptr, 0, ACT_NONE | ACT_A_STATIC_FLAG, nullptr,
+                     fuse ? &l_v : nullptr);
             } else {
-                for (int b = 0; b < NB; ++b)
+                for (int b = 0; b < NB; ++b) {
+                    const LnFuse l_v{2, f_v.wsum, f_v.wb, 1e-5f, fuse ? st0 + (size_t)b * HW * nst0 * 2 : nullptr, nst0, nullptr};
                     gemm(aw, 1, n1.p + (long)b * HW * n1.ld, HW, n1.ld, vt + (long)b * cols_img, ldvt, 0, nullptr, nullptr,
-                         nullptr, 0, ACT_NONE | ACT_A_STATIC_FLAG);
+                         nullptr, 0, ACT_NONE | ACT_A_STATIC_FLAG, nullptr, fuse ? &l_v : nullptr);
+                }
             }
             end_side();
         }
-        gemm(n1.act_rows(), 1, wb(tb + ".attn1.qk.weight"), qk.c, C, qk.p, qk.ld, 0, nullptr, nullptr, nullptr, 0, ACT_NONE);
+        gemm(n1.act_rows(), 1, wb(tb + ".attn1.qk.weight"), qk.c, C, qk.p, qk.ld, 0, fuse ? f_qk.wb : nullptr, nullptr, nullptr, 0, ACT_NONE,
+             nullptr, fuse ? &l_qk : nullptr);
         join_next();
         View a1 = alloc(NB, x.h, x.w, C);
         attention(qk.p, qk.ld, qk.p + heads * dkp, qk.ld, vt, ldvt, a1, heads, d, HW, HW, HW, HW, cols_img, C);
         View h1 = alloc(NB, x.h, x.w, C);
-        gemm(a1.act_rows(), 1, wb(tb + ".attn1.to_out.0.weight"), C, C, h1.p, h1.ld, 0, wf(tb + ".attn1.to_out.0.bias"),
-             nullptr, h0.p, h0.ld, ACT_NONE);
+        const int nst1 = gemm(a1.act_rows(), 1, wb(tb + ".attn1.to_out.0.weight"), C, C, h1.p, h1.ld, 0, wf(tb + ".attn1.to_out.0.bias"),
+                              nullptr, h0.p, h0.ld, ACT_NONE, nullptr, fuse ? &p1 : nullptr);
         // cross attention against the cached context projections
-        View n2 = alloc(NB, x.h, x.w, C);
-        layernorm(h1, tb + ".norm2", n2);
+        View n2 = h1;
+        if (!fuse) {
+            n2 = alloc(NB, x.h, x.w, C);
+            layernorm(h1, tb + ".norm2", n2);
+        }
+        const LnFuse l_q2{1, f_q2.wsum, nullptr, 1e-5f, st1, nst1, nullptr};
         View q2 = alloc(NB, x.h, x.w, heads * dkp);
-        gemm(n2.act_rows(), 1, wb(tb + ".attn2.to_q.weight"), q2.c, C, q2.p, q2.ld, 0, nullptr, nullptr, nullptr, 0, ACT_NONE);
+        gemm(n2.act_rows(), 1, wb(tb + ".attn2.to_q.weight"), q2.c, C, q2.p, q2.ld, 0, fuse ? f_q2.wb : nullptr, nullptr, nullptr, 0, ACT_NONE,
+             nullptr, fuse ? &l_q2 : nullptr);
         const Engine::XAttn* xa = nullptr;
         for (auto& c : e->xattn)
             if (c.prefix == tb) xa = &c;
@@ -642,14 +759,18 @@ struct Builder {
         View a2 = alloc(NB, x.h, x.w, C);
         if (!rc) attention(q2.p, q2.ld, xa->k2, heads * dkp, xa->v2t, NB * 128, a2, heads, d, HW, 77, HW, 128, 128, C);
         View h2 = alloc(NB, x.h, x.w, C);
-        gemm(a2.act_rows(), 1, wb(tb + ".attn2.to_out.0.weight"), C, C, h2.p, h2.ld, 0, wf(tb + ".attn2.to_out.0.bias"),
-             nullptr, h1.p, h1.ld, ACT_NONE);
+        const int nst2 = gemm(a2.act_rows(), 1, wb(tb + ".attn2.to_out.0.weight"), C, C, h2.p, h2.ld, 0, wf(tb + ".attn2.to_out.0.bias"),
+                              nullptr, h1.p, h1.ld, ACT_NONE, nullptr, fuse ? &p2 : nullptr);
         // feed-forward (GEGLU fused into the first GEMM's epilogue)
-        View n3 = alloc(NB, x.h, x.w, C);
-        layernorm(h2, tb + ".norm3", n3);
+        View n3 = h2;
+        if (!fuse) {
+            n3 = alloc(NB, x.h, x.w, C);
+            layernorm(h2, tb + ".norm3", n3);
+        }
+        const LnFuse l_ff{1, f_ff.wsum, nullptr, 1e-5f, st2, nst2, nullptr};
         View ff = alloc(NB, x.h, x.w, 4 * C);
-        gemm(n3.act_rows(), 1, wb(tb + ".ff.net.0.proj.weight"), 8 * C, C, ff.p, ff.ld, 0, wf(tb + ".ff.net.0.proj.bias"),
-             nullptr, nullptr, 0, ACT_GEGLU);
+        gemm(n3.act_rows(), 1, wb(tb + ".ff.net.0.proj.weight"), 8 * C, C, ff.p, ff.ld, 0,
+             fuse ? f_ff.wb : wf(tb + ".ff.net.0.proj.bias"), nullptr, nullptr, 0, ACT_GEGLU, nullptr, fuse ? &l_ff : nullptr);
         View h3 = alloc(NB, x.h, x.w, C);
         gemm(ff.act_rows(), 1, wb(tb + ".ff.net.2.weight"), C, 4 * C, h3.p, h3.ld, 0, wf(tb + ".ff.net.2.bias"), nullptr,
              h2.p, h2.ld, ACT_NONE);
@@ -1775,7 +1896,10 @@ void vsd_destroy(vsd_ctx* c) {
     cudaStreamSynchronize(c->e.stream);
     free_graphs(&c->e);
     if (c->e.owns_weights)
-        for (auto& kv : c->e.w) cudaFree(kv.second.p);
+        for (auto& kv : c->e.w) {
+            ln_unfold_forget(kv.second.p);
+            cudaFree(kv.second.p);
+        }
     c->e.arena.destroy();
     if (c->e.splitk_ws) cudaFree(c->e.splitk_ws);
     for (int k = 0; k < 2; ++k) {
@@ -1785,6 +1909,7 @@ void vsd_destroy(vsd_ctx* c) {
         if (c->e.side[k]) cudaStreamDestroy(c->e.side[k]);
     }
     if (c->e.flush_buf) cudaFree(c->e.flush_buf);
+    if (c->e.tune_w) cudaFree(c->e.tune_w);
     free_resize(&c->e);
     free_clip(&c->e);
     for (auto& kv : c->e.derived) cudaFree(kv.second);

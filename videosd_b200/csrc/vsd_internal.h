@@ -75,10 +75,15 @@ int make_tmap_2d(CUtensorMap* m, const void* base, int K, int rows, int ld, int 
 // ---- tcgen05 implicit-GEMM convolution / linear kernel -------------------------------------------
 // out[pixel, n] = epilogue( sum_{tap, c} A[pixel + tap offset, c] * Wt[n, tap*cin + c] )
 enum { ACT_NONE = 0, ACT_GEGLU = 1, ACT_QUICK_GELU = 2,   // x * sigmoid(1.702 x) after the bias (CLIP MLP)
-       ACT_RELU_FLAG = 16,
+       ACT_RELU_FLAG = 16,       // ReLU (after the residual add) may be OR-ed in
        ACT_A_STATIC_FLAG = 32,   // the row operand is the constant one (swapped-operand V^T projection)
-       ACT_NO_STATIC_FLAG = 64,
-       ACT_RES_F32_FLAG = 128 };  // the residual operand is fp32 (with an fp32 output: an fp32 residual stream updated in place)  // neither operand is constant  // ReLU (after the residual add) may be OR-ed in
+       ACT_NO_STATIC_FLAG = 64,  // neither operand is constant
+       ACT_RES_F32_FLAG = 128,   // the residual operand is fp32 (with an fp32 output: an fp32 residual stream updated in place)
+       // LayerNorm folded into this GEMM (see LnFuse): the row statistics come from the GEMM that produced the normalised
+       // operand (ACT_ROWSTATS_FLAG there) and are applied to the accumulator in the epilogue
+       ACT_LN_A_FLAG = 256,      // the normalised operand is A (rows of the output)
+       ACT_LN_B_FLAG = 512,      // the normalised operand is B (columns of the output: swapped-operand V^T projection)
+       ACT_ROWSTATS_FLAG = 1024 };  // the epilogue also leaves per-row partial sums of x, x^2 of the tensor it stores
 
 struct GemmParams {
     // A operand traversal (NHWC activation, stride-1 taps; linear layers use H=NB=1, W=rows)
@@ -119,7 +124,22 @@ struct GemmParams {
     int sbw, sbh, sbn;
     unsigned int stage_off, bar_off;   // byte offsets of the staging region / the mbarrier block in dynamic smem
     long long* dbg;       // optional: CTA (0,0,0) writes clock64() phase stamps here (bring-up only)
+    // LayerNorm folded into the GEMM: W' = W * gamma (done once at load), out = rstd * (acc - mean * wsum) + (W beta + b).
+    // ln_mode 1: mean / rstd per output ROW (A operand rows), wsum per column, the bias pointer carries W beta + b.
+    // ln_mode 2: mean / rstd per output COLUMN (B operand rows), ln_wsum and ln_rowbias per output row.
+    // The statistics come from the GEMM that produced the normalised tensor: ln_stats [rows][ln_nst][2] = per N tile of that
+    // GEMM, sum x and sum x^2 of the row (rowstats_out of the producer; ln_nst = its N tile count).
+    int ln_mode;
+    const float* ln_wsum;
+    const float* ln_rowbias;
+    float ln_eps;
+    const float* ln_stats;
+    int ln_nst;
+    float* rowstats_out;  // producer side: [rows][gridDim.y][2]
 };
+
+// optional LayerNorm plumbing of one GEMM: consumer side (mode != 0) and / or producer side (stats_out != null)
+struct LnFuse { int mode; const float* wsum; const float* rowbias; float eps; const float* stats; int nst; float* stats_out; };
 
 struct GemmOp {
     CUtensorMap mapA, mapB, mapC, mapR;
@@ -139,7 +159,7 @@ struct ActView {
 int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N, int ldw, void* out, int ldo,
                   int out_f32, const float* bias, const float* rowvec, const bf16* residual, int ldr, int act,
                   float* partial_ws, size_t partial_ws_bytes, int force_block_n, int force_splits,
-                  int force_occupancy = 0, int force_kb_per_stage = 0, int force_halo = 0);
+                  int force_occupancy = 0, int force_kb_per_stage = 0, int force_halo = 0, const LnFuse* ln = nullptr);
 int launch_gemm_op(const GemmOp& op, cudaStream_t st);
 int gemm_init();  // sets func attributes; call once per process after a device is selected
 
@@ -175,6 +195,9 @@ int launch_softmax_rows(const float* S, int lds, bf16* P, int ldp, int rows, int
 int launch_kl_sample(const float* enc8, const float* wq, const float* bq, const float* noise, float* z, long px, float scaling,
                      cudaStream_t st);
 int launch_kl_post_quant(const float* lat, const float* wp, const float* bp, float* out, long px, float inv_scaling, cudaStream_t st);
+int launch_rowstats(const bf16* x, int ldx, int rows, int C, float* out, cudaStream_t st);
+int launch_ln_fold_weight(bf16* W, int N, int K, const float* gamma, const float* beta, const float* bias, float* wsum, float* wb,
+                          cudaStream_t st);
 int launch_fold_v_bias(const bf16* wo, const float* bv, const float* bo, float* out, int C, cudaStream_t st);
 int launch_splitk_reduce(const GemmParams& p, long rows, cudaStream_t st);
 int launch_conv3x3_small_cin(const void* x, int x_kind, int NB, int H, int W, int Cin, const float* w, const float* bias,

@@ -122,6 +122,71 @@ int vsd_op_conv_gemm_timed(const void* x, int nb, int h, int w, int c, int ldx, 
     return launch_gemm_op(op, reinterpret_cast<cudaStream_t>(stream));
 }
 
+/* Linear(LayerNorm(x)) with the LayerNorm folded into the GEMM (tests): w_raw is the ORIGINAL bf16 weight [n][c]; a scratch copy
+ * is scaled by gamma, then out = rstd * (W' x - mean * wsum) + (W beta + bias). swapped = 0: x [rows][ldx] is the row operand,
+ * out [rows][ldo]; swapped = 1: out^T = W LN(x)^T, out [n][ldo] with the tokens along the columns (the V^T projection).
+ * act: 0 or 1 (GEGLU; weight / bias rows interleaved per 128-row tile). stats: [rows][nst][2] partial row sums of x, x^2 as a
+ * producing GEMM leaves them (vsd_op_linear_stats), or NULL to have them computed here. */
+int vsd_op_linear_ln(const void* x, int rows, int c, int ldx, const void* w_raw, int n, const float* gamma, const float* beta,
+                     const float* bias, float eps, void* out, int ldo, int swapped, int act, int block_n, const float* stats,
+                     int nst, void* stream) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    bf16* w = nullptr;
+    float *wsum = nullptr, *wb = nullptr, *own = nullptr;
+    VSD_CHECK_CUDA(cudaMalloc(&w, (size_t)n * c * 2));
+    VSD_CHECK_CUDA(cudaMalloc(&wsum, (size_t)n * 4));
+    VSD_CHECK_CUDA(cudaMalloc(&wb, (size_t)n * 4));
+    VSD_CHECK_CUDA(cudaMemcpyAsync(w, w_raw, (size_t)n * c * 2, cudaMemcpyDeviceToDevice, st));
+    rc = launch_ln_fold_weight(w, n, c, gamma, beta, bias, wsum, wb, st);
+    if (!rc && !stats) {
+        VSD_CHECK_CUDA(cudaMalloc(&own, (size_t)rows * 8));
+        rc = launch_rowstats(reinterpret_cast<const bf16*>(x), ldx, rows, c, own, st);
+        stats = own;
+        nst = 1;
+    }
+    GemmOp op;
+    if (!rc) {
+        if (swapped) {
+            LnFuse ln{2, wsum, wb, eps, stats, nst, nullptr};
+            ActView aw{w, 1, 1, n, c, c};
+            rc = build_gemm_op(&op, aw, 1, reinterpret_cast<const bf16*>(x), rows, ldx, out, ldo, 0, nullptr, nullptr, nullptr, 0,
+                               ACT_NONE | ACT_A_STATIC_FLAG, nullptr, 0, block_n, 1, 0, 0, 0, &ln);
+        } else {
+            LnFuse ln{1, wsum, nullptr, eps, stats, nst, nullptr};
+            ActView ax{x, 1, 1, rows, c, ldx};
+            rc = build_gemm_op(&op, ax, 1, w, n, c, out, ldo, 0, wb, nullptr, nullptr, 0, act, nullptr, 0, block_n, 1, 0, 0, 0, &ln);
+        }
+    }
+    if (!rc) rc = launch_gemm_op(op, st);
+    cudaStreamSynchronize(st);
+    cudaFree(w); cudaFree(wsum); cudaFree(wb);
+    if (own) cudaFree(own);
+    return rc;
+}
+
+/* out = x W^T + bias (+ residual), and per row and per N tile the sums of the stored values and of their squares in
+ * stats_out [rows][n_tiles][2] (what a LayerNorm folded into the next GEMM consumes). mode: 0 plain, 1 CTA pairs, 8 in-cluster
+ * split-K (splits > 1). Returns the N tile count (> 0) or a negative error. */
+int vsd_op_linear_stats(const void* x, int rows, int c, int ldx, const void* w, int n, const float* bias, const void* residual,
+                        int ldr, void* out, int ldo, float* stats_out, int block_n, int splits, int mode, void* stream) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    LnFuse ln{0, nullptr, nullptr, 0.f, nullptr, 0, stats_out};
+    rc = ensure_ws((size_t)16 * rows * n * 4 + 1024);   // the common split-K bound (the in-cluster reduction does not touch it)
+    if (rc) return rc < 0 ? rc : -1;
+    GemmOp op;
+    ActView ax{x, 1, 1, rows, c, ldx};
+    rc = build_gemm_op(&op, ax, 1, reinterpret_cast<const bf16*>(w), n, c, out, ldo, 0, bias, nullptr,
+                       reinterpret_cast<const bf16*>(residual), ldr, ACT_NONE, g_ws, g_ws_bytes, block_n, splits > 1 ? splits : 1, 0, 0,
+                       mode == 1 ? 2 : (splits > 1 ? 8 : 16), &ln);
+    if (rc) return rc < 0 ? rc : -1;
+    rc = launch_gemm_op(op, reinterpret_cast<cudaStream_t>(stream));
+    if (rc) return rc < 0 ? rc : -1;
+    return (int)op.grid.y;
+}
+
 int vsd_op_attention(const void* q, int ldq, const void* k, int ldk, const void* vt, int ldvt, void* out, int ldo,
                      int batch, int heads, int d, int nq, int nk, int q_rows_per_img, int k_rows_per_img,
                      int vt_cols_per_img, int vt_rows, void* stream) {

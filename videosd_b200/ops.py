@@ -36,6 +36,40 @@ def conv_gemm(x, weight_ohwi, taps, bias=None, rowvec=None, residual=None, act=0
     return out
 
 
+def linear_ln(x, w_raw, gamma, beta, bias=None, eps=1e-5, swapped=False, act=0, block_n=0, stats=None):
+    """Linear(LayerNorm(x)) with the LayerNorm folded into the GEMM. x: bf16 (rows, c); w_raw: bf16 (n, c); stats: fp32
+    (rows, nst, 2) from linear_stats (None: computed by a helper kernel).
+    Returns (rows, n) -- (rows, n/2) for act=1 (GEGLU) -- or, swapped, (n, rows8) with rows padded to a multiple of 8."""
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1 and w_raw.dtype == torch.bfloat16 and w_raw.is_contiguous()
+    rows, c = x.shape
+    n = w_raw.shape[0]
+    if swapped:
+        out = torch.zeros((n, (rows + 7) // 8 * 8), device=x.device, dtype=torch.bfloat16)
+    else:
+        out = torch.empty((rows, n // 2 if act == 1 else n), device=x.device, dtype=torch.bfloat16)
+    nst = 0 if stats is None else stats.shape[1]
+    check(lib().vsd_op_linear_ln(_p(x), c_int(rows), c_int(c), c_int(x.stride(0)), _p(w_raw), c_int(n), _p(gamma), _p(beta), _p(bias),
+                                 ctypes.c_float(eps), _p(out), c_int(out.stride(0)), c_int(1 if swapped else 0), c_int(act),
+                                 c_int(block_n), _p(stats), c_int(nst), cur_stream()), "vsd_op_linear_ln")
+    return out
+
+
+def linear_stats(x, w, bias=None, residual=None, block_n=0, splits=1, pair=False):
+    """x W^T + bias (+ residual) -> (out bf16 (rows, n), stats fp32 (rows, n_tiles, 2)): the partial row sums a LayerNorm folded
+    into the next GEMM consumes."""
+    rows, c = x.shape
+    n = w.shape[0]
+    out = torch.empty((rows, n), device=x.device, dtype=torch.bfloat16)
+    stats = torch.zeros((rows, (n + 31) // 32, 2), device=x.device, dtype=torch.float32)
+    nt = lib().vsd_op_linear_stats(_p(x), c_int(rows), c_int(c), c_int(x.stride(0)), _p(w), c_int(n), _p(bias), _p(residual),
+                                   c_int(residual.stride(0) if residual is not None else 0), _p(out), c_int(out.stride(0)), _p(stats),
+                                   c_int(block_n), c_int(splits), c_int(1 if pair else 0), cur_stream())
+    if nt <= 0:
+        check(nt if nt else -1, "vsd_op_linear_stats")
+    torch.cuda.synchronize()
+    return out, stats.view(-1)[: rows * nt * 2].view(rows, nt, 2).contiguous()
+
+
 def attn_dk_pad(d):
     return (d + 63) // 64 * 64
 
