@@ -62,6 +62,17 @@ int vsd_op_attention(const void* q, int ldq, const void* k, int ldk, const void*
                      int batch, int heads, int d, int nq, int nk, int q_rows_per_img, int k_rows_per_img,
                      int vt_cols_per_img, int vt_rows, void* stream);
 
+/* The (block_n, splits, occ, kb_per_stage, mode) configurations the engine's autotuner may pick for a GEMM shape, and a launch
+ * with one of them: the operator-level sweep (tests/test_gpu_tuner_sweep.py) checks every one against fp32, so what the tuner can
+ * select is what was tested. cand: host int[max_cand][5]; returns the count. stride2 / pad: 3x3 stride-2 taps through TMA element
+ * strides. act: 0, 1 (GEGLU), 2 (quick-GELU), | 16 ReLU. */
+int vsd_op_gemm_candidates(const void* x, int nb, int h, int w, int c, int ldx, int taps, int stride2, int pad, const void* wt, int n,
+                           void* out, int ldo, int out_f32, const float* bias, const float* rowvec, const void* residual, int ldr,
+                           int act, int* cand, int max_cand);
+int vsd_op_conv_gemm_cfg(const void* x, int nb, int h, int w, int c, int ldx, int taps, int stride2, int pad, const void* wt, int n,
+                         void* out, int ldo, int out_f32, const float* bias, const float* rowvec, const void* residual, int ldr, int act,
+                         int block_n, int splits, int occ, int kb_per_stage, int mode, void* stream);
+
 /* Linear(LayerNorm(x)) with the LayerNorm folded into the tcgen05 GEMM (BasicTransformerBlock.norm1/2/3 followed by
  * to_q|to_k / to_v / ff.net.0.proj): w_raw bf16 [n][c] is the original weight; swapped = 1 computes out^T (tokens along the
  * columns, the V^T projection); act = 1: GEGLU with value / gate rows interleaved per 128-row tile. stats [rows][nst][2]:

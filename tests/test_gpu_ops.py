@@ -30,6 +30,12 @@ def test_tcgen05_conv_gemm(chk):
     _run(chk, chk.check_gemm)
 
 
+def test_every_configuration_the_autotuner_may_pick(chk):
+    """SURVEY.md 8(b) determinism / VERDICT r1 #3: the benchmarked kernel set must be a tested kernel set. For every GEMM shape
+    of the committed tuning tables, every candidate configuration the tuner enumerates is run against torch fp32."""
+    _run(chk, chk.check_tuner_sweep)
+
+
 def test_tcgen05_attention(chk):
     _run(chk, chk.check_attn)
 

@@ -246,6 +246,92 @@ def check_gemm():
     run("ln_fold_geglu", ln_geglu)
 
 
+def tuning_table_keys():
+    """GEMM shape keys of every committed tuning table (videosd_b200/tuning/*.txt), deduplicated."""
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "videosd_b200", "tuning")
+    keys = set()
+    for fn in sorted(os.listdir(root)):
+        if fn.endswith(".txt"):
+            with open(os.path.join(root, fn)) as f:
+                for ln in f:
+                    if "|" in ln:
+                        keys.add(ln.split()[0])
+    return sorted(keys)
+
+
+def check_tuner_sweep(keys=None):
+    """For every GEMM shape of the committed tuning tables: EVERY configuration the autotuner may pick (block_n, split-K, CTAs
+    per SM, k-blocks per stage, halo / pairs / persistent / in-cluster reduce -- the list comes from the library itself,
+    vsd_op_gemm_candidates) against torch fp32. What the tuner can select is what is tested."""
+    F = torch.nn.functional
+    total = 0
+    for key in (keys or tuning_table_keys()):
+        def one(key=key):
+            nonlocal total
+            dims, t, n, a, f, r = key.split("|")
+            nb, h, w, c = (int(v) for v in dims.split("x"))
+            tcode, n, act_key, out_f32, has_res = int(t[1:]), int(n[1:]), int(a[1:]), int(f[1:]), int(r[1:])
+            taps, stride2, pad = tcode % 100, (tcode // 100) % 10 == 1, 0 if tcode >= 1000 else 1
+            if act_key & 128:
+                return                                     # fp32 residual stream (AutoencoderKL attention): no operator-level wrapper
+            base = act_key & 0xF
+            act = base | (act_key & (16 | 32 | 64))        # the LayerNorm / row-statistics variants are swept as the plain GEMM
+            x = randn((nb, h, w, c), 201).bfloat16()
+            wt_f = randn((n, taps * c), 202, scale=(taps * c) ** -0.5)
+            ho, wo = ((h + 2 * pad - 3 + (0 if pad else 1)) // 2 + 1, (w + 2 * pad - 3 + (0 if pad else 1)) // 2 + 1) if stride2 else (h, w)
+            bias = randn((n,), 203)
+            rowvec = randn((nb, n), 204) if (taps == 9 and not has_res and not out_f32 and base == 0 and not stride2) else None
+            n_out = n // 2 if base == 1 else n
+            res = randn((nb, ho, wo, n_out), 205).bfloat16() if has_res else None
+            xf = x.float().permute(0, 3, 1, 2)
+            if base == 1:                                  # GEGLU: value / gate rows interleaved per 128-row tile
+                half = n // 2
+                idx = []
+                for tt in range(half // 64):
+                    idx += list(range(tt * 64, tt * 64 + 64)) + list(range(half + tt * 64, half + tt * 64 + 64))
+                idx = torch.tensor(idx, device=DEV)
+                wt = wt_f[idx].bfloat16().contiguous()
+                b_dev = bias[idx].contiguous()
+                hfull = x.float().reshape(-1, c) @ wt_f.bfloat16().float().t() + bias
+                ref = (hfull[:, :half] * F.gelu(hfull[:, half:])).view(nb, h, w, half)
+            else:
+                wt = wt_f.bfloat16().contiguous()
+                b_dev = bias
+                wf = wt.float()
+                if taps == 9:
+                    w4 = wf.view(n, 3, 3, c).permute(0, 3, 1, 2)
+                    if stride2 and pad == 0:
+                        y = F.conv2d(F.pad(xf, (0, 1, 0, 1)), w4, stride=2)
+                    else:
+                        y = F.conv2d(xf, w4, padding=1, stride=2 if stride2 else 1)
+                else:
+                    y = F.conv2d(xf, wf.view(n, c, 1, 1))
+                ref = y.permute(0, 2, 3, 1) + bias.view(1, 1, 1, n)
+                if rowvec is not None:
+                    ref = ref + rowvec.view(nb, 1, 1, n)
+                if res is not None:
+                    ref = ref + res.float()
+                if act_key & 16:
+                    ref = torch.relu(ref)
+                if base == 2:
+                    ref = ref * torch.sigmoid(1.702 * ref)
+            out = torch.empty((nb, ho, wo, n_out), device=DEV, dtype=torch.float32 if out_f32 else torch.bfloat16)
+            cands = ops.gemm_candidates(x, wt, taps, out, bias=b_dev, rowvec=rowvec, residual=res, act=act, stride2=stride2, pad=pad)
+            worst, worst_cfg = 0.0, None
+            scale = float(ref.abs().max().clamp_min(1e-12))
+            for cfg in cands:
+                out.fill_(float("nan"))
+                ops.conv_gemm_cfg(x, wt, taps, out, cfg, bias=b_dev, rowvec=rowvec, residual=res, act=act, stride2=stride2, pad=pad)
+                d = (out.float() - ref).abs().max()
+                e = float(d) / scale
+                if not (e <= worst):                        # also catches NaN
+                    worst, worst_cfg = e, cfg
+            total += len(cands)
+            record(f"sweep_{key}", worst if cands else float("nan"), 1e-2, {"candidates": len(cands), "worst_cfg": worst_cfg})
+        run(f"sweep_{key}", one)
+    print(f"SWEEP {total} configurations", flush=True)
+
+
 def bench_gemm():
     """Rough timings (CUDA events) of representative layers; not a benchmark of record."""
     cases = [
@@ -287,9 +373,9 @@ def bench_gemm():
 
 
 # ------------------------------------------------------------------------------------------------ attention
-def attn_case(name, batch, heads, d, nq, nk, k_slot=None, tol=1.5e-2):
+def attn_case(name, batch, heads, d, nq, nk, k_slot=None, tol=1.5e-2, qscale=1.0):
     def fn():
-        q = randn((batch, nq, heads, d), 21)
+        q = randn((batch, nq, heads, d), 21) * qscale
         k = randn((batch, nk, heads, d), 22)
         v = randn((batch, nk, heads, d), 23)
         qb, kb, vb = q.bfloat16(), k.bfloat16(), v.bfloat16()
@@ -303,8 +389,13 @@ def attn_case(name, batch, heads, d, nq, nk, k_slot=None, tol=1.5e-2):
         vt = vfull.reshape(batch * slot, heads * d).t().contiguous()
         o = ops.attention(qp, kp, vt, batch, heads, d, nq, nk, k_rows_per_img=slot, vt_cols_per_img=slot)
         torch.cuda.synchronize()
-        ref = torch.nn.functional.scaled_dot_product_attention(
-            qb.float().transpose(1, 2), kb.float().transpose(1, 2), vb.float().transpose(1, 2))
+        # plain fp32 reference softmax(Q K^T / sqrt(d)) V (matmul + softmax; no fused library attention kernel in the checker)
+        qf, kf, vf = qb.float().transpose(1, 2), kb.float().transpose(1, 2), vb.float().transpose(1, 2)
+        ref = torch.empty_like(qf)
+        for bi in range(batch):
+            for hi in range(heads):
+                sc = (qf[bi, hi] @ kf[bi, hi].t()) * (d ** -0.5)
+                ref[bi, hi] = torch.softmax(sc, dim=-1) @ vf[bi, hi]
         ref = ref.transpose(1, 2).reshape(batch * nq, heads * d)
         record(name, rel_err(o, ref), tol, {"b": batch, "h": heads, "d": d, "nq": nq, "nk": nk})
 
@@ -325,9 +416,23 @@ def check_attn():
     attn_case("attn_d40_b2_1024", 2, 8, 40, 1024, 1024)
     attn_case("attn_d40_odd_b2_920", 2, 8, 40, 920, 920)
     attn_case("attn_d40_9216", 1, 8, 40, 9216, 9216)
+    # two-tile kernel edge cases: a lone first tile in the last CTA, partial last key block, batch > 1, d = 64, 2 key blocks
+    attn_case("attn_d40_3600", 1, 8, 40, 3600, 3600)
+    attn_case("attn_d40_b3_400", 3, 8, 40, 400, 400)
+    attn_case("attn_d64_b2_1024", 2, 4, 64, 1024, 1024)
+    attn_case("attn_d48_b2_129x300", 2, 2, 48, 129, 300, k_slot=304)
+    attn_case("attn_d40_b4_2304", 4, 8, 40, 2304, 2304)
+    attn_case("attn_d8_520", 1, 3, 8, 520, 520)
+    # peaky rows: the running maximum moves by more than 2^8 between key blocks (the lazy O rescale path)
+    attn_case("attn_d40_1024_peaky", 1, 8, 40, 1024, 1024, qscale=12.0)
+    attn_case("attn_d40_b2_920_peaky", 2, 8, 40, 920, 920, qscale=30.0)
 
+
+
+def check_attn_timing():
+    """Rough timings (CUDA events, 10 back-to-back launches); not a benchmark of record."""
     def timing():
-        for (b, h, d, n) in [(1, 8, 40, 4096), (1, 8, 80, 1024), (1, 8, 160, 256), (4, 8, 40, 9216)]:
+        for (b, h, d, n) in [(1, 8, 40, 4096), (1, 8, 80, 1024), (1, 8, 160, 256), (4, 8, 40, 9216), (1, 8, 40, 9216), (1, 8, 64, 4096)]:
             q = randn((b * n, h * d), 1).bfloat16()
             qp = ops.pad_heads(q, h, d)
             vt = q.t().contiguous()

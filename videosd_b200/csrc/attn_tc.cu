@@ -271,6 +271,285 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+// ------------------------------------------------------------------------------------------ two-tile kernel
+// attention2_kernel: the kernel for the long self-attention layers (head dim <= 64, >= 2 key blocks, >= 256 queries).
+// One CTA = 256 queries of one (image, head) as TWO 128-row tiles with their own S / O accumulators in TMEM
+// (S0 | S1 | O0 | O1 = 512 columns) and their own softmax warpgroup, so that the tensor core computes one tile's
+// Q K^T / P V while the other tile's softmax runs; per tile the next block's Q K^T is issued as soon as the softmax
+// threads hold the current S row in registers (s_free), i.e. it overlaps the exponentials as well.
+//   * one thread per query row: the whole 128-key row of S is read from TMEM ONCE, no cross-thread row exchange;
+//   * lazy rescale: the running maximum only moves when the block maximum exceeds it by more than 2^8 (P <= 256 is
+//     harmless in bf16 / fp32), so the TMEM read-modify-write of O happens in the first blocks only;
+//   * the kernel is bound by the MUFU pipe (16 ex2 / clk / SM), so every kPoly-th exponential is evaluated on the FMA
+//     pipe instead (Cody-Waite reduction + degree-3 polynomial, relative error 8e-5, far below the bf16 rounding of P);
+//   * Q K^T runs over ceil(d / 16) K-steps (48 columns for d = 40), not the 64-column padding.
+// warp 0: TMA | warp 1: MMA issue + TMEM alloc | warps 2..5: softmax of tile 0 | warps 6..9: softmax of tile 1
+static constexpr int kAttn2Threads = 320;
+
+__device__ __forceinline__ float max3f(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -126.f);
+    const float r = x + 12582912.f;            // 1.5 * 2^23: round(x) lands in the low mantissa bits
+    const float f = x - (r - 12582912.f);      // [-0.5, 0.5]
+    float q = fmaf(0.05508905f, f, 0.24260408f);
+    q = fmaf(q, f, 0.69327617f);
+    q = fmaf(q, f, 0.99992895f);
+    return __int_as_float(__float_as_int(q) + (__float_as_int(r) << 23));
+}
+
+// exponentials of one 32-key chunk of a row -> bf16 -> the row's 64 bytes in the swizzled P tile; returns their sum
+template <int kPoly>
+__device__ __forceinline__ float softmax_chunk32(const uint32_t (&u)[32], float sc, float ms, uint8_t* prow_atom, int chunk0, int rsw) {
+    float e[32];
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj) {
+        const float x = fmaf(__uint_as_float(u[jj]), sc, -ms);
+        e[jj] = (kPoly > 0 && (jj % (kPoly > 0 ? kPoly : 1)) == (kPoly - 1)) ? ex2_poly(x) : ex2_approx(x);
+    }
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < 32; jj += 4) { s0 += e[jj]; s1 += e[jj + 1]; s2 += e[jj + 2]; s3 += e[jj + 3]; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint4 w = make_uint4(pack_bf16x2(e[i * 8], e[i * 8 + 1]), pack_bf16x2(e[i * 8 + 2], e[i * 8 + 3]),
+                                   pack_bf16x2(e[i * 8 + 4], e[i * 8 + 5]), pack_bf16x2(e[i * 8 + 6], e[i * 8 + 7]));
+        *reinterpret_cast<uint4*>(prow_atom + (((chunk0 + i) ^ rsw) << 4)) = w;
+    }
+    return (s0 + s1) + (s2 + s3);
+}
+
+__device__ __forceinline__ float rowmax32(const uint32_t (&u)[32], float m) {
+    float a = m, b = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < 32; jj += 4) {
+        a = max3f(a, __uint_as_float(u[jj]), __uint_as_float(u[jj + 1]));
+        b = max3f(b, __uint_as_float(u[jj + 2]), __uint_as_float(u[jj + 3]));
+    }
+    return fmaxf(a, b);
+}
+
+__device__ __forceinline__ void mask32(uint32_t (&u)[32], int valid) {   // keys >= valid -> -inf
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj)
+        if (jj >= valid) u[jj] = 0xff800000u;
+}
+
+template <int kPoly>
+__global__ void __launch_bounds__(kAttn2Threads, 1)
+attention2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                  const __grid_constant__ CUtensorMap mapVt, const AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t v_tile = (uint32_t)p.dv_pad * 128u;          // one [dv_pad][64 keys] tile
+    const uint32_t stage_bytes = (uint32_t)kTileBytes + 2u * v_tile;
+    uint8_t* sQ = smem;                                         // [2 tiles][128][64]
+    uint8_t* sP = sQ + 2 * kTileBytes;                          // [2 tiles][2 atoms][128][64]
+    uint8_t* sKV = sP + 4 * kTileBytes;                         // [stages][K 128 x 64 | V^T 2 x dv_pad x 64]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + (size_t)p.stages * stage_bytes);
+    uint64_t* q_full = bars;
+    uint64_t* s_full = bars + 1;     // [2]
+    uint64_t* s_free = bars + 3;     // [2]
+    uint64_t* p_ready = bars + 5;    // [2]
+    uint64_t* pv_done = bars + 7;    // [2]
+    uint64_t* kv_full = bars + 9;
+    uint64_t* kv_empty = kv_full + p.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_empty + p.stages);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int nblocks = (p.nk + 127) >> 7;
+    const int ntiles = (qt * 256 + 128 < p.nq) ? 2 : 1;         // the second tile of the last CTA may lie past the queries
+    pdl_launch_dependents();
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapQ);
+        tma_prefetch_desc(&mapK);
+        tma_prefetch_desc(&mapVt);
+        mbar_init(q_full, 1);
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(&s_full[t], 1);
+            mbar_init(&s_free[t], 4);
+            mbar_init(&p_ready[t], 4);
+            mbar_init(&pv_done[t], 1);
+        }
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&kv_full[s], 1);
+            mbar_init(&kv_empty[s], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512u);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        pdl_wait();   // Q / K / V^T are produced by the preceding projection kernels
+        if (elect_one()) {
+            mbar_expect_tx(q_full, (uint32_t)ntiles * kTileBytes);
+            for (int t = 0; t < ntiles; ++t)
+                tma_load_2d(sQ + (size_t)t * kTileBytes, &mapQ, q_full, h * p.dk_pad, b * p.q_rows_per_img + qt * 256 + t * 128);
+        }
+        __syncwarp();
+        for (int j = 0; j < nblocks; ++j) {
+            const int s = j % p.stages;
+            if (j >= p.stages) mbar_wait(&kv_empty[s], (uint32_t)((j / p.stages) - 1) & 1u, 1);
+            if (elect_one()) {
+                mbar_expect_tx(&kv_full[s], stage_bytes);
+                uint8_t* st = sKV + (size_t)s * stage_bytes;
+                tma_load_2d(st, &mapK, &kv_full[s], h * p.dk_pad, b * p.k_rows_per_img + j * 128);
+                for (int a = 0; a < 2; ++a)
+                    tma_load_2d(st + kTileBytes + (size_t)a * v_tile, &mapVt, &kv_full[s], b * p.vt_cols_per_img + j * 128 + a * 64,
+                                h * p.d);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc_s = umma_idesc_bf16(128, 128);
+        const uint32_t idesc_o = umma_idesc_bf16(128, (uint32_t)p.dv_pad);
+        const int nk16 = (p.d + 15) >> 4;                       // K-steps of Q K^T (columns past d are zero padding)
+        const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP), kv_addr = smem_u32(sKV);
+        auto issue_qk = [&](int t, int s) {                     // S_t = Q_t K(stage s)^T
+            if (elect_one()) {
+                const uint32_t k_addr = kv_addr + (uint32_t)s * stage_bytes;
+                for (int k = 0; k < nk16; ++k)
+                    umma_bf16(tmem_base + (uint32_t)t * 128u, umma_desc_sw128(q_addr + (uint32_t)t * kTileBytes + (uint32_t)k * 32u),
+                              umma_desc_sw128(k_addr + (uint32_t)k * 32u), idesc_s, k > 0 ? 1u : 0u);
+                umma_commit(&s_full[t]);
+            }
+            __syncwarp();
+        };
+        mbar_wait(q_full, 0, 2);
+        mbar_wait(&kv_full[0], 0, 3);
+        tc_fence_after_sync();
+        for (int t = 0; t < ntiles; ++t) issue_qk(t, 0);
+        for (int j = 0; j < nblocks; ++j) {
+            const int s = j % p.stages;
+            if (j + 1 < nblocks) {
+                const int sn = (j + 1) % p.stages;
+                mbar_wait(&kv_full[sn], (uint32_t)((j + 1) / p.stages) & 1u, 3);
+                for (int t = 0; t < ntiles; ++t) {
+                    mbar_wait(&s_free[t], (uint32_t)j & 1u, 4);   // the softmax threads hold S_t(j) in registers
+                    tc_fence_after_sync();
+                    issue_qk(t, sn);
+                }
+            }
+            const uint32_t v_addr = kv_addr + (uint32_t)s * stage_bytes + (uint32_t)kTileBytes;
+            for (int t = 0; t < ntiles; ++t) {
+                mbar_wait(&p_ready[t], (uint32_t)j & 1u, 5);
+                tc_fence_after_sync();
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint32_t aoff = (uint32_t)t * 2u * kTileBytes + (uint32_t)(k >> 2) * kTileBytes + (uint32_t)(k & 3) * 32u;
+                        const uint32_t boff = (uint32_t)(k >> 2) * v_tile + (uint32_t)(k & 3) * 32u;
+                        umma_bf16(tmem_base + 256u + (uint32_t)t * 128u, umma_desc_sw128(p_addr + aoff), umma_desc_sw128(v_addr + boff),
+                                  idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&pv_done[t]);
+                    if (t == ntiles - 1) umma_commit(&kv_empty[s]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        const int t = (warp - 2) >> 2;                          // tile of this warpgroup
+        const int q = warp & 3;                                 // TMEM lane quarter
+        const int r = q * 32 + lane;
+        if (t < ntiles) {
+            const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+            const uint32_t tS = tmem_base + lane_off + (uint32_t)t * 128u;
+            const uint32_t tO = tmem_base + lane_off + 256u + (uint32_t)t * 128u;
+            uint8_t* prow = sP + (size_t)t * 2 * kTileBytes + (size_t)r * 128;
+            const int rsw = r & 7;
+            const float sc = p.scale_log2e;
+            float m_used = -INFINITY, l_run = 0.f;
+            pdl_wait();   // the output buffer may still be read by an earlier kernel
+            for (int j = 0; j < nblocks; ++j) {
+                mbar_wait(&s_full[t], (uint32_t)j & 1u, 6);
+                tc_fence_after_sync();
+                uint32_t u0[32], u1[32], u2[32], u3[32];
+                tmem_ld32(tS, u0);
+                tmem_ld32(tS + 32, u1);
+                tmem_ld32(tS + 64, u2);
+                tmem_ld32(tS + 96, u3);
+                tmem_ld_wait();
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_free[t]);         // the next Q K^T of this tile may overwrite S
+                const int valid = p.nk - j * 128;               // warp-uniform
+                if (valid < 128) { mask32(u0, valid); mask32(u1, valid - 32); mask32(u2, valid - 64); mask32(u3, valid - 96); }
+                const float mx = rowmax32(u3, rowmax32(u2, rowmax32(u1, rowmax32(u0, -INFINITY))));
+                if (j == 0) {
+                    m_used = mx;
+                } else {
+                    // O_t and the P_t buffer belong to the previous P V until it retires
+                    mbar_wait(&pv_done[t], (uint32_t)(j - 1) & 1u, 7);
+                    tc_fence_after_sync();
+                    const bool grow = (mx - m_used) * sc > 8.0f;
+                    if (__any_sync(0xffffffffu, grow)) {
+                        const float m_new = grow ? mx : m_used;
+                        const float alpha = ex2_approx((m_used - m_new) * sc);   // 1 for the rows that keep their maximum
+                        m_used = m_new;
+                        l_run *= alpha;
+#pragma unroll 1
+                        for (int c = 0; c < p.dv_pad; c += 16) {
+                            uint32_t o[16];
+                            tmem_ld16(tO + c, o);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int jj = 0; jj < 16; ++jj) o[jj] = __float_as_uint(__uint_as_float(o[jj]) * alpha);
+                            tmem_st16(tO + c, o);
+                        }
+                        tmem_st_wait();
+                    }
+                }
+                const float ms = m_used * sc;
+                float lsum = softmax_chunk32<kPoly>(u0, sc, ms, prow, 0, rsw);
+                lsum += softmax_chunk32<kPoly>(u1, sc, ms, prow, 4, rsw);
+                lsum += softmax_chunk32<kPoly>(u2, sc, ms, prow + kTileBytes, 0, rsw);
+                lsum += softmax_chunk32<kPoly>(u3, sc, ms, prow + kTileBytes, 4, rsw);
+                l_run += lsum;
+                tc_fence_before_sync();
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_ready[t]);
+            }
+            mbar_wait(&pv_done[t], (uint32_t)(nblocks - 1) & 1u, 8);
+            tc_fence_after_sync();
+            const float inv_l = 1.0f / l_run;
+            const int qrow = qt * 256 + t * 128 + r;
+            const bool row_ok = qrow < p.nq;
+            bf16* orow = p.out + ((long)b * p.nq + qrow) * p.ldo + h * p.d;
+#pragma unroll 1
+            for (int c = 0; c < p.d; c += 16) {
+                uint32_t o[16];
+                tmem_ld16(tO + c, o);
+                tmem_ld_wait();
+                float f[16];
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) f[jj] = __uint_as_float(o[jj]) * inv_l;
+                if (row_ok) {
+                    *reinterpret_cast<uint4*>(orow + c) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                                                     pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+                    if (c + 8 < p.d)
+                        *reinterpret_cast<uint4*>(orow + c + 8) = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
+                                                                             pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+                }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512u);
+}
+
 // ------------------------------------------------------------------------------------------ host side
 static int g_attn_max_smem = 227 * 1024;
 
@@ -279,6 +558,10 @@ int attn_init() {
     VSD_CHECK_CUDA(cudaGetDevice(&dev));
     VSD_CHECK_CUDA(cudaDeviceGetAttribute(&g_attn_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     VSD_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_attn_max_smem));
+    VSD_CHECK_CUDA(cudaFuncSetAttribute(attention2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_attn_max_smem));
+    VSD_CHECK_CUDA(cudaFuncSetAttribute(attention2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_attn_max_smem));
+    VSD_CHECK_CUDA(cudaFuncSetAttribute(attention2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_attn_max_smem));
+    VSD_CHECK_CUDA(cudaFuncSetAttribute(attention2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_attn_max_smem));
     return 0;
 }
 
@@ -290,12 +573,42 @@ int build_attn_op(AttnOp* op, const bf16* q, int ldq, const bf16* k, int ldk, co
                   int vt_cols_per_img, int vt_rows) {
     VSD_REQUIRE(d % 8 == 0 && d <= 256, "head dim must be a multiple of 8 and <= 256");
     VSD_REQUIRE(nq > 0 && nk > 0, "empty attention");
+    // the V^T tiles start at column b * vt_cols_per_img + j * 128: TMA needs 16-byte aligned box origins along the contiguous dimension
+    VSD_REQUIRE(batch == 1 || (vt_cols_per_img % 8) == 0, "V^T columns per image must be a multiple of 8 when batch > 1");
     op->heads = heads; op->d = d; op->dk_pad = attn_dk_pad(d); op->dv_pad = attn_dv_pad(d);
     op->nq = nq; op->nk = nk; op->batch = batch;
     op->q_rows_per_img = q_rows_per_img; op->k_rows_per_img = k_rows_per_img; op->vt_cols_per_img = vt_cols_per_img;
     op->out = out; op->ldo = ldo;
     op->scale_log2e = (1.0f / sqrtf((float)d)) * 1.4426950408889634f;
     VSD_REQUIRE((ldo % 8) == 0 && ((heads * d) <= ldo), "attention output stride");
+    int rc = make_tmap_2d(&op->mapQ, q, heads * op->dk_pad, batch * q_rows_per_img, ldq, 128);
+    if (rc) return rc;
+    rc = make_tmap_2d(&op->mapK, k, heads * op->dk_pad, batch * k_rows_per_img, ldk, 128);
+    if (rc) return rc;
+    rc = make_tmap_2d(&op->mapVt, vt, batch * vt_cols_per_img, vt_rows, ldvt, op->dv_pad);
+    if (rc) return rc;
+    // Long self-attention (head dim <= 64): the two-tile kernel (attention2_kernel). VSD_ATTN_V2=0 keeps the one-tile kernel,
+    // VSD_ATTN_POLY = n: every n-th exponential on the FMA pipe (0: all on the MUFU pipe).
+    static const bool v2_ok = !(getenv("VSD_ATTN_V2") && atoi(getenv("VSD_ATTN_V2")) == 0);
+    static const int poly = getenv("VSD_ATTN_POLY") ? atoi(getenv("VSD_ATTN_POLY")) : 0;
+    op->variant = 0;
+    if (v2_ok && op->dk_pad == 64 && nk > 128 && nq > 128) {
+        const int stage2 = kTileBytes + 2 * op->dv_pad * 128;
+        const int fixed2 = 6 * kTileBytes + 1024 /*align slack*/ + 512 /*barriers*/;
+        int st2 = (g_attn_max_smem - fixed2) / stage2;
+        const int nb2 = (nk + 127) / 128;
+        if (st2 > nb2) st2 = nb2;
+        if (st2 > 6) st2 = 6;
+        if (st2 >= 2) {
+            op->variant = 2;
+            op->poly = (poly == 2 || poly == 3 || poly == 4) ? poly : 0;
+            op->stages = st2;
+            op->tmem_cols = 512;
+            op->smem_bytes = std::max(fixed2 + st2 * stage2, std::min(512 * 450, g_attn_max_smem));   // 512 TMEM columns: the SM is ours
+            op->grid = dim3((nq + 255) / 256, heads, batch);
+            return 0;
+        }
+    }
     const int nkc = op->dk_pad / 64;
     const int stage_bytes = nkc * kTileBytes + 2 * op->dv_pad * 128;
     const int fixed = nkc * kTileBytes + 2 * kTileBytes + 1024 + 256 + 1024 + 32;   // + row-exchange scratch
@@ -310,12 +623,6 @@ int build_attn_op(AttnOp* op, const bf16* q, int ldq, const bf16* k, int ldk, co
     op->tmem_cols = cols <= 256 ? 256 : 512;
     // TMEM over-subscription guard under programmatic dependent launch (see build_gemm_op)
     if (op->smem_bytes < op->tmem_cols * 450) op->smem_bytes = std::min(op->tmem_cols * 450, g_attn_max_smem);
-    int rc = make_tmap_2d(&op->mapQ, q, heads * op->dk_pad, batch * q_rows_per_img, ldq, 128);
-    if (rc) return rc;
-    rc = make_tmap_2d(&op->mapK, k, heads * op->dk_pad, batch * k_rows_per_img, ldk, 128);
-    if (rc) return rc;
-    rc = make_tmap_2d(&op->mapVt, vt, batch * vt_cols_per_img, vt_rows, ldvt, op->dv_pad);
-    if (rc) return rc;
     op->grid = dim3((nq + 127) / 128, heads, batch);
     return 0;
 }
@@ -326,6 +633,11 @@ int launch_attn_op(const AttnOp& op, cudaStream_t st) {
     p.nq = op.nq; p.nk = op.nk;
     p.q_rows_per_img = op.q_rows_per_img; p.k_rows_per_img = op.k_rows_per_img; p.vt_cols_per_img = op.vt_cols_per_img;
     p.out = op.out; p.ldo = op.ldo; p.scale_log2e = op.scale_log2e; p.stages = op.stages; p.tmem_cols = op.tmem_cols;
+    if (op.variant == 2) {
+        auto kern = op.poly == 2 ? attention2_kernel<2> : (op.poly == 3 ? attention2_kernel<3> : (op.poly == 4 ? attention2_kernel<4> : attention2_kernel<0>));
+        VSD_CHECK_CUDA(launch_k(kern, op.grid, dim3(kAttn2Threads), (size_t)op.smem_bytes, st, op.mapQ, op.mapK, op.mapVt, p));
+        return 0;
+    }
     VSD_CHECK_CUDA(launch_k(attention_kernel, op.grid, dim3(kAttnThreads), (size_t)op.smem_bytes, st, op.mapQ, op.mapK, op.mapVt, p));
     return 0;
 }

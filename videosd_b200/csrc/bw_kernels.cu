@@ -466,6 +466,52 @@ int launch_ln_fold_weight(bf16* W, int N, int K, const float* gamma, const float
     return 0;
 }
 
+// Two consecutive linear maps with a residual in between collapse into ONE GEMM over a concatenated K (the transformer tail
+// ff.net.2 -> +h2 -> proj_out):   Wp (W2 f + b2 + h) + bp = [Wp W2 | Wp] [f ; h] + (Wp b2 + bp).
+// Computed once per weight set at plan build: Wc [C][K2 + C] bf16 (fp32 accumulation), bc [C] fp32.
+__global__ void chain_weight_kernel(const bf16* __restrict__ Wp, const bf16* __restrict__ W2, bf16* __restrict__ Wc, int C, int K2) {
+    extern __shared__ float srow[];   // Wp[n][:]
+    const int n = blockIdx.y;
+    for (int j = threadIdx.x; j < C; j += blockDim.x) srow[j] = __bfloat162float(Wp[(long)n * C + j]);
+    __syncthreads();
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K2 + C) return;
+    float acc;
+    if (k < K2) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int j = 0;
+        for (; j + 3 < C; j += 4) {
+            a0 = fmaf(srow[j], __bfloat162float(W2[(long)j * K2 + k]), a0);
+            a1 = fmaf(srow[j + 1], __bfloat162float(W2[(long)(j + 1) * K2 + k]), a1);
+            a2 = fmaf(srow[j + 2], __bfloat162float(W2[(long)(j + 2) * K2 + k]), a2);
+            a3 = fmaf(srow[j + 3], __bfloat162float(W2[(long)(j + 3) * K2 + k]), a3);
+        }
+        for (; j < C; ++j) a0 = fmaf(srow[j], __bfloat162float(W2[(long)j * K2 + k]), a0);
+        acc = (a0 + a1) + (a2 + a3);
+    } else {
+        acc = srow[k - K2];
+    }
+    Wc[(long)n * (K2 + C) + k] = __float2bfloat16(acc);
+}
+__global__ void chain_bias_kernel(const bf16* __restrict__ Wp, const float* __restrict__ b2, const float* __restrict__ bp,
+                                  float* __restrict__ bc, int C) {
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (n >= C) return;
+    float a = 0.f;
+    for (int j = lane; j < C; j += 32) a += __bfloat162float(Wp[(long)n * C + j]) * b2[j];
+    a = warp_sum(a);
+    if (lane == 0) bc[n] = a + bp[n];
+}
+int launch_chain_weights(const bf16* Wp, const bf16* W2, const float* b2, const float* bp, bf16* Wc, float* bc, int C, int K2,
+                         cudaStream_t st) {
+    chain_weight_kernel<<<dim3((K2 + C + 255) / 256, C), 256, (size_t)C * 4, st>>>(Wp, W2, Wc, C, K2);
+    VSD_CHECK_CUDA(cudaGetLastError());
+    chain_bias_kernel<<<(C + 7) / 8, 256, 0, st>>>(Wp, b2, bp, bc, C);
+    VSD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------ data movement
 // torch F.interpolate(mode="nearest"): src = min(floor(dst * in/out), in-1)
 __global__ void upsample_nearest_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy, int NB,

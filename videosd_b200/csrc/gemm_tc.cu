@@ -18,6 +18,7 @@
 #include "vsd_internal.h"
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <vector>
 
 namespace vsd {
 
@@ -1367,6 +1368,64 @@ int build_gemm_op(GemmOp* op, const ActView& ain, int taps, const bf16* wt, int 
     // zeros / clips the stores, the direct epilogue masks the rows)
     op->grid = dim3(pair ? (m_tiles + 1) & ~1 : m_tiles, n_tiles, splits);
     return 0;
+}
+
+// Every (block_n, split-K, CTAs/SM, k-blocks per stage, mode) configuration of the kernel family that is valid for a shape:
+// the list the engine's autotuner times (vsd_engine.cu: tune_gemm) and the operator-level sweep test checks against fp32
+// (tests/test_gpu_tuner_sweep.py), so a configuration the tuner may pick is a configuration that was tested.
+// mode word: bit 0 halo tiles, bit 1 CTA pairs, bit 2 persistent weight-stationary kernel, bit 3 split-K reduced inside the
+// cluster, bit 4 separate reduce kernel.
+int enumerate_gemm_candidates(const ActView& a, int taps, const bf16* wt, int N, int ldw, void* outp, int ldo, int out_f32,
+                              const float* bias, const float* rowvec, const bf16* res, int ldr, int act, float* ws, size_t ws_bytes,
+                              const LnFuse* ln, std::vector<GemmCand>* out) {
+    out->clear();
+    const bool geglu = (act & 0xF) == ACT_GEGLU;
+    const bool ln_consumer = ln != nullptr && ln->mode != 0;   // no split-K (the epilogue is not linear in the partial sums)
+    const int bns[8] = {32, 64, 96, 128, 160, 192, 224, 256};
+    const int kbss[3] = {1, 2, 4};
+    const int sps[8] = {1, 2, 3, 4, 6, 8, 12, 16};
+    const int kb_total = taps * (a.C / 64);
+    static const int persist_ok = !(getenv("VSD_TUNE_PERSIST") && atoi(getenv("VSD_TUNE_PERSIST")) == 0);
+    static const int pairs_ok = !(getenv("VSD_TUNE_PAIRS") && atoi(getenv("VSD_TUNE_PAIRS")) == 0);
+    static const int only_occ = getenv("VSD_TUNE_OCC") ? atoi(getenv("VSD_TUNE_OCC")) : 0;   // experiment knob
+    GemmOp op;
+    // persistent weight-stationary variant for the TAESD-shaped 3x3 convolutions (mode 4)
+    if (persist_ok && taps == 9 && a.stride == 1 && a.C == 64 && N <= 64 && N % 8 == 0 && !out_f32 && rowvec == nullptr && a.H >= 16 &&
+        a.W >= 8 && (act & 0xF) == ACT_NONE && ln == nullptr &&
+        !build_gemm_op(&op, a, taps, wt, N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act, ws, ws_bytes, 0, 1, 1, 1, 4))
+        out->push_back(GemmCand{op.p.block_n, 1, 1, 1, 4});
+    for (int bi = 0; bi < 8; ++bi) {
+        const int bn = bns[bi];
+        if (geglu && bn != 128) continue;
+        if (bn != 32 && bn > ((N + 31) / 32) * 32) continue;
+        for (int si = 0; si < 8; ++si) {
+            const int sp = sps[si];
+            if (sp > 1 && (geglu || ln_consumer || kb_total / sp < 2)) continue;
+            for (int occ = 1; occ <= 2; ++occ) {
+                if (only_occ && occ != only_occ) continue;
+                for (int ki = 0; ki < 4; ++ki) {
+                    const int use_halo = (ki == 3) ? 1 : 0;             // 4th variant: 3x3 halo mode
+                    if (use_halo && (taps != 9 || a.stride != 1 || a.H < 16 || a.W < 8)) continue;
+                    const int kbs = use_halo ? 1 : kbss[ki];
+                    for (int pc = 0; pc < 3; ++pc) {                    // plain | CTA pairs (cta_group::2, whole-SM CTAs only) | in-cluster split-K
+                        const int pair = pc == 1 ? 1 : 0, ck = pc == 2 ? 1 : 0;
+                        if (pair && (occ == 2 || !pairs_ok || ln_consumer)) continue;
+                        if (ck && (sp < 2 || sp > 8)) continue;
+                        const int mode = use_halo | (pair << 1) | (ck ? 8 : 16);
+                        if (build_gemm_op(&op, a, taps, wt, N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act, ws, ws_bytes, bn, sp, occ,
+                                          kbs, mode, ln))
+                            continue;   // does not fit (workspace / smem) or not offered for this epilogue: skip
+                        if (op.p.splits != sp || op.p.kb_per_stage != kbs || op.p.halo != use_halo || op.p.pair != pair || op.p.cluster_k != ck) continue;
+                        const long ctas = (long)op.grid.x * op.grid.y * op.grid.z;
+                        if (sp > 1 && ctas > 4 * 148) continue;
+                        if (occ == 2 && op.smem_bytes > 114 * 1024) continue;   // would not actually co-reside
+                        out->push_back(GemmCand{bn, sp, occ, kbs, mode});
+                    }
+                }
+            }
+        }
+    }
+    return (int)out->size();
 }
 
 int launch_gemm_op(const GemmOp& op, cudaStream_t st) {

@@ -189,6 +189,13 @@ static bool ln_fuse_enabled() {
     static const bool on = !(getenv("VSD_LN_FUSE") && atoi(getenv("VSD_LN_FUSE")) == 0);
     return on;
 }
+// Transformer tail folded into one GEMM (launch_chain_weights): keyed by the ff.net.2 weight pointer, shared like the LN folds.
+struct ChainW { bf16* wc; float* bc; };
+static std::unordered_map<const void*, ChainW> g_chain;
+static bool ff_out_fuse_enabled() {
+    static const bool on = !(getenv("VSD_FF_OUT_FUSE") && atoi(getenv("VSD_FF_OUT_FUSE")) == 0);
+    return on;
+}
 static void ln_unfold_forget(const void* w) {   // the weight buffer is being freed / replaced
     std::lock_guard<std::mutex> lk(g_ln_mu);
     auto it = g_ln_folded.find(w);
@@ -196,6 +203,12 @@ static void ln_unfold_forget(const void* w) {   // the weight buffer is being fr
         cudaFree(it->second.wsum);
         cudaFree(it->second.wb);
         g_ln_folded.erase(it);
+    }
+    auto ic = g_chain.find(w);
+    if (ic != g_chain.end()) {
+        cudaFree(ic->second.wc);
+        cudaFree(ic->second.bc);
+        g_chain.erase(ic);
     }
 }
 
@@ -390,77 +403,27 @@ static int tune_gemm(Engine* e, const ActView& a, int taps, const bf16* wt, int 
             wcopy[i] = reinterpret_cast<const bf16*>(reinterpret_cast<char*>(e->tune_w) + i * wbytes);
         }
     }
-    const bool geglu = (act & 0xF) == ACT_GEGLU;
-    const bool ln_consumer = ln != nullptr && ln->mode != 0;   // no split-K (the epilogue is not linear in the partial sums)
-    const int bns[8] = {32, 64, 96, 128, 160, 192, 224, 256};
-    const int kbss[3] = {1, 2, 4};
-    const int sps[8] = {1, 2, 3, 4, 6, 8, 12, 16};
-    const int kb_total = taps * (a.C / 64);
+    // every configuration the kernel family offers for this shape (enumerate_gemm_candidates, gemm_tc.cu: the same list the
+    // operator-level sweep test runs against fp32), timed on the cold weight copies
+    std::vector<GemmCand> cands;
+    enumerate_gemm_candidates(a, taps, wcopy[0], N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act, e->splitk_ws, e->splitk_bytes, ln,
+                              &cands);
     Engine::Tuned best{0, 1, 0, 1, 0, 1e30f};
     float best_cost = 1e30f;
-    {   // persistent weight-stationary variant for the TAESD-shaped 3x3 convolutions (mode 4)
-        static const int persist_ok = !(getenv("VSD_TUNE_PERSIST") && atoi(getenv("VSD_TUNE_PERSIST")) == 0);
-        if (persist_ok && taps == 9 && a.C == 64 && N <= 64 && N % 8 == 0 && !out_f32 && rowvec == nullptr && a.H >= 16 && a.W >= 8 &&
-            (act & 0xF) == ACT_NONE) {
-            GemmOp ops[kTuneCopies];
-            bool ok = true;
-            for (int i = 0; i < kTuneCopies && ok; ++i)
-                ok = !build_gemm_op(&ops[i], a, taps, wcopy[i], N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act, e->splitk_ws,
-                                    e->splitk_bytes, 0, 1, 1, 1, 4);
-            if (ok) {
-                float us = 0.f;
-                int rc = time_gemm(e, ops, kTuneCopies, &us);
-                if (rc) return rc;
-                const float util = std::min(1.0f, (float)ops[0].grid.x / 148.0f);
-                best_cost = us * std::max(util, 1.0f / (float)std::max(e->autotune, 1));
-                best = Engine::Tuned{ops[0].p.block_n, 1, 1, 1, 4, us};
-            }
-        }
-    }
-    for (int bi = 0; bi < 8; ++bi) {
-        const int bn = bns[bi];
-        if (geglu && bn != 128) continue;
-        if (bn != 32 && bn > ((N + 31) / 32) * 32) continue;
-        for (int si = 0; si < 8; ++si) {
-            const int sp = sps[si];
-            if (sp > 1 && (geglu || ln_consumer || kb_total / sp < 2)) continue;
-            for (int occ = 1; occ <= 2; ++occ) {
-                static const int only_occ = getenv("VSD_TUNE_OCC") ? atoi(getenv("VSD_TUNE_OCC")) : 0;   // experiment knob
-                if (only_occ && occ != only_occ) continue;
-                for (int ki = 0; ki < 4; ++ki) {
-                    const int use_halo = (ki == 3) ? 1 : 0;             // 4th variant: 3x3 halo mode
-                    if (use_halo && (taps != 9 || a.H < 16 || a.W < 8)) continue;
-                    const int kbs = use_halo ? 1 : kbss[ki];
-                    for (int pc = 0; pc < 3; ++pc) {                    // plain | CTA pairs (cta_group::2, whole-SM CTAs only) | in-cluster split-K
-                        static const int pairs_ok = !(getenv("VSD_TUNE_PAIRS") && atoi(getenv("VSD_TUNE_PAIRS")) == 0);
-                        const int pair = pc == 1 ? 1 : 0, ck = pc == 2 ? 1 : 0;
-                        if (pair && (occ == 2 || !pairs_ok || ln_consumer)) continue;
-                        if (ck && (sp < 2 || sp > 8)) continue;
-                        const int mode = use_halo | (pair << 1) | (ck ? 8 : 16);   // bit 3: reduce inside the cluster, bit 4: separate reduce kernel
-                        GemmOp ops[kTuneCopies];
-                        GemmOp& op = ops[0];
-                        if (build_gemm_op(&op, a, taps, wcopy[0], N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act,
-                                          e->splitk_ws, e->splitk_bytes, bn, sp, occ, kbs, mode, ln))
-                            continue;   // does not fit (workspace / smem): skip
-                        if (op.p.splits != sp || op.p.kb_per_stage != kbs || op.p.halo != use_halo || op.p.pair != pair || op.p.cluster_k != ck) continue;
-                        const long ctas = (long)op.grid.x * op.grid.y * op.grid.z;
-                        if (sp > 1 && ctas > 4 * 148) continue;
-                        if (occ == 2 && op.smem_bytes > 114 * 1024) continue;   // would not actually co-reside
-                        bool ok = true;
-                        for (int i = 1; i < kTuneCopies && ok; ++i)
-                            ok = !build_gemm_op(&ops[i], a, taps, wcopy[i], N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act,
-                                                e->splitk_ws, e->splitk_bytes, bn, sp, occ, kbs, mode, ln);
-                        if (!ok) continue;
-                        float us = 0.f;
-                        int rc = time_gemm(e, ops, kTuneCopies, &us);
-                        if (rc) return rc;
-                        const float util = std::min(1.0f, (float)ctas / (148.0f * (float)occ));
-                        const float cost = us * std::max(util, 1.0f / (float)std::max(e->autotune, 1));
-                        if (cost < best_cost) { best_cost = cost; best = Engine::Tuned{bn, sp, occ, kbs, mode, us}; }
-                    }
-                }
-            }
-        }
+    for (const GemmCand& c : cands) {
+        GemmOp ops[kTuneCopies];
+        bool ok = true;
+        for (int i = 0; i < kTuneCopies && ok; ++i)
+            ok = !build_gemm_op(&ops[i], a, taps, wcopy[i], N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act, e->splitk_ws,
+                                e->splitk_bytes, c.bn, c.splits, c.occ, c.kbs, c.mode, ln);
+        if (!ok) continue;
+        float us = 0.f;
+        int rc = time_gemm(e, ops, kTuneCopies, &us);
+        if (rc) return rc;
+        const long ctas = (long)ops[0].grid.x * ops[0].grid.y * ops[0].grid.z;
+        const float util = std::min(1.0f, (float)ctas / (148.0f * (float)c.occ));
+        const float cost = us * std::max(util, 1.0f / (float)std::max(e->autotune, 1));
+        if (cost < best_cost) { best_cost = cost; best = Engine::Tuned{c.bn, c.splits, c.occ, c.kbs, c.mode, us}; }
     }
     if (best.bn == 0) { set_error("autotune found no valid GEMM configuration"); return -1; }
     *result = best;
@@ -647,6 +610,31 @@ struct Builder {
         return f;
     }
 
+    // [Wp W2 | Wp], Wp b2 + bp for the transformer tail (computed once per weight set)
+    ChainW chain_weights(const std::string& w2name, const std::string& b2name, const std::string& wpname, const std::string& bpname) {
+        ChainW c{nullptr, nullptr};
+        auto i2 = e->w.find(w2name);
+        auto ip = e->w.find(wpname);
+        const float* b2 = wf(b2name);
+        const float* bp = wf(bpname);
+        if (i2 == e->w.end() || !i2->second.is_bf16) { miss(w2name); return c; }
+        if (ip == e->w.end() || !ip->second.is_bf16) { miss(wpname); return c; }
+        if (rc) return c;
+        std::lock_guard<std::mutex> lk(g_ln_mu);
+        auto fi = g_chain.find(i2->second.p);
+        if (fi != g_chain.end()) return fi->second;
+        const int C = (int)i2->second.shape[0], K2 = (int)i2->second.shape[1];
+        if (cudaMalloc(&c.wc, (size_t)C * (K2 + C) * 2) != cudaSuccess || cudaMalloc(&c.bc, (size_t)C * 4) != cudaSuccess ||
+            launch_chain_weights(reinterpret_cast<const bf16*>(ip->second.p), reinterpret_cast<const bf16*>(i2->second.p), b2, bp, c.wc,
+                                 c.bc, C, K2, e->stream) ||
+            cudaStreamSynchronize(e->stream) != cudaSuccess) {
+            bad("transformer tail fold failed for " + w2name);
+            return ChainW{nullptr, nullptr};
+        }
+        g_chain.emplace(i2->second.p, c);
+        return c;
+    }
+
     // ---- diffusers ResnetBlock2D (Appendix A.3)
     void resnet(const View& x, const std::string& p, const float* temb_rowvec, const View& o, float eps = 1e-5f) {
         Scope sc_(short_name(p));
@@ -758,7 +746,10 @@ struct Builder {
         if (!xa) bad("cross-attention cache missing for " + tb);
         View a2 = alloc(NB, x.h, x.w, C);
         if (!rc) attention(q2.p, q2.ld, xa->k2, heads * dkp, xa->v2t, NB * 128, a2, heads, d, HW, 77, HW, 128, 128, C);
-        View h2 = alloc(NB, x.h, x.w, C);
+        // ff.net.2 (+ h2) and proj_out (+ x) are one GEMM over K = [ff | h2] (chain_weights): ff and h2 live side by side
+        const bool fuse_out = ff_out_fuse_enabled();
+        View cat = fuse_out ? alloc(NB, x.h, x.w, 5 * C) : View();
+        View h2 = fuse_out ? cat.slice(4 * C, C) : alloc(NB, x.h, x.w, C);
         const int nst2 = gemm(a2.act_rows(), 1, wb(tb + ".attn2.to_out.0.weight"), C, C, h2.p, h2.ld, 0, wf(tb + ".attn2.to_out.0.bias"),
                               nullptr, h1.p, h1.ld, ACT_NONE, nullptr, fuse ? &p2 : nullptr);
         // feed-forward (GEGLU fused into the first GEMM's epilogue)
@@ -768,9 +759,15 @@ struct Builder {
             layernorm(h2, tb + ".norm3", n3);
         }
         const LnFuse l_ff{1, f_ff.wsum, nullptr, 1e-5f, st2, nst2, nullptr};
-        View ff = alloc(NB, x.h, x.w, 4 * C);
+        View ff = fuse_out ? cat.slice(0, 4 * C) : alloc(NB, x.h, x.w, 4 * C);
         gemm(n3.act_rows(), 1, wb(tb + ".ff.net.0.proj.weight"), 8 * C, C, ff.p, ff.ld, 0,
              fuse ? f_ff.wb : wf(tb + ".ff.net.0.proj.bias"), nullptr, nullptr, 0, ACT_GEGLU, nullptr, fuse ? &l_ff : nullptr);
+        if (fuse_out) {
+            const ChainW cw = chain_weights(tb + ".ff.net.2.weight", tb + ".ff.net.2.bias", p + ".proj_out.weight", p + ".proj_out.bias");
+            gemm(cat.act(), 1, cw.wc, C, 5 * C, o.p, o.ld, 0, cw.bc, nullptr, x.p, x.ld, ACT_NONE);
+            e->arena.release(m);
+            return;
+        }
         View h3 = alloc(NB, x.h, x.w, C);
         gemm(ff.act_rows(), 1, wb(tb + ".ff.net.2.weight"), C, 4 * C, h3.p, h3.ld, 0, wf(tb + ".ff.net.2.bias"), nullptr,
              h2.p, h2.ld, ACT_NONE);

@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <string>
+#include <vector>
 
 namespace vsd {
 
@@ -161,6 +162,10 @@ int build_gemm_op(GemmOp* op, const ActView& a, int taps, const bf16* wt, int N,
                   float* partial_ws, size_t partial_ws_bytes, int force_block_n, int force_splits,
                   int force_occupancy = 0, int force_kb_per_stage = 0, int force_halo = 0, const LnFuse* ln = nullptr);
 int launch_gemm_op(const GemmOp& op, cudaStream_t st);
+struct GemmCand { int bn, splits, occ, kbs, mode; };
+int enumerate_gemm_candidates(const ActView& a, int taps, const bf16* wt, int N, int ldw, void* outp, int ldo, int out_f32,
+                              const float* bias, const float* rowvec, const bf16* res, int ldr, int act, float* ws, size_t ws_bytes,
+                              const LnFuse* ln, std::vector<GemmCand>* out);
 int gemm_init();  // sets func attributes; call once per process after a device is selected
 
 // ---- tcgen05 attention ---------------------------------------------------------------------------
@@ -173,6 +178,7 @@ struct AttnOp {
     bf16* out; int ldo;
     float scale_log2e;
     int stages, tmem_cols, smem_bytes;
+    int variant, poly;   // 0: attention_kernel (one 128-query tile per CTA); 2: attention2_kernel (two tiles), every poly-th ex2 on the FMA pipe
     dim3 grid;
 };
 int build_attn_op(AttnOp* op, const bf16* q, int ldq, const bf16* k, int ldk, const bf16* vt, int ldvt, bf16* out,
@@ -198,6 +204,8 @@ int launch_kl_post_quant(const float* lat, const float* wp, const float* bp, flo
 int launch_rowstats(const bf16* x, int ldx, int rows, int C, float* out, cudaStream_t st);
 int launch_ln_fold_weight(bf16* W, int N, int K, const float* gamma, const float* beta, const float* bias, float* wsum, float* wb,
                           cudaStream_t st);
+int launch_chain_weights(const bf16* Wp, const bf16* W2, const float* b2, const float* bp, bf16* Wc, float* bc, int C, int K2,
+                         cudaStream_t st);
 int launch_fold_v_bias(const bf16* wo, const float* bv, const float* bo, float* out, int C, cudaStream_t st);
 int launch_splitk_reduce(const GemmParams& p, long rows, cudaStream_t st);
 int launch_conv3x3_small_cin(const void* x, int x_kind, int NB, int H, int W, int Cin, const float* w, const float* bias,

@@ -105,6 +105,45 @@ int vsd_op_conv_gemm(const void* x, int nb, int h, int w, int c, int ldx, int ta
     return launch_gemm_op(op, reinterpret_cast<cudaStream_t>(stream));
 }
 
+/* The configurations the autotuner may pick for this GEMM (enumerate_gemm_candidates): cand receives up to max_cand rows of
+ * (block_n, splits, occ, kb_per_stage, mode). act: ACT_* flags as in vsd_op_conv_gemm (no test knobs); stride2 / pad as there.
+ * Returns the number of candidates (>= 0) or a negative error. */
+int vsd_op_gemm_candidates(const void* x, int nb, int h, int w, int c, int ldx, int taps, int stride2, int pad, const void* wt, int n,
+                           void* out, int ldo, int out_f32, const float* bias, const float* rowvec, const void* residual, int ldr,
+                           int act, int* cand, int max_cand) {
+    int rc = ensure_init();
+    if (rc) return rc < 0 ? rc : -1;
+    rc = ensure_ws((size_t)16 * nb * h * w * n * 4 + 1024);
+    if (rc) return rc < 0 ? rc : -1;
+    ActView a{x, nb, h, w, c, ldx};
+    if (stride2) { a.stride = 2; a.pad = pad; }
+    std::vector<GemmCand> v;
+    enumerate_gemm_candidates(a, taps, reinterpret_cast<const bf16*>(wt), n, taps * c, out, ldo, out_f32, bias, rowvec,
+                              reinterpret_cast<const bf16*>(residual), ldr, act, g_ws, g_ws_bytes, nullptr, &v);
+    int k = 0;
+    for (; k < (int)v.size() && k < max_cand; ++k) {
+        cand[k * 5 + 0] = v[k].bn; cand[k * 5 + 1] = v[k].splits; cand[k * 5 + 2] = v[k].occ; cand[k * 5 + 3] = v[k].kbs; cand[k * 5 + 4] = v[k].mode;
+    }
+    return k;
+}
+
+/* One explicit configuration (a row of vsd_op_gemm_candidates). */
+int vsd_op_conv_gemm_cfg(const void* x, int nb, int h, int w, int c, int ldx, int taps, int stride2, int pad, const void* wt, int n,
+                         void* out, int ldo, int out_f32, const float* bias, const float* rowvec, const void* residual, int ldr, int act,
+                         int block_n, int splits, int occ, int kb_per_stage, int mode, void* stream) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    rc = ensure_ws((size_t)16 * nb * h * w * n * 4 + 1024);
+    if (rc) return rc;
+    ActView a{x, nb, h, w, c, ldx};
+    if (stride2) { a.stride = 2; a.pad = pad; }
+    GemmOp op;
+    rc = build_gemm_op(&op, a, taps, reinterpret_cast<const bf16*>(wt), n, taps * c, out, ldo, out_f32, bias, rowvec,
+                       reinterpret_cast<const bf16*>(residual), ldr, act, g_ws, g_ws_bytes, block_n, splits, occ, kb_per_stage, mode);
+    if (rc) return rc;
+    return launch_gemm_op(op, reinterpret_cast<cudaStream_t>(stream));
+}
+
 /* bring-up: same as vsd_op_conv_gemm but CTA (0,0,0) records 7 clock64() phase stamps into dbg (device int64[8]) */
 int vsd_op_conv_gemm_timed(const void* x, int nb, int h, int w, int c, int ldx, int taps, const void* wt, int n, void* out,
                            int ldo, const float* bias, int block_n, int splits, int occ, int kb_per_stage, long long* dbg,

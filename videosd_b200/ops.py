@@ -36,6 +36,33 @@ def conv_gemm(x, weight_ohwi, taps, bias=None, rowvec=None, residual=None, act=0
     return out
 
 
+def gemm_candidates(x, weight_ohwi, taps, out, bias=None, rowvec=None, residual=None, act=0, stride2=False, pad=1):
+    """The (block_n, splits, occ, kb_per_stage, mode) configurations the engine's autotuner may pick for this GEMM."""
+    nb, h, w, c = x.shape
+    n = weight_ohwi.shape[0]
+    buf = (ctypes.c_int * (5 * 4096))()
+    k = lib().vsd_op_gemm_candidates(_p(x), c_int(nb), c_int(h), c_int(w), c_int(c), c_int(x.stride(2)), c_int(taps),
+                                     c_int(1 if stride2 else 0), c_int(pad), _p(weight_ohwi), c_int(n), _p(out), c_int(out.stride(2)),
+                                     c_int(1 if out.dtype == torch.float32 else 0), _p(bias), _p(rowvec), _p(residual),
+                                     c_int(residual.stride(2) if residual is not None else 0), c_int(act), buf, c_int(4096))
+    if k < 0:
+        check(k, "vsd_op_gemm_candidates")
+    return [tuple(buf[i * 5 + j] for j in range(5)) for i in range(k)]
+
+
+def conv_gemm_cfg(x, weight_ohwi, taps, out, cfg, bias=None, rowvec=None, residual=None, act=0, stride2=False, pad=1):
+    """conv_gemm with one explicit configuration (a tuple from gemm_candidates) into `out`."""
+    nb, h, w, c = x.shape
+    n = weight_ohwi.shape[0]
+    bn, sp, occ, kbs, mode = cfg
+    check(lib().vsd_op_conv_gemm_cfg(_p(x), c_int(nb), c_int(h), c_int(w), c_int(c), c_int(x.stride(2)), c_int(taps),
+                                     c_int(1 if stride2 else 0), c_int(pad), _p(weight_ohwi), c_int(n), _p(out), c_int(out.stride(2)),
+                                     c_int(1 if out.dtype == torch.float32 else 0), _p(bias), _p(rowvec), _p(residual),
+                                     c_int(residual.stride(2) if residual is not None else 0), c_int(act), c_int(bn), c_int(sp),
+                                     c_int(occ), c_int(kbs), c_int(mode), cur_stream()), "vsd_op_conv_gemm_cfg")
+    return out
+
+
 def linear_ln(x, w_raw, gamma, beta, bias=None, eps=1e-5, swapped=False, act=0, block_n=0, stats=None):
     """Linear(LayerNorm(x)) with the LayerNorm folded into the GEMM. x: bf16 (rows, c); w_raw: bf16 (n, c); stats: fp32
     (rows, nst, 2) from linear_stats (None: computed by a helper kernel).
