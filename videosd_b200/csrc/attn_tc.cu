@@ -28,6 +28,7 @@ struct AttnParams {
     int ldo;
     float scale_log2e;
     int stages, tmem_cols;
+    int stagger;
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {   // one MUFU op; ex2(-inf) = 0
@@ -278,13 +279,20 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
 // Q K^T / P V while the other tile's softmax runs; per tile the next block's Q K^T is issued as soon as the softmax
 // threads hold the current S row in registers (s_free), i.e. it overlaps the exponentials as well.
 //   * one thread per query row: the whole 128-key row of S is read from TMEM ONCE, no cross-thread row exchange;
+//   * P is DOUBLE-BUFFERED per tile: the softmax of block j writes P[j & 1] while P V of block j - 1 still reads the other
+//     buffer, so a warpgroup never waits for the tensor core between two blocks (ncu of the single-buffer version: 19 % of the
+//     softmax warps' time was the wait for the previous P V; profiles/r02_attention2.md);
 //   * lazy rescale: the running maximum only moves when the block maximum exceeds it by more than 2^8 (P <= 256 is
-//     harmless in bf16 / fp32), so the TMEM read-modify-write of O happens in the first blocks only;
-//   * the kernel is bound by the MUFU pipe (16 ex2 / clk / SM), so every kPoly-th exponential is evaluated on the FMA
-//     pipe instead (Cody-Waite reduction + degree-3 polynomial, relative error 8e-5, far below the bf16 rounding of P);
+//     harmless in bf16 / fp32), so the TMEM read-modify-write of O (which does need the previous P V) happens in the first
+//     blocks only;
+//   * K and V^T have their own rings: a K tile is dead as soon as its Q K^T retires (a block earlier than the V^T tile), so the
+//     next K arrives a whole block ahead with only two slots each;
+//   * optional: every kPoly-th exponential on the FMA pipe (Cody-Waite reduction + degree-3 polynomial, relative error 8e-5)
+//     -- measured slower than all-MUFU at this head dimension (the kernel is not MUFU-bound enough), kept as a knob;
 //   * Q K^T runs over ceil(d / 16) K-steps (48 columns for d = 40), not the 64-column padding.
-// warp 0: TMA | warp 1: MMA issue + TMEM alloc | warps 2..5: softmax of tile 0 | warps 6..9: softmax of tile 1
-static constexpr int kAttn2Threads = 320;
+// warp 0: TMA | warps 1, 2: MMA issue for tile 0 / tile 1 (warp 1 also allocates TMEM) | warp 3: idle |
+// warps 4..7: softmax of tile 0 | warps 8..11: softmax of tile 1
+static constexpr int kAttn2Threads = 384;   // TMA warp, one MMA warp per tile, an idle warp, two softmax warpgroups
 
 __device__ __forceinline__ float max3f(float a, float b, float c) {
     float d;
@@ -302,9 +310,14 @@ __device__ __forceinline__ float ex2_poly(float x) {
     return __int_as_float(__float_as_int(q) + (__float_as_int(r) << 23));
 }
 
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // exponentials of one 32-key chunk of a row -> bf16 -> the row's 64 bytes in the swizzled P tile; returns their sum
+// prow_atom: shared-space address of this row inside the [128][64] atom
 template <int kPoly>
-__device__ __forceinline__ float softmax_chunk32(const uint32_t (&u)[32], float sc, float ms, uint8_t* prow_atom, int chunk0, int rsw) {
+__device__ __forceinline__ float softmax_chunk32(const uint32_t (&u)[32], float sc, float ms, uint32_t prow_atom, int chunk0, int rsw) {
     float e[32];
 #pragma unroll
     for (int jj = 0; jj < 32; ++jj) {
@@ -315,11 +328,9 @@ __device__ __forceinline__ float softmax_chunk32(const uint32_t (&u)[32], float 
 #pragma unroll
     for (int jj = 0; jj < 32; jj += 4) { s0 += e[jj]; s1 += e[jj + 1]; s2 += e[jj + 2]; s3 += e[jj + 3]; }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const uint4 w = make_uint4(pack_bf16x2(e[i * 8], e[i * 8 + 1]), pack_bf16x2(e[i * 8 + 2], e[i * 8 + 3]),
-                                   pack_bf16x2(e[i * 8 + 4], e[i * 8 + 5]), pack_bf16x2(e[i * 8 + 6], e[i * 8 + 7]));
-        *reinterpret_cast<uint4*>(prow_atom + (((chunk0 + i) ^ rsw) << 4)) = w;
-    }
+    for (int i = 0; i < 4; ++i)
+        sts128(prow_atom + (uint32_t)(((chunk0 + i) ^ rsw) << 4), pack_bf16x2(e[i * 8], e[i * 8 + 1]), pack_bf16x2(e[i * 8 + 2], e[i * 8 + 3]),
+               pack_bf16x2(e[i * 8 + 4], e[i * 8 + 5]), pack_bf16x2(e[i * 8 + 6], e[i * 8 + 7]));
     return (s0 + s1) + (s2 + s3);
 }
 
@@ -345,20 +356,24 @@ attention2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                   const __grid_constant__ CUtensorMap mapVt, const AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int KS = 2, VS = 2;                               // K / V^T ring depths
     const uint32_t v_tile = (uint32_t)p.dv_pad * 128u;          // one [dv_pad][64 keys] tile
-    const uint32_t stage_bytes = (uint32_t)kTileBytes + 2u * v_tile;
     uint8_t* sQ = smem;                                         // [2 tiles][128][64]
-    uint8_t* sP = sQ + 2 * kTileBytes;                          // [2 tiles][2 atoms][128][64]
-    uint8_t* sKV = sP + 4 * kTileBytes;                         // [stages][K 128 x 64 | V^T 2 x dv_pad x 64]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + (size_t)p.stages * stage_bytes);
+    uint8_t* sP = sQ + 2 * kTileBytes;                          // [2 tiles][2 buffers][2 atoms][128][64]
+    uint8_t* sK = sP + 8 * kTileBytes;                          // [KS][128 keys][64]
+    uint8_t* sV = sK + KS * kTileBytes;                         // [VS][2][dv_pad][64 keys]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + (size_t)VS * 2 * v_tile);
     uint64_t* q_full = bars;
-    uint64_t* s_full = bars + 1;     // [2]
-    uint64_t* s_free = bars + 3;     // [2]
-    uint64_t* p_ready = bars + 5;    // [2]
-    uint64_t* pv_done = bars + 7;    // [2]
-    uint64_t* kv_full = bars + 9;
-    uint64_t* kv_empty = kv_full + p.stages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_empty + p.stages);
+    uint64_t* s_full = bars + 1;     // [tile]
+    uint64_t* s_free = bars + 3;     // [tile]
+    uint64_t* p_ready = bars + 5;    // [tile][buffer]
+    uint64_t* pv_done = bars + 9;    // [tile][buffer]
+    uint64_t* k_full = bars + 13;    // [KS]
+    uint64_t* k_empty = bars + 15;
+    uint64_t* v_full = bars + 17;    // [VS]
+    uint64_t* v_empty = bars + 19;
+    uint64_t* stagger = bars + 21;   // tile 0's warpgroup has reached its first exponentials
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -374,13 +389,18 @@ attention2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         for (int t = 0; t < 2; ++t) {
             mbar_init(&s_full[t], 1);
             mbar_init(&s_free[t], 4);
-            mbar_init(&p_ready[t], 4);
-            mbar_init(&pv_done[t], 1);
+            for (int k = 0; k < 2; ++k) {
+                mbar_init(&p_ready[t * 2 + k], 4);
+                mbar_init(&pv_done[t * 2 + k], 1);
+            }
         }
-        for (int s = 0; s < p.stages; ++s) {
-            mbar_init(&kv_full[s], 1);
-            mbar_init(&kv_empty[s], 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&k_full[s], 1);
+            mbar_init(&k_empty[s], (uint32_t)ntiles);           // one tcgen05.commit per tile's MMA warp
+            mbar_init(&v_full[s], 1);
+            mbar_init(&v_empty[s], (uint32_t)ntiles);
         }
+        mbar_init(stagger, 4);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512u);
@@ -395,84 +415,90 @@ attention2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
             mbar_expect_tx(q_full, (uint32_t)ntiles * kTileBytes);
             for (int t = 0; t < ntiles; ++t)
                 tma_load_2d(sQ + (size_t)t * kTileBytes, &mapQ, q_full, h * p.dk_pad, b * p.q_rows_per_img + qt * 256 + t * 128);
+            auto load_k = [&](int j) {
+                const int s = j % KS;
+                if (j >= KS) mbar_wait(&k_empty[s], (uint32_t)((j / KS) - 1) & 1u, 1);
+                mbar_expect_tx(&k_full[s], (uint32_t)kTileBytes);
+                tma_load_2d(sK + (size_t)s * kTileBytes, &mapK, &k_full[s], h * p.dk_pad, b * p.k_rows_per_img + j * 128);
+            };
+            auto load_v = [&](int j) {
+                const int s = j % VS;
+                if (j >= VS) mbar_wait(&v_empty[s], (uint32_t)((j / VS) - 1) & 1u, 2);
+                mbar_expect_tx(&v_full[s], 2u * v_tile);
+                for (int a = 0; a < 2; ++a)
+                    tma_load_2d(sV + ((size_t)s * 2 + a) * v_tile, &mapVt, &v_full[s], b * p.vt_cols_per_img + j * 128 + a * 64, h * p.d);
+            };
+            // K runs one block ahead of V^T (it is needed a block earlier): K0, K1, V0, K2, V1, ...
+            load_k(0);
+            for (int j = 0; j < nblocks; ++j) {
+                if (j + 1 < nblocks) load_k(j + 1);
+                load_v(j);
+            }
         }
         __syncwarp();
-        for (int j = 0; j < nblocks; ++j) {
-            const int s = j % p.stages;
-            if (j >= p.stages) mbar_wait(&kv_empty[s], (uint32_t)((j / p.stages) - 1) & 1u, 1);
-            if (elect_one()) {
-                mbar_expect_tx(&kv_full[s], stage_bytes);
-                uint8_t* st = sKV + (size_t)s * stage_bytes;
-                tma_load_2d(st, &mapK, &kv_full[s], h * p.dk_pad, b * p.k_rows_per_img + j * 128);
-                for (int a = 0; a < 2; ++a)
-                    tma_load_2d(st + kTileBytes + (size_t)a * v_tile, &mapVt, &kv_full[s], b * p.vt_cols_per_img + j * 128 + a * 64,
-                                h * p.d);
-            }
-            __syncwarp();
-        }
-    } else if (warp == 1) {
-        const uint32_t idesc_s = umma_idesc_bf16(128, 128);
-        const uint32_t idesc_o = umma_idesc_bf16(128, (uint32_t)p.dv_pad);
-        const int nk16 = (p.d + 15) >> 4;                       // K-steps of Q K^T (columns past d are zero padding)
-        const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP), kv_addr = smem_u32(sKV);
-        auto issue_qk = [&](int t, int s) {                     // S_t = Q_t K(stage s)^T
-            if (elect_one()) {
-                const uint32_t k_addr = kv_addr + (uint32_t)s * stage_bytes;
-                for (int k = 0; k < nk16; ++k)
-                    umma_bf16(tmem_base + (uint32_t)t * 128u, umma_desc_sw128(q_addr + (uint32_t)t * kTileBytes + (uint32_t)k * 32u),
-                              umma_desc_sw128(k_addr + (uint32_t)k * 32u), idesc_s, k > 0 ? 1u : 0u);
+    } else if (warp == 1 || warp == 2) {
+        // One MMA warp PER TILE (ncu of the one-warp version: that warp was busy 85 % of the time -- 22 tcgen05.mma, 6 commits
+        // and 6 barrier polls per key block in one instruction stream -- and the softmax warps waited for it). A single elected
+        // thread runs the whole loop: waits, descriptor arithmetic in uniform registers, issue.
+        const int t = warp - 1;
+        if (t < ntiles && elect_one()) {
+            const uint32_t idesc_s = umma_idesc_bf16(128, 128);
+            const uint32_t idesc_o = umma_idesc_bf16(128, (uint32_t)p.dv_pad);
+            const int nk16 = (p.d + 15) >> 4;                   // K-steps of Q K^T (columns past d are zero padding)
+            // shared-memory descriptors differ only in their 14-bit start-address field ((addr & 0x3FFFF) >> 4)
+            const uint64_t dq = umma_desc_sw128(smem_u32(sQ) + (uint32_t)t * kTileBytes), dk = umma_desc_sw128(smem_u32(sK)),
+                           dp = umma_desc_sw128(smem_u32(sP) + (uint32_t)t * 4u * kTileBytes), dv = umma_desc_sw128(smem_u32(sV));
+            const uint32_t tS = tmem_base + (uint32_t)t * 128u, tO = tmem_base + 256u + (uint32_t)t * 128u;
+            auto issue_qk = [&](int j) {                        // S_t = Q_t K(j)^T
+                const uint64_t b0 = dk + (uint64_t)((uint32_t)(j % KS) * (kTileBytes >> 4));
+                for (int k = 0; k < nk16; ++k) umma_bf16(tS, dq + (uint64_t)(2 * k), b0 + (uint64_t)(2 * k), idesc_s, k > 0 ? 1u : 0u);
                 umma_commit(&s_full[t]);
-            }
-            __syncwarp();
-        };
-        mbar_wait(q_full, 0, 2);
-        mbar_wait(&kv_full[0], 0, 3);
-        tc_fence_after_sync();
-        for (int t = 0; t < ntiles; ++t) issue_qk(t, 0);
-        for (int j = 0; j < nblocks; ++j) {
-            const int s = j % p.stages;
-            if (j + 1 < nblocks) {
-                const int sn = (j + 1) % p.stages;
-                mbar_wait(&kv_full[sn], (uint32_t)((j + 1) / p.stages) & 1u, 3);
-                for (int t = 0; t < ntiles; ++t) {
-                    mbar_wait(&s_free[t], (uint32_t)j & 1u, 4);   // the softmax threads hold S_t(j) in registers
+                umma_commit(&k_empty[j % KS]);
+            };
+            mbar_wait(q_full, 0, 3);
+            mbar_wait(&k_full[0], 0, 4);
+            tc_fence_after_sync();
+            issue_qk(0);
+            for (int j = 0; j < nblocks; ++j) {
+                if (j + 1 < nblocks) {
+                    mbar_wait(&k_full[(j + 1) % KS], (uint32_t)((j + 1) / KS) & 1u, 4);
+                    mbar_wait(&s_free[t], (uint32_t)j & 1u, 5);   // the softmax threads hold S_t(j) in registers
                     tc_fence_after_sync();
-                    issue_qk(t, sn);
+                    issue_qk(j + 1);
                 }
-            }
-            const uint32_t v_addr = kv_addr + (uint32_t)s * stage_bytes + (uint32_t)kTileBytes;
-            for (int t = 0; t < ntiles; ++t) {
-                mbar_wait(&p_ready[t], (uint32_t)j & 1u, 5);
+                mbar_wait(&v_full[j % VS], (uint32_t)(j / VS) & 1u, 6);
+                mbar_wait(&p_ready[t * 2 + (j & 1)], (uint32_t)(j >> 1) & 1u, 7);
                 tc_fence_after_sync();
-                if (elect_one()) {
+                const uint64_t a0 = dp + (uint64_t)((uint32_t)(j & 1) * ((2u * kTileBytes) >> 4));
+                const uint64_t b0 = dv + (uint64_t)((uint32_t)(j % VS) * ((2u * v_tile) >> 4));
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const uint32_t aoff = (uint32_t)t * 2u * kTileBytes + (uint32_t)(k >> 2) * kTileBytes + (uint32_t)(k & 3) * 32u;
-                        const uint32_t boff = (uint32_t)(k >> 2) * v_tile + (uint32_t)(k & 3) * 32u;
-                        umma_bf16(tmem_base + 256u + (uint32_t)t * 128u, umma_desc_sw128(p_addr + aoff), umma_desc_sw128(v_addr + boff),
-                                  idesc_o, (j > 0 || k > 0) ? 1u : 0u);
-                    }
-                    umma_commit(&pv_done[t]);
-                    if (t == ntiles - 1) umma_commit(&kv_empty[s]);
-                }
-                __syncwarp();
+                for (int k = 0; k < 8; ++k)
+                    umma_bf16(tO, a0 + (uint64_t)((k >> 2) * (kTileBytes >> 4) + (k & 3) * 2),
+                              b0 + (uint64_t)((uint32_t)(k >> 2) * (v_tile >> 4) + (uint32_t)(k & 3) * 2u), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&pv_done[t * 2 + (j & 1)]);
+                umma_commit(&v_empty[j % VS]);
             }
         }
-    } else {
-        const int t = (warp - 2) >> 2;                          // tile of this warpgroup
+        __syncwarp();
+    } else if (warp >= 4) {
+        const int t = (warp - 4) >> 2;                          // tile of this warpgroup
         const int q = warp & 3;                                 // TMEM lane quarter
         const int r = q * 32 + lane;
         if (t < ntiles) {
             const uint32_t lane_off = (uint32_t)(q * 32) << 16;
             const uint32_t tS = tmem_base + lane_off + (uint32_t)t * 128u;
             const uint32_t tO = tmem_base + lane_off + 256u + (uint32_t)t * 128u;
-            uint8_t* prow = sP + (size_t)t * 2 * kTileBytes + (size_t)r * 128;
+            const uint32_t prow_t = smem_u32(sP) + (uint32_t)t * 4u * kTileBytes + (uint32_t)r * 128u;
             const int rsw = r & 7;
             const float sc = p.scale_log2e;
             float m_used = -INFINITY, l_run = 0.f;
             pdl_wait();   // the output buffer may still be read by an earlier kernel
+            // The two warpgroups share each scheduler's MUFU pipe. Started together they load S / search the row maximum at the
+            // same time (MUFU idle) and then contend for the exponentials; tile 1 therefore starts when tile 0 reaches its first
+            // exponentials, so that one group's S load + maximum overlaps the other's exponentials (VSD_ATTN_STAGGER knob).
+            if (t == 1 && p.stagger) mbar_wait(stagger, 0, 12);
             for (int j = 0; j < nblocks; ++j) {
-                mbar_wait(&s_full[t], (uint32_t)j & 1u, 6);
+                mbar_wait(&s_full[t], (uint32_t)j & 1u, 8);
                 tc_fence_after_sync();
                 uint32_t u0[32], u1[32], u2[32], u3[32];
                 tmem_ld32(tS, u0);
@@ -488,12 +514,13 @@ attention2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                 const float mx = rowmax32(u3, rowmax32(u2, rowmax32(u1, rowmax32(u0, -INFINITY))));
                 if (j == 0) {
                     m_used = mx;
+                    if (t == 0 && lane == 0) mbar_arrive(stagger);
                 } else {
-                    // O_t and the P_t buffer belong to the previous P V until it retires
-                    mbar_wait(&pv_done[t], (uint32_t)(j - 1) & 1u, 7);
-                    tc_fence_after_sync();
                     const bool grow = (mx - m_used) * sc > 8.0f;
                     if (__any_sync(0xffffffffu, grow)) {
+                        // O_t belongs to the previous P V until it retires
+                        mbar_wait(&pv_done[t * 2 + ((j - 1) & 1)], (uint32_t)((j - 1) >> 1) & 1u, 9);
+                        tc_fence_after_sync();
                         const float m_new = grow ? mx : m_used;
                         const float alpha = ex2_approx((m_used - m_new) * sc);   // 1 for the rows that keep their maximum
                         m_used = m_new;
@@ -509,8 +536,11 @@ attention2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                         }
                         tmem_st_wait();
                     }
+                    // this block's P buffer was last read by the P V of block j - 2
+                    if (j >= 2) mbar_wait(&pv_done[t * 2 + (j & 1)], (uint32_t)((j >> 1) - 1) & 1u, 10);
                 }
                 const float ms = m_used * sc;
+                const uint32_t prow = prow_t + (uint32_t)(j & 1) * 2u * kTileBytes;
                 float lsum = softmax_chunk32<kPoly>(u0, sc, ms, prow, 0, rsw);
                 lsum += softmax_chunk32<kPoly>(u1, sc, ms, prow, 4, rsw);
                 lsum += softmax_chunk32<kPoly>(u2, sc, ms, prow + kTileBytes, 0, rsw);
@@ -519,9 +549,9 @@ attention2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                 tc_fence_before_sync();
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&p_ready[t]);
+                if (lane == 0) mbar_arrive(&p_ready[t * 2 + (j & 1)]);
             }
-            mbar_wait(&pv_done[t], (uint32_t)(nblocks - 1) & 1u, 8);
+            mbar_wait(&pv_done[t * 2 + ((nblocks - 1) & 1)], (uint32_t)((nblocks - 1) >> 1) & 1u, 11);
             tc_fence_after_sync();
             const float inv_l = 1.0f / l_run;
             const int qrow = qt * 256 + t * 128 + r;
@@ -593,18 +623,14 @@ int build_attn_op(AttnOp* op, const bf16* q, int ldq, const bf16* k, int ldk, co
     static const int poly = getenv("VSD_ATTN_POLY") ? atoi(getenv("VSD_ATTN_POLY")) : 0;
     op->variant = 0;
     if (v2_ok && op->dk_pad == 64 && nk > 128 && nq > 128) {
-        const int stage2 = kTileBytes + 2 * op->dv_pad * 128;
-        const int fixed2 = 6 * kTileBytes + 1024 /*align slack*/ + 512 /*barriers*/;
-        int st2 = (g_attn_max_smem - fixed2) / stage2;
-        const int nb2 = (nk + 127) / 128;
-        if (st2 > nb2) st2 = nb2;
-        if (st2 > 6) st2 = 6;
-        if (st2 >= 2) {
+        // Q (2 tiles) + P (2 tiles x 2 buffers x 2 atoms) + K ring (2) + V^T ring (2 x 2 x dv_pad x 128 B) + barriers
+        const int need2 = 12 * kTileBytes + 4 * op->dv_pad * 128 + 1024 /*align slack*/ + 512 /*barriers*/;
+        if (need2 <= g_attn_max_smem) {
             op->variant = 2;
             op->poly = (poly == 2 || poly == 3 || poly == 4) ? poly : 0;
-            op->stages = st2;
+            op->stages = 2;
             op->tmem_cols = 512;
-            op->smem_bytes = std::max(fixed2 + st2 * stage2, std::min(512 * 450, g_attn_max_smem));   // 512 TMEM columns: the SM is ours
+            op->smem_bytes = std::max(need2, std::min(512 * 450, g_attn_max_smem));   // 512 TMEM columns: the SM is ours
             op->grid = dim3((nq + 255) / 256, heads, batch);
             return 0;
         }
@@ -633,6 +659,8 @@ int launch_attn_op(const AttnOp& op, cudaStream_t st) {
     p.nq = op.nq; p.nk = op.nk;
     p.q_rows_per_img = op.q_rows_per_img; p.k_rows_per_img = op.k_rows_per_img; p.vt_cols_per_img = op.vt_cols_per_img;
     p.out = op.out; p.ldo = op.ldo; p.scale_log2e = op.scale_log2e; p.stages = op.stages; p.tmem_cols = op.tmem_cols;
+    static const int stagger = getenv("VSD_ATTN_STAGGER") ? atoi(getenv("VSD_ATTN_STAGGER")) : 0;   // measured: no effect either way
+    p.stagger = stagger;
     if (op.variant == 2) {
         auto kern = op.poly == 2 ? attention2_kernel<2> : (op.poly == 3 ? attention2_kernel<3> : (op.poly == 4 ? attention2_kernel<4> : attention2_kernel<0>));
         VSD_CHECK_CUDA(launch_k(kern, op.grid, dim3(kAttn2Threads), (size_t)op.smem_bytes, st, op.mapQ, op.mapK, op.mapVt, p));
