@@ -28,6 +28,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("VSD_WATCHDOG_S", "60")    # a stuck device aborts the bench with a message instead of hanging the driver
 os.environ.setdefault("VIDEOSD_NO_RAY", "1")     # the bench reads engine-level counters behind the handle: in-process actors
 
 # SURVEY.md 8(d) / Appendix B, algorithmic FLOPs per frame (2 x MAC; norms, activations and data movement count 0)

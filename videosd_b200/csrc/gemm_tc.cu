@@ -34,6 +34,7 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 // Every loop is fully unrolled with compile-time indices so v[] stays in registers.
 //   sbias : optional shared-memory copy of (bias [+ rowvec]) for this tile's columns (index 0 = this chunk)
 //   rpre  : optional residual values for this chunk, already loaded (4 x uint4 = 32 bf16)
+template <bool kMisc = true>   // kMisc: out_scale / fp32 residual / quick-GELU compiled in (CLIP, AutoencoderKL); the UNet / TAESD GEMMs never use them
 __device__ __forceinline__ void epilogue_math32(const GemmParams& p, float (&v)[32], int n_img, long grow, int col,
                                                 int ncols, const float* sbias, bool rowvec_in_sbias,
                                                 const uint4* rpre) {
@@ -75,12 +76,12 @@ __device__ __forceinline__ void epilogue_math32(const GemmParams& p, float (&v)[
                 if (j < ncols) v[j] += __ldg(rv + j);
         }
     }
-    if (p.out_scale) {
+    if (kMisc && p.out_scale) {
         const float sc = __ldg(p.out_scale);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= sc;
     }
-    if (p.residual && p.res_f32) {
+    if (kMisc && p.residual && p.res_f32) {
         const float* r = reinterpret_cast<const float*>(p.residual) + grow * p.ldr + col;
         if (full && ((p.ldr & 3) == 0) && ((col & 3) == 0)) {
 #pragma unroll
@@ -114,18 +115,19 @@ __device__ __forceinline__ void epilogue_math32(const GemmParams& p, float (&v)[
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
     }
-    if (p.act == ACT_QUICK_GELU) {
+    if (kMisc && p.act == ACT_QUICK_GELU) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.f + __expf(-1.702f * v[j]));
     }
 }
 
+template <bool kMisc = true>
 __device__ __forceinline__ void epilogue_store32(const GemmParams& p, float (&v)[32], int n_img, long grow, int col,
                                                  int ncols, const float* sbias, bool rowvec_in_sbias,
                                                  const uint4* rpre) {
     if (ncols <= 0) return;
     const bool full = (ncols >= 32);
-    epilogue_math32(p, v, n_img, grow, col, ncols, sbias, rowvec_in_sbias, rpre);
+    epilogue_math32<kMisc>(p, v, n_img, grow, col, ncols, sbias, rowvec_in_sbias, rpre);
     if (p.out_f32) {
         float* o = reinterpret_cast<float*>(p.out) + grow * p.ldo + col;
         if (full && ((p.ldo & 3) == 0) && ((col & 3) == 0)) {
@@ -205,7 +207,13 @@ __device__ __forceinline__ void splitk_finish4(const GemmParams& p, float (&v)[4
 // kPair: the kernel runs as CTA pairs (cluster (2,1,1) over adjacent 128-row tiles): ONE tcgen05.mma.cta_group::2 of the
 // leader drives both SMs' tensor cores on a 256 x block_n tile, each CTA streams its own 128 activation rows but only
 // HALF of the weight tile (block_n / 2 rows) -- the weight bytes entering each SM are halved.
-template <int kEpi, bool kPair>   // 0: direct st.global epilogue, 1: bf16 tile through smem + TMA store, 2: fp32 split-K partials through TMA,
+// kFeat: epilogue features compiled into this instantiation (bit 0 GEGLU, bit 1 folded-LayerNorm consumer, bit 2 row statistics
+// for a LayerNorm consumer, bit 3 out_scale / fp32 residual / quick-GELU). The full kernel is ~8 300 SASS instructions (133 KB,
+// more than the SM's instruction cache) and ncu shows the epilogue warps of these 10-20 us kernels stalled on instruction fetch
+// (`no_inst` = 27 % of their samples, profiles/r02_summary.md); most layers need none of the features, so they run a lean
+// instantiation. launch_gemm_op picks the smallest instantiated superset.
+enum { FEAT_GEGLU = 1, FEAT_LN = 2, FEAT_STATS = 4, FEAT_MISC = 8, FEAT_ALL = 15 };
+template <int kEpi, bool kPair, int kFeat>   // kEpi 0: direct st.global epilogue, 1: bf16 tile through smem + TMA store, 2: fp32 split-K partials through TMA,
                       // 3: split-K across a thread-block cluster, reduced through distributed shared memory
 __global__ void __launch_bounds__(kGemmThreads, ((kEpi == 1 || kEpi == 3) && !kPair ? 2 : 1))
 conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
@@ -234,7 +242,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    constexpr bool fGeglu = (kFeat & FEAT_GEGLU) != 0, fMisc = (kFeat & FEAT_MISC) != 0;
+    const bool geglu = fGeglu && p.act == ACT_GEGLU;
+    const int ln_mode = (kFeat & FEAT_LN) ? p.ln_mode : 0;
+    float* const rowstats_out = (kFeat & FEAT_STATS) ? p.rowstats_out : nullptr;
+    // phase stamps (tools/gemm_phase_timing.py) are compiled in only with -DVSD_GEMM_STAMPS: they sit in the hot loops
+#ifdef VSD_GEMM_STAMPS
     const bool dbg_cta = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+#else
+    constexpr bool dbg_cta = false;
+#endif
 #define VSD_STAMP(i) do { if (dbg_cta) { p.dbg[i] = clock64(); p.dbg[100 + (i)] = (long long)globaltimer_ns(); } } while (0)
     if (threadIdx.x == 0) VSD_STAMP(0);
     pdl_launch_dependents();   // the next kernel may begin its own prologue / weight prefetch now
@@ -462,16 +479,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 sbias[i] = bv;
             }
         }
-        if (p.ln_mode == 1)
+        if (ln_mode == 1)
             for (int i = threadIdx.x - 64; i < p.block_n; i += 128) swsum[i] = (col0 + i < p.N) ? __ldg(p.ln_wsum + col0 + i) : 0.f;
         pdl_wait();   // bias / time-embedding rows above are constants; everything below depends on earlier kernels
         // LayerNorm folded into this GEMM (GemmParams::ln_mode): the GEMM that PRODUCED the normalised operand left, per row
         // and per N tile of its own grid, the partial sums of x and x^2 of the values it stored (rowstats_out below). Reduce
         // them here (fixed order) to mean / rstd: per output row (mode 1) or per output column (mode 2, swapped operands).
         float ln_mean = 0.f, ln_rstd = 1.f;
-        if (p.ln_mode) {
+        if (ln_mode) {
             const float inv_k = 1.0f / (float)(p.cin * p.taps);
-            if (p.ln_mode == 1) {
+            if (ln_mode == 1) {
                 if (row_ok) {
                     const float2* st = reinterpret_cast<const float2*>(p.ln_stats) + grow * p.ln_nst;
                     float a = 0.f, b = 0.f;
@@ -493,7 +510,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             }
         }
         const bool res_vec = (p.residual != nullptr) && row_ok && ((p.ldr & 7) == 0) && ((col0 & 7) == 0) &&
-                             (p.splits == 1) && (p.act != ACT_GEGLU) && !p.tma_res && !p.res_f32;
+                             (p.splits == 1) && !geglu && !p.tma_res && !(fMisc && p.res_f32);
         // this warp's 32 rows as a sub-box of the tile rectangle (all extents are powers of two)
         const int sw0 = w0 + (q * 32) % p.BW, sh0 = h0 + ((q * 32) / p.BW) % p.BH, sn0 = n0 + (q * 32) / (p.BW * p.BH);
         uint4 rnext[4];
@@ -529,7 +546,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 }
             }
             tma_store_wait_all();
-        } else if (kEpi == 1 && p.act == ACT_GEGLU) {
+        } else if (kEpi == 1 && geglu) {
             const int half = p.block_n >> 1;
             const int ocol0 = col0 >> 1;
             for (int c = 0; c < half; c += 32) {
@@ -542,7 +559,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 tmem_ld_wait();
                 const float4* bu = reinterpret_cast<const float4*>(sbias + c);
                 const float4* bg = reinterpret_cast<const float4*>(sbias + half + c);
-                if (p.ln_mode == 1) {          // folded LayerNorm (norm3 -> GEGLU projection)
+                if (ln_mode == 1) {          // folded LayerNorm (norm3 -> GEGLU projection)
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         u[j] = __float_as_uint(ln_rstd * (__uint_as_float(u[j]) - ln_mean * swsum[c + j]));
@@ -573,8 +590,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             }
             tma_store_wait_all();
         } else if (kEpi == 1) {
-            const float ln_ws_row = (p.ln_mode == 2 && row_ok) ? __ldg(p.ln_wsum + grow) : 0.f;
-            const float ln_rb_row = (p.ln_mode == 2 && row_ok && p.ln_rowbias) ? __ldg(p.ln_rowbias + grow) : 0.f;
+            const float ln_ws_row = (ln_mode == 2 && row_ok) ? __ldg(p.ln_wsum + grow) : 0.f;
+            const float ln_rb_row = (ln_mode == 2 && row_ok && p.ln_rowbias) ? __ldg(p.ln_rowbias + grow) : 0.f;
             float rst_s = 0.f, rst_q = 0.f;
             if (p.tma_res) mbar_wait(res_bar, 0, 4);
             for (int c = 0; c < p.block_n; c += 32) {
@@ -600,10 +617,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]);
-                if (p.ln_mode == 1) {          // folded LayerNorm over the rows of A: out = rstd * (acc - mean * colsum(W')) + bias'
+                if (ln_mode == 1) {          // folded LayerNorm over the rows of A: out = rstd * (acc - mean * colsum(W')) + bias'
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = ln_rstd * (v[j] - ln_mean * swsum[c + j]);
-                } else if (p.ln_mode == 2) {   // ... over the rows of B (output columns); per-row constants of the weight operand
+                } else if (ln_mode == 2) {   // ... over the rows of B (output columns); per-row constants of the weight operand
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = scol[c + j] * (v[j] - swsum[c + j] * ln_ws_row) + ln_rb_row;
                 }
@@ -612,12 +629,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         uint4 rs[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) rs[j] = *reinterpret_cast<const uint4*>(myrow + ((j ^ sx) << 4));
-                        epilogue_math32(p, v, n_img, grow, col, ncols, use_sbias ? sbias + c : nullptr, rowvec_in_sbias, rs);
+                        epilogue_math32<fMisc>(p, v, n_img, grow, col, ncols, use_sbias ? sbias + c : nullptr, rowvec_in_sbias, rs);
                     } else {
-                        epilogue_math32(p, v, n_img, grow, col, ncols, use_sbias ? sbias + c : nullptr, rowvec_in_sbias,
-                                        have_pre ? rcur : nullptr);
+                        epilogue_math32<fMisc>(p, v, n_img, grow, col, ncols, use_sbias ? sbias + c : nullptr, rowvec_in_sbias,
+                                               have_pre ? rcur : nullptr);
                     }
-                    if (p.rowstats_out) {      // a LayerNorm consumes this tensor: partial row sums of what is being stored
+                    if (rowstats_out) {      // a LayerNorm consumes this tensor: partial row sums of what is being stored
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             if (j < ncols) { rst_s += v[j]; rst_q += v[j] * v[j]; }
@@ -635,8 +652,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     tma_store_commit();
                 }
             }
-            if (p.rowstats_out && row_ok)
-                reinterpret_cast<float2*>(p.rowstats_out)[grow * gridDim.y + blockIdx.y] = make_float2(rst_s, rst_q);
+            if (rowstats_out && row_ok)
+                reinterpret_cast<float2*>(rowstats_out)[grow * gridDim.y + blockIdx.y] = make_float2(rst_s, rst_q);
             tma_store_wait_all();
         } else if (kEpi != 0) {
         } else if (p.splits > 1) {
@@ -661,7 +678,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     }
                 }
             }
-        } else if (p.act == ACT_GEGLU) {
+        } else if (geglu) {
             // weight rows were interleaved at load time: tile = [half value rows | half gate rows]
             const int half = p.block_n >> 1;
             const int ocol0 = col0 >> 1;
@@ -712,8 +729,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]);
                 if (row_ok)
-                    epilogue_store32(p, v, n_img, grow, col, ncols, use_sbias ? sbias + c : nullptr, rowvec_in_sbias,
-                                     have_pre ? rcur : nullptr);
+                    epilogue_store32<fMisc>(p, v, n_img, grow, col, ncols, use_sbias ? sbias + c : nullptr, rowvec_in_sbias,
+                                            have_pre ? rcur : nullptr);
             }
         }
     }
@@ -785,13 +802,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     for (int j = 0; j < 4; ++j)
                         if (col + j < p.N) { rst_s += v[j]; rst_q += v[j] * v[j]; }
                 }
-                if (p.rowstats_out) {                    // LayerNorm consumer downstream: the lanes sharing a row fold their sums
+                if (rowstats_out) {                    // LayerNorm consumer downstream: the lanes sharing a row fold their sums
                     for (int o = lanes_row >> 1; o > 0; o >>= 1) {
                         rst_s += __shfl_xor_sync(0xffffffffu, rst_s, o);
                         rst_q += __shfl_xor_sync(0xffffffffu, rst_q, o);
                     }
                     if (rok && lane_g == 0)
-                        reinterpret_cast<float2*>(p.rowstats_out)[grow * gridDim.y + blockIdx.y] = make_float2(rst_s, rst_q);
+                        reinterpret_cast<float2*>(rowstats_out)[grow * gridDim.y + blockIdx.y] = make_float2(rst_s, rst_q);
                 }
             }
         }
@@ -1070,18 +1087,49 @@ int make_tmap_2d(CUtensorMap* m, const void* base, int K, int rows, int ld, int 
 static int g_num_sms = 148;
 static int g_max_smem = 227 * 1024;
 
+// The instantiated (epilogue kind, pairs, feature set) combinations; a launch needing `feat` gets the smallest instantiated
+// superset (*got). Epilogue 0 (fp32 / unaligned outputs: rare) and any unusual combination run the all-features kernel.
+typedef void (*GemmKernel)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, GemmParams);
+static GemmKernel gemm_kernel_for(int epi, int pair, int feat, int* got) {
+#define VSD_K(E, P, F) do { *got = (F); return conv_gemm_kernel<E, P, F>; } while (0)
+    if (epi == 0) { if (pair) VSD_K(0, true, FEAT_ALL); VSD_K(0, false, FEAT_ALL); }
+    if (epi == 2) { if (pair) VSD_K(2, true, 0); VSD_K(2, false, 0); }
+    if (epi == 3) { if (pair) return nullptr; if (feat & FEAT_STATS) VSD_K(3, false, FEAT_STATS); VSD_K(3, false, 0); }
+    if (epi == 1 && pair) {
+        switch (feat) {
+            case 0: VSD_K(1, true, 0);
+            case FEAT_GEGLU: VSD_K(1, true, FEAT_GEGLU);
+            case FEAT_STATS: VSD_K(1, true, FEAT_STATS);
+            default: VSD_K(1, true, FEAT_ALL);
+        }
+    }
+    if (epi == 1) {
+        switch (feat) {
+            case 0: VSD_K(1, false, 0);
+            case FEAT_GEGLU: VSD_K(1, false, FEAT_GEGLU);
+            case FEAT_LN: VSD_K(1, false, FEAT_LN);
+            case FEAT_GEGLU | FEAT_LN: VSD_K(1, false, FEAT_GEGLU | FEAT_LN);
+            case FEAT_STATS: VSD_K(1, false, FEAT_STATS);
+            default: VSD_K(1, false, FEAT_ALL);
+        }
+    }
+#undef VSD_K
+    return nullptr;
+}
+
 int gemm_init() {
     int dev = 0;
     VSD_CHECK_CUDA(cudaGetDevice(&dev));
     VSD_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     VSD_CHECK_CUDA(cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
-    VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
-    VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
-    VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
-    VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
-    VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
-    VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    for (int epi = 0; epi < 4; ++epi)
+        for (int pair = 0; pair < 2; ++pair)
+            for (int feat = 0; feat <= FEAT_ALL; ++feat) {
+                int got = -1;
+                GemmKernel k = gemm_kernel_for(epi, pair, feat, &got);
+                if (k && got == feat)   // each instantiation once
+                    VSD_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+            }
     VSD_CHECK_CUDA(cudaFuncSetAttribute(conv_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
     return 0;
 }
@@ -1433,17 +1481,22 @@ int launch_gemm_op(const GemmOp& op, cudaStream_t st) {
         VSD_CHECK_CUDA(launch_k(conv_persist_kernel, op.grid, dim3(kGemmThreads), (size_t)op.smem_bytes, st, op.mapA, op.mapB, op.mapC, op.p));
         return 0;
     }
+    const GemmParams& q = op.p;
+    const int feat = ((q.act == ACT_GEGLU) ? FEAT_GEGLU : 0) | (q.ln_mode ? FEAT_LN : 0) | (q.rowstats_out ? FEAT_STATS : 0) |
+                     ((q.act == ACT_QUICK_GELU || q.out_scale != nullptr || q.res_f32) ? FEAT_MISC : 0);
+    int got = 0;
     if (op.p.cluster_k) {
-        VSD_CHECK_CUDA(launch_k_cluster(conv_gemm_kernel<3, false>, op.grid, dim3(kGemmThreads), (size_t)op.smem_bytes, 1, op.p.splits, st,
+        GemmKernel kern = gemm_kernel_for(3, 0, feat, &got);
+        VSD_CHECK_CUDA(launch_k_cluster(kern, op.grid, dim3(kGemmThreads), (size_t)op.smem_bytes, 1, op.p.splits, st,
                                         op.mapA, op.mapB, op.mapC, op.mapR, op.p));
         return 0;
     }
+    GemmKernel kern = gemm_kernel_for(op.p.tma_out, op.p.pair ? 1 : 0, feat, &got);
+    VSD_REQUIRE(kern != nullptr, "no GEMM kernel instantiation for this configuration");
     if (op.p.pair) {
-        auto kern = op.p.tma_out == 2 ? conv_gemm_kernel<2, true> : (op.p.tma_out == 1 ? conv_gemm_kernel<1, true> : conv_gemm_kernel<0, true>);
         VSD_CHECK_CUDA(launch_k_cluster(kern, op.grid, dim3(kGemmThreads), (size_t)op.smem_bytes, 2, 1, st, op.mapA, op.mapB, op.mapC,
                                         op.mapR, op.p));
     } else {
-        auto kern = op.p.tma_out == 2 ? conv_gemm_kernel<2, false> : (op.p.tma_out == 1 ? conv_gemm_kernel<1, false> : conv_gemm_kernel<0, false>);
         VSD_CHECK_CUDA(launch_k(kern, op.grid, dim3(kGemmThreads), (size_t)op.smem_bytes, st, op.mapA, op.mapB, op.mapC, op.mapR, op.p));
     }
     if (op.p.splits > 1) {

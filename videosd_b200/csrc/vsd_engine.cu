@@ -9,7 +9,11 @@
 // several frames in flight on one copy of the weights.
 #include "vsd_internal.h"
 #include "../../include/videosd.h"
+#include <atomic>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <unistd.h>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -210,6 +214,60 @@ static void ln_unfold_forget(const void* w) {   // the weight buffer is being fr
         cudaFree(ic->second.bc);
         g_chain.erase(ic);
     }
+}
+
+// ------------------------------------------------------------------------------------------------ watchdog
+// VSD_WATCHDOG_S=<seconds> (off by default; bench.py and the GPU tests switch it on): a stream synchronisation that does not
+// return within that time means a kernel is stuck on the device (nothing in-process can recover that), so the process reports
+// it on stderr and aborts instead of hanging its caller forever.
+static std::mutex g_wd_mu;
+static std::vector<long long> g_wd_deadlines;   // one entry per synchronisation in progress (milliseconds, steady clock)
+static long long now_ms() {
+    return std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static int watchdog_seconds() {
+    static const int s = getenv("VSD_WATCHDOG_S") ? atoi(getenv("VSD_WATCHDOG_S")) : 0;
+    return s;
+}
+static void watchdog_start_once() {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        std::thread([] {
+            for (;;) {
+                std::this_thread::sleep_for(std::chrono::milliseconds(500));
+                const long long t = now_ms();
+                bool late = false;
+                {
+                    std::lock_guard<std::mutex> lk(g_wd_mu);
+                    for (long long d : g_wd_deadlines) late = late || t > d;
+                }
+                if (late) {
+                    fprintf(stderr, "videosd: the device did not finish a frame within %d s (VSD_WATCHDOG_S): a kernel is stuck; aborting\n",
+                            watchdog_seconds());
+                    fflush(stderr);
+                    _exit(86);
+                }
+            }
+        }).detach();
+    });
+}
+// cudaStreamSynchronize under the watchdog
+static cudaError_t sync_stream(cudaStream_t st) {
+    const int wd = watchdog_seconds();
+    if (wd <= 0) return cudaStreamSynchronize(st);
+    watchdog_start_once();
+    const long long mine = now_ms() + 1000LL * wd;
+    {
+        std::lock_guard<std::mutex> lk(g_wd_mu);
+        g_wd_deadlines.push_back(mine);
+    }
+    const cudaError_t r = cudaStreamSynchronize(st);
+    {
+        std::lock_guard<std::mutex> lk(g_wd_mu);
+        for (size_t i = 0; i < g_wd_deadlines.size(); ++i)
+            if (g_wd_deadlines[i] == mine) { g_wd_deadlines.erase(g_wd_deadlines.begin() + (long)i); break; }
+    }
+    return r;
 }
 
 // ------------------------------------------------------------------------------------------------ weights
@@ -1459,7 +1517,7 @@ static int encode_prompt(Engine* e, const int* ids_host, float* out_host) {
     if (rc) return rc;
     std::vector<uint16_t> t((size_t)77 * 768);
     VSD_CHECK_CUDA(cudaMemcpyAsync(t.data(), c.out, t.size() * 2, cudaMemcpyDeviceToHost, e->stream));
-    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    VSD_CHECK_CUDA(sync_stream(e->stream));
     for (size_t i = 0; i < t.size(); ++i) {
         const uint32_t u = (uint32_t)t[i] << 16;
         memcpy(&out_host[i], &u, 4);
@@ -1478,7 +1536,7 @@ static void free_resize(Engine* e) {
 static int configure(Engine* e, int nb, int H, int W) {
     ENG_REQUIRE(nb >= 1 && nb <= 64, "batch must be in [1, 64]");
     ENG_REQUIRE(H % 8 == 0 && W % 8 == 0 && H >= 16 && W >= 16, "height and width must be multiples of 8 (>= 16)");
-    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    VSD_CHECK_CUDA(sync_stream(e->stream));
     free_graphs(e);
     free_resize(e);
     e->arena.destroy();
@@ -1536,7 +1594,7 @@ static int set_schedule(Engine* e, int steps, const int* timesteps, const float*
                         float an_b, const float* w_emb256, int has_step_noise) {
     ENG_REQUIRE(e->configured, "configure() first");
     ENG_REQUIRE(steps >= 1 && steps <= kMaxSteps, "1..50 steps");
-    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    VSD_CHECK_CUDA(sync_stream(e->stream));
     free_graphs(e);
     e->arena.release(e->arena_static_mark);
     e->temb.clear(); e->eps.clear(); e->lat.clear(); e->den.clear();
@@ -1595,7 +1653,7 @@ static int set_schedule(Engine* e, int steps, const int* timesteps, const float*
             sinus[160 + k] = sinf(a);
         }
         VSD_CHECK_CUDA(cudaMemcpyAsync(d_sin, sinus.data(), 320 * 4, cudaMemcpyHostToDevice, e->stream));
-        VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+        VSD_CHECK_CUDA(sync_stream(e->stream));
         // t_emb_in = sinusoid + cond_proj(w_emb)   (bias pointer reused as the additive term)
         int rc = launch_gemv_f32(w_cond, d_wemb, d_sin, e->t_emb_in, 320, 256, 0, 0, e->stream);
         if (rc) return rc;
@@ -1637,7 +1695,7 @@ static int set_schedule(Engine* e, int steps, const int* timesteps, const float*
             }
         }
     }
-    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    VSD_CHECK_CUDA(sync_stream(e->stream));
     e->schedule_set = true;
 
     // ---- build the launch plans on top of the static + schedule allocations
@@ -1770,7 +1828,7 @@ static int set_context(Engine* e, int b, const float* ctx_host) {
     for (long i = 0; i < 77L * 768; ++i) t[i] = f32_to_bf16_rne(ctx_host[i]);
     bf16* dctx = e->ctx_bf16 + (size_t)b * 128 * 768;
     VSD_CHECK_CUDA(cudaMemcpyAsync(dctx, t.data(), t.size() * 2, cudaMemcpyHostToDevice, e->stream));
-    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    VSD_CHECK_CUDA(sync_stream(e->stream));
     for (auto& xa : e->xattn) {
         auto wk = e->w.find(xa.prefix + ".attn2.to_k.weight");
         auto wv = e->w.find(xa.prefix + ".attn2.to_v.weight");
@@ -1791,7 +1849,7 @@ static int set_context(Engine* e, int b, const float* ctx_host) {
         rc = launch_gemm_op(op, e->stream);
         if (rc) return rc;
     }
-    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    VSD_CHECK_CUDA(sync_stream(e->stream));
     e->context_set = true;
     return 0;
 }
@@ -1819,7 +1877,7 @@ static int capture(Engine* e, bool yuv, cudaGraphExec_t* exec) {
 static int finish_frame(Engine* e) {
     for (int i = 0; i < 2; ++i)
         VSD_CHECK_CUDA(cudaMemcpyAsync(e->fault_host + i, e->fault_dev[i], sizeof(unsigned int), cudaMemcpyDeviceToHost, e->stream));
-    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    VSD_CHECK_CUDA(sync_stream(e->stream));
     if (e->fault_host[0] | e->fault_host[1]) return vsd_check_pipeline_fault();   // reads, reports and clears
     return 0;
 }
@@ -1999,10 +2057,10 @@ int vsd_set_controlnet(vsd_ctx* c, int enabled, const float* scales13) {
     }
     if (scales13) {
         VSD_CHECK_CUDA(cudaMemcpyAsync(e->cn_scales, scales13, 13 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-        VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+        VSD_CHECK_CUDA(sync_stream(e->stream));
     }
     if ((enabled != 0) != e->cn_enabled) {
-        VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+        VSD_CHECK_CUDA(sync_stream(e->stream));
         free_graphs(e);
         e->cn_enabled = enabled != 0;
         e->schedule_set = false;
@@ -2021,7 +2079,7 @@ int vsd_set_vae(vsd_ctx* c, int kind) {
     ENG_REQUIRE(kind == 0 || kind == 1, "vae kind must be 0 (AutoencoderTiny) or 1 (AutoencoderKL)");
     Engine* e = &c->e;
     if (e->vae_kind != kind) {
-        VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+        VSD_CHECK_CUDA(sync_stream(e->stream));
         free_graphs(e);
         e->vae_kind = kind;
         e->schedule_set = false;
@@ -2036,7 +2094,7 @@ int vsd_set_vae_noise(vsd_ctx* c, const float* noise_nhwc) {
     ENG_REQUIRE(e->configured, "configure() first");
     const size_t lpx = (size_t)e->NB * e->h8 * e->w8;
     VSD_CHECK_CUDA(cudaMemcpyAsync(e->vae_noise, noise_nhwc, lpx * 16, cudaMemcpyHostToDevice, e->stream));
-    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    VSD_CHECK_CUDA(sync_stream(e->stream));
     return 0;
 }
 
@@ -2053,7 +2111,7 @@ int vsd_set_noise(vsd_ctx* c, const float* init_noise_nhwc, const float* step_no
     VSD_CHECK_CUDA(cudaMemcpyAsync(e->init_noise, init_noise_nhwc, lpx * 16, cudaMemcpyHostToDevice, e->stream));
     if (step_noise_nhwc && e->has_step_noise)
         VSD_CHECK_CUDA(cudaMemcpyAsync(e->step_noise, step_noise_nhwc, lpx * 16 * e->steps, cudaMemcpyHostToDevice, e->stream));
-    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    VSD_CHECK_CUDA(sync_stream(e->stream));
     return 0;
 }
 
@@ -2085,7 +2143,7 @@ int vsd_download_yuv420(vsd_ctx* c, uint8_t* y, uint8_t* u, uint8_t* v) {
 
 int vsd_sync(vsd_ctx* c) {
     CTX_GUARD(c);
-    VSD_CHECK_CUDA(cudaStreamSynchronize(c->e.stream));
+    VSD_CHECK_CUDA(sync_stream(c->e.stream));
     return vsd_check_pipeline_fault();
 }
 
@@ -2119,7 +2177,7 @@ int vsd_set_resize(vsd_ctx* c, int in_w, int in_h, int x0, int y0, int cw, int c
     ENG_REQUIRE(e->configured, "configure() first");
     ENG_REQUIRE(in_w > 0 && in_h > 0 && cw > 0 && ch > 0 && x0 >= 0 && y0 >= 0 && x0 + cw <= in_w && y0 + ch <= in_h,
                 "crop rectangle outside the input frame");
-    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    VSD_CHECK_CUDA(sync_stream(e->stream));
     free_resize(e);
     Engine::Resize& r = e->rz;
     r.in_w = in_w; r.in_h = in_h; r.x0 = x0; r.y0 = y0; r.cw = cw; r.ch = ch; r.hks = h_ksize; r.vks = v_ksize;
@@ -2182,7 +2240,7 @@ int vsd_infer_yuv420_resized(vsd_ctx* c, const uint8_t* y, const uint8_t* u, con
 int vsd_debug_read_rgb_in(vsd_ctx* c, uint8_t* host) {
     CTX_GUARD(c);
     Engine* e = &c->e;
-    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    VSD_CHECK_CUDA(sync_stream(e->stream));
     VSD_CHECK_CUDA(cudaMemcpy(host, e->d_rgb_in, (size_t)e->NB * e->H * e->W * 3, cudaMemcpyDeviceToHost));
     return 0;
 }
@@ -2215,7 +2273,7 @@ int vsd_debug_read(vsd_ctx* c, const char* what, int index, float* host, long nf
     else if (w == "latents" && index >= 0 && index < (int)e->lat.size()) src = e->lat[index];
     else if (w == "denoised" && index >= 0 && index < (int)e->den.size()) src = e->den[index];
     ENG_REQUIRE(src != nullptr, "unknown debug tap " + w);
-    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    VSD_CHECK_CUDA(sync_stream(e->stream));
     VSD_CHECK_CUDA(cudaMemcpy(host, src, (size_t)nfloats * 4, cudaMemcpyDeviceToHost));
     return 0;
 }
@@ -2232,7 +2290,7 @@ int vsd_debug_unet(vsd_ctx* c, const float* latents_nhwc, int step, float* eps_n
     int rc = run_plan(e, e->plan_unet[step], e->stream);
     if (rc) return rc;
     VSD_CHECK_CUDA(cudaMemcpyAsync(eps_nhwc, e->eps[step], lpx * 16, cudaMemcpyDeviceToHost, e->stream));
-    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    VSD_CHECK_CUDA(sync_stream(e->stream));
     return vsd_check_pipeline_fault();
 }
 
@@ -2309,7 +2367,7 @@ int vsd_debug_run_eager(vsd_ctx* c, int yuv) {
     if (!rc) rc = run_plan(e, e->plan_core, e->stream);
     if (!rc) rc = run_plan(e, e->plan_post, e->stream);
     if (rc) return rc;
-    VSD_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    VSD_CHECK_CUDA(sync_stream(e->stream));
     return vsd_check_pipeline_fault();
 }
 
