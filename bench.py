@@ -505,7 +505,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--strength", type=float, default=0.5)
     ap.add_argument("--lcm-steps", type=int, default=4)
-    ap.add_argument("--lanes", type=int, default=4, help="frames in flight per GPU (lanes sharing one weight copy)")
+    ap.add_argument("--lanes", type=int, default=6, help="frames in flight per GPU (lanes sharing one weight copy); 6 keeps p50 <= 50 ms")
     ap.add_argument("--lanes-c768", type=int, default=0, help="batches in flight for --config c768b4 (default 1)")
     ap.add_argument("--paced-frames", type=int, default=90, help="frames of the paced 30 fps latency run inside the default config")
     ap.add_argument("--streams", type=int, default=32)

@@ -332,6 +332,17 @@ def check_tuner_sweep(keys=None):
     print(f"SWEEP {total} configurations", flush=True)
 
 
+def check_s2_sweep():
+    """3x3 stride-2 convolutions through TMA element strides (VSD_TMA_S2=1 in the engine): every tuner candidate at the odd
+    360x640 geometry (45x80 -> 23x40 -> 12x20 -> 6x10) and at 512 / 768, pad 1 (UNet / TAESD) and pad 0 (AutoencoderKL)."""
+    keys = []
+    for (h, w, c) in [(45, 80, 320), (23, 40, 640), (12, 20, 1280), (64, 64, 320), (32, 32, 640), (16, 16, 1280), (96, 96, 320),
+                      (90, 160, 64), (180, 320, 64), (128, 128, 64)]:
+        keys.append(f"1x{h}x{w}x{c}|t109|n{c}|a0|f0|r0")
+    keys += ["2x45x80x320|t109|n320|a0|f0|r0", "1x45x80x128|t1109|n128|a0|f0|r0", "1x64x64x128|t1109|n128|a0|f0|r0"]
+    check_tuner_sweep(keys)
+
+
 def bench_gemm():
     """Rough timings (CUDA events) of representative layers; not a benchmark of record."""
     cases = [

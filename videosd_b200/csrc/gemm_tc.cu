@@ -625,15 +625,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     for (int j = 0; j < 32; ++j) v[j] = scol[c + j] * (v[j] - swsum[c + j] * ln_ws_row) + ln_rb_row;
                 }
                 if (row_ok) {
+                    // one instance of the (fully unrolled) epilogue arithmetic: the residual chunk comes from the TMA-staged tile
+                    // or from the prefetched registers
                     if (p.tma_res) {
-                        uint4 rs[4];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) rs[j] = *reinterpret_cast<const uint4*>(myrow + ((j ^ sx) << 4));
-                        epilogue_math32<fMisc>(p, v, n_img, grow, col, ncols, use_sbias ? sbias + c : nullptr, rowvec_in_sbias, rs);
-                    } else {
-                        epilogue_math32<fMisc>(p, v, n_img, grow, col, ncols, use_sbias ? sbias + c : nullptr, rowvec_in_sbias,
-                                               have_pre ? rcur : nullptr);
+                        for (int j = 0; j < 4; ++j) rcur[j] = *reinterpret_cast<const uint4*>(myrow + ((j ^ sx) << 4));
                     }
+                    epilogue_math32<fMisc>(p, v, n_img, grow, col, ncols, use_sbias ? sbias + c : nullptr, rowvec_in_sbias,
+                                           (p.tma_res || have_pre) ? rcur : nullptr);
                     if (rowstats_out) {      // a LayerNorm consumes this tensor: partial row sums of what is being stored
 #pragma unroll
                         for (int j = 0; j < 32; ++j)

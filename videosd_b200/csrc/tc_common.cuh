@@ -62,9 +62,9 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
         : "memory");
     return ok;
 }
-// Bounded wait: see g_trap_code.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t where = 0) {
-    if (mbar_try_wait(bar, parity)) return;
+// Bounded wait: see g_trap_code. The polling loop is a separate (not inlined) function: a kernel has a dozen wait sites and the
+// instruction footprint of these kernels matters (instruction-fetch stalls, profiles/r02_summary.md).
+static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, uint32_t where) {
     const long long t0 = clock64();
     uint32_t polls = 0;
     while (!mbar_try_wait(bar, parity)) {
@@ -76,6 +76,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
             }
         }
     }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t where = 0) {
+    if (mbar_try_wait(bar, parity)) return;
+    if (mbar_try_wait(bar, parity)) return;
+    mbar_wait_slow(bar, parity, where);
 }
 
 // ---------------------------------------------------------------- TMA
