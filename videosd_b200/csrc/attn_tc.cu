@@ -127,7 +127,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
             const uint32_t v_addr = k_addr + (uint32_t)nkc * kTileBytes;
             const uint32_t p_addr = smem_u32(sP);
             if (elect_one()) {
-                const int nk16 = p.dk_pad >> 4;
+                const int nk16 = (p.d + 15) >> 4;   // columns past d are zero padding: skip their K-steps
                 for (int k = 0; k < nk16; ++k) {
                     const uint32_t off = (uint32_t)(k >> 2) * kTileBytes + (uint32_t)(k & 3) * 32u;
                     umma_bf16(tS, umma_desc_sw128(q_addr + off), umma_desc_sw128(k_addr + off), idesc_s, k > 0 ? 1u : 0u);
@@ -205,7 +205,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
             // pass 2: probabilities -> bf16, one 128-byte row of P tile atom `half` (swizzled K-major layout)
             float lsum = 0.f;
             const float mscaled = m_new * p.scale_log2e;
-            uint8_t* prow = sP + (size_t)half * kTileBytes + (size_t)r * 128;
+            const uint32_t prow = smem_u32(sP) + (uint32_t)half * kTileBytes + (uint32_t)r * 128u;
 #pragma unroll
             for (int c = 0; c < 64; c += 32) {
                 uint32_t u[32];
@@ -231,9 +231,9 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int chunk = (c >> 3) + i;  // 16-byte chunk inside the 128-byte row
-                    const uint4 w = make_uint4(pack_bf16x2(pv[i * 8], pv[i * 8 + 1]), pack_bf16x2(pv[i * 8 + 2], pv[i * 8 + 3]),
-                                               pack_bf16x2(pv[i * 8 + 4], pv[i * 8 + 5]), pack_bf16x2(pv[i * 8 + 6], pv[i * 8 + 7]));
-                    *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) = w;
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (uint32_t)((chunk ^ (r & 7)) << 4)),
+                                 "r"(pack_bf16x2(pv[i * 8], pv[i * 8 + 1])), "r"(pack_bf16x2(pv[i * 8 + 2], pv[i * 8 + 3])),
+                                 "r"(pack_bf16x2(pv[i * 8 + 4], pv[i * 8 + 5])), "r"(pack_bf16x2(pv[i * 8 + 6], pv[i * 8 + 7])) : "memory");
                 }
             }
             l_run += lsum;

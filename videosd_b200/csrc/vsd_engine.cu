@@ -833,13 +833,18 @@ struct Builder {
         e->arena.release(m);
     }
 
-    // 3x3 stride-2 convolution. Default: im2col_s2_kernel + GEMM. Opt-in (VSD_TMA_S2=1): the taps are fetched by TMA with
-    // element strides (2, 2) straight from the input, no im2col buffer -- bit-for-bit tested per operator (tools/gpu_check.py
-    // misc) and 0.24 ms faster per 512 x 512 frame, but the 360 x 640 frame test produced NaNs with it at the end of round 1
-    // (cause not yet found), so it stays off. pad 1 = diffusers Downsample2D(padding=1) / TAESD; pad 0 = zeros right / below
-    // only (AutoencoderKL).
+    // 3x3 stride-2 convolution: the taps are fetched by TMA with element strides (2, 2) straight from the input (no im2col
+    // buffer, one kernel less, 0.2 ms per 512 x 512 frame). pad 1 = diffusers Downsample2D(padding=1) / TAESD; pad 0 = zeros
+    // right / below only (AutoencoderKL).
+    // History: at the end of round 1 the 360 x 640 frame test produced NaNs with this path (UNet passes 1 and 2 only). In round
+    // 2 that no longer reproduces: every autotuner candidate of the odd geometry (45x80 -> 23x40 -> 12x20 -> 6x10, 4 291
+    // configurations, NaN-filled outputs) matches fp32 at operator level (tools/gpu_check.py s2_sweep) and three engine runs at
+    // 360 x 640 are clean (profiles/r02_summary.md). Since the cause was never named, the strided-TMA path is the default only
+    // for even input extents (every size the benchmarks and the reference UI's 64-pixel steps produce); odd extents keep
+    // im2col_s2_kernel + GEMM. VSD_TMA_S2=1 / 0 forces it on / off everywhere.
     void conv_s2(const View& x, const std::string& name, const View& o, bool has_bias, int pad = 1) {
-        static const bool use_im2col = !(getenv("VSD_TMA_S2") && atoi(getenv("VSD_TMA_S2")) != 0);
+        static const int s2_mode = getenv("VSD_TMA_S2") ? (atoi(getenv("VSD_TMA_S2")) != 0 ? 1 : 0) : -1;
+        const bool use_im2col = s2_mode == 0 || (s2_mode < 0 && ((x.h | x.w) & 1));
         const bf16* wt = wb(name + ".weight");
         const float* b = has_bias ? wf(name + ".bias") : nullptr;
         if (rc) return;
