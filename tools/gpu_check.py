@@ -193,6 +193,8 @@ def check_gemm():
             record(f"ln_fold_rows_{rows}x{c}x{n}_bn{bn}", rel_err(y, ref), 1e-2)
             y2 = ops.linear_ln(x, w, gam, bet, bias=b, block_n=bn)
             record(f"ln_fold_rows_{rows}x{c}x{n}_bn{bn}_deterministic", float((y.float() - y2.float()).abs().max()), 0.0)
+            y3 = ops.linear_ln(x, w, gam, bet, bias=b, block_n=bn, pair=True)      # CTA pairs (cta_group::2)
+            record(f"ln_fold_rows_{rows}x{c}x{n}_bn{bn}_pair", rel_err(y3, ref), 1e-2)
         run("ln_fold_rows", ln_a)
     for (rows, c, bn) in [(4096, 320, 0), (4096, 320, 256), (1024, 640, 160), (256, 1280, 64), (64, 1280, 32), (920, 640, 96), (3600, 320, 128)]:
         def ln_b(rows=rows, c=c, bn=bn):
@@ -229,7 +231,8 @@ def check_gemm():
         run("ln_fold_chain", chain)
 
     def ln_geglu():
-        for (m, c) in [(4096, 320), (256, 1280), (64, 1280)]:
+        for (m, c, bn, pair) in [(4096, 320, 128, False), (256, 1280, 128, False), (64, 1280, 128, False), (4096, 320, 256, False),
+                                 (4096, 320, 256, True), (1024, 640, 128, True), (256, 1280, 256, True), (64, 1280, 256, False)]:
             x = (randn((m, c), 81) * 2 + 0.3).bfloat16()
             w_full = randn((8 * c, c), 82, scale=c ** -0.5)
             b_full = randn((8 * c,), 83)
@@ -239,10 +242,10 @@ def check_gemm():
             for t in range(half // 64):
                 idx += list(range(t * 64, t * 64 + 64)) + list(range(half + t * 64, half + t * 64 + 64))
             idx = torch.tensor(idx, device=DEV)
-            y = ops.linear_ln(x, w_full[idx].bfloat16().contiguous(), gam, bet, bias=b_full[idx].contiguous(), act=1, block_n=128)
+            y = ops.linear_ln(x, w_full[idx].bfloat16().contiguous(), gam, bet, bias=b_full[idx].contiguous(), act=1, block_n=bn, pair=pair)
             hfull = F.layer_norm(x.float(), (c,), gam, bet, 1e-5) @ w_full.bfloat16().float().t() + b_full
             ref = hfull[:, :half] * F.gelu(hfull[:, half:])
-            record(f"ln_fold_geglu_{m}x{c}", rel_err(y, ref), 1e-2)
+            record(f"ln_fold_geglu_{m}x{c}_bn{bn}_p{int(pair)}", rel_err(y, ref), 1e-2)
     run("ln_fold_geglu", ln_geglu)
 
 

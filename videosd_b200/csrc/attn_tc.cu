@@ -29,6 +29,7 @@ struct AttnParams {
     float scale_log2e;
     int stages, tmem_cols;
     int stagger;
+    unsigned int* trace;
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {   // one MUFU op; ex2(-inf) = 0
@@ -60,8 +61,8 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-    pdl_launch_dependents();
     const int nblocks = (p.nk + 127) >> 7;
+    if (p.trace && threadIdx.x == 0) atomicAdd(p.trace, 1u);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapQ);
@@ -82,6 +83,8 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();               // only after this CTA owns its TMEM columns (see conv_gemm_kernel)
+    if (p.trace && threadIdx.x == 0) atomicAdd(p.trace + 1, 1u);
     const uint32_t tS = tmem_base;         // 128 fp32 columns
     const uint32_t tO = tmem_base + 128u;  // dv_pad fp32 columns
 
@@ -270,6 +273,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (p.trace && threadIdx.x == 0) atomicAdd(p.trace + 2, 1u);
 }
 
 // ------------------------------------------------------------------------------------------ two-tile kernel
@@ -379,7 +383,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int nblocks = (p.nk + 127) >> 7;
     const int ntiles = (qt * 256 + 128 < p.nq) ? 2 : 1;         // the second tile of the last CTA may lie past the queries
-    pdl_launch_dependents();
+    if (p.trace && threadIdx.x == 0) atomicAdd(p.trace, 1u);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapQ);
@@ -408,6 +412,8 @@ attention2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();   // only after this CTA owns its TMEM columns (see conv_gemm_kernel)
+    if (p.trace && threadIdx.x == 0) atomicAdd(p.trace + 1, 1u);
 
     if (warp == 0) {
         pdl_wait();   // Q / K / V^T are produced by the preceding projection kernels
@@ -578,6 +584,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 512u);
+    if (p.trace && threadIdx.x == 0) atomicAdd(p.trace + 2, 1u);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -622,6 +629,7 @@ int build_attn_op(AttnOp* op, const bf16* q, int ldq, const bf16* k, int ldk, co
     static const bool v2_ok = !(getenv("VSD_ATTN_V2") && atoi(getenv("VSD_ATTN_V2")) == 0);
     static const int poly = getenv("VSD_ATTN_POLY") ? atoi(getenv("VSD_ATTN_POLY")) : 0;
     op->variant = 0;
+    op->trace = nullptr;
     if (v2_ok && op->dk_pad == 64 && nk > 128 && nq > 128) {
         // Q (2 tiles) + P (2 tiles x 2 buffers x 2 atoms) + K ring (2) + V^T ring (2 x 2 x dv_pad x 128 B) + barriers
         const int need2 = 12 * kTileBytes + 4 * op->dv_pad * 128 + 1024 /*align slack*/ + 512 /*barriers*/;
@@ -661,6 +669,7 @@ int launch_attn_op(const AttnOp& op, cudaStream_t st) {
     p.out = op.out; p.ldo = op.ldo; p.scale_log2e = op.scale_log2e; p.stages = op.stages; p.tmem_cols = op.tmem_cols;
     static const int stagger = getenv("VSD_ATTN_STAGGER") ? atoi(getenv("VSD_ATTN_STAGGER")) : 0;   // measured: no effect either way
     p.stagger = stagger;
+    p.trace = op.trace;
     if (op.variant == 2) {
         auto kern = op.poly == 2 ? attention2_kernel<2> : (op.poly == 3 ? attention2_kernel<3> : (op.poly == 4 ? attention2_kernel<4> : attention2_kernel<0>));
         VSD_CHECK_CUDA(launch_k(kern, op.grid, dim3(kAttn2Threads), (size_t)op.smem_bytes, st, op.mapQ, op.mapK, op.mapVt, p));

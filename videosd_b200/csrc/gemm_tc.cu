@@ -254,7 +254,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #endif
 #define VSD_STAMP(i) do { if (dbg_cta) { p.dbg[i] = clock64(); p.dbg[100 + (i)] = (long long)globaltimer_ns(); } } while (0)
     if (threadIdx.x == 0) VSD_STAMP(0);
-    pdl_launch_dependents();   // the next kernel may begin its own prologue / weight prefetch now
+    if (p.trace && threadIdx.x == 0) atomicAdd(p.trace, 1u);
 
     const int mt = blockIdx.x;
     const int tw = mt % p.tiles_w;
@@ -328,15 +328,34 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
         __syncwarp();
     }
-    if (warp == 1) {
-        if (kPair) tmem_alloc_pair(tmem_slot, (uint32_t)p.tmem_cols);
-        else tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    if (kPair) {
+        // Both CTAs of the pair must be running before tcgen05.alloc.cta_group::2 reaches into the peer SM's tensor memory.
+        // The two CTAs of a cluster are co-scheduled but do not start at the same instant; with several lanes and PDL keeping
+        // every SM busy the skew grows, and an allocation issued before the peer CTA had started never returned (VSD_TRACE:
+        // pairs that entered the kernel and never owned their columns while nothing else was running on the GPU).
+        cluster_sync_all();
+        if (p.trace && threadIdx.x == 0) atomicAdd(p.trace + 3, 1u);
+        if (warp == 0) {
+            if (elect_one()) early_prefetch();            // the peer's barriers exist now
+            __syncwarp();
+        }
+        if (warp == 1) tmem_alloc_pair(tmem_slot, (uint32_t)p.tmem_cols);
+    } else if (warp == 1) {
+        tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     }
     tc_fence_before_sync();
     if (kPair) cluster_sync_all(); else __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    // The next kernel may begin its own prologue / weight prefetch now -- but only now that this CTA OWNS its TMEM columns.
+    // Triggered before the allocation (as in round 1), CTAs of the dependent kernel could become co-resident and take columns
+    // first: capacity is guaranteed (shared-memory guard in build_gemm_op), contiguity is not, and a dependent that fragments
+    // the free space (or the common range a cta_group::2 allocation needs on both SMs) waits for this kernel, which waits for
+    // its columns: a rare, timing-dependent deadlock (seen once in a single-engine run and once with two batch-4 lanes; the
+    // device watchdog caught the second). With the trigger after the allocation every TMEM wait is on an older kernel.
+    pdl_launch_dependents();
     if (threadIdx.x == 0) VSD_STAMP(1);
+    if (p.trace && threadIdx.x == 0) atomicAdd(p.trace + 1, 1u);
 
     if (warp == 0) {
         // One elected thread runs the whole producer loop (single active thread => ptxas keeps the loop state in
@@ -347,7 +366,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             int cb = kb_begin - tap * kpt;
             int s = 0, dbg_it = 0;
             uint32_t ph = 0;
-            if (kPair) early_prefetch();
             pdl_wait();
             VSD_STAMP(7);
             // The residual tile rides behind the first ring pass: [chunk of 32 columns][128 rows][64 B], 64-byte swizzle
@@ -550,20 +568,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             const int half = p.block_n >> 1;
             const int ocol0 = col0 >> 1;
             for (int c = 0; c < half; c += 32) {
+                // the weight rows are interleaved in groups of 128 = 64 value rows + their 64 gate rows (at load time), so a
+                // 128- or 256-column tile holds whole groups: output column c pairs tile columns vc and vc + 64
+                const int vc = ((c >> 6) << 7) + (c & 63);
                 uint32_t u[32], g[32];
-                tmem_ld32(tbase + c, u);
-                tmem_ld32(tbase + half + c, g);
+                tmem_ld32(tbase + vc, u);
+                tmem_ld32(tbase + vc + 64, g);
                 uint8_t* buf = stag + (size_t)((c >> 5) * 4 + q) * 2048;
                 uint8_t* myrow = buf + lane * 64;
                 const int sx = (lane >> 1) & 3;
                 tmem_ld_wait();
-                const float4* bu = reinterpret_cast<const float4*>(sbias + c);
-                const float4* bg = reinterpret_cast<const float4*>(sbias + half + c);
+                const float4* bu = reinterpret_cast<const float4*>(sbias + vc);
+                const float4* bg = reinterpret_cast<const float4*>(sbias + vc + 64);
                 if (ln_mode == 1) {          // folded LayerNorm (norm3 -> GEGLU projection)
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        u[j] = __float_as_uint(ln_rstd * (__uint_as_float(u[j]) - ln_mean * swsum[c + j]));
-                        g[j] = __float_as_uint(ln_rstd * (__uint_as_float(g[j]) - ln_mean * swsum[half + c + j]));
+                        u[j] = __float_as_uint(ln_rstd * (__uint_as_float(u[j]) - ln_mean * swsum[vc + j]));
+                        g[j] = __float_as_uint(ln_rstd * (__uint_as_float(g[j]) - ln_mean * swsum[vc + 64 + j]));
                     }
                 }
 #pragma unroll
@@ -678,17 +699,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 }
             }
         } else if (geglu) {
-            // weight rows were interleaved at load time: tile = [half value rows | half gate rows]
             const int half = p.block_n >> 1;
             const int ocol0 = col0 >> 1;
             for (int c = 0; c < half; c += 32) {
+                const int vc = ((c >> 6) << 7) + (c & 63);   // see the tensor-store GEGLU epilogue
                 uint32_t u[32], g[32];
-                tmem_ld32(tbase + c, u);
-                tmem_ld32(tbase + half + c, g);
+                tmem_ld32(tbase + vc, u);
+                tmem_ld32(tbase + vc + 64, g);
                 tmem_ld_wait();
                 float v[32];
-                const float4* bu = reinterpret_cast<const float4*>(sbias + c);
-                const float4* bg = reinterpret_cast<const float4*>(sbias + half + c);
+                const float4* bu = reinterpret_cast<const float4*>(sbias + vc);
+                const float4* bg = reinterpret_cast<const float4*>(sbias + vc + 64);
 #pragma unroll
                 for (int q4 = 0; q4 < 8; ++q4) {
                     const float4 tu = bu[q4], tg = bg[q4];
@@ -821,6 +842,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     }
     if (threadIdx.x == 32) VSD_STAMP(6);
+    if (p.trace && threadIdx.x == 0) atomicAdd(p.trace + 2, 1u);
 #undef VSD_STAMP
 }
 
@@ -849,7 +871,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-    pdl_launch_dependents();
+    if (p.trace && threadIdx.x == 0) atomicAdd(p.trace, 1u);
     if (warp == 0 && elect_one()) {
         tma_prefetch_desc(&mapA);
         tma_prefetch_desc(&mapB);
@@ -867,6 +889,8 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();                                  // after the TMEM allocation: see conv_gemm_kernel
+    if (p.trace && threadIdx.x == 0) atomicAdd(p.trace + 1, 1u);
     const uint32_t acc_cols = (uint32_t)p.tmem_cols >> 1;     // columns of one accumulator buffer
 
     if (warp == 0) {
@@ -984,6 +1008,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (p.trace && threadIdx.x == 0) atomicAdd(p.trace + 2, 1u);
 }
 
 // Sums split-K partials (fixed order => deterministic) and applies the epilogue. One thread per (row, 4 columns):
@@ -1098,6 +1123,8 @@ static GemmKernel gemm_kernel_for(int epi, int pair, int feat, int* got) {
         switch (feat) {
             case 0: VSD_K(1, true, 0);
             case FEAT_GEGLU: VSD_K(1, true, FEAT_GEGLU);
+            case FEAT_LN: VSD_K(1, true, FEAT_LN);
+            case FEAT_GEGLU | FEAT_LN: VSD_K(1, true, FEAT_GEGLU | FEAT_LN);
             case FEAT_STATS: VSD_K(1, true, FEAT_STATS);
             default: VSD_K(1, true, FEAT_ALL);
         }
@@ -1268,7 +1295,7 @@ int build_gemm_op(GemmOp* op, const ActView& ain, int taps, const bf16* wt, int 
         }
     }
     VSD_REQUIRE(bn % 32 == 0 && bn >= 32 && bn <= 256, "block_n must be a multiple of 32 in [32,256]");
-    if (act == ACT_GEGLU) VSD_REQUIRE(bn % 64 == 0 && N % bn == 0 && bias != nullptr, "GEGLU needs block_n | N and a bias");
+    if (act == ACT_GEGLU) VSD_REQUIRE(bn % 128 == 0 && N % bn == 0 && bias != nullptr, "GEGLU needs block_n = 128 or 256 dividing N, and a bias");
     p.block_n = bn;
     p.tmem_cols = pow2_at_least(bn);
     const int n_tiles = (N + bn - 1) / bn;
@@ -1340,7 +1367,8 @@ int build_gemm_op(GemmOp* op, const ActView& ain, int taps, const bf16* wt, int 
     int stages = 0, stage_total = 0;
     for (;;) {
         // the residual tile needs its own region (it is in flight while the ring is busy); plain staging reuses the ring
-        const int ring_budget = smem_budget - 3072 - (tma_res ? stag_bytes : 0);
+        // reserve: alignment slack, barriers, staged bias (+ the folded-LayerNorm column vectors)
+        const int ring_budget = smem_budget - 3072 - ((ln && ln->mode) ? 2 * bn * 4 : 0) - (tma_res ? stag_bytes : 0);
         int k2 = kbs;
         while (k2 > 1 && (ring_budget / (k2 * stage_bytes) < (force_kb_per_stage > 0 ? 2 : 3) || k2 > p.kb_per_split)) --k2;
         stage_total = halo ? (kHaloABytes + 3 * b_tile) : k2 * stage_bytes;
@@ -1389,6 +1417,15 @@ int build_gemm_op(GemmOp* op, const ActView& ain, int taps, const bf16* wt, int 
     // scheduler's accounting, so bound the CTAs per SM through shared memory: smem >= tmem_cols * 450 B guarantees that
     // the co-resident CTAs' TMEM columns sum to <= 512 (otherwise tcgen05.alloc of a CTA the others wait on could spin).
     if (op->smem_bytes < p.tmem_cols * 450) op->smem_bytes = p.tmem_cols * 450;
+    // Capacity is not contiguity: with kernels of several streams (lanes, the ControlNet branch) on one SM a tcgen05.alloc may
+    // wait for a neighbour to finish. That is harmless for a CTA nobody waits on, but a cluster CTA (CTA pair, in-cluster
+    // split-K) is waited on by its peers *while they hold their own columns*: cluster {a on SM0, b on SM1} and cluster
+    // {c on SM1, d on SM0} with a, c allocated and b, d waiting for space a, c fragment is a cycle. Cluster kernels therefore
+    // take their SMs alone (no second TMEM user fits beside them: the smallest needs 32 * 450 B + 1 KB), so their allocation
+    // never waits on a running CTA and every wait chain ends at a kernel that needs nothing more.
+    static const int cluster_alone = getenv("VSD_CLUSTER_ALONE") ? atoi(getenv("VSD_CLUSTER_ALONE")) : 1;
+    if ((pair || cluster_k) && cluster_alone && op->smem_bytes < g_max_smem - 8192) op->smem_bytes = g_max_smem - 8192;
+    VSD_REQUIRE(op->smem_bytes <= g_max_smem, "GEMM configuration does not fit shared memory");
 
     p.out = out; p.ldo = ldo; p.out_f32 = out_f32;
     p.bias = bias; p.rowvec = rowvec; p.residual = residual; p.ldr = ldr;
@@ -1443,7 +1480,7 @@ int enumerate_gemm_candidates(const ActView& a, int taps, const bf16* wt, int N,
         out->push_back(GemmCand{op.p.block_n, 1, 1, 1, 4});
     for (int bi = 0; bi < 8; ++bi) {
         const int bn = bns[bi];
-        if (geglu && bn != 128) continue;
+        if (geglu && bn != 128 && bn != 256) continue;
         if (bn != 32 && bn > ((N + 31) / 32) * 32) continue;
         for (int si = 0; si < 8; ++si) {
             const int sp = sps[si];
@@ -1456,7 +1493,7 @@ int enumerate_gemm_candidates(const ActView& a, int taps, const bf16* wt, int N,
                     const int kbs = use_halo ? 1 : kbss[ki];
                     for (int pc = 0; pc < 3; ++pc) {                    // plain | CTA pairs (cta_group::2, whole-SM CTAs only) | in-cluster split-K
                         const int pair = pc == 1 ? 1 : 0, ck = pc == 2 ? 1 : 0;
-                        if (pair && (occ == 2 || !pairs_ok || ln_consumer)) continue;
+                        if (pair && (occ == 2 || !pairs_ok || (ln_consumer && ln->mode == 2))) continue;   // swapped-operand LN: no pairs
                         if (ck && (sp < 2 || sp > 8)) continue;
                         const int mode = use_halo | (pair << 1) | (ck ? 8 : 16);
                         if (build_gemm_op(&op, a, taps, wt, N, ldw, outp, ldo, out_f32, bias, rowvec, res, ldr, act, ws, ws_bytes, bn, sp, occ,

@@ -168,6 +168,11 @@ struct Engine {
     bool cn_enabled = false;
     float* cn_scales = nullptr;        // device [13]: logspace(-1,0,13) * conditioning scale (guess mode)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t done_ev = nullptr;   // blocking-sync completion event (sync_engine)
+    // VSD_TRACE=1: per tensor-core launch of the plans three device counters (GemmParams::trace), dumped by the watchdog
+    unsigned int* trace_dev = nullptr;
+    std::vector<std::string> trace_tags;
+    std::vector<int> trace_ctas;
     // device-side wait-timeout words of the two tensor-core translation units, copied behind every frame into pinned host
     // memory so the production entry points can report a fault without an extra synchronisation
     const unsigned int* fault_dev[2] = {nullptr, nullptr};
@@ -221,6 +226,7 @@ static void ln_unfold_forget(const void* w) {   // the weight buffer is being fr
 // return within that time means a kernel is stuck on the device (nothing in-process can recover that), so the process reports
 // it on stderr and aborts instead of hanging its caller forever.
 static std::mutex g_wd_mu;
+static char g_tune_now[256] = "";   // the candidate the autotuner is timing right now (watchdog / hang diagnostics)
 static std::vector<long long> g_wd_deadlines;   // one entry per synchronisation in progress (milliseconds, steady clock)
 static long long now_ms() {
     return std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -228,6 +234,61 @@ static long long now_ms() {
 static int watchdog_seconds() {
     static const int s = getenv("VSD_WATCHDOG_S") ? atoi(getenv("VSD_WATCHDOG_S")) : 0;
     return s;
+}
+static constexpr int kTraceSlots = 16384;
+static std::mutex g_trace_mu;
+static std::vector<Engine*> g_trace_engines;
+static bool trace_enabled() {
+    static const bool on = getenv("VSD_TRACE") && atoi(getenv("VSD_TRACE")) != 0;
+    return on;
+}
+// a counter triple for the tensor-core launch being added to a plan (null when tracing is off / the table is full)
+static unsigned int* trace_slot(Engine* e, const std::string& tag, int ctas) {
+    if (!trace_enabled()) return nullptr;
+    std::lock_guard<std::mutex> lk(g_trace_mu);
+    if (!e->trace_dev) {
+        if (cudaMalloc(reinterpret_cast<void**>(&e->trace_dev), (size_t)kTraceSlots * 4 * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+        cudaMemset(e->trace_dev, 0, (size_t)kTraceSlots * 4 * sizeof(unsigned int));
+        g_trace_engines.push_back(e);
+    }
+    if ((int)e->trace_tags.size() >= kTraceSlots) return nullptr;
+    e->trace_tags.push_back(tag);
+    e->trace_ctas.push_back(ctas);
+    return e->trace_dev + 4 * (e->trace_tags.size() - 1);
+}
+static void trace_forget(Engine* e) {
+    std::lock_guard<std::mutex> lk(g_trace_mu);
+    for (size_t i = 0; i < g_trace_engines.size(); ++i)
+        if (g_trace_engines[i] == e) { g_trace_engines.erase(g_trace_engines.begin() + (long)i); break; }
+    if (e->trace_dev) cudaFree(e->trace_dev);
+    e->trace_dev = nullptr;
+}
+// called by the watchdog thread while a kernel is stuck: copies run on their own stream (the copy engines still work)
+static void trace_dump() {
+    std::lock_guard<std::mutex> lk(g_trace_mu);
+    for (Engine* e : g_trace_engines) {
+        if (cudaSetDevice(e->device) != cudaSuccess) continue;
+        cudaStream_t st = nullptr;
+        if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) continue;
+        const size_t n = e->trace_tags.size();
+        std::vector<unsigned int> h(n * 4);
+        if (cudaMemcpyAsync(h.data(), e->trace_dev, n * 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) {
+            fprintf(stderr, "videosd trace: engine %p: copy failed\n", (void*)e);
+            continue;
+        }
+        int shown = 0;
+        for (size_t i = 0; i < n; ++i) {
+            const unsigned in = h[4 * i], own = h[4 * i + 1], out = h[4 * i + 2], met = h[4 * i + 3];
+            if (in == out && in == own) continue;
+            fprintf(stderr, "videosd trace: engine %p (lane %d, %dx%dx%d) launch %zu %s: %d CTAs per launch, entered %u, met the peer %u, own TMEM %u, finished %u\n",
+                    (void*)e, e->lane_index, e->NB, e->H, e->W, i, e->trace_tags[i].c_str(), e->trace_ctas[i], in, met, own, out);
+            if (++shown >= 40) break;
+        }
+        if (!shown) fprintf(stderr, "videosd trace: engine %p (lane %d, %dx%dx%d): every traced launch finished (%zu traced)\n",
+                            (void*)e, e->lane_index, e->NB, e->H, e->W, n);
+    }
+    fflush(stderr);
 }
 static void watchdog_start_once() {
     static std::once_flag once;
@@ -242,32 +303,48 @@ static void watchdog_start_once() {
                     for (long long d : g_wd_deadlines) late = late || t > d;
                 }
                 if (late) {
-                    fprintf(stderr, "videosd: the device did not finish a frame within %d s (VSD_WATCHDOG_S): a kernel is stuck; aborting\n",
-                            watchdog_seconds());
+                    fprintf(stderr, "videosd: the device did not finish a frame within %d s (VSD_WATCHDOG_S): a kernel is stuck; aborting%s%s\n",
+                            watchdog_seconds(), g_tune_now[0] ? " -- the autotuner was timing " : "", g_tune_now);
                     fflush(stderr);
+                    trace_dump();
                     _exit(86);
                 }
             }
         }).detach();
     });
 }
-// cudaStreamSynchronize under the watchdog
-static cudaError_t sync_stream(cudaStream_t st) {
-    const int wd = watchdog_seconds();
-    if (wd <= 0) return cudaStreamSynchronize(st);
-    watchdog_start_once();
-    const long long mine = now_ms() + 1000LL * wd;
-    {
+struct WatchdogScope {   // registers a deadline for the synchronisation in progress
+    long long mine = 0;
+    WatchdogScope() {
+        const int wd = watchdog_seconds();
+        if (wd <= 0) return;
+        watchdog_start_once();
+        mine = now_ms() + 1000LL * wd;
         std::lock_guard<std::mutex> lk(g_wd_mu);
         g_wd_deadlines.push_back(mine);
     }
-    const cudaError_t r = cudaStreamSynchronize(st);
-    {
+    ~WatchdogScope() {
+        if (!mine) return;
         std::lock_guard<std::mutex> lk(g_wd_mu);
         for (size_t i = 0; i < g_wd_deadlines.size(); ++i)
             if (g_wd_deadlines[i] == mine) { g_wd_deadlines.erase(g_wd_deadlines.begin() + (long)i); break; }
     }
-    return r;
+};
+// Wait for the engine's stream. cudaStreamSynchronize spins on a host core; with several frames in flight per GPU (one host
+// thread per lane, 6 lanes x 8 ranks on a 32-core box) that is more spinning threads than cores, so lanes and lane-pool roots
+// block on an event created with cudaEventBlockingSync instead (VSD_BLOCKING_SYNC=0 / 1 forces spinning / blocking).
+static cudaError_t sync_engine(Engine* e) {
+    static const int mode = getenv("VSD_BLOCKING_SYNC") ? atoi(getenv("VSD_BLOCKING_SYNC")) : -1;
+    const bool blocking = mode > 0 || (mode < 0 && (e->autotune > 1 || !e->owns_weights));
+    WatchdogScope wd;
+    if (!blocking) return cudaStreamSynchronize(e->stream);
+    if (!e->done_ev) {
+        const cudaError_t r = cudaEventCreateWithFlags(&e->done_ev, cudaEventBlockingSync | cudaEventDisableTiming);
+        if (r != cudaSuccess) return r;
+    }
+    const cudaError_t r = cudaEventRecord(e->done_ev, e->stream);
+    if (r != cudaSuccess) return r;
+    return cudaEventSynchronize(e->done_ev);
 }
 
 // ------------------------------------------------------------------------------------------------ weights
@@ -426,7 +503,10 @@ static int time_gemm(Engine* e, const GemmOp* ops, int nops, float* us) {
             if (rc) return rc;
         }
         VSD_CHECK_CUDA(cudaEventRecord(e->ev1, e->stream));
-        VSD_CHECK_CUDA(cudaEventSynchronize(e->ev1));
+        {
+            WatchdogScope wd;
+            VSD_CHECK_CUDA(cudaEventSynchronize(e->ev1));
+        }
         float ms = 0.f;
         VSD_CHECK_CUDA(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
         const float t = ms * 1e3f / (float)nops;
@@ -469,6 +549,8 @@ static int tune_gemm(Engine* e, const ActView& a, int taps, const bf16* wt, int 
     Engine::Tuned best{0, 1, 0, 1, 0, 1e30f};
     float best_cost = 1e30f;
     for (const GemmCand& c : cands) {
+        snprintf(g_tune_now, sizeof(g_tune_now), "%dx%dx%dx%d taps %d N %d act %d: bn=%d splits=%d occ=%d kbs=%d mode=%d", a.NB, a.H, a.W, a.C, taps, N,
+                 act, c.bn, c.splits, c.occ, c.kbs, c.mode);
         GemmOp ops[kTuneCopies];
         bool ok = true;
         for (int i = 0; i < kTuneCopies && ok; ++i)
@@ -483,6 +565,7 @@ static int tune_gemm(Engine* e, const ActView& a, int taps, const bf16* wt, int 
         const float cost = us * std::max(util, 1.0f / (float)std::max(e->autotune, 1));
         if (cost < best_cost) { best_cost = cost; best = Engine::Tuned{c.bn, c.splits, c.occ, c.kbs, c.mode, us}; }
     }
+    g_tune_now[0] = 0;
     if (best.bn == 0) { set_error("autotune found no valid GEMM configuration"); return -1; }
     *result = best;
     return 0;
@@ -602,6 +685,12 @@ struct Builder {
         }
         if (r) { rc = r; fail = get_error(); return 0; }
         op.p.out_scale = out_scale;
+        {
+            char what[160];
+            snprintf(what, sizeof(what), ".gemm[%dx%dx%dx%d t%d N%d act%d bn%d sp%d pair%d ck%d halo%d persist%d smem%d tmem%d]", a.NB, a.H, a.W, a.C, taps, N, act,
+                     op.p.block_n, op.p.splits, op.p.pair, op.p.cluster_k, op.p.halo, op.p.persist, op.smem_bytes, op.p.tmem_cols);
+            op.p.trace = trace_slot(e, g_scope + what, (int)(op.grid.x * op.grid.y * op.grid.z));
+        }
         const size_t first = out->size();
         out->push_back(mk([op](cudaStream_t st) { return launch_gemm_op(op, st); }, "gemm"));
         mark_join(first);
@@ -641,6 +730,11 @@ struct Builder {
         int r = build_attn_op(&op, q, ldq, k, ldk, vt, ldvt, o.p, o.ld, o.nb, heads, d, nq, nk, q_rows, k_rows, vt_cols,
                               vt_rows);
         if (r) { rc = r; fail = get_error(); return; }
+        {
+            char what[128];
+            snprintf(what, sizeof(what), ".attn[b%d h%d d%d nq%d nk%d variant%d smem%d tmem%d]", o.nb, heads, d, nq, nk, op.variant, op.smem_bytes, op.tmem_cols);
+            op.trace = trace_slot(e, g_scope + what, (int)(op.grid.x * op.grid.y * op.grid.z));
+        }
         const size_t first = out->size();
         out->push_back(mk([op](cudaStream_t st) { return launch_attn_op(op, st); }, "attn"));
         mark_join(first);
@@ -1522,7 +1616,7 @@ static int encode_prompt(Engine* e, const int* ids_host, float* out_host) {
     if (rc) return rc;
     std::vector<uint16_t> t((size_t)77 * 768);
     VSD_CHECK_CUDA(cudaMemcpyAsync(t.data(), c.out, t.size() * 2, cudaMemcpyDeviceToHost, e->stream));
-    VSD_CHECK_CUDA(sync_stream(e->stream));
+    VSD_CHECK_CUDA(sync_engine(e));
     for (size_t i = 0; i < t.size(); ++i) {
         const uint32_t u = (uint32_t)t[i] << 16;
         memcpy(&out_host[i], &u, 4);
@@ -1541,7 +1635,7 @@ static void free_resize(Engine* e) {
 static int configure(Engine* e, int nb, int H, int W) {
     ENG_REQUIRE(nb >= 1 && nb <= 64, "batch must be in [1, 64]");
     ENG_REQUIRE(H % 8 == 0 && W % 8 == 0 && H >= 16 && W >= 16, "height and width must be multiples of 8 (>= 16)");
-    VSD_CHECK_CUDA(sync_stream(e->stream));
+    VSD_CHECK_CUDA(sync_engine(e));
     free_graphs(e);
     free_resize(e);
     e->arena.destroy();
@@ -1599,7 +1693,7 @@ static int set_schedule(Engine* e, int steps, const int* timesteps, const float*
                         float an_b, const float* w_emb256, int has_step_noise) {
     ENG_REQUIRE(e->configured, "configure() first");
     ENG_REQUIRE(steps >= 1 && steps <= kMaxSteps, "1..50 steps");
-    VSD_CHECK_CUDA(sync_stream(e->stream));
+    VSD_CHECK_CUDA(sync_engine(e));
     free_graphs(e);
     e->arena.release(e->arena_static_mark);
     e->temb.clear(); e->eps.clear(); e->lat.clear(); e->den.clear();
@@ -1658,7 +1752,7 @@ static int set_schedule(Engine* e, int steps, const int* timesteps, const float*
             sinus[160 + k] = sinf(a);
         }
         VSD_CHECK_CUDA(cudaMemcpyAsync(d_sin, sinus.data(), 320 * 4, cudaMemcpyHostToDevice, e->stream));
-        VSD_CHECK_CUDA(sync_stream(e->stream));
+        VSD_CHECK_CUDA(sync_engine(e));
         // t_emb_in = sinusoid + cond_proj(w_emb)   (bias pointer reused as the additive term)
         int rc = launch_gemv_f32(w_cond, d_wemb, d_sin, e->t_emb_in, 320, 256, 0, 0, e->stream);
         if (rc) return rc;
@@ -1700,7 +1794,7 @@ static int set_schedule(Engine* e, int steps, const int* timesteps, const float*
             }
         }
     }
-    VSD_CHECK_CUDA(sync_stream(e->stream));
+    VSD_CHECK_CUDA(sync_engine(e));
     e->schedule_set = true;
 
     // ---- build the launch plans on top of the static + schedule allocations
@@ -1833,7 +1927,7 @@ static int set_context(Engine* e, int b, const float* ctx_host) {
     for (long i = 0; i < 77L * 768; ++i) t[i] = f32_to_bf16_rne(ctx_host[i]);
     bf16* dctx = e->ctx_bf16 + (size_t)b * 128 * 768;
     VSD_CHECK_CUDA(cudaMemcpyAsync(dctx, t.data(), t.size() * 2, cudaMemcpyHostToDevice, e->stream));
-    VSD_CHECK_CUDA(sync_stream(e->stream));
+    VSD_CHECK_CUDA(sync_engine(e));
     for (auto& xa : e->xattn) {
         auto wk = e->w.find(xa.prefix + ".attn2.to_k.weight");
         auto wv = e->w.find(xa.prefix + ".attn2.to_v.weight");
@@ -1854,7 +1948,7 @@ static int set_context(Engine* e, int b, const float* ctx_host) {
         rc = launch_gemm_op(op, e->stream);
         if (rc) return rc;
     }
-    VSD_CHECK_CUDA(sync_stream(e->stream));
+    VSD_CHECK_CUDA(sync_engine(e));
     e->context_set = true;
     return 0;
 }
@@ -1882,7 +1976,7 @@ static int capture(Engine* e, bool yuv, cudaGraphExec_t* exec) {
 static int finish_frame(Engine* e) {
     for (int i = 0; i < 2; ++i)
         VSD_CHECK_CUDA(cudaMemcpyAsync(e->fault_host + i, e->fault_dev[i], sizeof(unsigned int), cudaMemcpyDeviceToHost, e->stream));
-    VSD_CHECK_CUDA(sync_stream(e->stream));
+    VSD_CHECK_CUDA(sync_engine(e));
     if (e->fault_host[0] | e->fault_host[1]) return vsd_check_pipeline_fault();   // reads, reports and clears
     return 0;
 }
@@ -1968,6 +2062,8 @@ void vsd_destroy(vsd_ctx* c) {
         if (c->e.ev_join[k]) cudaEventDestroy(c->e.ev_join[k]);
         if (c->e.side[k]) cudaStreamDestroy(c->e.side[k]);
     }
+    if (c->e.done_ev) cudaEventDestroy(c->e.done_ev);
+    trace_forget(&c->e);
     if (c->e.flush_buf) cudaFree(c->e.flush_buf);
     if (c->e.tune_w) cudaFree(c->e.tune_w);
     free_resize(&c->e);
@@ -2062,10 +2158,10 @@ int vsd_set_controlnet(vsd_ctx* c, int enabled, const float* scales13) {
     }
     if (scales13) {
         VSD_CHECK_CUDA(cudaMemcpyAsync(e->cn_scales, scales13, 13 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-        VSD_CHECK_CUDA(sync_stream(e->stream));
+        VSD_CHECK_CUDA(sync_engine(e));
     }
     if ((enabled != 0) != e->cn_enabled) {
-        VSD_CHECK_CUDA(sync_stream(e->stream));
+        VSD_CHECK_CUDA(sync_engine(e));
         free_graphs(e);
         e->cn_enabled = enabled != 0;
         e->schedule_set = false;
@@ -2084,7 +2180,7 @@ int vsd_set_vae(vsd_ctx* c, int kind) {
     ENG_REQUIRE(kind == 0 || kind == 1, "vae kind must be 0 (AutoencoderTiny) or 1 (AutoencoderKL)");
     Engine* e = &c->e;
     if (e->vae_kind != kind) {
-        VSD_CHECK_CUDA(sync_stream(e->stream));
+        VSD_CHECK_CUDA(sync_engine(e));
         free_graphs(e);
         e->vae_kind = kind;
         e->schedule_set = false;
@@ -2099,7 +2195,7 @@ int vsd_set_vae_noise(vsd_ctx* c, const float* noise_nhwc) {
     ENG_REQUIRE(e->configured, "configure() first");
     const size_t lpx = (size_t)e->NB * e->h8 * e->w8;
     VSD_CHECK_CUDA(cudaMemcpyAsync(e->vae_noise, noise_nhwc, lpx * 16, cudaMemcpyHostToDevice, e->stream));
-    VSD_CHECK_CUDA(sync_stream(e->stream));
+    VSD_CHECK_CUDA(sync_engine(e));
     return 0;
 }
 
@@ -2116,7 +2212,7 @@ int vsd_set_noise(vsd_ctx* c, const float* init_noise_nhwc, const float* step_no
     VSD_CHECK_CUDA(cudaMemcpyAsync(e->init_noise, init_noise_nhwc, lpx * 16, cudaMemcpyHostToDevice, e->stream));
     if (step_noise_nhwc && e->has_step_noise)
         VSD_CHECK_CUDA(cudaMemcpyAsync(e->step_noise, step_noise_nhwc, lpx * 16 * e->steps, cudaMemcpyHostToDevice, e->stream));
-    VSD_CHECK_CUDA(sync_stream(e->stream));
+    VSD_CHECK_CUDA(sync_engine(e));
     return 0;
 }
 
@@ -2148,7 +2244,7 @@ int vsd_download_yuv420(vsd_ctx* c, uint8_t* y, uint8_t* u, uint8_t* v) {
 
 int vsd_sync(vsd_ctx* c) {
     CTX_GUARD(c);
-    VSD_CHECK_CUDA(sync_stream(c->e.stream));
+    VSD_CHECK_CUDA(sync_engine(&c->e));
     return vsd_check_pipeline_fault();
 }
 
@@ -2182,7 +2278,7 @@ int vsd_set_resize(vsd_ctx* c, int in_w, int in_h, int x0, int y0, int cw, int c
     ENG_REQUIRE(e->configured, "configure() first");
     ENG_REQUIRE(in_w > 0 && in_h > 0 && cw > 0 && ch > 0 && x0 >= 0 && y0 >= 0 && x0 + cw <= in_w && y0 + ch <= in_h,
                 "crop rectangle outside the input frame");
-    VSD_CHECK_CUDA(sync_stream(e->stream));
+    VSD_CHECK_CUDA(sync_engine(e));
     free_resize(e);
     Engine::Resize& r = e->rz;
     r.in_w = in_w; r.in_h = in_h; r.x0 = x0; r.y0 = y0; r.cw = cw; r.ch = ch; r.hks = h_ksize; r.vks = v_ksize;
@@ -2245,7 +2341,7 @@ int vsd_infer_yuv420_resized(vsd_ctx* c, const uint8_t* y, const uint8_t* u, con
 int vsd_debug_read_rgb_in(vsd_ctx* c, uint8_t* host) {
     CTX_GUARD(c);
     Engine* e = &c->e;
-    VSD_CHECK_CUDA(sync_stream(e->stream));
+    VSD_CHECK_CUDA(sync_engine(e));
     VSD_CHECK_CUDA(cudaMemcpy(host, e->d_rgb_in, (size_t)e->NB * e->H * e->W * 3, cudaMemcpyDeviceToHost));
     return 0;
 }
@@ -2278,7 +2374,7 @@ int vsd_debug_read(vsd_ctx* c, const char* what, int index, float* host, long nf
     else if (w == "latents" && index >= 0 && index < (int)e->lat.size()) src = e->lat[index];
     else if (w == "denoised" && index >= 0 && index < (int)e->den.size()) src = e->den[index];
     ENG_REQUIRE(src != nullptr, "unknown debug tap " + w);
-    VSD_CHECK_CUDA(sync_stream(e->stream));
+    VSD_CHECK_CUDA(sync_engine(e));
     VSD_CHECK_CUDA(cudaMemcpy(host, src, (size_t)nfloats * 4, cudaMemcpyDeviceToHost));
     return 0;
 }
@@ -2295,7 +2391,7 @@ int vsd_debug_unet(vsd_ctx* c, const float* latents_nhwc, int step, float* eps_n
     int rc = run_plan(e, e->plan_unet[step], e->stream);
     if (rc) return rc;
     VSD_CHECK_CUDA(cudaMemcpyAsync(eps_nhwc, e->eps[step], lpx * 16, cudaMemcpyDeviceToHost, e->stream));
-    VSD_CHECK_CUDA(sync_stream(e->stream));
+    VSD_CHECK_CUDA(sync_engine(e));
     return vsd_check_pipeline_fault();
 }
 
@@ -2372,7 +2468,7 @@ int vsd_debug_run_eager(vsd_ctx* c, int yuv) {
     if (!rc) rc = run_plan(e, e->plan_core, e->stream);
     if (!rc) rc = run_plan(e, e->plan_post, e->stream);
     if (rc) return rc;
-    VSD_CHECK_CUDA(sync_stream(e->stream));
+    VSD_CHECK_CUDA(sync_engine(e));
     return vsd_check_pipeline_fault();
 }
 

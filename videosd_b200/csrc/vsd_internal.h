@@ -125,6 +125,8 @@ struct GemmParams {
     int sbw, sbh, sbn;
     unsigned int stage_off, bar_off;   // byte offsets of the staging region / the mbarrier block in dynamic smem
     long long* dbg;       // optional: CTA (0,0,0) writes clock64() phase stamps here (bring-up only)
+    unsigned int* trace;  // optional (VSD_TRACE=1): four device counters -- CTAs entered / CTAs that own their TMEM columns /
+                          // CTAs finished / pair CTAs past the first cluster barrier -- read by the host watchdog when the device stops making progress
     // LayerNorm folded into the GEMM: W' = W * gamma (done once at load), out = rstd * (acc - mean * wsum) + (W beta + b).
     // ln_mode 1: mean / rstd per output ROW (A operand rows), wsum per column, the bias pointer carries W beta + b.
     // ln_mode 2: mean / rstd per output COLUMN (B operand rows), ln_wsum and ln_rowbias per output row.
@@ -178,6 +180,7 @@ struct AttnOp {
     bf16* out; int ldo;
     float scale_log2e;
     int stages, tmem_cols, smem_bytes;
+    unsigned int* trace; // see GemmParams::trace
     int variant, poly;   // 0: attention_kernel (one 128-query tile per CTA); 2: attention2_kernel (two tiles), every poly-th ex2 on the FMA pipe
     dim3 grid;
 };

@@ -186,6 +186,8 @@ int vsd_op_linear_ln(const void* x, int rows, int c, int ldx, const void* w_raw,
         nst = 1;
     }
     GemmOp op;
+    const int mode = (act & 256) ? 2 : 0;   // test knob: bit 8 = CTA pairs (non-swapped only)
+    act &= ~256;
     if (!rc) {
         if (swapped) {
             LnFuse ln{2, wsum, wb, eps, stats, nst, nullptr};
@@ -195,7 +197,7 @@ int vsd_op_linear_ln(const void* x, int rows, int c, int ldx, const void* w_raw,
         } else {
             LnFuse ln{1, wsum, nullptr, eps, stats, nst, nullptr};
             ActView ax{x, 1, 1, rows, c, ldx};
-            rc = build_gemm_op(&op, ax, 1, w, n, c, out, ldo, 0, wb, nullptr, nullptr, 0, act, nullptr, 0, block_n, 1, 0, 0, 0, &ln);
+            rc = build_gemm_op(&op, ax, 1, w, n, c, out, ldo, 0, wb, nullptr, nullptr, 0, act, nullptr, 0, block_n, 1, mode ? 1 : 0, 0, mode, &ln);
         }
     }
     if (!rc) rc = launch_gemm_op(op, st);

@@ -63,7 +63,7 @@ def conv_gemm_cfg(x, weight_ohwi, taps, out, cfg, bias=None, rowvec=None, residu
     return out
 
 
-def linear_ln(x, w_raw, gamma, beta, bias=None, eps=1e-5, swapped=False, act=0, block_n=0, stats=None):
+def linear_ln(x, w_raw, gamma, beta, bias=None, eps=1e-5, swapped=False, act=0, block_n=0, stats=None, pair=False):
     """Linear(LayerNorm(x)) with the LayerNorm folded into the GEMM. x: bf16 (rows, c); w_raw: bf16 (n, c); stats: fp32
     (rows, nst, 2) from linear_stats (None: computed by a helper kernel).
     Returns (rows, n) -- (rows, n/2) for act=1 (GEGLU) -- or, swapped, (n, rows8) with rows padded to a multiple of 8."""
@@ -76,7 +76,7 @@ def linear_ln(x, w_raw, gamma, beta, bias=None, eps=1e-5, swapped=False, act=0, 
         out = torch.empty((rows, n // 2 if act == 1 else n), device=x.device, dtype=torch.bfloat16)
     nst = 0 if stats is None else stats.shape[1]
     check(lib().vsd_op_linear_ln(_p(x), c_int(rows), c_int(c), c_int(x.stride(0)), _p(w_raw), c_int(n), _p(gamma), _p(beta), _p(bias),
-                                 ctypes.c_float(eps), _p(out), c_int(out.stride(0)), c_int(1 if swapped else 0), c_int(act),
+                                 ctypes.c_float(eps), _p(out), c_int(out.stride(0)), c_int(1 if swapped else 0), c_int(act | (256 if pair else 0)),
                                  c_int(block_n), _p(stats), c_int(nst), cur_stream()), "vsd_op_linear_ln")
     return out
 
