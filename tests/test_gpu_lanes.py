@@ -130,6 +130,39 @@ def test_sessions_merged_into_a_batch_get_their_own_frame():
             assert all(psnr(out[0], alone[j][0]) < psnr(out[0], alone[i][0]) for j in range(8) if j != i)
 
 
+def test_sessions_on_two_lanes_with_batches_and_context_switches_complete():
+    """BASELINE config 5 in small: 12 sessions over two lanes, batches of <= 4, every session switching its prompt every
+    third frame. Regression test of the device hang of round 2 (a CTA-pair tcgen05.alloc issued before the peer CTA had
+    started never returned; it needed several batch engines and per-slot context projections in flight to show): the run
+    must complete under the device watchdog (conftest: VSD_WATCHDOG_S), and a session's frames must still be its own."""
+    import threading
+
+    from videosd_b200.videopipeline import VideoSDPipeline
+
+    H = W = 256
+    pipe = VideoSDPipeline.remote(frames_in_flight=2, max_batch=4, **CFG)
+    frames = _frames(12, H, W)
+    alone = [pipe.infer_yuv420.remote(*frames[i], strength=0.5, steps=4, seed=7, prompt="session prompt 0").result(timeout=900)
+             for i in range(12)]
+    results = [[] for _ in range(12)]
+
+    def session(i):
+        for f in range(12):
+            results[i].append(pipe.infer_yuv420.remote(*frames[i], strength=0.5, steps=4, seed=7,
+                                                       prompt=f"session prompt {(f // 3 + i) % 4}").result(timeout=900))
+
+    ths = [threading.Thread(target=session, args=(i,)) for i in range(12)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    st = pipe._obj.dispatcher.stats
+    assert st["frames"] == 12 + 12 * 12 and st["merged"] > 0 and st["context_switches"] > 12
+    for i in range(12):
+        assert len(results[i]) == 12
+        for f in (0, 1, 2):          # the frames of the first prompt period of session 0 ... those with prompt 0: compare with `alone`
+            if (f // 3 + i) % 4 == 0:
+                assert psnr(results[i][f][0], alone[i][0]) >= 45.0, (i, f)
+
+
 def test_config3_768x768_batch4_per_step_latents_and_psnr(oracle_models):
     """BASELINE.json configs[2]: 768x768, frame batch 4 (latent 4x4x96x96, 9216-key self-attention), four contexts."""
     from oracle import imageproc, pipeline

@@ -93,8 +93,15 @@ class Engine:
         timed on the device when the plan is built (tuning_misses() counts them). Returns the entries loaded."""
         if self._tune_for <= 0 or os.environ.get("VSD_TUNING_TABLES") == "0" or self.batch is None:
             return 0
-        path = tuning_table_path(self.batch, self.height, self.width, self._tune_for)
-        if path in self._tables_loaded or not os.path.exists(path):
+        # no table for exactly this many frames in flight: the nearest smaller count (the same file in every process, so the
+        # kernels still do not depend on device timing; live tuning of ~80 shapes would stall the stream for 20 s)
+        path = None
+        for n in range(max(1, int(self._tune_for)), 0, -1):
+            cand = tuning_table_path(self.batch, self.height, self.width, n)
+            if os.path.exists(cand):
+                path = cand
+                break
+        if path is None or path in self._tables_loaded:
             return 0
         self._tables_loaded.add(path)
         with open(path) as f:
