@@ -17,7 +17,7 @@ from videosd_b200 import weights  # noqa: E402
 from videosd_b200.engine import Engine  # noqa: E402
 
 DEFAULT = ["512x512x1:1:cn:kl", "512x512x1:6", "512x512x1:4", "512x512x1:2", "512x512x1:3", "768x768x4:1", "768x768x1:1", "512x512x4:2", "512x512x4:1",
-           "512x512x2:1", "512x512x2:2", "512x512x3:2", "360x640x1:1", "256x256x1:1:cn:kl", "256x256x3:1", "256x256x2:1", "256x256x4:1", "128x128x1:1", "64x64x1:1:cn"]
+           "512x512x2:1", "512x512x2:2", "512x512x3:2", "512x512x2:3", "512x512x3:3", "512x512x4:3", "360x640x1:1", "256x256x1:1:cn:kl", "256x256x3:1", "256x256x2:1", "256x256x4:1", "128x128x1:1", "64x64x1:1:cn"]
 
 
 def main():
