@@ -62,23 +62,36 @@ class ClockSampler:
         self._t = None
 
     def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
+        try:
+            for line in self._proc.stdout:
+                parts = [p.strip() for p in line.strip().split(",")]
                 if len(parts) >= 7:
                     self.rows.append(parts)
-            except Exception:  # noqa: BLE001
-                pass
-            self._stop.wait(0.2)
+                if self._stop.is_set():
+                    break
+        except Exception:  # noqa: BLE001
+            pass
 
     def start(self):
+        # ONE long-running nvidia-smi in loop mode (-lms 200, the recipe's form): spawning a process per sample costs a full
+        # NVML initialisation over all GPUs of the box every 200 ms per rank, which the lane threads of 8 ranks feel
+        self._proc = None
+        try:
+            self._proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                           "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                          stderr=subprocess.DEVNULL, text=True)
+        except Exception:  # noqa: BLE001
+            return
         self._t = threading.Thread(target=self._run, daemon=True)
         self._t.start()
 
     def stop(self):
         self._stop.set()
+        if getattr(self, "_proc", None) is not None:
+            try:
+                self._proc.terminate()
+            except Exception:  # noqa: BLE001
+                pass
         if self._t:
             self._t.join(timeout=6)
         sm = []

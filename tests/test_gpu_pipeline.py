@@ -258,7 +258,8 @@ def test_prompt_goes_through_gpu_text_encoder(setup):
 def test_autoencoder_kl_option(setup):
     """AutoencoderKL encode (`latent_dist.sample() * scaling_factor`) and decode around the same
     UNet loop. 22 resnets + two 1024-token single-head attentions per direction in bf16: the sampled latents are within 3e-2
-    of the fp32 oracle (tolerance of this option, wider than the TAESD path's 1e-2), the frame within the 40 dB bar."""
+    of the fp32 oracle (tolerance of this option, wider than the TAESD path's 1e-2: bf16 rounding of the WEIGHTS alone moves
+    them by 0.97e-2, see tests/kl_bf16_rounding_experiment.py), the frame within the 40 dB bar."""
     from oracle import imageproc, pipeline
     from oracle.weights import KLAdapter, build_vae_kl, random_context
 
@@ -283,6 +284,11 @@ def test_autoencoder_kl_option(setup):
         eng.infer_yuv420(y, u, v, oy, ou, ov)
         eng.sync()
         assert rel(eng.debug_read("init_latents"), ref["init_latents"]) < 3e-2
+        # free-running per-step latents: the encoder's bf16 rounding (tests/kl_bf16_rounding_experiment.py: 2.4e-2 from bf16
+        # storage alone, 0.97e-2 from bf16 weights alone) carried through the four UNet steps
+        errs = [rel(eng.debug_read("latents", i), ref["latents"][i]) for i in range(4)]
+        print("AutoencoderKL per-step latent errors:", errs)
+        assert max(errs) < 2e-2, errs    # measured 1.1e-2
         ry, ru, rv = imageproc.rgb_to_yuv420(ref["rgb"][0])
         assert psnr(oy[0], ry) >= 40.0 and psnr(ou[0], ru) >= 40.0 and psnr(ov[0], rv) >= 40.0
         oy2, ou2, ov2 = np.empty_like(y), np.empty_like(u), np.empty_like(v)
