@@ -249,3 +249,26 @@ def test_safetensors_directory_loader(tmp_path):
     assert torch.equal(got[keys[-1]], sd[keys[-1]]) and torch.equal(got[keys[0]], sd[keys[0]].to(torch.float16).float())
     with pytest.raises(FileNotFoundError):
         weights.load_safetensors_dir(str(tmp_path))
+
+
+def test_tuning_table_resolution_prefers_exact_then_nearest_smaller_frames_in_flight():
+    """Engine.configure loads the committed GEMM table of (size, batch, frames in flight); a count without its own table uses
+    the nearest smaller one (never a live timing run, never a table of another batch / size)."""
+    import os
+
+    from videosd_b200.engine import TUNING_DIR, resolve_tuning_table
+
+    def name(p):
+        return None if p is None else os.path.basename(p)
+
+    assert name(resolve_tuning_table(1, 512, 512, 6)) == "512x512x1_n6.txt"      # bench.py default
+    assert name(resolve_tuning_table(1, 512, 512, 5)) == "512x512x1_n4.txt"
+    assert name(resolve_tuning_table(1, 512, 512, 64)) == "512x512x1_n6.txt"
+    assert name(resolve_tuning_table(4, 512, 512, 3)) == "512x512x4_n3.txt"      # sessions config
+    assert name(resolve_tuning_table(4, 768, 768, 2)) == "768x768x4_n1.txt"
+    assert resolve_tuning_table(7, 512, 512, 1) is None and resolve_tuning_table(1, 520, 512, 1) is None
+    # every committed table parses: "<shape key> bn=.. splits=.. occ=.. kbs=.. halo=.. us=.."
+    for f in sorted(os.listdir(TUNING_DIR)):
+        for ln in open(os.path.join(TUNING_DIR, f)):
+            parts = ln.split()
+            assert len(parts) == 7 and parts[0].count("|") == 5 and [p.split("=")[0] for p in parts[1:]] == ["bn", "splits", "occ", "kbs", "halo", "us"], (f, ln)

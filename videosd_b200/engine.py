@@ -25,6 +25,17 @@ def tuning_table_path(batch, height, width, frames_in_flight):
     return os.path.join(TUNING_DIR, f"{height}x{width}x{batch}_n{max(1, int(frames_in_flight))}.txt")
 
 
+def resolve_tuning_table(batch, height, width, frames_in_flight):
+    """Path of the committed table to load: the one for exactly this many frames in flight, else the nearest smaller count
+    (the same file in every process, so the kernels still do not depend on device timing; live tuning of ~80 shapes would
+    stall the stream for 20 s). None when the (size, batch) has no table at all."""
+    for n in range(max(1, int(frames_in_flight)), 0, -1):
+        cand = tuning_table_path(batch, height, width, n)
+        if os.path.exists(cand):
+            return cand
+    return None
+
+
 def _fptr(a):
     return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
 
@@ -93,14 +104,7 @@ class Engine:
         timed on the device when the plan is built (tuning_misses() counts them). Returns the entries loaded."""
         if self._tune_for <= 0 or os.environ.get("VSD_TUNING_TABLES") == "0" or self.batch is None:
             return 0
-        # no table for exactly this many frames in flight: the nearest smaller count (the same file in every process, so the
-        # kernels still do not depend on device timing; live tuning of ~80 shapes would stall the stream for 20 s)
-        path = None
-        for n in range(max(1, int(self._tune_for)), 0, -1):
-            cand = tuning_table_path(self.batch, self.height, self.width, n)
-            if os.path.exists(cand):
-                path = cand
-                break
+        path = resolve_tuning_table(self.batch, self.height, self.width, self._tune_for)
         if path is None or path in self._tables_loaded:
             return 0
         self._tables_loaded.add(path)
