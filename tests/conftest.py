@@ -9,6 +9,9 @@ if ROOT not in sys.path:
 
 
 os.environ.setdefault("VSD_WATCHDOG_S", "120")   # libvideosd: abort with a message if the device stops answering (never hang the run)
+# operator tests: the library fills a GEMM's split-K workspace and dense output with NaN bytes before every launch, so a tile
+# a configuration fails to write cannot hide behind what an earlier configuration of the same shape left in the buffer
+os.environ.setdefault("VSD_POISON", "1")
 
 
 def pytest_configure(config):

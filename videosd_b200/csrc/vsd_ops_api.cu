@@ -61,6 +61,21 @@ static int ensure_ws(size_t bytes) {
     return 0;
 }
 
+// VSD_POISON=1 (operator tests): before a GEMM is launched its split-K workspace and -- when it is a dense tensor of its own --
+// its output are filled with 0xFF bytes (NaN as bf16 and as fp32), so that a tile the kernel fails to write shows up as NaN
+// instead of as whatever an earlier, correct configuration of the same shape left there (the sweeps run thousands of
+// configurations over the same buffers).
+static int poison_for_test(const GemmOp& op, void* out, int ldo, int out_f32, int n_out, const void* residual, cudaStream_t st) {
+    static const bool on = getenv("VSD_POISON") && atoi(getenv("VSD_POISON")) != 0;
+    if (!on) return 0;
+    const long rows_out = (long)op.p.NB * op.p.H * op.p.W;   // output geometry (strided convolutions: not the input's)
+    if (op.p.splits > 1 && op.p.partial)
+        VSD_CHECK_CUDA(cudaMemsetAsync(op.p.partial, 0xFF, (size_t)op.p.splits * rows_out * op.p.N * 4, st));
+    if (ldo == n_out && residual != out)
+        VSD_CHECK_CUDA(cudaMemsetAsync(out, 0xFF, (size_t)rows_out * ldo * (out_f32 ? 4 : 2), st));
+    return 0;
+}
+
 }  // namespace vsd
 
 using namespace vsd;
@@ -102,6 +117,8 @@ int vsd_op_conv_gemm(const void* x, int nb, int h, int w, int c, int ldx, int ta
     rc = build_gemm_op(&op, a, taps, reinterpret_cast<const bf16*>(wt), n, taps * c, out, ldo, out_f32, bias, rowvec,
                        reinterpret_cast<const bf16*>(residual), ldr, act, g_ws, g_ws_bytes, block_n, splits, 0, 0, want_halo);
     if (rc) return rc;
+    rc = poison_for_test(op, out, ldo, out_f32, (act & 0xF) == ACT_GEGLU ? n / 2 : n, residual, reinterpret_cast<cudaStream_t>(stream));
+    if (rc) return rc;
     return launch_gemm_op(op, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -140,6 +157,8 @@ int vsd_op_conv_gemm_cfg(const void* x, int nb, int h, int w, int c, int ldx, in
     GemmOp op;
     rc = build_gemm_op(&op, a, taps, reinterpret_cast<const bf16*>(wt), n, taps * c, out, ldo, out_f32, bias, rowvec,
                        reinterpret_cast<const bf16*>(residual), ldr, act, g_ws, g_ws_bytes, block_n, splits, occ, kb_per_stage, mode);
+    if (rc) return rc;
+    rc = poison_for_test(op, out, ldo, out_f32, (act & 0xF) == ACT_GEGLU ? n / 2 : n, residual, reinterpret_cast<cudaStream_t>(stream));
     if (rc) return rc;
     return launch_gemm_op(op, reinterpret_cast<cudaStream_t>(stream));
 }
