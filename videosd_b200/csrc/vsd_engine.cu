@@ -334,11 +334,13 @@ struct WatchdogScope {   // registers a deadline for the synchronisation in prog
 // Wait for the engine's stream. cudaStreamSynchronize spins on a host core; with several frames in flight per GPU (one host
 // thread per lane, 6 lanes x 8 ranks on a 32-core box) that is more spinning threads than cores. Blocking on a
 // cudaEventBlockingSync event instead costs 0.5 - 1 ms of wake-up latency per frame (measured: e2e 142.5 against 146.1 fps
-// with spinning, single stream 70.3 against 73.3). So lanes and lane-pool roots wait for a FRAME in two phases: the wait of a
-// frame repeats (same graph, same load), so the thread sleeps for 94 % of the predicted wait and polls the event only for
-// the remainder -- a few per cent of one core per lane whatever the number of lanes and ranks -- and falls back to the
-// blocking wait when the frame is much later than predicted. Every other synchronisation of a lane blocks; a single-lane
-// engine spins. VSD_BLOCKING_SYNC = 0 / 1 / 2 forces spinning / blocking / the two-phase wait.
+// with spinning, single stream 70.3 against 73.3). So lanes and lane-pool roots wait for a FRAME by napping: the thread
+// sleeps in short naps (a quarter of the time left until the predicted completion, at most 300 us) and looks at the
+// completion event between them, polls with yields once the predicted completion (the shorter of the last wait and their
+// moving average) is less than 0.6 ms away, and falls back to the blocking wait when the frame is much later than predicted.
+// A frame that finishes EARLY (the load dropped: other lanes went idle) is noticed within one nap, not at the predicted
+// time. Cost: ~2 % of one core per lane whatever the number of lanes and ranks. Every other synchronisation of a lane
+// blocks; a single-lane engine spins. VSD_BLOCKING_SYNC = 0 / 1 / 2 forces spinning / blocking / napping.
 static double elapsed_us(std::chrono::steady_clock::time_point t0) {
     return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
 }
@@ -357,16 +359,17 @@ static cudaError_t sync_engine(Engine* e, bool frame = false) {
     const auto t0 = std::chrono::steady_clock::now();
     bool done = false;
     if (e->wait_ema_us > 0.0) {
-        const double pred = std::min(e->wait_ema_us, e->wait_last_us);    // shorter of the two: rather poll longer than wake late
-        const double sleep_us = pred * 0.94 - 150.0;
-        if (sleep_us > 200.0) std::this_thread::sleep_for(std::chrono::microseconds((long long)sleep_us));
+        const double pred = std::min(e->wait_ema_us, e->wait_last_us);
         const double limit_us = pred * 1.25 + 2000.0;
         for (;;) {
             const cudaError_t q = cudaEventQuery(e->done_ev);
             if (q == cudaSuccess) { done = true; break; }
             if (q != cudaErrorNotReady) return q;
-            if (elapsed_us(t0) > limit_us) break;        // much later than predicted: stop burning a core
-            std::this_thread::yield();
+            const double t = elapsed_us(t0);
+            if (t > limit_us) break;                      // much later than predicted: stop polling
+            const double left = pred - t;
+            if (left > 600.0) std::this_thread::sleep_for(std::chrono::microseconds((long long)std::min(300.0, left * 0.25)));
+            else std::this_thread::yield();
         }
     }
     if (!done) {
